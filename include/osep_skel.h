@@ -1,0 +1,187 @@
+/* include/osep_skel.h -- C ABI of libosep_skel.so, the B200 (sm_100a) implementation of
+ * osep_skeleton_decomp's per-frame skeleton-extraction hot path.
+ *
+ * The reference has no FFI/plugin layer: its seam is the two C++ classes
+ *   Rosa  (osep_skeleton_decomp/include/rosa.hpp:48-53:  ctor, rosa_run(), input_cloud(), output_vertices())
+ *   GSkel (osep_skeleton_decomp/include/gskel.hpp:106-112: ctor, gskel_run(), input_vertices(), output_gskel())
+ * driven by RosaNode::process_tick (src/rosa_node.cpp:120-140) and GSkelNode::process_tick
+ * (src/gskel_node.cpp:114-147).  Every entry point below names the member it replaces.  The
+ * C++ shim classes with the reference's member names live in osep_path_planner_b200/host/
+ * (rosa.hpp, gskel.hpp) and call only this ABI; INTEGRATION.md shows the node-side binding.
+ *
+ * Conventions: plain pointers and sizes, POD structs, no exceptions, no PCL/Eigen/ROS/torch
+ * types.  Inputs are caller owned; outputs are library owned and valid until the next call on
+ * the same handle.  A handle is used from one thread at a time (the reference classes are
+ * non-reentrant too: rosa.hpp:74-95 member scratch).  Different handles may run concurrently.
+ * There is no CPU fallback: every call fails with OSEP_ERR_CUDA when no sm_100-class device
+ * is usable.
+ */
+#ifndef OSEP_SKEL_H_
+#define OSEP_SKEL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSEP_ABI_VERSION 1
+
+/* ---- status codes.  1..7 = index of the failing stage, mirroring RUN_STEP (rosa.hpp:12-18,
+ * gskel.hpp:15-21): the reference returns false at the first stage that fails. */
+enum {
+    OSEP_OK = 0,
+    OSEP_STAGE_1 = 1, /* Rosa: preprocess                      | GSkel: increment_skeleton      */
+    OSEP_STAGE_2 = 2, /* Rosa: rosa_init                       | GSkel: graph_adj               */
+    OSEP_STAGE_3 = 3, /* Rosa: similarity_neighbor_extraction  | GSkel: mst                     */
+    OSEP_STAGE_4 = 4, /* Rosa: drosa                           | GSkel: vertex_merge            */
+    OSEP_STAGE_5 = 5, /* Rosa: dcrosa                          | GSkel: prune                   */
+    OSEP_STAGE_6 = 6, /* Rosa: vertex_sampling                 | GSkel: smooth_vertex_positions */
+    OSEP_STAGE_7 = 7, /* Rosa: vertex_smooth                   | GSkel: extract_branches        */
+    OSEP_ERR_CUDA = -1,     /* CUDA runtime error / no usable device (see osep_last_error) */
+    OSEP_ERR_ARG = -2,      /* bad argument */
+    OSEP_ERR_CAPACITY = -3  /* a device buffer sized at create time is too small for this frame */
+};
+
+/* ---- result flags (bit set) */
+enum {
+    OSEP_FLAG_LEAF_NOT_CONVERGED = 1u, /* 8 VoxelGrid passes exhausted (rosa.cpp:125-146): leaf_size != leaf_used */
+    OSEP_FLAG_POOR_FIXUP_OOB = 2u,     /* goodCenters[gid] out of bounds = UB in the reference (rosa.cpp:374); pset left unchanged */
+    OSEP_FLAG_VOXEL_OVERFLOW = 4u,     /* PCL VoxelGrid int32 guard hit (output = input) */
+    OSEP_FLAG_NONFINITE_PSET = 8u      /* vertex_sampling dropped non-finite rows (rosa.cpp:439-448) */
+};
+
+/* RosaConfig (rosa.hpp:20-33); defaults are the ROS parameter defaults (rosa_node.cpp:50-60). */
+typedef struct osep_rosa_config {
+    int32_t max_points;     /* rosa_max_points            1000 */
+    int32_t min_points;     /* rosa_min_points             100 */
+    float pts_dist_lim;     /* rosa_point_dist_lim         50  */
+    int32_t ne_knn;         /* rosa_ne_knn                  20 */
+    int32_t nb_knn;         /* rosa_nb_knn                  10 */
+    float max_proj_range;   /* rosa_max_projection_range    10 */
+    int32_t niter_drosa;    /* rosa_niter_drosa              6 */
+    int32_t niter_dcrosa;   /* rosa_niter_dcrosa             5 */
+    int32_t niter_smooth;   /* rosa_niter_smooth             3 */
+    float alpha_recenter;   /* rosa_recenter_alpha         0.3 */
+    float radius_smooth;    /* rosa_smooth_radius            5 */
+} osep_rosa_config;
+
+/* GSkelConfig (gskel.hpp:23-33); defaults gskel_node.cpp:62-70. */
+typedef struct osep_gskel_config {
+    float gnd_th;               /* gskel_gnd_th               60  */
+    float fuse_dist_th;         /* gskel_fuse_dist_th          3  */
+    float fuse_conf_th;         /* gskel_fuse_conf_th         0.1 */
+    float lkf_pn;               /* gskel_lkf_pn              1e-4 */
+    float lkf_mn;               /* gskel_lkf_mn               0.1 */
+    int32_t max_obs_wo_conf;    /* gskel_max_obs_wo_conf       5  */
+    int32_t niter_smooth_vertex;/* gskel_niter_vertex_smooth   3  */
+    float vertex_smooth_coef;   /* gskel_vertex_smooth_coef   0.3 */
+    int32_t min_branch_length;  /* gskel_min_branch_length     5  */
+} osep_gskel_config;
+
+void osep_rosa_default_config(osep_rosa_config* cfg);
+void osep_gskel_default_config(osep_gskel_config* cfg);
+
+/* Summary of one frame (what rosa_run prints, rosa.cpp:38,40,48, plus parity scalars). */
+typedef struct osep_rosa_result {
+    int32_t status;        /* OSEP_OK, failing stage 1..7, or OSEP_ERR_* */
+    uint32_t flags;        /* OSEP_FLAG_* */
+    int32_t n_input;       /* "PointCloud size before downsampling" */
+    int32_t n_filtered;    /* N' after the distance/finite filter (rosa.cpp:67-88) */
+    int32_t n_downsampled; /* M = pcd_size_ after preprocess */
+    int32_t n_vertices;    /* V = skelver.rows() */
+    int32_t n_passes;      /* VoxelGrid passes executed (1..8) */
+    int32_t n_simi;        /* sum of similarity-neighbour list lengths */
+    float leaf_size;       /* Rosa::leaf_size (rosa.cpp:148) */
+    float leaf_used;       /* leaf of the pass that produced the downsampled cloud */
+    float gpu_ms;          /* device time of the frame (CUDA events), 0 when not measured */
+} osep_rosa_result;
+
+typedef struct osep_rosa osep_rosa;
+typedef struct osep_gskel osep_gskel;
+
+const char* osep_last_error(void);
+int osep_abi_version(void);
+int osep_device_count(void);
+
+/* ---- Rosa ---------------------------------------------------------------------------- */
+
+/* Rosa::Rosa(const RosaConfig&) (rosa.cpp:15-34).  Allocates the device arena once:
+ * capacity_points = largest frame the handle accepts. */
+int osep_rosa_create(const osep_rosa_config* cfg, int device, int capacity_points, osep_rosa** out);
+int osep_rosa_destroy(osep_rosa* h);
+
+/* input_cloud() write + rosa_run() (rosa_node.cpp:129,137): HOST cloud, `stride_floats`
+ * floats per point (4 for pcl::PointXYZ's 16-byte layout, 3 for packed xyz).  Copies the
+ * cloud to the device, runs the 7 stages, copies the vertices back.  Returns res->status. */
+int osep_rosa_run(osep_rosa* h, const float* xyz_host, int n, int stride_floats, osep_rosa_result* res);
+
+/* Same frame, DEVICE-resident input; enqueues on the handle's stream and returns without a
+ * host synchronisation.  Follow with osep_rosa_finish() to wait and read the summary. */
+int osep_rosa_run_device(osep_rosa* h, const float* xyz_dev, int n, int stride_floats);
+int osep_rosa_finish(osep_rosa* h, osep_rosa_result* res);
+/* cudaStream_t the handle enqueues on (for event timing by the caller). */
+void* osep_rosa_stream(osep_rosa* h);
+
+/* output_vertices() (rosa.hpp:53): V x 3 float32, COLUMN-MAJOR like Eigen::MatrixXf
+ * (x[V], y[V], z[V]); host pointer owned by the handle, valid until the next run. */
+int osep_rosa_vertices(osep_rosa* h, const float** data, int* n_vertices);
+
+/* Debug taps for parity tests.  Copies the named intermediate to `dst`
+ * (host) when it fits in cap_bytes; returns the element count, or -1 for an unknown name.
+ * float3 rows count 3 per row.  Names: "filtered" "filt_idx" "normals_full" "knn_full"
+ * "leaf_hist" "nvox_hist" "vox_keys" "vox_count" "pts" "nrms" "surf_off" "surf_idx"
+ * "simi_off" "simi_idx" "vset" "vset_iters" "vvar" "pset" "pset_drosa" "poor_idx"
+ * "active_size" "corresp" "seeds" "skelver_sampled" "skelver" "stage_ms". */
+long osep_rosa_get(osep_rosa* h, const char* name, void* dst, long cap_bytes);
+/* Enable per-stage taps that cost extra copies (vset_iters, knn_full, skelver_sampled ...). */
+int osep_rosa_set_debug(osep_rosa* h, int enable);
+
+/* Batched independent frames (BASELINE.json configs[3]): B host clouds, processed on an
+ * internal pool of `lanes` streams of this handle's device.  results[b] receives each
+ * frame's summary; vertices of frame b are fetched with osep_rosa_batch_vertices. */
+int osep_rosa_run_batch(osep_rosa* h, const float* const* xyz_host, const int* n, int n_frames,
+                        int stride_floats, osep_rosa_result* results);
+int osep_rosa_run_batch_device(osep_rosa* h, const float* const* xyz_dev, const int* n, int n_frames,
+                               int stride_floats, osep_rosa_result* results);
+int osep_rosa_batch_vertices(osep_rosa* h, int frame, const float** data, int* n_vertices);
+int osep_rosa_set_lanes(osep_rosa* h, int lanes);
+
+/* ---- stateless skeleton graph over a vertex set: graph_adj + mst + graph_decomp
+ * (gskel.cpp:201-281, 539-567) on the device.  xyz: host, `stride_floats` per vertex.
+ * Outputs (host, library owned): MST edge list (u,v) in Kruskal order, CSR adjacency,
+ * type per vertex (1 = leaf, 0 otherwise -- the reference's fall-through, gskel.cpp:554-562),
+ * joints, leafs. */
+typedef struct osep_graph_view {
+    int32_t n_vertices;
+    int32_t n_edges;
+    const int32_t* edges;     /* 2 * n_edges */
+    const float* edge_w;      /* n_edges */
+    const int32_t* adj_off;   /* n_vertices + 1 */
+    const int32_t* adj_idx;   /* 2 * n_edges, push order of gskel.cpp:270-275 */
+    const int32_t* type;      /* n_vertices */
+    const int32_t* joints; int32_t n_joints;
+    const int32_t* leafs; int32_t n_leafs;
+    const int32_t* rng_off;   /* graph_adj adjacency before the MST (duplicates kept) */
+    const int32_t* rng_idx;
+} osep_graph_view;
+int osep_rosa_graph(osep_rosa* h, float fuse_dist_th, osep_graph_view* out);  /* graph of the last frame's vertices */
+
+/* ---- GSkel --------------------------------------------------------------------------- */
+int osep_gskel_create(const osep_gskel_config* cfg, int device, int capacity_vertices, osep_gskel** out);
+int osep_gskel_destroy(osep_gskel* h);
+/* input_vertices() write + gskel_run() (gskel_node.cpp:139-141).  cand_xyz: host, already in
+ * the global frame (the TF transform, gskel_node.cpp:124-138, stays with the caller). */
+int osep_gskel_run(osep_gskel* h, const float* cand_xyz, int n, int stride_floats);
+/* output_gskel() (gskel.hpp:112): G points, 16-byte {x,y,z,1} like pcl::PointXYZ. */
+int osep_gskel_vertices(osep_gskel* h, const float** xyz4, int* n_vertices);
+int osep_gskel_graph(osep_gskel* h, osep_graph_view* out);
+long osep_gskel_get(osep_gskel* h, const char* name, void* dst, long cap_bytes);
+/* graph of an arbitrary host vertex set on the device (stateless; used by tests and the tiled-map path) */
+int osep_graph_build(osep_gskel* h, const float* xyz, int n, int stride_floats, float fuse_dist_th, osep_graph_view* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSEP_SKEL_H_ */

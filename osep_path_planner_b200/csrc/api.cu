@@ -1,0 +1,381 @@
+// csrc/api.cu -- C ABI of libosep_skel.so (include/osep_skel.h): handle management, the
+// host-buffer and device-buffer entry points of Rosa::rosa_run, debug taps, batched frames.
+#include "rosa_impl.cuh"
+#include <cstdio>
+#include <cstring>
+#include <cstdarg>
+#include <string>
+#include <algorithm>
+
+namespace osep {
+
+void mscale_set_attributes(int Mcap);
+struct GraphHost;
+GraphHost* graph_create(int cap, int device, cudaStream_t stream);
+void graph_destroy(GraphHost* g);
+int graph_run_device(GraphHost* g, const float4* pos_dev, int G, float fuse_dist_th, osep_graph_view* out);
+
+
+static thread_local std::string g_err;
+static void set_err(const char* fmt, ...) {
+    char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    g_err = buf;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); return OSEP_ERR_CUDA; } } while (0)
+
+template <class T> static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
+
+static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
+    RosaDev& d = h->d;
+    const osep_rosa_config& c = h->cfg;
+    d.Ncap = std::max(capacity_points, 1024);
+    d.Mcap = 4096;
+    d.W = d.Mcap / 32;
+    d.Scap = d.Mcap * 128;
+    d.T = 1; while (d.T < 2 * d.Ncap) d.T <<= 1;
+    d.nchunks = div_up(d.Ncap, 512);
+    d.knn = c.ne_knn; d.nbk = c.nb_knn;
+    const size_t N = d.Ncap, M = d.Mcap, T = d.T;
+    const size_t tmpcap = std::max<size_t>(N, d.Scap);
+    CK(dalloc(&d.st, 1)); CK(cudaMemset(d.st, 0, sizeof(FrameState)));
+    CK(dalloc(&d.in, N * 4));
+    CK(dalloc(&d.P, N)); CK(dalloc(&d.filt_idx, N)); CK(dalloc(&d.blk_cnt, N / 256 + 2));
+    { unsigned* g3; CK(dalloc(&g3, 3 * T)); d.gtab = (unsigned long long*)g3; d.g_cnt = (int*)(g3 + T); d.g_fill = (int*)(g3 + 2 * T); }
+    CK(dalloc(&d.g_start, T)); CK(dalloc(&d.p_slot, N)); CK(dalloc(&d.Pc, N)); CK(dalloc(&d.Nrm, N));
+    CK(dalloc(&d.vtab, T)); CK(cudaMemset(d.vtab, 0, T * sizeof(unsigned long long)));
+    CK(dalloc(&d.vkeys, M)); CK(dalloc(&d.vid, N)); CK(dalloc(&d.vox_cnt, M + 2));
+    CK(dalloc(&d.rk0, tmpcap)); CK(dalloc(&d.rk1, tmpcap)); CK(dalloc(&d.rv0, tmpcap)); CK(dalloc(&d.rv1, tmpcap));
+    CK(dalloc(&d.rhist, (size_t)256 * d.nchunks + 1024));
+    CK(dalloc(&d.pts, M)); CK(dalloc(&d.nrms, M)); CK(dalloc(&d.pset, M)); CK(dalloc(&d.pset2, M)); CK(dalloc(&d.vset, M)); CK(dalloc(&d.vnew, M));
+    CK(dalloc(&d.vvar, M)); CK(dalloc(&d.surf, M * (size_t)std::max(d.nbk, 1)));
+    CK(dalloc(&d.simi_off, M + 2)); CK(dalloc(&d.simi_idx, (size_t)d.Scap));
+    CK(dalloc(&d.level, M)); CK(dalloc(&d.level_off, M + 2)); CK(dalloc(&d.level_pts, M));
+    CK(dalloc(&d.good, M)); CK(dalloc(&d.centers, M)); CK(dalloc(&d.good_rank, M + 2)); CK(dalloc(&d.poor_idx, M));
+    CK(dalloc(&d.active_size, M)); CK(dalloc(&d.pcloud, M)); CK(dalloc(&d.adj_bits, M * (size_t)d.W));
+    CK(dalloc(&d.seeds, M)); CK(dalloc(&d.corresp, M));
+    CK(dalloc(&d.skel, M)); CK(dalloc(&d.skel2, M)); CK(dalloc(&d.skel_sampled, M)); CK(dalloc(&d.vtmp, M));
+    CK(dalloc(&d.vs_off, M + 2)); CK(dalloc(&d.vs_idx, (size_t)d.Scap));
+    CK(cudaMallocHost((void**)&h->st_host, sizeof(FrameState)));
+    CK(cudaMallocHost((void**)&h->skel_host, sizeof(float4) * M));
+    memset(h->st_host, 0, sizeof(FrameState));
+    mscale_set_attributes(d.Mcap);
+    return OSEP_OK;
+}
+
+static void rosa_free(osep_rosa_impl* h) {
+    RosaDev& d = h->d;
+    void* ptrs[] = {d.st, d.in, d.P, d.filt_idx, d.blk_cnt, d.gtab, d.g_start, d.p_slot, d.Pc, d.Nrm, d.knn_full, d.vtab, d.vkeys, d.vid,
+                    d.vox_cnt, d.rk0, d.rk1, d.rv0, d.rv1, d.rhist, d.pts, d.nrms, d.pset, d.pset2, d.vset, d.vnew, d.vvar, d.surf,
+                    d.simi_off, d.simi_idx, d.level, d.level_off, d.level_pts, d.good, d.centers, d.good_rank, d.poor_idx, d.active_size,
+                    d.pcloud, d.adj_bits, d.seeds, d.corresp, d.skel, d.skel2, d.skel_sampled, d.vtmp, d.vs_off, d.vs_idx, d.vset_iters};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (h->graph) graph_destroy(h->graph);
+    if (h->st_host) cudaFreeHost(h->st_host);
+    if (h->skel_host) cudaFreeHost(h->skel_host);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+}
+
+static int rosa_enqueue(osep_rosa_impl* h, const float* xyz_dev, int n, int stride) {
+    RosaDev& d = h->d;
+    h->last_n = n;
+    cudaEventRecord(h->ev0, h->stream);
+    launch_preprocess(h, xyz_dev, n, stride);
+    launch_mscale(h);
+    cudaMemcpyAsync(h->st_host, d.st, sizeof(FrameState), cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(h->skel_host, d.skel, sizeof(float4) * d.Mcap / 4, cudaMemcpyDeviceToHost, h->stream);   // first Mcap/4 vertices; rest on demand
+    cudaEventRecord(h->ev1, h->stream);
+    CK(cudaGetLastError());
+    return OSEP_OK;
+}
+
+static int rosa_collect(osep_rosa_impl* h, osep_rosa_result* res) {
+    CK(cudaStreamSynchronize(h->stream));
+    const FrameState& s = *h->st_host;
+    RosaDev& d = h->d;
+    int V = (s.status == 0) ? s.V : 0;
+    if (V > d.Mcap / 4) CK(cudaMemcpy(h->skel_host, d.skel, sizeof(float4) * V, cudaMemcpyDeviceToHost));
+    h->vertices_colmajor.resize((size_t)3 * V);
+    for (int i = 0; i < V; ++i) {
+        h->vertices_colmajor[i] = h->skel_host[i].x;
+        h->vertices_colmajor[(size_t)V + i] = h->skel_host[i].y;
+        h->vertices_colmajor[(size_t)2 * V + i] = h->skel_host[i].z;
+    }
+    if (res) {
+        res->status = s.status; res->flags = s.flags; res->n_input = h->last_n; res->n_filtered = s.n_filt;
+        res->n_downsampled = s.M; res->n_vertices = V; res->n_passes = s.n_pass; res->n_simi = s.S;
+        res->leaf_size = s.leaf_size; res->leaf_used = s.leaf_used;
+        float ms = 0.f; cudaEventElapsedTime(&ms, h->ev0, h->ev1); res->gpu_ms = ms;
+    }
+    return s.status;
+}
+
+}  // namespace osep
+
+using namespace osep;
+
+struct osep_rosa { osep_rosa_impl impl; };
+
+extern "C" {
+
+const char* osep_last_error(void) { return g_err.c_str(); }
+int osep_abi_version(void) { return OSEP_ABI_VERSION; }
+int osep_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+
+void osep_rosa_default_config(osep_rosa_config* c) {
+    if (!c) return;
+    c->max_points = 1000; c->min_points = 100; c->pts_dist_lim = 50.0f; c->ne_knn = 20; c->nb_knn = 10; c->max_proj_range = 10.0f;
+    c->niter_drosa = 6; c->niter_dcrosa = 5; c->niter_smooth = 3; c->alpha_recenter = 0.3f; c->radius_smooth = 5.0f;
+}
+void osep_gskel_default_config(osep_gskel_config* c) {
+    if (!c) return;
+    c->gnd_th = 60.0f; c->fuse_dist_th = 3.0f; c->fuse_conf_th = 0.1f; c->lkf_pn = 1e-4f; c->lkf_mn = 0.1f; c->max_obs_wo_conf = 5;
+    c->niter_smooth_vertex = 3; c->vertex_smooth_coef = 0.3f; c->min_branch_length = 5;
+}
+
+int osep_rosa_create(const osep_rosa_config* cfg, int device, int capacity_points, osep_rosa** out) {
+    if (!out) { set_err("osep_rosa_create: out is null"); return OSEP_ERR_ARG; }
+    *out = nullptr;
+    osep_rosa_config c; osep_rosa_default_config(&c);
+    if (cfg) c = *cfg;
+    if (c.ne_knn < 1 || c.ne_knn > KNN_MAX || c.nb_knn < 1 || c.nb_knn > 32) { set_err("ne_knn must be in [1,%d], nb_knn in [1,32]", KNN_MAX); return OSEP_ERR_ARG; }
+    if (c.max_points < 1 || c.max_points > 2048) { set_err("max_points must be in [1,2048] (device arena holds 4096 downsampled points)"); return OSEP_ERR_ARG; }
+    if (capacity_points < 1) { set_err("capacity_points must be positive"); return OSEP_ERR_ARG; }
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { set_err("device %d not present (%d CUDA devices)", device, ndev); return OSEP_ERR_CUDA; }
+    CK(cudaSetDevice(device));
+    osep_rosa* h = new osep_rosa();
+    h->impl.cfg = c; h->impl.device = device;
+    int rc = OSEP_OK;
+    do {
+        if (cudaStreamCreateWithFlags(&h->impl.stream, cudaStreamNonBlocking) != cudaSuccess) { set_err("cudaStreamCreate failed"); rc = OSEP_ERR_CUDA; break; }
+        cudaEventCreate(&h->impl.ev0); cudaEventCreate(&h->impl.ev1);
+        rc = rosa_alloc(&h->impl, capacity_points);
+    } while (0);
+    if (rc != OSEP_OK) { rosa_free(&h->impl); delete h; return rc; }
+    *out = h;
+    return OSEP_OK;
+}
+
+int osep_rosa_destroy(osep_rosa* h) {
+    if (!h) return OSEP_ERR_ARG;
+    cudaSetDevice(h->impl.device);
+    for (osep_rosa_impl* l : h->impl.lanes) { rosa_free(l); delete reinterpret_cast<osep_rosa*>(l); }
+    rosa_free(&h->impl);
+    delete h;
+    return OSEP_OK;
+}
+
+void* osep_rosa_stream(osep_rosa* h) { return h ? (void*)h->impl.stream : nullptr; }
+
+int osep_rosa_set_debug(osep_rosa* h, int enable) {
+    if (!h) return OSEP_ERR_ARG;
+    osep_rosa_impl& I = h->impl;
+    CK(cudaSetDevice(I.device));
+    I.debug = enable != 0;
+    if (I.debug && !I.d.knn_full) {
+        CK(dalloc(&I.d.knn_full, (size_t)I.d.Ncap * I.d.knn));
+        CK(dalloc(&I.d.vset_iters, (size_t)I.d.Mcap * std::max(1, I.cfg.niter_drosa)));
+    }
+    return OSEP_OK;
+}
+
+static int check_frame(osep_rosa_impl& I, int n, int stride) {
+    if (n < 0 || stride < 3) { set_err("bad frame: n=%d stride=%d", n, stride); return OSEP_ERR_ARG; }
+    if (n > I.d.Ncap) { set_err("frame of %d points exceeds the handle capacity %d", n, I.d.Ncap); return OSEP_ERR_CAPACITY; }
+    return OSEP_OK;
+}
+
+int osep_rosa_run_device(osep_rosa* h, const float* xyz_dev, int n, int stride_floats) {
+    if (!h) return OSEP_ERR_ARG;
+    osep_rosa_impl& I = h->impl;
+    int rc = check_frame(I, n, stride_floats); if (rc) return rc;
+    CK(cudaSetDevice(I.device));
+    if (n == 0) {                       // rosa.cpp:63-65: empty input fails preprocess
+        memset(I.st_host, 0, sizeof(FrameState)); I.st_host->status = OSEP_STAGE_1; I.last_n = 0;
+        cudaEventRecord(I.ev0, I.stream); cudaEventRecord(I.ev1, I.stream);
+        return OSEP_OK;
+    }
+    return rosa_enqueue(&I, xyz_dev, n, stride_floats);
+}
+
+int osep_rosa_finish(osep_rosa* h, osep_rosa_result* res) {
+    if (!h) return OSEP_ERR_ARG;
+    CK(cudaSetDevice(h->impl.device));
+    return rosa_collect(&h->impl, res);
+}
+
+int osep_rosa_run(osep_rosa* h, const float* xyz_host, int n, int stride_floats, osep_rosa_result* res) {
+    if (!h) return OSEP_ERR_ARG;
+    osep_rosa_impl& I = h->impl;
+    int rc = check_frame(I, n, stride_floats);
+    if (rc) { if (res) { memset(res, 0, sizeof(*res)); res->status = rc; } return rc; }
+    CK(cudaSetDevice(I.device));
+    if (n > 0) {
+        if (stride_floats > 4) {        // pack wide points on the host side of the copy: only xyz travels
+            set_err("stride_floats > 4 not supported by the host entry point"); return OSEP_ERR_ARG;
+        }
+        CK(cudaMemcpyAsync(I.d.in, xyz_host, sizeof(float) * (size_t)n * stride_floats, cudaMemcpyHostToDevice, I.stream));
+    }
+    rc = osep_rosa_run_device(h, I.d.in, n, stride_floats);
+    if (rc) { if (res) { memset(res, 0, sizeof(*res)); res->status = rc; } return rc; }
+    return rosa_collect(&I, res);
+}
+
+int osep_rosa_vertices(osep_rosa* h, const float** data, int* n_vertices) {
+    if (!h || !data || !n_vertices) return OSEP_ERR_ARG;
+    *n_vertices = (int)(h->impl.vertices_colmajor.size() / 3);
+    *data = h->impl.vertices_colmajor.data();
+    return OSEP_OK;
+}
+
+// ---- taps
+namespace {
+long tap_copy(void* dst, long cap, const void* dev, size_t count, size_t elem) {
+    if (dst && cap >= (long)(count * elem) && count) {
+        if (cudaMemcpy(dst, dev, count * elem, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+    }
+    return (long)count;
+}
+long tap_f4_as_f3(void* dst, long cap, const float4* dev, size_t rows) {
+    if (dst && cap >= (long)(rows * 12) && rows) {
+        std::vector<float4> tmp(rows);
+        if (cudaMemcpy(tmp.data(), dev, rows * 16, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+        float* o = (float*)dst;
+        for (size_t i = 0; i < rows; ++i) { o[3 * i] = tmp[i].x; o[3 * i + 1] = tmp[i].y; o[3 * i + 2] = tmp[i].z; }
+    }
+    return (long)rows * 3;
+}
+}  // namespace
+
+long osep_rosa_get(osep_rosa* h, const char* name, void* dst, long cap) {
+    if (!h || !name) return -1;
+    osep_rosa_impl& I = h->impl;
+    if (cudaSetDevice(I.device) != cudaSuccess) return -2;
+    cudaStreamSynchronize(I.stream);
+    RosaDev& d = I.d;
+    const FrameState& s = *I.st_host;
+    const std::string nm(name);
+    const size_t N = (size_t)s.n_filt, M = (size_t)s.M, V = (size_t)((s.status == 0 || s.status == OSEP_STAGE_7) ? s.V : 0);
+    if (nm == "filtered") return tap_f4_as_f3(dst, cap, d.P, N);
+    if (nm == "filt_idx") return tap_copy(dst, cap, d.filt_idx, N, 4);
+    if (nm == "normals_full") return tap_f4_as_f3(dst, cap, d.Nrm, N);
+    if (nm == "knn_full") { if (!d.knn_full) return 0; return tap_copy(dst, cap, d.knn_full, N * (size_t)std::min<int>(d.knn, (int)N), 4); }
+    if (nm == "leaf_hist") { if (dst && cap >= (long)(4 * s.n_pass)) memcpy(dst, s.leaf_hist, 4 * s.n_pass); return s.n_pass; }
+    if (nm == "nvox_hist") { if (dst && cap >= (long)(4 * s.n_pass)) memcpy(dst, s.nvox_hist, 4 * s.n_pass); return s.n_pass; }
+    if (nm == "vox_keys") return tap_copy(dst, cap, d.vkeys, M, 4);
+    if (nm == "vox_count") {
+        std::vector<int> off(M + 1);
+        if (M && cudaMemcpy(off.data(), d.vox_cnt, (M + 1) * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+        if (dst && cap >= (long)(M * 4)) for (size_t i = 0; i < M; ++i) ((int*)dst)[i] = off[i + 1] - off[i];
+        return (long)M;
+    }
+    if (nm == "pts") return tap_f4_as_f3(dst, cap, d.pts, M);
+    if (nm == "nrms") return tap_f4_as_f3(dst, cap, d.nrms, M);
+    if (nm == "surf_idx") return tap_copy(dst, cap, d.surf, M * (size_t)d.nbk, 4);
+    if (nm == "surf_off") { if (dst && cap >= (long)((M + 1) * 4)) for (size_t i = 0; i <= M; ++i) ((int*)dst)[i] = (int)(i * d.nbk); return (long)M + 1; }
+    if (nm == "simi_off") return tap_copy(dst, cap, d.simi_off, M + 1, 4);
+    if (nm == "simi_idx") return tap_copy(dst, cap, d.simi_idx, (size_t)s.S, 4);
+    if (nm == "vset") return tap_f4_as_f3(dst, cap, d.vset, M);
+    if (nm == "vset_iters") {
+        if (!d.vset_iters) return 0;
+        const int nit = I.cfg.niter_drosa;
+        if (dst && cap >= (long)(M * 12 * nit)) for (int it = 0; it < nit; ++it) tap_f4_as_f3((char*)dst + (size_t)it * M * 12, (long)(M * 12), d.vset_iters + (size_t)it * d.Mcap, M);
+        return (long)(M * 3 * nit);
+    }
+    if (nm == "vvar") return tap_copy(dst, cap, d.vvar, M, 4);
+    if (nm == "pset") return tap_f4_as_f3(dst, cap, d.pset, M);
+    if (nm == "pset_drosa") { if (!I.debug) return 0; return tap_f4_as_f3(dst, cap, d.centers, M); }
+    if (nm == "poor_idx") return tap_copy(dst, cap, d.poor_idx, (size_t)s.n_poor, 4);
+    if (nm == "active_size") return tap_copy(dst, cap, d.active_size, M, 4);
+    if (nm == "corresp") return tap_copy(dst, cap, d.corresp, (size_t)s.Mc, 4);
+    if (nm == "seeds") return tap_copy(dst, cap, d.seeds, V, 4);
+    if (nm == "skelver_sampled") return tap_f4_as_f3(dst, cap, d.skel_sampled, V);
+    if (nm == "skelver") return tap_f4_as_f3(dst, cap, d.skel, V);
+    if (nm == "levels") return tap_copy(dst, cap, d.level, M, 4);
+    return -1;
+}
+
+// graph_adj + mst + graph_decomp (gskel.cpp:201-281,539-567) over the last frame's vertices,
+// which are still resident on the device (no host round trip of the positions).
+int osep_rosa_graph(osep_rosa* h, float fuse_dist_th, osep_graph_view* out) {
+    if (!h || !out) return OSEP_ERR_ARG;
+    osep_rosa_impl& I = h->impl;
+    CK(cudaSetDevice(I.device));
+    CK(cudaStreamSynchronize(I.stream));
+    if (!I.graph) { I.graph = graph_create(I.d.Mcap, I.device, I.stream); if (!I.graph) { set_err("graph arena allocation failed"); return OSEP_ERR_CUDA; } }
+    const int V = (I.st_host->status == 0) ? I.st_host->V : 0;
+    return graph_run_device(I.graph, I.d.skel, V, fuse_dist_th, out);
+}
+
+// ---- batched independent frames: `lanes` sub-handles, each with its own stream and arena
+int osep_rosa_set_lanes(osep_rosa* h, int lanes) {
+    if (!h || lanes < 1 || lanes > 64) return OSEP_ERR_ARG;
+    osep_rosa_impl& I = h->impl;
+    CK(cudaSetDevice(I.device));
+    while ((int)I.lanes.size() < lanes - 1) {
+        osep_rosa* l = nullptr;
+        int rc = osep_rosa_create(&I.cfg, I.device, I.d.Ncap, &l);
+        if (rc) return rc;
+        I.lanes.push_back(&l->impl);
+    }
+    while ((int)I.lanes.size() > lanes - 1) { osep_rosa_impl* l = I.lanes.back(); I.lanes.pop_back(); rosa_free(l); delete reinterpret_cast<osep_rosa*>(l); }
+    return OSEP_OK;
+}
+
+static int run_batch(osep_rosa* h, const float* const* xyz, const int* n, int B, int stride, osep_rosa_result* results, bool host) {
+    if (!h || !xyz || !n || B < 0) return OSEP_ERR_ARG;
+    osep_rosa_impl& I = h->impl;
+    CK(cudaSetDevice(I.device));
+    if (I.lanes.empty()) { int rc = osep_rosa_set_lanes(h, 8); if (rc) return rc; }
+    std::vector<osep_rosa_impl*> L; L.push_back(&I); for (auto* l : I.lanes) L.push_back(l);
+    const int nl = (int)L.size();
+    I.batch_vertices.assign(B, {});
+    int worst = OSEP_OK;
+    std::vector<int> inflight(nl, -1);
+    auto collect = [&](int lane) {
+        const int b = inflight[lane];
+        if (b < 0) return;
+        osep_rosa_result r; memset(&r, 0, sizeof(r));
+        rosa_collect(L[lane], &r);
+        if (results) results[b] = r;
+        I.batch_vertices[b] = L[lane]->vertices_colmajor;
+        if (r.status < 0) worst = r.status;
+        inflight[lane] = -1;
+    };
+    for (int b = 0; b < B; ++b) {
+        const int lane = b % nl;
+        collect(lane);
+        osep_rosa_impl* l = L[lane];
+        int rc = check_frame(*l, n[b], stride);
+        if (rc == OSEP_OK && n[b] == 0) rc = OSEP_STAGE_1;
+        if (rc != OSEP_OK) { if (results) { memset(&results[b], 0, sizeof(osep_rosa_result)); results[b].status = rc; } if (rc < 0) worst = rc; continue; }
+        const float* src = xyz[b];
+        if (host) { cudaMemcpyAsync(l->d.in, xyz[b], sizeof(float) * (size_t)n[b] * stride, cudaMemcpyHostToDevice, l->stream); src = l->d.in; }
+        rc = rosa_enqueue(l, src, n[b], stride);
+        if (rc) return rc;
+        inflight[lane] = b;
+    }
+    for (int lane = 0; lane < nl; ++lane) collect(lane);
+    return worst;
+}
+
+int osep_rosa_run_batch(osep_rosa* h, const float* const* xyz_host, const int* n, int n_frames, int stride_floats, osep_rosa_result* results) {
+    if (stride_floats > 4 || stride_floats < 3) { set_err("stride_floats must be 3 or 4"); return OSEP_ERR_ARG; }
+    return run_batch(h, xyz_host, n, n_frames, stride_floats, results, true);
+}
+int osep_rosa_run_batch_device(osep_rosa* h, const float* const* xyz_dev, const int* n, int n_frames, int stride_floats, osep_rosa_result* results) {
+    return run_batch(h, xyz_dev, n, n_frames, stride_floats, results, false);
+}
+int osep_rosa_batch_vertices(osep_rosa* h, int frame, const float** data, int* n_vertices) {
+    if (!h || !data || !n_vertices) return OSEP_ERR_ARG;
+    osep_rosa_impl& I = h->impl;
+    if (frame < 0 || frame >= (int)I.batch_vertices.size()) return OSEP_ERR_ARG;
+    *n_vertices = (int)(I.batch_vertices[frame].size() / 3);
+    *data = I.batch_vertices[frame].data();
+    return OSEP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,647 @@
+// csrc/nscale.cu -- N-scale stages of Rosa::preprocess (rosa.cpp:57-181) on sm_100a:
+//   R3  distance/finite filter, stable compaction            (rosa.cpp:67-88)
+//   R4  min_points gate                                      (rosa.cpp:91-95)
+//   R7  estimate_leaf_from_bbox                              (rosa.hpp:99-110)
+//   R8  leaf-adaptation loop, device resident                (rosa.cpp:120-148)
+//   R5  kNN(ne_knn) normals on a sparse hash grid            (rosa.cpp:97-101, PCL NormalEstimation)
+//   R9  pcl::VoxelGrid<PointNormal>::filter                  (rosa.cpp:126-128, PCL VoxelGrid)
+//   R10 unpack + renormalise, R11 rosa_init                  (rosa.cpp:150-199)
+//
+// Order of execution differs from the reference's source order on purpose: the leaf loop
+// depends on positions only, so it runs BEFORE the normals (it also supplies the density
+// estimate that sizes the kNN grid), and only the final pass carries normals.  Results are
+// identical: VoxelGrid keys/counts never read the normals (PCL applyFilter steps 2-7).
+//
+// HBM layout: filtered cloud P as float4 AoS {x,y,z,1} (pcl::PointXYZ's own 16-byte layout:
+// one coalesced 16 B load per point); the kNN copy Pc is the same points regrouped by grid
+// cell with the filtered index in .w; normals Nrm float4 {nx,ny,nz,0}.  All tables (2 hash
+// tables, radix histograms) are L2 resident at 100k points (< 10 MB of the 126 MB L2).
+#include "rosa_impl.cuh"
+
+namespace osep {
+
+constexpr int NT = 256;                 // threads per block for N-scale kernels
+constexpr int RADIX_CH = 512;           // elements per warp-chunk in the stable radix sort
+constexpr int RADIX_WARPS = 4;          // warps per block in the radix kernels
+
+// ------------------------------------------------------------------------------------------
+// single-block exclusive scan (in place) over n ints; returns the total to every thread.
+// 1024 threads, 4 items per thread per tile, carry across tiles.
+__device__ int block_excl_scan(int* data, int n) {
+    __shared__ int wsum[32];
+    __shared__ int s_carry, s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    const int tile = blockDim.x * 4;
+    for (int base = 0; base < n; base += tile) {
+        const int i0 = base + tid * 4;
+        int v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (i0 + k < n) ? data[i0 + k] : 0;
+        const int tsum = v[0] + v[1] + v[2] + v[3];
+        int incl = tsum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += t; }
+        if (lane == 31) wsum[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            const int ws = (lane < nw) ? wsum[lane] : 0;
+            int wi = ws;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, off); if (lane >= off) wi += t; }
+            wsum[lane] = wi - ws;
+            if (lane == 31) s_tile = wi;
+        }
+        __syncthreads();
+        int excl = s_carry + wsum[wid] + (incl - tsum);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { if (i0 + k < n) data[i0 + k] = excl; excl += v[k]; }
+        __syncthreads();
+        if (tid == 0) s_carry += s_tile;
+        __syncthreads();
+    }
+    return s_carry;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_frame_init(FrameState* st, int n_in) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const unsigned epoch = st->epoch;
+    FrameState z;
+    memset(&z, 0, sizeof(z));
+    z.epoch = epoch;                 // table epochs persist across frames
+    z.n_in = n_in;
+    for (int d = 0; d < 3; ++d) { z.bb_lo[d] = 0x7fffffff; z.bb_hi[d] = (int)0x80000000; }
+    *st = z;
+}
+
+// ---- R3: filter (rosa.cpp:76-82): keep iff finite and x*x + y*y + z*z <= lim^2
+__device__ __forceinline__ bool keep_point(float x, float y, float z, float r2) {
+    const float d2 = x * x + y * y + z * z;
+    return fin(x) && fin(y) && fin(z) && d2 <= r2;
+}
+
+__global__ void k_filter_count(const float* __restrict__ in, int n, int stride, float r2, int* __restrict__ blk_cnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false;
+    if (i < n) {
+        const float* p = in + (size_t)i * stride;
+        keep = keep_point(p[0], p[1], p[2], r2);
+    }
+    const int c = __syncthreads_count(keep);
+    if (threadIdx.x == 0) blk_cnt[blockIdx.x] = c;
+}
+
+// single block: scan the per-block counts; R4 gate (rosa.cpp:91-95)
+__global__ void k_filter_scan(int* blk_cnt, int nblk, FrameState* st, int min_points) {
+    const int total = block_excl_scan(blk_cnt, nblk);
+    if (threadIdx.x == 0) {
+        st->n_filt = total;
+        if (total < min_points) st->status = OSEP_STAGE_1;
+    }
+}
+
+__global__ void k_filter_scatter(const float* __restrict__ in, int n, int stride, float r2, const int* __restrict__ blk_off,
+                                 float4* __restrict__ P, int* __restrict__ filt_idx, FrameState* st) {
+    __shared__ int warp_cnt[NT / 32];
+    __shared__ int s_lo[3], s_hi[3];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x < 3) { s_lo[threadIdx.x] = 0x7fffffff; s_hi[threadIdx.x] = (int)0x80000000; }
+    float x = 0, y = 0, z = 0; bool keep = false;
+    if (i < n) {
+        const float* p = in + (size_t)i * stride;
+        x = p[0]; y = p[1]; z = p[2];
+        keep = keep_point(x, y, z, r2);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_cnt[wid] = __popc(m);
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < wid; ++w) woff += warp_cnt[w];
+    if (keep) {
+        const int pos = blk_off[blockIdx.x] + woff + __popc(m & ((1u << lane) - 1u));
+        P[pos] = make_float4(x, y, z, 1.0f);
+        filt_idx[pos] = i;
+        atomicMin(&s_lo[0], f2ord(x)); atomicMax(&s_hi[0], f2ord(x));
+        atomicMin(&s_lo[1], f2ord(y)); atomicMax(&s_hi[1], f2ord(y));
+        atomicMin(&s_lo[2], f2ord(z)); atomicMax(&s_hi[2], f2ord(z));
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        if (s_lo[threadIdx.x] != 0x7fffffff) {
+            atomicMin(&st->bb_lo[threadIdx.x], s_lo[threadIdx.x]);
+            atomicMax(&st->bb_hi[threadIdx.x], s_hi[threadIdx.x]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// R7 + R8: the leaf-size control law, one thread, no host round trip.
+// step p = 0..8: consume the voxel count of pass p-1 exactly as the body of the loop at
+// rosa.cpp:125-146 does, then (p < 8, not finished) set up pass p.
+__global__ void k_leaf_step(FrameState* st, int p, int max_points) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (st->status != 0) return;
+    const float tol = 0.05f, leaf_min = 1e-4f, leaf_max = 1e4f;
+    if (p == 0) {
+        for (int d = 0; d < 3; ++d) { st->bmin[d] = ord2f(st->bb_lo[d]); st->bmax[d] = ord2f(st->bb_hi[d]); }
+        // estimate_leaf_from_bbox (rosa.hpp:99-110)
+        const float dx = smax(1e-6f, st->bmax[0] - st->bmin[0]);
+        const float dy = smax(1e-6f, st->bmax[1] - st->bmin[1]);
+        const float dz = smax(1e-6f, st->bmax[2] - st->bmin[2]);
+        const float vol = dx * dy * dz;
+        st->leaf = (max_points == 0) ? 0.0f : canon_cbrtf(vol / smax(1.0f, (float)(size_t)max_points));
+        st->leaf_done = 0;
+    }
+    float leaf = st->leaf;
+    int done = st->leaf_done;
+    if (!done && p > 0) {
+        const int N = st->pass_overflow ? st->n_filt : st->nvox;
+        st->nvox_hist[p - 1] = N;
+        if (N == 0) {
+            leaf *= 0.5f;
+            if (leaf < leaf_min) { leaf = leaf_min; done = 1; }
+        } else {
+            const float ratio_out = (float)N / (float)max_points;
+            if (fabsf(ratio_out - 1.0f) <= tol) { done = 2; }      // converged: break before the update
+            else {
+                leaf *= canon_cbrtf(ratio_out);
+                if (!fin(leaf)) leaf = 0.05f;
+                if (leaf < leaf_min) leaf = leaf_min;
+                if (leaf > leaf_max) leaf = leaf_max;
+            }
+        }
+    }
+    int active = 0;
+    if (!done && p < LEAF_MAX_ITERS) {
+        active = 1;
+        st->leaf_used = leaf;
+        st->leaf_hist[p] = leaf;
+        st->n_pass = p + 1;
+        // PCL VoxelGrid::applyFilter set-up
+        const float inv = 1.0f / leaf;
+        st->inv_leaf = inv;
+        const long long ddx = (long long)((st->bmax[0] - st->bmin[0]) * inv) + 1;
+        const long long ddy = (long long)((st->bmax[1] - st->bmin[1]) * inv) + 1;
+        const long long ddz = (long long)((st->bmax[2] - st->bmin[2]) * inv) + 1;
+        st->pass_overflow = (ddx * ddy * ddz > 2147483647LL) ? 1 : 0;
+        for (int d = 0; d < 3; ++d) {
+            const int mn = (int)floorf(st->bmin[d] * inv);
+            const int mx = (int)floorf(st->bmax[d] * inv);
+            st->minb[d] = mn; st->divb[d] = mx - mn + 1;
+        }
+        st->nvox = 0;
+        st->epoch += 1;
+    }
+    st->cnt0 = active;           // "pass active" flag read by k_vox_count
+    st->leaf = leaf;
+    st->leaf_done = done;
+    if (p == LEAF_MAX_ITERS || done) {
+        st->leaf_size = leaf;                                   // rosa.cpp:148
+        if (done != 2) st->flags |= OSEP_FLAG_LEAF_NOT_CONVERGED;
+        else st->flags &= ~OSEP_FLAG_LEAF_NOT_CONVERGED;
+        if (st->pass_overflow) st->flags |= OSEP_FLAG_VOXEL_OVERFLOW;
+    }
+}
+
+// voxel key of PCL VoxelGrid::applyFilter step 5
+__device__ __forceinline__ unsigned voxel_key(const float4& p, float inv, int mb0, int mb1, int mb2, int db0, int db1) {
+    const int i0 = (int)(floorf(p.x * inv) - (float)mb0);
+    const int i1 = (int)(floorf(p.y * inv) - (float)mb1);
+    const int i2 = (int)(floorf(p.z * inv) - (float)mb2);
+    return (unsigned)(i0 + i1 * db0 + i2 * (db0 * db1));
+}
+
+// insert (epoch, key) into the open-addressing set; returns true when this thread created it
+__device__ __forceinline__ bool vset_insert(unsigned long long* tab, unsigned mask, unsigned epoch, unsigned key) {
+    const unsigned long long want = ((unsigned long long)epoch << 32) | key;
+    unsigned s = hash_u32(key) & mask;
+    while (true) {
+        unsigned long long cur = tab[s];
+        if (cur == want) return false;
+        if ((unsigned)(cur >> 32) != epoch) {
+            const unsigned long long old = atomicCAS(&tab[s], cur, want);
+            if (old == cur) return true;
+            if (old == want) return false;
+            if ((unsigned)(old >> 32) != epoch) continue;       // stale value changed under us: retry this slot
+        }
+        s = (s + 1) & mask;
+    }
+}
+
+// count-only VoxelGrid pass: number of distinct voxel keys at the current leaf
+__global__ void k_vox_count(const float4* __restrict__ P, FrameState* st, unsigned long long* vtab, unsigned mask) {
+    if (st->status != 0 || !st->cnt0 || st->pass_overflow) return;
+    const int n = st->n_filt;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool isnew = false;
+    if (i < n) {
+        const unsigned key = voxel_key(P[i], st->inv_leaf, st->minb[0], st->minb[1], st->minb[2], st->divb[0], st->divb[1]);
+        isnew = vset_insert(vtab, mask, st->epoch, key);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, isnew);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&st->nvox, __popc(m));
+}
+
+// ------------------------------------------------------------------------------------------
+// kNN grid: sparse uniform grid in a hash table keyed by the linear cell id.
+__global__ void k_grid_params(FrameState* st, int target_ppc) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (st->status != 0) return;
+    const int n = st->n_filt;
+    const int nv = st->pass_overflow ? n : st->nvox;
+    // density estimate from the last VoxelGrid pass: nv occupied voxels of size leaf_used hold n points;
+    // for a surface-like cloud a cell of size h holds ~ (h/leaf)^2 * n/nv points.
+    float h = st->leaf_used * sqrtf((float)target_ppc * (float)(nv > 0 ? nv : 1) / (float)(n > 0 ? n : 1));
+    if (!(h > 1e-6f) || !fin(h)) h = 1.0f;
+    float ext = 0.0f;
+    for (int d = 0; d < 3; ++d) ext = fmaxf(ext, st->bmax[d] - st->bmin[d]);
+    if (ext / h > 1000.0f) h = ext / 1000.0f;       // keep the linear cell id inside 30 bits
+    st->g_h = h; st->g_inv_h = 1.0f / h;
+    for (int d = 0; d < 3; ++d) {
+        int dim = (int)floorf((st->bmax[d] - st->bmin[d]) * st->g_inv_h) + 1;
+        if (dim < 1) dim = 1; if (dim > 1023) dim = 1023;
+        st->g_dim[d] = dim;
+    }
+    st->g_cells_used = 0;
+}
+
+__device__ __forceinline__ void cell_of(const FrameState* st, float x, float y, float z, int& cx, int& cy, int& cz) {
+    cx = (int)floorf((x - st->bmin[0]) * st->g_inv_h);
+    cy = (int)floorf((y - st->bmin[1]) * st->g_inv_h);
+    cz = (int)floorf((z - st->bmin[2]) * st->g_inv_h);
+    cx = max(0, min(cx, st->g_dim[0] - 1)); cy = max(0, min(cy, st->g_dim[1] - 1)); cz = max(0, min(cz, st->g_dim[2] - 1));
+}
+
+// gtab stores key+1 (0 = empty) so one memset clears keys, counts and fills together
+__global__ void k_grid_insert(const float4* __restrict__ P, const FrameState* __restrict__ st, unsigned* gtab, int* g_cnt,
+                              int* __restrict__ p_slot, unsigned mask) {
+    if (st->status != 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st->n_filt) return;
+    const float4 p = P[i];
+    int cx, cy, cz; cell_of(st, p.x, p.y, p.z, cx, cy, cz);
+    const unsigned key1 = (unsigned)((cz * st->g_dim[1] + cy) * st->g_dim[0] + cx) + 1u;
+    unsigned s = hash_u32(key1) & mask;
+    while (true) {
+        const unsigned cur = gtab[s];
+        if (cur == key1) break;
+        if (cur == 0u) { const unsigned old = atomicCAS(&gtab[s], 0u, key1); if (old == 0u || old == key1) break; }
+        s = (s + 1) & mask;
+    }
+    atomicAdd(&g_cnt[s], 1);
+    p_slot[i] = (int)s;
+}
+__global__ void k_grid_alloc(FrameState* st, const int* __restrict__ g_cnt, int* __restrict__ g_start, int T) {
+    if (st->status != 0) return;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= T) return;
+    const int c = g_cnt[s];
+    if (c > 0) g_start[s] = atomicAdd(&st->g_cells_used, c);
+}
+__global__ void k_grid_scatter(const float4* __restrict__ P, const FrameState* __restrict__ st, const int* __restrict__ p_slot,
+                               const int* __restrict__ g_start, int* g_fill, float4* __restrict__ Pc) {
+    if (st->status != 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st->n_filt) return;
+    const int s = p_slot[i];
+    const int pos = g_start[s] + atomicAdd(&g_fill[s], 1);
+    float4 p = P[i]; p.w = __int_as_float(i);
+    Pc[pos] = p;
+}
+
+// ---- register-resident top-K by (d2, index); sentinels (inf, INT_MAX) mark empty slots
+template <int K> struct TopK {
+    float d[K]; int id[K];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int t = 0; t < K; ++t) { d[t] = __int_as_float(0x7f800000); id[t] = 0x7fffffff; }
+    }
+    __device__ __forceinline__ void push(float dd, int ii) {
+        if (!nb_less(dd, ii, d[K - 1], id[K - 1])) return;
+#pragma unroll
+        for (int t = K - 1; t > 0; --t) {
+            const bool lt_prev = nb_less(dd, ii, d[t - 1], id[t - 1]);
+            const bool lt_cur = nb_less(dd, ii, d[t], id[t]);
+            d[t] = lt_prev ? d[t - 1] : (lt_cur ? dd : d[t]);
+            id[t] = lt_prev ? id[t - 1] : (lt_cur ? ii : id[t]);
+        }
+        if (nb_less(dd, ii, d[0], id[0])) { d[0] = dd; id[0] = ii; }
+    }
+};
+
+// R5: one thread per query (queries in cell order => neighbouring threads scan the same cells).
+// Exact kNN: scan the (2R+1)^3 block of cells; accept when the K-th distance is strictly below
+// the distance to the block boundary (minus a float safety margin), otherwise grow R; beyond
+// R = 3 scan everything.  Then PCL computeMeanAndCovarianceMatrix (shifted by the nearest
+// neighbour, sums in neighbour order) -> smallest eigenvector -> flip towards the viewpoint.
+template <int K>
+__global__ void __launch_bounds__(128) k_knn_normals(const float4* __restrict__ Pc, const float4* __restrict__ P,
+                                                     const FrameState* __restrict__ st,
+                                                     const unsigned* __restrict__ gtab, const int* __restrict__ g_cnt,
+                                                     const int* __restrict__ g_start, unsigned mask, float4* __restrict__ Nrm,
+                                                     int* __restrict__ knn_out, int k_req) {
+    if (st->status != 0) return;
+    const int n = st->n_filt;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const float4 q = Pc[t];
+    const int qi = __float_as_int(q.w);
+    const int k_eff = min(k_req, n);
+    const int dimx = st->g_dim[0], dimy = st->g_dim[1], dimz = st->g_dim[2];
+    const float h = st->g_h;
+    int cx, cy, cz; cell_of(st, q.x, q.y, q.z, cx, cy, cz);
+    const float rx = q.x - st->bmin[0], ry = q.y - st->bmin[1], rz = q.z - st->bmin[2];
+
+    TopK<K> tk;
+    for (int R = 1;; ++R) {
+        tk.init();
+        const bool all = (R > 3);
+        if (all) {
+            for (int e = 0; e < n; ++e) { const float4 c = Pc[e]; tk.push(dist2(q.x, q.y, q.z, c.x, c.y, c.z), __float_as_int(c.w)); }
+            break;
+        }
+        const int x0 = max(cx - R, 0), x1 = min(cx + R, dimx - 1);
+        const int y0 = max(cy - R, 0), y1 = min(cy + R, dimy - 1);
+        const int z0 = max(cz - R, 0), z1 = min(cz + R, dimz - 1);
+        for (int z = z0; z <= z1; ++z) for (int y = y0; y <= y1; ++y) for (int x = x0; x <= x1; ++x) {
+            const unsigned key1 = (unsigned)((z * dimy + y) * dimx + x) + 1u;
+            unsigned s = hash_u32(key1) & mask;
+            unsigned cur;
+            while ((cur = gtab[s]) != key1 && cur != 0u) s = (s + 1) & mask;
+            if (cur == 0u) continue;
+            const int b = g_start[s], c = g_cnt[s];
+            for (int e = b; e < b + c; ++e) { const float4 cc = Pc[e]; tk.push(dist2(q.x, q.y, q.z, cc.x, cc.y, cc.z), __float_as_int(cc.w)); }
+        }
+        // whole grid covered?
+        if (x0 == 0 && y0 == 0 && z0 == 0 && x1 == dimx - 1 && y1 == dimy - 1 && z1 == dimz - 1) break;
+        // distance from q to the faces of the scanned block that have unscanned cells behind them
+        float bound = 3.0e38f;
+        if (x0 > 0) bound = fminf(bound, rx - (float)x0 * h);
+        if (x1 < dimx - 1) bound = fminf(bound, (float)(x1 + 1) * h - rx);
+        if (y0 > 0) bound = fminf(bound, ry - (float)y0 * h);
+        if (y1 < dimy - 1) bound = fminf(bound, (float)(y1 + 1) * h - ry);
+        if (z0 > 0) bound = fminf(bound, rz - (float)z0 * h);
+        if (z1 < dimz - 1) bound = fminf(bound, (float)(z1 + 1) * h - rz);
+        bound -= 1e-3f * h;
+        float wd = 0.0f; int wi = 0x7fffffff;
+#pragma unroll
+        for (int u = 0; u < K; ++u) if (u == k_eff - 1) { wd = tk.d[u]; wi = tk.id[u]; }
+        if (bound > 0.0f && wi != 0x7fffffff && wd < bound * bound) break;
+    }
+
+    if (knn_out) {
+#pragma unroll
+        for (int u = 0; u < K; ++u) if (u < k_eff) knn_out[(size_t)qi * k_eff + u] = tk.id[u];
+    }
+    const float qnan = __int_as_float(0x7fc00000);
+    float4 out = make_float4(qnan, qnan, qnan, 0.0f);
+    if (k_eff >= 3) {
+        // PCL computeMeanAndCovarianceMatrix, float, shifted by the first neighbour
+        const float4 Kp = P[tk.id[0]];
+        float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;
+#pragma unroll
+        for (int u = 0; u < K; ++u) {
+            if (u < k_eff) {
+                const float4 c = P[tk.id[u]];
+                const float x = c.x - Kp.x, y = c.y - Kp.y, z = c.z - Kp.z;
+                a0 += x * x; a1 += x * y; a2 += x * z; a3 += y * y; a4 += y * z; a5 += z * z; a6 += x; a7 += y; a8 += z;
+            }
+        }
+        const float cnt = (float)k_eff;
+        a0 /= cnt; a1 /= cnt; a2 /= cnt; a3 /= cnt; a4 /= cnt; a5 /= cnt; a6 /= cnt; a7 /= cnt; a8 /= cnt;
+        const float c00 = a0 - a6 * a6, c01 = a1 - a6 * a7, c02 = a2 - a6 * a8;
+        const float c11 = a3 - a7 * a7, c12 = a4 - a7 * a8, c22 = a5 - a8 * a8;
+        const Eig3 E = eig3_sym(c00, c01, c11, c02, c12, c22);
+        f3 nv = eig_col(E, 0);
+        // flipNormalTowardsViewpoint(point, 0, 0, 0, nx, ny, nz)
+        const float vx = 0.0f - q.x, vy = 0.0f - q.y, vz = 0.0f - q.z;
+        const float cos_theta = (vx * nv.x + vy * nv.y + vz * nv.z);
+        if (cos_theta < 0.0f) { nv.x *= -1.0f; nv.y *= -1.0f; nv.z *= -1.0f; }
+        out = make_float4(nv.x, nv.y, nv.z, 0.0f);
+    }
+    Nrm[qi] = out;
+}
+
+// ------------------------------------------------------------------------------------------
+// R9 final pass: distinct voxel keys -> sorted -> dense voxel ids -> stable radix sort of
+// (voxel id, point index) -> per-voxel sums in ascending point index.
+__global__ void k_vox_collect(FrameState* st, const unsigned long long* __restrict__ vtab, int T, unsigned* __restrict__ vkeys, int Mcap) {
+    if (st->status != 0) return;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= T) return;
+    const unsigned long long e = vtab[s];
+    if ((unsigned)(e >> 32) == st->epoch) {
+        const int pos = atomicAdd(&st->cnt1, 1);
+        if (pos < Mcap) vkeys[pos] = (unsigned)e;
+    }
+}
+
+// single block: finalise M, capacity check, bitonic sort of the keys in shared memory
+__global__ void k_vox_sortkeys(FrameState* st, unsigned* vkeys, int Mcap, int* vox_cnt) {
+    extern __shared__ unsigned sk[];
+    if (st->status != 0) return;
+    __shared__ int sM;
+    if (threadIdx.x == 0) {
+        int M = st->cnt1;
+        if (st->pass_overflow) { st->status = OSEP_ERR_CAPACITY; M = 0; }     // VoxelGrid output = input: not supported on device
+        else if (M > Mcap) { st->status = OSEP_ERR_CAPACITY; M = 0; }
+        st->M = M;
+        sM = M;
+    }
+    __syncthreads();
+    const int M = sM;
+    int P2 = 1; while (P2 < M) P2 <<= 1;
+    for (int i = threadIdx.x; i < P2; i += blockDim.x) sk[i] = (i < M) ? vkeys[i] : 0xffffffffu;
+    for (int i = threadIdx.x; i <= M; i += blockDim.x) vox_cnt[i] = 0;
+    __syncthreads();
+    for (int k = 2; k <= P2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < P2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned a = sk[i], b = sk[ixj];
+                    const bool up = ((i & k) == 0);
+                    if ((a > b) == up) { sk[i] = b; sk[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < M; i += blockDim.x) vkeys[i] = sk[i];
+}
+
+__global__ void k_vox_assign(const float4* __restrict__ P, const FrameState* __restrict__ st, const unsigned* __restrict__ vkeys,
+                             unsigned* __restrict__ rk, int* __restrict__ rv, int* vox_cnt) {
+    if (st->status != 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st->n_filt) return;
+    const unsigned key = voxel_key(P[i], st->inv_leaf, st->minb[0], st->minb[1], st->minb[2], st->divb[0], st->divb[1]);
+    int lo = 0, hi = st->M - 1;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (vkeys[mid] < key) lo = mid + 1; else hi = mid; }
+    rk[i] = (unsigned)lo; rv[i] = i;
+    atomicAdd(&vox_cnt[lo], 1);
+}
+
+__global__ void k_scan_counts(const FrameState* __restrict__ st, int* data, int which /*0: M+1 entries*/) {
+    if (st->status != 0) return;
+    block_excl_scan(data, st->M + 1);
+}
+
+// ---- stable LSD radix sort, 8-bit digits; one warp owns RADIX_CH consecutive elements
+__global__ void k_radix_hist(const unsigned* __restrict__ keys, const FrameState* __restrict__ st, int shift, int* __restrict__ hist, int nchunks) {
+    __shared__ int cnt[RADIX_WARPS][256];
+    if (st->status != 0) return;
+    const int n = st->n_filt;
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunk = blockIdx.x * RADIX_WARPS + wid;
+    for (int d = lane; d < 256; d += 32) cnt[wid][d] = 0;
+    __syncwarp();
+    const int base = chunk * RADIX_CH;
+    if (chunk < nchunks && base < n) {
+        for (int it = 0; it < RADIX_CH / 32; ++it) {
+            const int i = base + it * 32 + lane;
+            const bool valid = i < n;
+            const unsigned dg = valid ? ((keys[i] >> shift) & 255u) : 256u + lane;
+            const unsigned peers = __match_any_sync(0xffffffffu, dg);
+            if (valid && (int)lane == __ffs(peers) - 1) cnt[wid][dg] += __popc(peers);
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    if (chunk < nchunks) for (int d = lane; d < 256; d += 32) hist[d * nchunks + chunk] = cnt[wid][d];
+}
+__global__ void k_radix_scan(const FrameState* __restrict__ st, int* hist, int total) {
+    if (st->status != 0) return;
+    block_excl_scan(hist, total);
+}
+__global__ void k_radix_scatter(const unsigned* __restrict__ keys, const int* __restrict__ vals, const FrameState* __restrict__ st, int shift,
+                                const int* __restrict__ hist, int nchunks, unsigned* __restrict__ keys_out, int* __restrict__ vals_out) {
+    __shared__ int base_s[RADIX_WARPS][256];
+    if (st->status != 0) return;
+    const int n = st->n_filt;
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunk = blockIdx.x * RADIX_WARPS + wid;
+    if (chunk >= nchunks) return;
+    const int base = chunk * RADIX_CH;
+    if (base >= n) return;
+    for (int d = lane; d < 256; d += 32) base_s[wid][d] = hist[d * nchunks + chunk];
+    __syncwarp();
+    for (int it = 0; it < RADIX_CH / 32; ++it) {
+        const int i = base + it * 32 + lane;
+        const bool valid = i < n;
+        unsigned k = 0; int v = 0;
+        if (valid) { k = keys[i]; v = vals[i]; }
+        const unsigned dg = valid ? ((k >> shift) & 255u) : 256u + lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, dg);
+        int pos = 0;
+        if (valid) pos = base_s[wid][dg] + __popc(peers & ((1u << lane) - 1u));
+        __syncwarp();
+        if (valid && (int)lane == __ffs(peers) - 1) base_s[wid][dg] += __popc(peers);
+        __syncwarp();
+        if (valid) { keys_out[pos] = k; vals_out[pos] = v; }
+    }
+}
+
+// per-voxel centroid (pcl::CentroidPoint<PointNormal>), then R10 + R11 fused
+__global__ void k_vox_reduce(FrameState* st, const int* __restrict__ sorted_idx, const int* __restrict__ vox_off,
+                             const float4* __restrict__ P, const float4* __restrict__ Nrm,
+                             float4* __restrict__ pts, float4* __restrict__ nrms, float4* __restrict__ pset, float4* __restrict__ vset) {
+    if (st->status != 0) return;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int M = st->M;
+    if (v >= M) return;
+    const int b = vox_off[v], e = vox_off[v + 1];
+    float sx = 0, sy = 0, sz = 0, n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+    for (int t = b; t < e; ++t) {
+        const int i = sorted_idx[t];
+        const float4 p = P[i]; const float4 nn = Nrm[i];
+        sx += p.x; sy += p.y; sz += p.z;
+        n0 += nn.x; n1 += nn.y; n2 += nn.z; n3 += 0.0f;
+    }
+    const float cnt = (float)(e - b);
+    const float px = sx / cnt, py = sy / cnt, pz = sz / cnt;
+    // AccumulatorNormal::get: Vector4f::normalized(); squaredNorm is packet-reduced (a0+a2)+(a1+a3)
+    const float zz = (n0 * n0 + n2 * n2) + (n1 * n1 + n3 * n3);
+    f3 nv{n0, n1, n2};
+    if (zz > 0.0f) { const float r = sqrtf(zz); nv = {n0 / r, n1 / r, n2 / r}; }
+    // R10 (rosa.cpp:156-165)
+    const float L = norm3(nv);
+    if (L > 1e-6f) nv = div3(nv, L); else nv = {0.0f, 0.0f, 0.0f};
+    pts[v] = make_float4(px, py, pz, 1.0f);
+    nrms[v] = make_float4(nv.x, nv.y, nv.z, 0.0f);
+    // R11 (rosa.cpp:183-199, rosa.hpp:112-128): pset = pts, vset = column 0 of the orthonormal frame
+    pset[v] = make_float4(px, py, pz, 1.0f);
+    f3 vs;
+    const float nn_ = norm3(nv);
+    if (nn_ == 0.0f) vs = {1.0f, 0.0f, 0.0f};
+    else {
+        const f3 z = div3(nv, nn_);
+        const bool use_x = (double)fabsf(z.x) < 0.9;
+        const f3 a = use_x ? f3{1.0f, 0.0f, 0.0f} : f3{0.0f, 1.0f, 0.0f};
+        const float az = dot3(a, z);
+        vs = normalize3(sub3(a, mul3(z, az)));
+    }
+    vset[v] = make_float4(vs.x, vs.y, vs.z, 0.0f);
+}
+
+// ------------------------------------------------------------------------------------------
+template <int K>
+static void launch_knn(osep_rosa_impl* h, int n, int k_req) {
+    RosaDev& d = h->d;
+    k_knn_normals<K><<<div_up(n, 128), 128, 0, h->stream>>>(d.Pc, d.P, d.st, (const unsigned*)d.gtab, d.g_cnt, d.g_start,
+                                                           (unsigned)(d.T - 1), d.Nrm, h->debug ? d.knn_full : nullptr, k_req);
+}
+
+void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int stride) {
+    RosaDev& d = h->d;
+    cudaStream_t s = h->stream;
+    const osep_rosa_config& c = h->cfg;
+    const int nb = div_up(n, NT);
+    const float r2 = c.pts_dist_lim * c.pts_dist_lim;
+    k_frame_init<<<1, 1, 0, s>>>(d.st, n);
+    // R3/R4
+    k_filter_count<<<nb, NT, 0, s>>>(xyz_dev, n, stride, r2, d.blk_cnt);
+    k_filter_scan<<<1, 1024, 0, s>>>(d.blk_cnt, nb, d.st, c.min_points);
+    k_filter_scatter<<<nb, NT, 0, s>>>(xyz_dev, n, stride, r2, d.blk_cnt, d.P, d.filt_idx, d.st);
+    // R7/R8: device-resident leaf loop (count-only passes)
+    for (int p = 0; p < LEAF_MAX_ITERS; ++p) {
+        k_leaf_step<<<1, 1, 0, s>>>(d.st, p, c.max_points);
+        k_vox_count<<<nb, NT, 0, s>>>(d.P, d.st, d.vtab, (unsigned)(d.T - 1));
+    }
+    k_leaf_step<<<1, 1, 0, s>>>(d.st, LEAF_MAX_ITERS, c.max_points);
+    // R5: grid + kNN normals
+    cudaMemsetAsync(d.gtab, 0, sizeof(unsigned) * 3 * (size_t)d.T, s);   // gtab | g_cnt | g_fill are contiguous
+    k_grid_params<<<1, 1, 0, s>>>(d.st, 10);
+    k_grid_insert<<<nb, NT, 0, s>>>(d.P, d.st, (unsigned*)d.gtab, d.g_cnt, d.p_slot, (unsigned)(d.T - 1));
+    k_grid_alloc<<<div_up(d.T, NT), NT, 0, s>>>(d.st, d.g_cnt, d.g_start, d.T);
+    k_grid_scatter<<<nb, NT, 0, s>>>(d.P, d.st, d.p_slot, d.g_start, d.g_fill, d.Pc);
+    const int k = c.ne_knn;
+    if (k == 20) launch_knn<20>(h, n, k);
+    else if (k <= 10) launch_knn<10>(h, n, k);
+    else if (k <= 16) launch_knn<16>(h, n, k);
+    else if (k <= 32) launch_knn<32>(h, n, k);
+    else launch_knn<64>(h, n, k);
+    // R9 final pass
+    k_vox_collect<<<div_up(d.T, NT), NT, 0, s>>>(d.st, d.vtab, d.T, d.vkeys, d.Mcap);
+    int P2 = 1; while (P2 < d.Mcap) P2 <<= 1;
+    k_vox_sortkeys<<<1, 1024, sizeof(unsigned) * P2, s>>>(d.st, d.vkeys, d.Mcap, d.vox_cnt);
+    k_vox_assign<<<nb, NT, 0, s>>>(d.P, d.st, d.vkeys, d.rk0, d.rv0, d.vox_cnt);
+    k_scan_counts<<<1, 1024, 0, s>>>(d.st, d.vox_cnt, 0);
+    const int nch = div_up(n, RADIX_CH);
+    const int rb = div_up(nch, RADIX_WARPS);
+    int passes = 1; { int bits = 0; while ((1 << bits) < d.Mcap) ++bits; passes = div_up(bits, 8); if (passes < 1) passes = 1; if (passes & 1) ++passes; }
+    unsigned* ka = d.rk0; unsigned* kb = d.rk1; int* va = d.rv0; int* vb = d.rv1;
+    for (int p = 0; p < passes; ++p) {
+        k_radix_hist<<<rb, RADIX_WARPS * 32, 0, s>>>(ka, d.st, p * 8, d.rhist, nch);
+        k_radix_scan<<<1, 1024, 0, s>>>(d.st, d.rhist, 256 * nch);
+        k_radix_scatter<<<rb, RADIX_WARPS * 32, 0, s>>>(ka, va, d.st, p * 8, d.rhist, nch, kb, vb);
+        std::swap(ka, kb); std::swap(va, vb);
+    }
+    // even number of passes: sorted data is back in rk0 / rv0
+    k_vox_reduce<<<div_up(d.Mcap, 128), 128, 0, s>>>(d.st, va, d.vox_cnt, d.P, d.Nrm, d.pts, d.nrms, d.pset, d.vset);
+}
+
+}  // namespace osep

@@ -1,0 +1,64 @@
+// csrc/osep_common.cuh -- device-resident frame state + launch helpers shared by the kernels.
+//
+// Design rule: one frame runs with ZERO host synchronisations.  Everything the reference
+// decides on the host between stages (filtered count, leaf-size control law, M, S, V, stage
+// failures) lives in one FrameState struct in HBM; kernels are launched with capacity-sized
+// grids, read their sizes from it and exit early.  That makes the whole frame one stream of
+// launches (CUDA-graph capturable) and lets many frames overlap on many streams.
+#pragma once
+#include "dev_math.cuh"
+#include "../../include/osep_skel.h"
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace osep {
+
+constexpr int LEAF_MAX_ITERS = 8;       // rosa.cpp:120
+constexpr int KNN_MAX = 64;             // largest ne_knn / nb_knn supported
+constexpr int WARPS_PER_BLOCK = 8;
+
+struct FrameState {
+    // ---- sizes
+    int n_in;
+    int n_filt;            // N'
+    int M;                 // downsampled points (pcd_size_)
+    int Mc;                // finite pset rows in vertex_sampling (rosa.cpp:448)
+    int S;                 // total similarity neighbours
+    int V;                 // vertices
+    int Vf;                // finite vertices in vertex_smooth (rosa.cpp:552)
+    int status;            // 0, failing stage 1..7, or OSEP_ERR_*
+    unsigned flags;
+    // ---- bbox of the filtered cloud (ordered-int encoding for atomics, then decoded)
+    int bb_lo[3], bb_hi[3];
+    float bmin[3], bmax[3];
+    // ---- kNN grid
+    float g_inv_h, g_h;
+    int g_dim[3];
+    int g_cells_used;      // allocation cursor (points)
+    // ---- leaf loop (rosa.cpp:118-148)
+    float leaf, leaf_used, leaf_size;
+    int leaf_done, n_pass, nvox;
+    int pass_overflow;
+    unsigned epoch;
+    float leaf_hist[LEAF_MAX_ITERS];
+    int nvox_hist[LEAF_MAX_ITERS];
+    // voxel-grid parameters of the current pass (PCL VoxelGrid::applyFilter)
+    float inv_leaf;
+    int minb[3], divb[3];
+    // ---- drosa bookkeeping
+    int n_levels;
+    int n_good, n_poor;
+    // ---- scratch counters
+    int cnt0, cnt1;
+};
+
+// ordered-int encoding of a float: monotone map so atomicMin/atomicMax(int) order floats
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned hash_u32(unsigned k) { k *= 2654435761u; k ^= k >> 15; k *= 2246822519u; k ^= k >> 13; return k; }
+
+inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace osep

@@ -1,0 +1,79 @@
+// csrc/rosa_impl.cuh -- the Rosa handle: device arena + launch entry points of the stages.
+#pragma once
+#include "osep_common.cuh"
+#include <vector>
+#include <string>
+
+namespace osep {
+
+struct RosaDev {
+    // ---- capacities (fixed at create)
+    int Ncap = 0;          // input points
+    int Mcap = 0;          // downsampled points
+    int Scap = 0;          // similarity CSR entries
+    int T = 0;             // hash table slots (power of two >= 2*Ncap)
+    int W = 0;             // bitmask words per row = Mcap/32
+    int nchunks = 0;       // radix chunks of RADIX_CH elements
+    int knn = 0, nbk = 0;  // ne_knn, nb_knn
+
+    FrameState* st = nullptr;
+    // N-scale
+    float* in = nullptr;               // staged input (host-buffer path), Ncap * 4 floats
+    float4* P = nullptr;               // filtered points (x,y,z,1)
+    int* filt_idx = nullptr;
+    int* blk_cnt = nullptr;
+    unsigned long long* gtab = nullptr;  // kNN grid: (epoch<<32 | cell key)
+    int* g_cnt = nullptr; int* g_start = nullptr; int* g_fill = nullptr;
+    int* p_slot = nullptr;
+    float4* Pc = nullptr;              // points in cell order, w = filtered index (int bits)
+    float4* Nrm = nullptr;             // normals of the filtered cloud
+    int* knn_full = nullptr;           // debug tap (Ncap * knn) or null
+    unsigned long long* vtab = nullptr;  // voxel set: (epoch<<32 | voxel key)
+    unsigned* vkeys = nullptr;         // distinct voxel keys, sorted
+    int* vid = nullptr;                // voxel id per filtered point
+    int* vox_cnt = nullptr; int* vox_off = nullptr;
+    unsigned* rk0 = nullptr; unsigned* rk1 = nullptr; int* rv0 = nullptr; int* rv1 = nullptr;
+    int* rhist = nullptr;
+    // M-scale
+    float4* pts = nullptr; float4* nrms = nullptr;
+    float4* pset = nullptr; float4* pset2 = nullptr; float4* vset = nullptr; float4* vnew = nullptr;
+    float* vvar = nullptr;
+    int* surf = nullptr;               // Mcap * nbk
+    int* simi_off = nullptr; int* simi_idx = nullptr;
+    int* level = nullptr; int* level_off = nullptr; int* level_pts = nullptr;
+    int* good = nullptr; float4* centers = nullptr; int* good_rank = nullptr; int* poor_idx = nullptr;
+    int* active_size = nullptr;
+    float4* pcloud = nullptr;          // compacted finite pset (vertex_sampling)
+    unsigned* adj_bits = nullptr;      // Mcap * W cover adjacency
+    int* seeds = nullptr; int* seed_vid = nullptr; int* corresp = nullptr;
+    float4* skel = nullptr; float4* skel2 = nullptr; float4* skel_sampled = nullptr; float4* vtmp = nullptr;
+    int* vs_off = nullptr; int* vs_idx = nullptr;   // vertex_smooth CSR (reuses Scap sizing)
+    float4* vset_iters = nullptr;      // debug tap: niter_drosa * Mcap
+};
+
+struct osep_rosa_impl {
+    osep_rosa_config cfg;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    RosaDev d;
+    bool debug = false;
+    // host mirrors
+    FrameState* st_host = nullptr;     // pinned
+    float* in_host = nullptr;          // pinned staging, Ncap*4 floats
+    float4* skel_host = nullptr;       // pinned, Mcap
+    std::vector<float> vertices_colmajor;
+    int last_n = 0;
+    bool timed = false;
+    // graph outputs (osep_rosa_graph)
+    struct GraphHost* graph = nullptr;
+    // batch
+    std::vector<osep_rosa_impl*> lanes;
+    std::vector<std::vector<float>> batch_vertices;
+};
+
+// stage launchers (all asynchronous on h->stream, no host sync)
+void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int stride);   // R3-R11
+void launch_mscale(osep_rosa_impl* h);                                                // R12-R22
+
+}  // namespace osep
