@@ -1,0 +1,54 @@
+"""Multi-GPU plumbing for the batched-frames configuration (BASELINE.json configs[3]).
+
+The path shards by independent frames: frame b belongs to rank b // ceil(B / P) (contiguous
+blocks).  There is NO data-path collective: each rank runs whole frames on its
+own GPU.  The only exchange is the final gather of the tiny per-frame results (vertex counts
++ capacity-padded vertex buffers) with torch.distributed all_gather (NCCL on GPUs, gloo in
+the CPU tests) and the max-over-ranks reduction of the timing.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def frames_of_rank(n_frames, rank, world):
+    per = -(-n_frames // world)
+    return list(range(min(rank * per, n_frames), min((rank + 1) * per, n_frames)))
+
+
+def _dev():
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def gather_frame_results(local, n_frames, cap=512):
+    """local: {frame id: (V_b, 3) float32}.  Returns (counts[n_frames], [vertices_b]) on every rank."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    per = -(-n_frames // world)
+    cnt = torch.zeros(per, dtype=torch.int32)
+    buf = torch.zeros(per, cap, 3, dtype=torch.float32)
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    for b, v in local.items():
+        k = b - rank * per
+        n = min(len(v), cap)
+        cnt[k] = len(v)
+        if n:
+            buf[k, :n] = torch.from_numpy(np.ascontiguousarray(v[:n], dtype=np.float32))
+    if world == 1:
+        counts = cnt.numpy()[:n_frames]
+        return counts, [buf[b, :min(counts[b], cap)].numpy() for b in range(n_frames)]
+    d = _dev()
+    cnt_all = [torch.zeros_like(cnt, device=d) for _ in range(world)]
+    buf_all = [torch.zeros_like(buf, device=d) for _ in range(world)]
+    dist.all_gather(cnt_all, cnt.to(d))
+    dist.all_gather(buf_all, buf.to(d))
+    counts = torch.cat(cnt_all).cpu().numpy()[:n_frames]
+    allbuf = torch.cat(buf_all).cpu().numpy()
+    return counts, [allbuf[b, :min(counts[b], cap)] for b in range(n_frames)]
+
+
+def max_over_ranks(x):
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(x)
+    t = torch.tensor([float(x)], dtype=torch.float64, device=_dev())
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

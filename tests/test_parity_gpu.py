@@ -1,0 +1,266 @@
+"""GPU parity tests (run on a B200: python -m pytest tests -m gpu).  Every test calls the CUDA
+path through the C ABI (libosep_skel.so via ctypes) and compares with the CPU oracle on the
+same seeded input.  Bars: bit-exact for indices, keys, counts and connectivity; vertex
+positions <= 1e-3 * leaf and orientations <= 1e-3 rad (BASELINE.json north_star) -- in
+practice the floats are bit-identical too, and the tests assert that as well."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_bit_equal
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+TAPS_EXACT = ["filt_idx", "filtered", "leaf_hist", "nvox_hist", "knn_full", "normals_full", "vox_keys", "vox_count", "pts", "nrms",
+              "surf_idx", "simi_off", "simi_idx", "vset_iters", "active_size", "poor_idx", "pset_drosa", "pset", "seeds", "corresp",
+              "skelver_sampled", "skelver"]
+
+
+@pytest.fixture(scope="module")
+def mods(built):
+    import osep_path_planner_b200 as osep
+    from oracle import pyoracle as po
+    from osep_path_planner_b200 import fixtures as fx
+    assert osep.load().osep_device_count() > 0, "no CUDA device: GPU tests need a B200"
+    return osep, po, fx
+
+
+def run_both(mods, P, cfgkw=None, debug=True):
+    osep, po, fx = mods
+    cfgkw = cfgkw or {}
+    o = po.RosaOracle(po.RosaConfig.default(**cfgkw))
+    ok_o = o.run(P)
+    r = osep.Rosa(osep.RosaConfig(**cfgkw), capacity_points=max(1024, P.shape[0]))
+    r.set_debug(debug)
+    r.set_input(P)
+    ok_g = r.rosa_run()
+    return o, ok_o, r, ok_g
+
+
+def check_all_taps(o, r):
+    res = r.result
+    assert res.n_filtered == len(o.tap("filt_idx")) and res.n_downsampled == len(o.tap("pts")) and res.n_vertices == len(o.tap("skelver"))
+    assert np.float32(res.leaf_size) == np.float32(o.leaf_size) and np.float32(res.leaf_used) == np.float32(o.leaf_used)
+    assert res.flags == o.flags
+    for tap in TAPS_EXACT:
+        a, b = r.tap(tap), o.tap(tap)
+        if tap == "knn_full":
+            a, b = a.reshape(-1), b.reshape(-1)
+        assert_bit_equal(a, b, tap)
+    # north_star tolerances, stated explicitly (they hold trivially when the bits match)
+    leaf = o.leaf_size
+    assert np.abs(r.tap("skelver") - o.tap("skelver")).max() <= 1e-3 * leaf
+    va, vb = r.tap("vset"), o.tap("vset")
+    cosang = np.clip(np.abs((va * vb).sum(1)), 0, 1)
+    assert np.arccos(cosang).max() <= 1e-3
+    # output_vertices(): V x 3 column-major (Eigen::MatrixXf layout, rosa.hpp:53)
+    v = r.output_vertices()
+    assert v.flags["F_CONTIGUOUS"] and v.dtype == np.float32
+    assert_bit_equal(np.ascontiguousarray(v), o.tap("skelver"), "output_vertices")
+
+
+@pytest.mark.parametrize("name", ["cyl5k", "cyl20k", "turbine100k"])
+def test_full_pipeline_bit_exact(mods, name):
+    osep, po, fx = mods
+    P = {"cyl5k": lambda: fx.cylinder(5000, seed=3), "cyl20k": fx.cylinder, "turbine100k": fx.turbine}[name]()
+    o, ok_o, r, ok_g = run_both(mods, P)
+    assert ok_o and ok_g
+    check_all_taps(o, r)
+    r.close()
+
+
+def test_golden_fixture_against_gpu(mods):
+    osep, po, fx = mods
+    g = np.load(os.path.join(GOLD, "cyl3k_k10_m300.npz"))
+    r = osep.Rosa(osep.RosaConfig(max_points=300, ne_knn=10, nb_knn=6), capacity_points=4096)
+    r.set_input(fx.cylinder(3000, seed=7))
+    assert r.rosa_run()
+    for tap in ["leaf_hist", "nvox_hist", "vox_keys", "vox_count", "pts", "nrms", "surf_idx", "vset", "pset", "poor_idx", "seeds", "corresp", "skelver"]:
+        assert_bit_equal(r.tap(tap), g[tap], tap)
+    assert_bit_equal(r.tap("simi_off"), g["simi_off"], "simi_off")
+    assert_bit_equal(r.graph(3.0)["edges"].reshape(-1), g["mst_edges"], "mst_edges")
+    r.close()
+
+
+@pytest.mark.parametrize("cfgkw", [dict(ne_knn=10, nb_knn=6, max_points=500), dict(ne_knn=30, nb_knn=12, niter_drosa=3, niter_dcrosa=2, niter_smooth=1),
+                                   dict(ne_knn=16, max_points=1500, radius_smooth=3.0, alpha_recenter=0.5)])
+def test_non_default_configs(mods, cfgkw):
+    osep, po, fx = mods
+    o, ok_o, r, ok_g = run_both(mods, fx.turbine(30000, seed=11), cfgkw)
+    assert ok_o and ok_g
+    check_all_taps(o, r)
+    r.close()
+
+
+def test_stage_failures_mirror_run_step(mods):
+    osep, po, fx = mods
+    r = osep.Rosa(capacity_points=4096)
+    r.input_cloud(0)
+    assert not r.rosa_run() and r.result.status == 1                                   # empty cloud (rosa.cpp:63-65)
+    r.set_input(fx.cylinder(50))
+    assert not r.rosa_run() and r.result.status == 1 and r.result.n_filtered == 50     # < min_points (rosa.cpp:91-95)
+    r.set_input(fx.cylinder(500) + np.array([100, 0, 0], np.float32))
+    assert not r.rosa_run() and r.result.status == 1 and r.result.n_filtered == 0      # everything beyond pts_dist_lim
+    assert r.output_vertices().shape == (0, 3)
+    # the handle recovers on the next good frame
+    P = fx.cylinder(3000, seed=1)
+    r.set_input(P)
+    assert r.rosa_run()
+    o = po.RosaOracle(); assert o.run(P)
+    assert_bit_equal(np.ascontiguousarray(r.output_vertices()), o.tap("skelver"), "vertices after failed frames")
+    with pytest.raises(osep.OsepError):
+        r.set_input(fx.cylinder(5000)); r.rosa_run()                                   # exceeds capacity: loud error
+    r.close()
+
+
+def test_ragged_input_nonfinite_far_points_duplicates_and_stride(mods):
+    osep, po, fx = mods
+    P = fx.cylinder(6000, seed=21)
+    P[5] = np.nan; P[77, 2] = np.inf; P[100] = [0, 0, 80]; P[200:260] = P[300:360]     # NaN, inf, far, exact duplicates (kNN ties)
+    P[1000:1100] = np.round(P[1000:1100] * 8) / 8                                       # lattice points -> equal distances
+    o, ok_o, r, ok_g = run_both(mods, P)
+    assert ok_o and ok_g
+    check_all_taps(o, r)
+    # 16-byte pcl::PointXYZ layout (stride 4) and packed xyz (stride 3) give identical results
+    L = osep.load()
+    import ctypes as C
+    res = osep.RosaResult()
+    P3 = np.ascontiguousarray(P)
+    assert L.osep_rosa_run(r._h, P3.ctypes.data_as(C.c_void_p), P3.shape[0], 3, C.byref(res)) == 0
+    assert_bit_equal(r.tap("skelver"), o.tap("skelver"), "stride 3")
+    r.close()
+
+
+def test_minimum_size_cloud_and_tiny_k(mods):
+    osep, po, fx = mods
+    o, ok_o, r, ok_g = run_both(mods, fx.cylinder(120, seed=2, h=10.0), dict(max_points=40, min_points=100))
+    assert ok_o == ok_g
+    if ok_o:
+        check_all_taps(o, r)
+    else:
+        assert r.result.status == o.failed_stage
+    r.close()
+
+
+def test_idempotent_and_handle_reuse(mods):
+    osep, po, fx = mods
+    r = osep.Rosa(capacity_points=120000)
+    A, B = fx.turbine(), fx.cylinder()
+    r.set_input(A); assert r.rosa_run(); va = np.ascontiguousarray(r.output_vertices()).copy()
+    r.set_input(B); assert r.rosa_run(); vb = np.ascontiguousarray(r.output_vertices()).copy()
+    r.set_input(A); assert r.rosa_run()
+    assert_bit_equal(np.ascontiguousarray(r.output_vertices()), va, "frame A repeated after frame B")
+    r.set_input(B); assert r.rosa_run()
+    assert_bit_equal(np.ascontiguousarray(r.output_vertices()), vb, "frame B repeated")
+    r.close()
+
+
+def test_device_resident_entry_point_matches_host_entry_point(mods):
+    import torch
+    osep, po, fx = mods
+    P = fx.to_xyz4(fx.cylinder())
+    r = osep.Rosa(capacity_points=32768)
+    r.set_input(P[:, :3]); assert r.rosa_run(); v_host = np.ascontiguousarray(r.output_vertices()).copy()
+    t = torch.from_numpy(P).cuda()
+    torch.cuda.synchronize()
+    r.run_device(t.data_ptr(), P.shape[0], 4)
+    assert r.finish()
+    assert_bit_equal(np.ascontiguousarray(r.output_vertices()), v_host, "device entry point")
+    assert r.result.gpu_ms > 0
+    r.close()
+
+
+def test_batched_frames_equal_single_frames(mods):
+    osep, po, fx = mods
+    frames = [fx.to_xyz4(fx.batch_frame(b, n=20000)) for b in range(6)] + [fx.to_xyz4(fx.cylinder(50))]
+    r = osep.Rosa(capacity_points=32768)
+    r.set_lanes(3)
+    res, verts = r.run_batch(frames)
+    assert [x.status for x in res[:6]] == [0] * 6 and res[6].status == 1
+    for b in range(6):
+        o = po.RosaOracle(); assert o.run(frames[b][:, :3].copy())
+        assert_bit_equal(verts[b], o.tap("skelver"), "batch frame %d" % b)
+        assert res[b].n_downsampled == len(o.tap("pts"))
+    assert verts[6].shape == (0, 3)
+    r.close()
+
+
+def test_skeleton_graph_bit_exact(mods):
+    osep, po, fx = mods
+    rng = np.random.default_rng(5)
+    for G in (1, 2, 9, 10, 11, 60, 333):
+        V = np.cumsum(rng.normal(size=(G, 3)) * 0.8 + np.array([0, 0, 1.2]), axis=0).astype(np.float32)
+        if G > 20:
+            V[7] = V[3]                                        # duplicate vertex -> zero-length edge, distance ties
+        g = osep.build_graph(V, 3.0)
+        go = po.GraphOracle(V, 3.0)
+        assert_bit_equal(g["edges"].reshape(-1), go.tap("mst_edges"), "mst edges G=%d" % G)
+        assert_bit_equal(g["edge_w"], go.tap("mst_w"), "mst weights")
+        assert_bit_equal(g["adj_off"], go.tap("adj_off"), "adj_off"); assert_bit_equal(g["adj_idx"], go.tap("adj_idx"), "adj_idx")
+        assert_bit_equal(g["rng_off"], go.tap("rng_off"), "rng_off"); assert_bit_equal(g["rng_idx"], go.tap("rng_idx"), "rng_idx")
+        assert_bit_equal(g["type"], go.tap("type"), "type")
+        assert_bit_equal(g["joints"], go.tap("joints"), "joints"); assert_bit_equal(g["leafs"], go.tap("leafs"), "leafs")
+
+
+def test_frame_to_graph(mods):
+    osep, po, fx = mods
+    P = fx.turbine(40000, seed=4)
+    o, ok_o, r, ok_g = run_both(mods, P, debug=False)
+    assert ok_o and ok_g
+    g = r.graph(3.0); go = po.GraphOracle(o.tap("skelver"), 3.0)
+    assert_bit_equal(g["edges"].reshape(-1), go.tap("mst_edges"), "frame graph edges")
+    assert_bit_equal(g["type"], go.tap("type"), "frame graph types")
+    r.close()
+
+
+def test_gskel_stateful_replay(mods):
+    """Stream of frames (BASELINE configs[2] in miniature): Rosa vertices -> analytic sensor->odom
+    transform -> GSkel::gskel_run, oracle and CUDA library side by side, compared every tick."""
+    osep, po, fx = mods
+    from osep_path_planner_b200 import GSkel, GSkelConfig
+    cfg_kw = dict(gnd_th=-100.0)           # fixtures sit below the default 60 m ground threshold
+    gs = GSkel(GSkelConfig(**cfg_kw)); go = po.GSkelOracle(po.GSkelConfig.default(**cfg_kw))
+    r = osep.Rosa(capacity_points=32768)
+    published = 0
+    for f in range(0, 24):
+        P, R, t = fx.stream_frame(f * 3, n=20000)
+        r.set_input(P)
+        if not r.rosa_run():
+            continue
+        v = np.ascontiguousarray(r.output_vertices())
+        v_odom = (v.astype(np.float64) @ R.T + t).astype(np.float32)
+        ok_g = gs.gskel_run() if gs.set_input(v_odom) is not None else False
+        ok_o = go.run(v_odom)
+        assert ok_g == ok_o and gs.failed_stage == go.failed_stage, "tick %d: stage %d vs %d" % (f, gs.failed_stage, go.failed_stage)
+        assert_bit_equal(gs.output_gskel()[:, :3].copy(), go.tap("global"), "global vertices tick %d" % f)
+        assert_bit_equal(gs.tap("prelim"), go.tap("prelim"), "prelim vertices tick %d" % f)
+        for tap in ["adj_off", "adj_idx", "joints", "leafs", "new_idx", "type", "obs", "branch_off", "branch_idx"]:
+            assert_bit_equal(gs.tap(tap), go.tap(tap), "%s tick %d" % (tap, f))
+        published += int(ok_g)
+    assert len(go.tap("global")) > 5
+    gs.close(); r.close()
+
+
+def test_full_size_properties_turbine100k(mods):
+    """Size-independent properties at BASELINE.json's full size (100k points)."""
+    osep, po, fx = mods
+    P = fx.turbine()
+    r = osep.Rosa(capacity_points=100000); r.set_debug(True); r.set_input(P); assert r.rosa_run()
+    idx = r.tap("filt_idx"); assert np.all(np.diff(idx) > 0)                             # stable compaction
+    keys = r.tap("vox_keys"); assert np.all(np.diff(keys.astype(np.int64)) > 0)          # ascending distinct voxel keys
+    assert r.tap("vox_count").sum() == len(idx)                                          # every point lands in one voxel
+    knn = r.tap("knn_full").reshape(len(idx), -1)
+    assert np.array_equal(knn[:, 0], np.arange(len(idx)))                                # nearest neighbour of a point is itself
+    F = r.tap("filtered")
+    d = ((F[knn[::97]] - F[::97, None, :]) ** 2).sum(-1); assert np.all(np.diff(d, axis=1) >= 0)   # ascending distances
+    n = r.tap("normals_full"); assert np.abs(np.linalg.norm(n, axis=1) - 1).max() < 1e-3
+    assert np.all((n * (-F)).sum(1) >= 0)                                                # flipped towards the viewpoint (origin)
+    corresp = r.tap("corresp"); assert corresp.min() >= 0 and corresp.max() == r.result.n_vertices - 1
+    seeds = r.tap("seeds"); assert np.all(np.diff(seeds) > 0)                            # greedy cover picks ascending seeds
+    pc = r.tap("pset"); R2 = np.float32(r.result.leaf_size) ** 2
+    dd = ((pc[seeds][:, None, :] - pc[seeds][None, :, :]) ** 2).sum(-1) + np.eye(len(seeds)) * 1e9
+    assert dd.min() >= R2 * 0.999                                                        # no seed lies inside another seed's cover
+    r.close()
