@@ -1,0 +1,274 @@
+#!/usr/bin/env python
+"""bench.py -- skeleton frames/s and ms/frame at 100k points (BASELINE.json metric).
+
+A step = one pass of the hot path (Rosa::rosa_run: point cloud -> skeleton vertices, plus the
+skeleton graph) over one synthetic 100k-point turbine frame (BASELINE.json configs[1]).
+  value : frames/s with the frame already resident in HBM (device entry point of the C ABI),
+          CUDA events on the library's stream, L2 flushed between steps.
+  e2e   : the same frames through the reference-facing call (osep_rosa_run: HOST pinned buffer
+          -> H2D -> 7 stages -> D2H of the vertices), wall clock around the synchronous call.
+N > 1 (torchrun): one process per GPU, each rank runs its own frames (independent frames are
+the unit the path shards by; no data-path collective), value = frames of all ranks / max time.
+--impl reference: the CPU restatement of the reference (oracle, faithful mode, the reference
+is single threaded) on the host cores, same metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np   # noqa: E402
+
+METRIC = "skeleton_frames_per_sec_100k_pts"
+WORKLOAD = "single frame, 100k-point synthetic wind-turbine cloud (tower + 3 blades, sigma 0.02 m), default RosaConfig"
+
+
+def env_int(k, d):
+    try:
+        return int(os.environ.get(k, d))
+    except ValueError:
+        return d
+
+
+def algorithmic_bytes(n_in, n_filt, L, M, V):
+    """16 N + N' (164 + 12 (L-1)) + 48 M + 12 V bytes per frame."""
+    return 16 * n_in + n_filt * (164 + 12 * (L - 1)) + 48 * M + 12 * V
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def time_oracle(P, frames, faithful=True):
+    from oracle import pyoracle as po
+    kw = dict(faithful_normals=1, faithful_order=1, libm_cbrt=1) if faithful else {}
+    o = po.RosaOracle(**kw)
+    ts, stages = [], None
+    for _ in range(frames):
+        t0 = time.perf_counter()
+        ok = o.run(P)
+        v = o.tap("skelver")
+        if ok:
+            po.GraphOracle(v, 3.0)
+        ts.append(time.perf_counter() - t0)
+        stages = o.stage_ms()
+    return ts, stages, int(len(o.tap("skelver")))
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's own CPU algorithm (restated; the C++ reference cannot be
+    compiled here -- no PCL/Eigen/FLANN/ROS 2) on the host cores.  Single thread: the reference
+    node is single threaded end to end (rosa.hpp:80, rclcpp::spin single-threaded executor)."""
+    if rank != 0:
+        return
+    from osep_path_planner_b200 import fixtures as fx
+    P = fx.turbine(args.points, seed=0)
+    time_oracle(P, max(1, min(args.warmup, 2)))
+    ts, stages, V = time_oracle(P, args.steps)
+    ms = 1e3 * float(np.mean(ts))
+    fps = 1e3 / ms
+    line = {"metric": METRIC, "value": fps, "unit": "frames/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "points": args.points, "n_vertices": V},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port",
+                             "sample": "%d full frames, oracle faithful mode (reference summation orders, PCL trig eigen33, libm cbrt), 1 thread" % args.steps,
+                             "stage_ms": dict(zip(["preprocess", "rosa_init", "similarity_neighbor_extraction", "drosa", "dcrosa", "vertex_sampling", "vertex_smooth"], stages)),
+                             "nproc": os.cpu_count()},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import osep_path_planner_b200 as osep
+    from osep_path_planner_b200 import fixtures as fx, shard
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # every rank owns its own frames (seed = rank): weak scaling over independent frames
+    P4 = fx.to_xyz4(fx.turbine(args.points, seed=rank))
+    n = P4.shape[0]
+    host = torch.from_numpy(P4).pin_memory()
+    dev = host.cuda(non_blocking=False)
+    r = osep.Rosa(device=local_rank, capacity_points=n)
+    r.set_profile(True)
+    stream = torch.cuda.ExternalStream(r.stream, device=local_rank)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")      # > 126 MB L2
+
+    def step_device():
+        r.run_device(dev.data_ptr(), n, 4)
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        step_device(); assert r.finish(), "frame failed: status %d" % r.result.status
+        g = r.graph(3.0)
+    res0 = r.result
+    launches0 = r.launches
+
+    # ---- timed: device-resident input, CUDA events on the library's stream, L2 flushed between steps
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage_acc = None
+    clocks = ClockSampler(local_rank)
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()                       # L2 flush, outside the per-step events
+            ev[k][0].record(stream)
+        step_device()
+        with torch.cuda.stream(stream):
+            ev[k][1].record(stream)
+        ok = r.finish()
+        assert ok
+        sm = r.tap("stage_ms")
+        stage_acc = sm if stage_acc is None else stage_acc + sm
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = r.launches - launches0
+    dev_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = shard.max_over_ranks(sum(dev_ms))
+    ms_per_step = total_ms / args.steps
+    value = world * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: host pinned buffer -> osep_rosa_run (H2D + frame + D2H vertices), synchronous call
+    import ctypes as C
+    L = osep.load()
+    res = osep.RosaResult()
+    for _ in range(max(1, args.warmup // 2)):
+        L.osep_rosa_run(r._h, C.c_void_p(host.data_ptr()), n, 4, C.byref(res))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rc = L.osep_rosa_run(r._h, C.c_void_p(host.data_ptr()), n, 4, C.byref(res))
+        assert rc == 0
+    barrier()
+    e2e_s = shard.max_over_ranks(time.perf_counter() - t0)
+    clk = clocks.stop()
+    e2e_value = world * args.steps / e2e_s
+    d2h = 16 * 1024 + 256        # vertices staging (first 1024 float4) + frame state
+
+    stage_ms = dict(zip(r.STAGE_NAMES, (stage_acc / args.steps).tolist()))
+    stage_ms.pop("-", None)
+    # dominant kernel group, timed live with the library's CUDA events on its stream
+    dom = max(stage_ms, key=stage_ms.get)
+    alg = algorithmic_bytes(n, res0.n_filtered, res0.n_passes, res0.n_downsampled, res0.n_vertices)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    frame_gbs = alg / (ms_per_step * 1e-3) / 1e9
+    knn_ms = stage_ms["knn_normals"]
+    knn_bytes = 28 * res0.n_filtered                       # SURVEY 8(d) phase (3): read 16 N', write 12 N'
+    roofline = {"bound": "hbm", "kernel": "whole frame (74 launches); dominant group: %s (%.3f ms, latency-bound M-scale chain, ~0 algorithmic HBM bytes)" % (dom, stage_ms[dom]),
+                "achieved": frame_gbs, "peak": peak, "unit": "GB/s", "frac": frame_gbs / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "algorithmic_bytes_per_frame": alg,
+                "knn_normals_kernel": {"ms": knn_ms, "algorithmic_bytes": knn_bytes, "achieved": knn_bytes / (knn_ms * 1e-3) / 1e9 if knn_ms > 0 else None,
+                                       "frac": (knn_bytes / (knn_ms * 1e-3) / 1e9) / peak if knn_ms > 0 else None},
+                "note": "a single frame is latency-bound (SURVEY.md H3): 26 MB of compulsory traffic = 4 us at peak; the fraction is reported, not a target"}
+
+    if world > 1:
+        counts, _ = shard.gather_frame_results({rank: np.ascontiguousarray(r.output_vertices())}, world, cap=1024)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        ts, cstages, _ = time_oracle(fx.turbine(args.points, seed=0), args.cpu_frames)
+        cpu_ms = 1e3 * float(np.mean(ts))
+        cpu_baseline = {"value": 1e3 / cpu_ms, "unit": "frames/s", "cores": 1, "kind": "port",
+                        "sample": "%d full 100k-point frames, oracle faithful mode, 1 thread (the reference is single-threaded)" % args.cpu_frames,
+                        "ms_per_frame": cpu_ms, "nproc": os.cpu_count()}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "points": n, "n_filtered": res0.n_filtered, "voxel_passes": res0.n_passes, "n_downsampled": res0.n_downsampled,
+                           "n_vertices": res0.n_vertices, "graph_edges": int(g["n_edges"]), "l2": "flushed between steps (256 MiB memset, outside the per-step events)",
+                           "parallelism": "1 frame per GPU per step; ranks = independent frames (no collective on the data path)"},
+                "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": 1e3 * e2e_s / args.steps, "h2d_bytes_per_step": int(n * 16), "d2h_bytes_per_step": d2h},
+                "gpu_launches": int(launches), "stage_ms": stage_ms, "clocks": clk, "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps}
+        print(json.dumps(line), flush=True)
+    r.close()
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=100000)
+    ap.add_argument("--cpu-frames", type=int, default=20, help="frames of the bounded CPU-baseline sample (~0.4 s each)")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    import __graft_entry__ as ge
+    if rank == 0 and not os.path.exists(os.path.join(ROOT, "osep_path_planner_b200", "libosep_skel.so")):
+        ge.build()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -137,6 +137,11 @@ int osep_rosa_vertices(osep_rosa* h, const float** data, int* n_vertices);
 long osep_rosa_get(osep_rosa* h, const char* name, void* dst, long cap_bytes);
 /* Enable per-stage taps that cost extra copies (vset_iters, knn_full, skelver_sampled ...). */
 int osep_rosa_set_debug(osep_rosa* h, int enable);
+/* Record a CUDA event after every stage group; "stage_ms" then returns 13 floats: device ms of
+ * filter, leaf loop, kNN grid build, kNN+normals, final voxel pass, similarity, surf kNN+levels,
+ * (unused), drosa orientation loop, position+fix-up, dcrosa, vertex_sampling, vertex_smooth.
+ * "launches" returns the number of kernels this handle has launched since create. */
+int osep_rosa_set_profile(osep_rosa* h, int enable);
 
 /* Batched independent frames (BASELINE.json configs[3]): B host clouds, processed on an
  * internal pool of `lanes` streams of this handle's device.  results[b] receives each

@@ -59,7 +59,7 @@ class GraphView(C.Structure):
 SYMBOLS = [
     "osep_last_error", "osep_abi_version", "osep_device_count", "osep_rosa_default_config", "osep_gskel_default_config",
     "osep_rosa_create", "osep_rosa_destroy", "osep_rosa_run", "osep_rosa_run_device", "osep_rosa_finish", "osep_rosa_stream",
-    "osep_rosa_vertices", "osep_rosa_get", "osep_rosa_set_debug", "osep_rosa_run_batch", "osep_rosa_run_batch_device",
+    "osep_rosa_vertices", "osep_rosa_get", "osep_rosa_set_debug", "osep_rosa_set_profile", "osep_rosa_run_batch", "osep_rosa_run_batch_device",
     "osep_rosa_batch_vertices", "osep_rosa_set_lanes", "osep_rosa_graph",
     "osep_gskel_create", "osep_gskel_destroy", "osep_gskel_run", "osep_gskel_vertices", "osep_gskel_graph", "osep_gskel_get",
     "osep_graph_build",
@@ -96,6 +96,7 @@ def load():
     L.osep_rosa_vertices.argtypes = [vp, C.POINTER(C.POINTER(C.c_float)), C.POINTER(ip)]
     L.osep_rosa_get.argtypes = [vp, C.c_char_p, vp, C.c_long]; L.osep_rosa_get.restype = C.c_long
     L.osep_rosa_set_debug.argtypes = [vp, ip]
+    L.osep_rosa_set_profile.argtypes = [vp, ip]
     L.osep_rosa_run_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(ip), ip, ip, C.POINTER(RosaResult)]
     L.osep_rosa_run_batch_device.argtypes = [vp, C.POINTER(vp), C.POINTER(ip), ip, ip, C.POINTER(RosaResult)]
     L.osep_rosa_batch_vertices.argtypes = [vp, ip, C.POINTER(C.POINTER(C.c_float)), C.POINTER(ip)]

@@ -72,6 +72,7 @@ static void rosa_free(osep_rosa_impl* h) {
     if (h->graph) graph_destroy(h->graph);
     if (h->st_host) cudaFreeHost(h->st_host);
     if (h->skel_host) cudaFreeHost(h->skel_host);
+    for (int i = 0; i < osep_rosa_impl::NSTAGE_EV; ++i) if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -179,6 +180,15 @@ int osep_rosa_set_debug(osep_rosa* h, int enable) {
         CK(dalloc(&I.d.knn_full, (size_t)I.d.Ncap * I.d.knn));
         CK(dalloc(&I.d.vset_iters, (size_t)I.d.Mcap * std::max(1, I.cfg.niter_drosa)));
     }
+    return OSEP_OK;
+}
+
+int osep_rosa_set_profile(osep_rosa* h, int enable) {
+    if (!h) return OSEP_ERR_ARG;
+    osep_rosa_impl& I = h->impl;
+    CK(cudaSetDevice(I.device));
+    I.profile = enable != 0;
+    if (I.profile) for (int i = 0; i < SM_COUNT; ++i) if (!I.stage_ev[i]) CK(cudaEventCreate(&I.stage_ev[i]));
     return OSEP_OK;
 }
 
@@ -295,6 +305,15 @@ long osep_rosa_get(osep_rosa* h, const char* name, void* dst, long cap) {
     if (nm == "skelver_sampled") return tap_f4_as_f3(dst, cap, d.skel_sampled, V);
     if (nm == "skelver") return tap_f4_as_f3(dst, cap, d.skel, V);
     if (nm == "levels") return tap_copy(dst, cap, d.level, M, 4);
+    if (nm == "stage_ms") {      // device ms between consecutive stage marks of the last frame (needs osep_rosa_set_profile)
+        if (!I.profile) return 0;
+        if (dst && cap >= (long)(4 * SM_COUNT)) {
+            cudaEvent_t prev = I.ev0;
+            for (int i = 0; i < SM_COUNT; ++i) { float ms = 0.f; cudaEventElapsedTime(&ms, prev, I.stage_ev[i]); ((float*)dst)[i] = ms; prev = I.stage_ev[i]; }
+        }
+        return SM_COUNT;
+    }
+    if (nm == "launches") { if (dst && cap >= 4) *(int*)dst = (int)I.n_launches; return 1; }
     return -1;
 }
 

@@ -766,9 +766,12 @@ void launch_mscale(osep_rosa_impl* h) {
     k_simi<false><<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.nrms, d.simi_off, d.simi_idx, nullptr, nullptr);
     k_simi_scan<<<1, 1024, 0, s>>>(d.st, d.simi_off, d.Scap);
     k_simi<true><<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.nrms, d.simi_off, d.simi_idx, d.rv1, (float*)d.rk1);
+    stage_mark(h, SM_SIMI);
     // R13 + level schedule
     if (d.nbk <= 10) launch_surf<10>(h); else if (d.nbk <= 16) launch_surf<16>(h); else if (d.nbk <= 32) launch_surf<32>(h); else launch_surf<64>(h);
     k_gs_levels<<<1, 32, sizeof(int) * d.Mcap, s>>>(d.st, d.surf, d.nbk, d.level, d.level_off, d.level_pts);
+    stage_mark(h, SM_SURF);
+    stage_mark(h, SM_DROSA_ORIENT);
     // R14-R17
     const size_t bfs_smem = (size_t)WARPS_PER_BLOCK * 4 * d.W * sizeof(unsigned);
     cudaMemsetAsync(d.vnew, 0, sizeof(float4) * d.Mcap, s);        // vnew = Zero (rosa.cpp:272)
@@ -777,26 +780,32 @@ void launch_mscale(osep_rosa_impl* h) {
         k_drosa_smooth<<<1, 32, 2 * sizeof(float4) * d.Mcap, s>>>(d.st, d.vnew, d.vvar, d.surf, d.nbk, d.level_off, d.level_pts, d.vset, d.Mcap);
         if (h->debug && d.vset_iters) cudaMemcpyAsync(d.vset_iters + (size_t)it * d.Mcap, d.vset, sizeof(float4) * d.Mcap, cudaMemcpyDeviceToDevice, s);
     }
+    stage_mark(h, SM_DROSA_SMOOTH);
     // R18-R19
     k_drosa_position<<<warp_blocks, tb, bfs_smem, s>>>(d.st, d.pts, d.nrms, d.pset, d.vset, d.simi_off, d.simi_idx, d.good, d.centers,
                                                       d.active_size, c.max_proj_range, d.W);
     k_poor_prepare<<<1, 1024, 0, s>>>(d.st, d.good, d.good_rank, d.centers, d.pset2, d.poor_idx, nullptr);
     k_poor_fix<<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.good, d.pset2, d.poor_idx, d.pset);
     if (h->debug) cudaMemcpyAsync(d.centers, d.pset, sizeof(float4) * d.Mcap, cudaMemcpyDeviceToDevice, s);   // tap: pset after drosa
+    stage_mark(h, SM_POSITION);
     // R20
     for (int it = 0; it < c.niter_dcrosa; ++it) {
         k_dcrosa_mean<<<tblocks, 128, 0, s>>>(d.st, d.pset, d.pset2, d.simi_off, d.simi_idx);
         k_dcrosa_line<<<tblocks, 128, 0, s>>>(d.st, d.pset2, d.pset, d.simi_off, d.simi_idx);
     }
+    stage_mark(h, SM_DCROSA);
     // R21
     k_vs_compact<<<1, 1024, 0, s>>>(d.st, d.pset, d.pcloud, d.good_rank);
     k_vs_adj<<<warp_blocks, tb, 0, s>>>(d.st, d.pcloud, d.adj_bits, d.W);
     k_vs_greedy<<<1, 32, sizeof(unsigned) * d.W, s>>>(d.st, d.adj_bits, d.W, d.seeds);
     k_vs_corresp<<<tblocks, 128, 0, s>>>(d.st, d.pcloud, d.seeds, d.corresp);
     k_vs_recenter<<<tblocks, 128, 0, s>>>(d.st, d.pts, d.pset, d.seeds, d.corresp, c.alpha_recenter, d.skel, d.skel_sampled);
+    stage_mark(h, SM_VSAMPLE);
     // R22
     k_vertex_smooth<<<1, 1024, 0, s>>>(d.st, d.skel, d.skel2, d.vtmp, d.vs_off, d.vs_idx, d.rv1, (float*)d.rk1, d.Scap,
                                        c.radius_smooth, c.alpha_recenter, c.niter_smooth);
+    stage_mark(h, SM_VSMOOTH);
+    h->n_launches += 1 + 3 + 1 + 1 + 2 * c.niter_drosa + 1 + 2 + 2 * c.niter_dcrosa + 5 + 1;
 }
 
 }  // namespace osep

@@ -606,24 +606,28 @@ void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int strid
     k_filter_count<<<nb, NT, 0, s>>>(xyz_dev, n, stride, r2, d.blk_cnt);
     k_filter_scan<<<1, 1024, 0, s>>>(d.blk_cnt, nb, d.st, c.min_points);
     k_filter_scatter<<<nb, NT, 0, s>>>(xyz_dev, n, stride, r2, d.blk_cnt, d.P, d.filt_idx, d.st);
+    stage_mark(h, SM_FILTER);
     // R7/R8: device-resident leaf loop (count-only passes)
     for (int p = 0; p < LEAF_MAX_ITERS; ++p) {
         k_leaf_step<<<1, 1, 0, s>>>(d.st, p, c.max_points);
         k_vox_count<<<nb, NT, 0, s>>>(d.P, d.st, d.vtab, (unsigned)(d.T - 1));
     }
     k_leaf_step<<<1, 1, 0, s>>>(d.st, LEAF_MAX_ITERS, c.max_points);
+    stage_mark(h, SM_LEAF);
     // R5: grid + kNN normals
     cudaMemsetAsync(d.gtab, 0, sizeof(unsigned) * 3 * (size_t)d.T, s);   // gtab | g_cnt | g_fill are contiguous
     k_grid_params<<<1, 1, 0, s>>>(d.st, 10);
     k_grid_insert<<<nb, NT, 0, s>>>(d.P, d.st, (unsigned*)d.gtab, d.g_cnt, d.p_slot, (unsigned)(d.T - 1));
     k_grid_alloc<<<div_up(d.T, NT), NT, 0, s>>>(d.st, d.g_cnt, d.g_start, d.T);
     k_grid_scatter<<<nb, NT, 0, s>>>(d.P, d.st, d.p_slot, d.g_start, d.g_fill, d.Pc);
+    stage_mark(h, SM_GRID);
     const int k = c.ne_knn;
     if (k == 20) launch_knn<20>(h, n, k);
     else if (k <= 10) launch_knn<10>(h, n, k);
     else if (k <= 16) launch_knn<16>(h, n, k);
     else if (k <= 32) launch_knn<32>(h, n, k);
     else launch_knn<64>(h, n, k);
+    stage_mark(h, SM_KNN);
     // R9 final pass
     k_vox_collect<<<div_up(d.T, NT), NT, 0, s>>>(d.st, d.vtab, d.T, d.vkeys, d.Mcap);
     int P2 = 1; while (P2 < d.Mcap) P2 <<= 1;
@@ -642,6 +646,8 @@ void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int strid
     }
     // even number of passes: sorted data is back in rk0 / rv0
     k_vox_reduce<<<div_up(d.Mcap, 128), 128, 0, s>>>(d.st, va, d.vox_cnt, d.P, d.Nrm, d.pts, d.nrms, d.pset, d.vset);
+    stage_mark(h, SM_VOXEL);
+    h->n_launches += 1 + 3 + (2 * LEAF_MAX_ITERS + 1) + 4 + 1 + 4 + 3 * passes + 1;
 }
 
 }  // namespace osep

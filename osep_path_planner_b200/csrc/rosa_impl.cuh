@@ -58,6 +58,11 @@ struct osep_rosa_impl {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     RosaDev d;
     bool debug = false;
+    bool profile = false;              // record a CUDA event after every stage group (osep_rosa_set_profile)
+    static constexpr int NSTAGE_EV = 16;
+    cudaEvent_t stage_ev[NSTAGE_EV] = {};
+    int n_stage_ev = 0;
+    long long n_launches = 0;          // kernels launched by this handle since create
     // host mirrors
     FrameState* st_host = nullptr;     // pinned
     float* in_host = nullptr;          // pinned staging, Ncap*4 floats
@@ -71,6 +76,13 @@ struct osep_rosa_impl {
     std::vector<osep_rosa_impl*> lanes;
     std::vector<std::vector<float>> batch_vertices;
 };
+
+// stage-group boundaries for the profile tap ("stage_ms"), in launch order
+enum StageMark { SM_FILTER = 0, SM_LEAF, SM_GRID, SM_KNN, SM_VOXEL, SM_SIMI, SM_SURF, SM_DROSA_ORIENT, SM_DROSA_SMOOTH, SM_POSITION,
+                 SM_DCROSA, SM_VSAMPLE, SM_VSMOOTH, SM_COUNT };
+inline void stage_mark(osep_rosa_impl* h, int which) {
+    if (h->profile && h->stage_ev[which]) cudaEventRecord(h->stage_ev[which], h->stream);
+}
 
 // stage launchers (all asynchronous on h->stream, no host sync)
 void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int stride);   // R3-R11

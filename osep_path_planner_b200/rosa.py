@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import RosaConfig, RosaResult, GraphView, OsepError, ROSA_STAGES
 
 _INT_TAPS = {"filt_idx", "knn_full", "nvox_hist", "vox_count", "surf_off", "surf_idx", "simi_off", "simi_idx",
-             "poor_idx", "active_size", "corresp", "seeds", "levels"}
+             "poor_idx", "active_size", "corresp", "seeds", "levels", "launches"}
 _U32_TAPS = {"vox_keys"}
 _V3_TAPS = {"filtered", "normals_full", "pts", "nrms", "vset", "vset_iters", "pset", "pset_drosa", "skelver_sampled", "skelver"}
 
@@ -116,6 +116,21 @@ class Rosa:
         rc = self._L.osep_rosa_set_debug(self._h, 1 if on else 0)
         if rc != 0:
             raise OsepError("osep_rosa_set_debug failed: %s" % _lib.last_error())
+
+    STAGE_NAMES = ["filter", "leaf_loop", "knn_grid", "knn_normals", "voxel_final", "similarity", "surf_knn_levels", "-",
+                   "drosa_orient_smooth", "position_fixup", "dcrosa", "vertex_sampling", "vertex_smooth"]
+
+    def set_profile(self, on=True):
+        rc = self._L.osep_rosa_set_profile(self._h, 1 if on else 0)
+        if rc != 0:
+            raise OsepError("osep_rosa_set_profile failed: %s" % _lib.last_error())
+
+    def stage_ms(self):
+        return dict(zip(self.STAGE_NAMES, self.tap("stage_ms").tolist()))
+
+    @property
+    def launches(self):
+        return int(self.tap("launches")[0])
 
     def set_lanes(self, lanes):
         rc = self._L.osep_rosa_set_lanes(self._h, lanes)
