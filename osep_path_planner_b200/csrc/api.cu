@@ -29,7 +29,7 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
     RosaDev& d = h->d;
     const osep_rosa_config& c = h->cfg;
     d.Ncap = std::max(capacity_points, 1024);
-    d.Mcap = 4096;
+    d.Mcap = 3072;
     d.W = d.Mcap / 32;
     d.Scap = d.Mcap * 128;
     d.T = 1; while (d.T < 2 * d.Ncap) d.T <<= 1;
@@ -47,7 +47,8 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
     CK(dalloc(&d.rk0, tmpcap)); CK(dalloc(&d.rk1, tmpcap)); CK(dalloc(&d.rv0, tmpcap)); CK(dalloc(&d.rv1, tmpcap));
     CK(dalloc(&d.rhist, (size_t)256 * d.nchunks + 1024));
     CK(dalloc(&d.pts, M)); CK(dalloc(&d.nrms, M)); CK(dalloc(&d.pset, M)); CK(dalloc(&d.pset2, M)); CK(dalloc(&d.vset, M)); CK(dalloc(&d.vnew, M));
-    CK(dalloc(&d.vvar, M)); CK(dalloc(&d.surf, M * (size_t)std::max(d.nbk, 1)));
+    CK(dalloc(&d.vvar, M)); CK(dalloc(&d.simi_bits, M * (size_t)d.W)); CK(dalloc(&d.nraw, M)); CK(dalloc(&d.vnd, M));
+    { int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device)); h->sms = sms > 0 ? sms : 148; } CK(dalloc(&d.surf, M * (size_t)std::max(d.nbk, 1)));
     CK(dalloc(&d.simi_off, M + 2)); CK(dalloc(&d.simi_idx, (size_t)d.Scap));
     CK(dalloc(&d.level, M)); CK(dalloc(&d.level_off, M + 2)); CK(dalloc(&d.level_pts, M));
     CK(dalloc(&d.good, M)); CK(dalloc(&d.centers, M)); CK(dalloc(&d.good_rank, M + 2)); CK(dalloc(&d.poor_idx, M));
@@ -66,7 +67,7 @@ static void rosa_free(osep_rosa_impl* h) {
     RosaDev& d = h->d;
     void* ptrs[] = {d.st, d.in, d.P, d.filt_idx, d.blk_cnt, d.gtab, d.g_start, d.p_slot, d.Pc, d.Nrm, d.knn_full, d.vtab, d.vkeys, d.vid,
                     d.vox_cnt, d.rk0, d.rk1, d.rv0, d.rv1, d.rhist, d.pts, d.nrms, d.pset, d.pset2, d.vset, d.vnew, d.vvar, d.surf,
-                    d.simi_off, d.simi_idx, d.level, d.level_off, d.level_pts, d.good, d.centers, d.good_rank, d.poor_idx, d.active_size,
+                    d.simi_off, d.simi_idx, d.simi_bits, d.nraw, d.vnd, d.level, d.level_off, d.level_pts, d.good, d.centers, d.good_rank, d.poor_idx, d.active_size,
                     d.pcloud, d.adj_bits, d.seeds, d.corresp, d.skel, d.skel2, d.skel_sampled, d.vtmp, d.vs_off, d.vs_idx, d.vset_iters};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->graph) graph_destroy(h->graph);
@@ -141,7 +142,7 @@ int osep_rosa_create(const osep_rosa_config* cfg, int device, int capacity_point
     osep_rosa_config c; osep_rosa_default_config(&c);
     if (cfg) c = *cfg;
     if (c.ne_knn < 1 || c.ne_knn > KNN_MAX || c.nb_knn < 1 || c.nb_knn > 32) { set_err("ne_knn must be in [1,%d], nb_knn in [1,32]", KNN_MAX); return OSEP_ERR_ARG; }
-    if (c.max_points < 1 || c.max_points > 2048) { set_err("max_points must be in [1,2048] (device arena holds 4096 downsampled points)"); return OSEP_ERR_ARG; }
+    if (c.max_points < 1 || c.max_points > 1536) { set_err("max_points must be in [1,1536] (device arena holds 3072 downsampled points)"); return OSEP_ERR_ARG; }
     if (capacity_points < 1) { set_err("capacity_points must be positive"); return OSEP_ERR_ARG; }
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));

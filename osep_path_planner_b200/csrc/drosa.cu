@@ -1,0 +1,432 @@
+// csrc/drosa.cu -- the drosa stage (rosa.cpp:258-380) on sm_100a: R14-R19.
+//
+// Data layout.  M ~ 1000 points; everything a seed touches is staged in shared memory once
+// per CTA (one CTA per SM, 148 CTAs):
+//   * the similarity graph as an M x ceil(M/32) BIT MATRIX (row i = simi_nbs[i]; 128 KB at
+//     M = 1003) -- the active set of a seed (connected component of the seed inside its slab,
+//     rosa.cpp:653-683) is then a bit-parallel BFS: one 32-bit word of slab / visited /
+//     frontier per LANE in registers, one LDS + OR per visited node, no atomics, no queue;
+//   * points, raw normals and the per-point unit normals (hoisted: the reference recomputes
+//     v / |v| inside every sum, rosa.cpp:693-696 -- same value every time).
+// One warp per seed; float sums run in the canonical lane-owner order (C4): lane l owns the
+// members of words w = l (mod 32), ascending, then an xor butterfly.
+// The in-place smoothing pass (Gauss-Seidel, rosa.cpp:295-308) is a dependent chain: one warp
+// walks the levels of its dependency DAG with all operands in shared memory.
+#include "rosa_impl.cuh"
+
+namespace osep {
+
+constexpr unsigned FULLM = 0xffffffffu;
+constexpr int SEED_WARPS = 8;
+constexpr int SEED_SMEM_BUDGET = 200 * 1024;
+constexpr int GS_THREADS = 256;
+constexpr int GS_SMEM_BUDGET = 200 * 1024;
+
+__device__ __forceinline__ f3 ld3f(const float4* a, int i) { const float4 v = a[i]; return {v.x, v.y, v.z}; }
+
+template <int K> __device__ __forceinline__ void bfly(float (&v)[K]) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = v[k] + __shfl_xor_sync(FULLM, v[k], off);
+    }
+}
+
+// per-point normal quantities used inside the active-set sums, computed once per frame:
+//   nraw[i] = (n, il_dd)  il_dd = (s2 > 1e-20f) ? (float)(1.0 / (double)sqrtf(s2)) : 0      rosa.cpp:764-766
+//   vnd[i]  = (n * ((double)s2 > 1e-20 ? 1/sqrtf(s2) : 0), il_f)                             rosa.cpp:694-696, 740-742
+//             il_f = (s2 > 1e-20f) ? 1.0f / sqrtf(s2) : 0                                    rosa.cpp:340-341, 717-718
+__global__ void k_normal_prep(const FrameState* __restrict__ st, const float4* __restrict__ nrms, float4* __restrict__ nraw, float4* __restrict__ vnd) {
+    if (st->status != 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st->M) return;
+    const f3 v = ld3f(nrms, i);
+    const float s2 = sqn3(v);
+    const float rt = sqrtf(s2);
+    const float il_dd = (s2 > 1e-20f) ? (float)(1.0 / (double)rt) : 0.0f;
+    const float il_d = ((double)s2 > 1e-20) ? 1.0f / rt : 0.0f;
+    const float il_f = (s2 > 1e-20f) ? 1.0f / rt : 0.0f;
+    nraw[i] = make_float4(v.x, v.y, v.z, il_dd);
+    const f3 u = mul3(v, il_d);
+    vnd[i] = make_float4(u.x, u.y, u.z, il_f);
+}
+
+struct SeedCtx {
+    const float4* pts; const float4* nraw; const float4* vnd;
+    const unsigned* bits; int bstride;
+    int M, Wn; float leaf;
+};
+
+// R14 compute_active_samples: returns |active|; vis[k] = this lane's word (lane + 32 k) of the member set
+template <int WPL>
+__device__ __forceinline__ int active_set(const SeedCtx& c, int seed, const f3& p, const f3& n, unsigned (&vis)[WPL]) {
+    const int lane = threadIdx.x & 31;
+    unsigned slab[WPL], front[WPL];
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) slab[k] = 0u;
+    for (int t = 0; t < c.Wn; ++t) {
+        const int i = t * 32 + lane;
+        bool in = false;
+        if (i < c.M) {
+            const float4 q = c.pts[i];
+            const float d = n.x * (p.x - q.x) + n.y * (p.y - q.y) + n.z * (p.z - q.z);      // rosa.cpp:660
+            in = fabsf(d) < c.leaf;
+        }
+        const unsigned word = __ballot_sync(FULLM, in);
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) if (t == lane + 32 * k) slab[k] = word;
+    }
+    const int sw = seed >> 5; const unsigned sbit = 1u << (seed & 31);
+    bool seed_in = false;
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) {
+        const bool mine = (sw == lane + 32 * k);
+        vis[k] = front[k] = (mine && (slab[k] & sbit)) ? sbit : 0u;
+        seed_in |= (vis[k] != 0u);
+    }
+    if (!__any_sync(FULLM, seed_in)) return 0;                                              // rosa.cpp:664
+    while (true) {
+        unsigned acc[WPL];
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) acc[k] = 0u;
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) {
+            unsigned nz = __ballot_sync(FULLM, front[k] != 0u);
+            while (nz) {
+                const int sl = __ffs(nz) - 1; nz &= nz - 1;
+                unsigned fw = __shfl_sync(FULLM, front[k], sl);
+                const int nbase = (sl + 32 * k) * 32;
+                while (fw) {
+                    const int b = __ffs(fw) - 1; fw &= fw - 1;
+                    const unsigned* row = c.bits + (size_t)(nbase + b) * c.bstride;
+#pragma unroll
+                    for (int kk = 0; kk < WPL; ++kk) { const int w = lane + 32 * kk; if (w < c.Wn) acc[kk] |= row[w]; }
+                }
+            }
+        }
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) { const unsigned nw = acc[k] & slab[k] & ~vis[k]; vis[k] |= nw; front[k] = nw; any |= (nw != 0u); }
+        if (!__any_sync(FULLM, any)) break;
+    }
+    int m = 0;
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) m += __popc(vis[k]);
+    return __reduce_add_sync(FULLM, m);
+}
+
+template <int WPL, class F> __device__ __forceinline__ void for_members(const unsigned (&vis)[WPL], F body) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) {
+        unsigned bits = vis[k];
+        const int base = (lane + 32 * k) * 32;
+        while (bits) { const int i = base + (__ffs(bits) - 1); bits &= bits - 1; body(i); }
+    }
+}
+
+// sums for the normal covariance (rosa.cpp:689-699, 735-745)
+template <int WPL> __device__ __forceinline__ void normal_cov_sums(const SeedCtx& c, const unsigned (&vis)[WPL], float (&s)[9]) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s[k] = 0.0f;
+    for_members<WPL>(vis, [&](int i) {
+        const float4 u = c.vnd[i];
+        s[0] += u.x; s[1] += u.y; s[2] += u.z;
+        s[3] += u.x * u.x; s[4] += u.y * u.x; s[5] += u.y * u.y;
+        s[6] += u.z * u.x; s[7] += u.z * u.y; s[8] += u.z * u.z;
+    });
+    bfly<9>(s);
+}
+// covariance = sum_outer * inv_m - mu mu^T (rosa.cpp:701-703, 747-749), lower triangle -> eigen
+__device__ __forceinline__ Eig3 normal_cov_eig(const float (&s)[9], float inv_m) {
+    const float mx = s[0] * inv_m, my = s[1] * inv_m, mz = s[2] * inv_m;
+    const float c00 = s[3] * inv_m - mx * mx;
+    const float c10 = s[4] * inv_m - my * mx;
+    const float c11 = s[5] * inv_m - my * my;
+    const float c20 = s[6] * inv_m - mz * mx;
+    const float c21 = s[7] * inv_m - mz * my;
+    const float c22 = s[8] * inv_m - mz * mz;
+    return eig3_sym(c00, c10, c11, c20, c21, c22);
+}
+
+struct SeedOut {
+    float4* vnew; float* vvar;                                    // orientation pass
+    float4* pset; int* good; float4* centers; int* active_size;   // position pass
+    float max_proj_range;
+};
+
+// MODE 0: R15-R17 Jacobi half of one drosa iteration (rosa.cpp:275-292)
+// MODE 1: R18 position step (rosa.cpp:317-365)
+template <int MODE, int WPL>
+__device__ __forceinline__ void seed_body(const SeedCtx& c, int seed, const f3& p, const f3& n, const SeedOut& o) {
+    const int lane = threadIdx.x & 31;
+    unsigned vis[WPL];
+    const int m = active_set<WPL>(c, seed, p, n, vis);
+    if (MODE == 0) {
+        if (m == 0) { if (lane == 0) o.vvar[seed] = 1.0f / (0.0f + 1e-5f); return; }   // vvar = 0 (rosa.cpp:285-287) -> 1/(0^4+eps); vnew row kept
+        float s[9];
+        normal_cov_sums<WPL>(c, vis, s);
+        const float inv_m = 1.0f / (float)m;
+        const Eig3 E = normal_cov_eig(s, inv_m);
+        const f3 sym = eig_col(E, 0);                                                   // compute_symmetrynormal (rosa.cpp:685-706)
+        float a2[2] = {0.0f, 0.0f};                                                     // symmnormal_variance (rosa.cpp:708-732)
+        for_members<WPL>(vis, [&](int i) {
+            const float4 v = c.nraw[i];
+            const float il = c.vnd[i].w;
+            const float a = dot3(f3{v.x, v.y, v.z}, sym) * il;
+            a2[0] += a; a2[1] += a * a;
+        });
+        bfly<2>(a2);
+        const float mu = a2[0] * inv_m;
+        float var = a2[1] * inv_m - mu * mu;
+        if (m > 1) var *= (float)m / (float)(m - 1);
+        if (lane == 0) {
+            o.vnew[seed] = make_float4(sym.x, sym.y, sym.z, 0.0f);
+            float a = var * var; a = a * a;
+            o.vvar[seed] = 1.0f / (a + 1e-5f);                                          // rosa.cpp:291-292
+        }
+    } else {
+        if (lane == 0) o.active_size[seed] = m;
+        if (m == 0) { if (lane == 0) o.good[seed] = 0; return; }
+        float s[9];
+        normal_cov_sums<WPL>(c, vis, s);                                                // cov_eigs_from_normals (rosa.cpp:734-753)
+        const float inv_m = 1.0f / (float)m;
+        const Eig3 E = normal_cov_eig(s, inv_m);
+        const float planar_score = (E.ev[1] - E.ev[0]) / smax(E.ev[2], 1e-6f);
+        f3 center;
+        if (planar_score < 0.1f) {                                                      // rosa.cpp:334-349
+            float t[6] = {0, 0, 0, 0, 0, 0};
+            for_members<WPL>(vis, [&](int i) {
+                const float4 q = c.pts[i]; const float4 v = c.nraw[i]; const float il = c.vnd[i].w;
+                t[0] += q.x; t[1] += q.y; t[2] += q.z; t[3] += v.x * il; t[4] += v.y * il; t[5] += v.z * il;
+            });
+            bfly<6>(t);
+            const f3 mean_p{t[0] * inv_m, t[1] * inv_m, t[2] * inv_m};
+            const f3 mean_n{t[3] * inv_m, t[4] * inv_m, t[5] * inv_m};
+            center = sub3(mean_p, mul3(mean_n, 0.5f * o.max_proj_range));
+        } else {                                                                        // closest_projection_point (rosa.cpp:755-791)
+            float t[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) t[k] = 0.0f;
+            for_members<WPL>(vis, [&](int i) {
+                const float4 q = c.pts[i]; const float4 v = c.nraw[i];
+                const f3 vn{v.x * v.w, v.y * v.w, v.z * v.w};
+                const float P00 = 1.0f - vn.x * vn.x, P01 = 0.0f - vn.x * vn.y, P02 = 0.0f - vn.x * vn.z;
+                const float P10 = 0.0f - vn.y * vn.x, P11 = 1.0f - vn.y * vn.y, P12 = 0.0f - vn.y * vn.z;
+                const float P20 = 0.0f - vn.z * vn.x, P21 = 0.0f - vn.z * vn.y, P22 = 1.0f - vn.z * vn.z;
+                t[0] += P00; t[1] += P01; t[2] += P02; t[3] += P10; t[4] += P11; t[5] += P12; t[6] += P20; t[7] += P21; t[8] += P22;
+                t[9] += sum3(P00 * q.x, P01 * q.y, P02 * q.z);
+                t[10] += sum3(P10 * q.x, P11 * q.y, P12 * q.z);
+                t[11] += sum3(P20 * q.x, P21 * q.y, P22 * q.z);
+            });
+            bfly<12>(t);
+            const float tr = sum3(t[0], t[4], t[8]);
+            const float reg = 1e-6f * smax(tr, 1e-6f);
+            float Mm[9] = {t[0] + reg, t[1], t[2], t[3], t[4] + reg, t[5], t[6], t[7], t[8] + reg};
+            const f3 B{t[9], t[10], t[11]};
+            if (!llt3_solve(Mm, B, center)) { if (!ldlt3_solve(Mm, B, center)) center = {1e8f, 1e8f, 1e8f}; }
+        }
+        const bool ok = fin3(center) && (norm3(sub3(center, p)) < o.max_proj_range);
+        if (lane == 0) {
+            o.good[seed] = ok ? 1 : 0;
+            if (ok) { o.pset[seed] = make_float4(center.x, center.y, center.z, 1.0f); o.centers[seed] = make_float4(center.x, center.y, center.z, 1.0f); }
+        }
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(SEED_WARPS * 32)
+k_drosa_seed(FrameState* st, const float4* __restrict__ pts, const float4* __restrict__ nraw, const float4* __restrict__ vnd,
+             float4* pset, const float4* __restrict__ vset, const unsigned* __restrict__ bits, int W, SeedOut o) {
+    extern __shared__ uint4 seed_smem[];
+    if (st->status != 0) return;
+    const int M = st->M;
+    if ((int)blockIdx.x >= M) return;
+    const int Wn = (M + 31) >> 5;
+    const size_t small_bytes = (size_t)3 * 16 * M;
+    const bool small_in = small_bytes <= (size_t)SEED_SMEM_BUDGET;
+    const bool mat_in = small_in && (small_bytes + (size_t)4 * M * Wn <= (size_t)SEED_SMEM_BUDGET);
+    float4* s_pts = reinterpret_cast<float4*>(seed_smem);
+    float4* s_nraw = s_pts + M; float4* s_vnd = s_nraw + M;
+    unsigned* s_bits = reinterpret_cast<unsigned*>(s_vnd + M);
+    if (small_in) {
+        for (int i = threadIdx.x; i < M; i += blockDim.x) { s_pts[i] = pts[i]; s_nraw[i] = nraw[i]; s_vnd[i] = vnd[i]; }
+    }
+    if (mat_in) {
+        for (int r = threadIdx.x >> 5; r < M; r += (blockDim.x >> 5)) {
+            const unsigned* src = bits + (size_t)r * W; unsigned* dst = s_bits + (size_t)r * Wn;
+            for (int w = threadIdx.x & 31; w < Wn; w += 32) dst[w] = src[w];
+        }
+    }
+    __syncthreads();
+    SeedCtx c;
+    c.pts = small_in ? s_pts : pts; c.nraw = small_in ? s_nraw : nraw; c.vnd = small_in ? s_vnd : vnd;
+    c.bits = mat_in ? s_bits : bits; c.bstride = mat_in ? Wn : W;
+    c.M = M; c.Wn = Wn; c.leaf = st->leaf_size;
+    const int wib = threadIdx.x >> 5;
+    for (int seed = blockIdx.x + gridDim.x * wib; seed < M; seed += gridDim.x * SEED_WARPS) {
+        const f3 p = ld3f(pset, seed), n = ld3f(vset, seed);
+        if (Wn <= 32) seed_body<MODE, 1>(c, seed, p, n, o);
+        else if (Wn <= 64) seed_body<MODE, 2>(c, seed, p, n, o);
+        else seed_body<MODE, 4>(c, seed, p, n, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Dependency levels of the in-place smoothing pass (rosa.cpp:295-308): p reads the updated
+// orientation of every surf neighbour j < p, so level[p] = 1 + max level[j < p].  Computed by
+// parallel relaxation in shared memory (one cheap round per level of depth, ~230 rounds), then
+// points are bucketed by level (order inside a level is irrelevant: they are independent).
+__global__ void __launch_bounds__(1024) k_gs_levels2(FrameState* st, const int* __restrict__ surf, int nbk, int* __restrict__ level,
+                                                     int* __restrict__ level_off, int* __restrict__ level_pts) {
+    extern __shared__ int lsm[];          // lv[M] | cnt[M+1] | surf as ushort [M*nbk]
+    if (st->status != 0) return;
+    const int M = st->M;
+    int* lv = lsm; int* cnt = lsm + M;
+    unsigned short* ss = reinterpret_cast<unsigned short*>(cnt + M + 1);
+    const int k_eff = min(nbk, M);
+    for (int p = threadIdx.x; p < M; p += blockDim.x) lv[p] = 1;
+    for (int i = threadIdx.x; i < M * nbk; i += blockDim.x) { const int j = surf[i]; ss[i] = (unsigned short)(j < 0 ? 0xffff : j); }
+    __syncthreads();
+    while (true) {
+        int changed = 0;
+        for (int p = threadIdx.x; p < M; p += blockDim.x) {
+            int v = 0;
+            for (int u = 0; u < k_eff; ++u) { const int j = ss[p * nbk + u]; if (j < p) v = max(v, lv[j]); }
+            v += 1;
+            if (v != lv[p]) { lv[p] = v; changed = 1; }       // monotone: racing reads only delay convergence
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    int mx = 0;
+    for (int p = threadIdx.x; p < M; p += blockDim.x) mx = max(mx, lv[p]);
+    mx = __reduce_max_sync(FULLM, mx);
+    __shared__ int s_mx;
+    if (threadIdx.x == 0) s_mx = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) atomicMax(&s_mx, mx);
+    for (int l = threadIdx.x; l <= M; l += blockDim.x) cnt[l] = 0;
+    __syncthreads();
+    const int nl = s_mx;
+    for (int p = threadIdx.x; p < M; p += blockDim.x) { level[p] = lv[p]; atomicAdd(&cnt[lv[p] - 1], 1); }
+    __syncthreads();
+    if (threadIdx.x < 32) {               // exclusive scan of cnt[0..nl] by one warp
+        int carry = 0;
+        for (int b = 0; b <= nl; b += 32) {
+            const int l = b + threadIdx.x;
+            const int v = (l <= nl) ? cnt[l] : 0;
+            int incl = v;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(FULLM, incl, off); if ((int)threadIdx.x >= off) incl += t; }
+            if (l <= nl) { cnt[l] = carry + incl - v; level_off[l] = carry + incl - v; }
+            carry += __shfl_sync(FULLM, incl, 31);
+        }
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < M; p += blockDim.x) { const int pos = atomicAdd(&cnt[lv[p] - 1], 1); level_pts[pos] = p; }
+    if (threadIdx.x == 0) st->n_levels = nl;
+}
+
+// R17 smoothing half, level by level.  All operands in shared memory; one warp walks the chain.
+// sold = orientation after the Jacobi half (vset = vnew, rosa.cpp:289) with the weight in .w;
+// snew = orientations already rewritten by this pass.  p reads snew[j] for j < p, sold[j] otherwise.
+template <int NBK>
+__device__ __forceinline__ float4 gs_point(int p, const float4* sold, const float4* snew, const unsigned short* ssurf, int nbk, int k_eff) {
+    float m00 = 0, m10 = 0, m11 = 0, m20 = 0, m21 = 0, m22 = 0;
+    if (NBK > 0) {
+        int j[NBK > 0 ? NBK : 1];
+#pragma unroll
+        for (int u = 0; u < NBK; ++u) j[u] = ssurf[p * NBK + u];
+        float4 v[NBK > 0 ? NBK : 1];
+#pragma unroll
+        for (int u = 0; u < NBK; ++u) v[u] = (j[u] < p) ? snew[j[u]] : sold[j[u]];
+#pragma unroll
+        for (int u = 0; u < NBK; ++u) {
+            const float wx = v[u].x * v[u].w, wy = v[u].y * v[u].w, wz = v[u].z * v[u].w;      // (w v) v^T, lower triangle (rosa.cpp:300-304)
+            m00 += wx * v[u].x; m10 += wy * v[u].x; m11 += wy * v[u].y; m20 += wz * v[u].x; m21 += wz * v[u].y; m22 += wz * v[u].z;
+        }
+    } else {
+        for (int u = 0; u < k_eff; ++u) {
+            const int jj = ssurf[p * nbk + u];
+            const float4 v = (jj < p) ? snew[jj] : sold[jj];
+            const float wx = v.x * v.w, wy = v.y * v.w, wz = v.z * v.w;
+            m00 += wx * v.x; m10 += wy * v.x; m11 += wy * v.y; m20 += wz * v.x; m21 += wz * v.y; m22 += wz * v.z;
+        }
+    }
+    const Eig3 E = eig3_sym(m00, m10, m11, m20, m21, m22);
+    const f3 d = normalize3(eig_col(E, 2));                                                    // rosa.cpp:305-307
+    return make_float4(d.x, d.y, d.z, sold[p].w);
+}
+
+__global__ void __launch_bounds__(GS_THREADS)
+k_drosa_smooth2(FrameState* st, const float4* __restrict__ vnew, const float* __restrict__ vvar, const int* __restrict__ surf, int nbk,
+                const int* __restrict__ level_off, const int* __restrict__ level_pts, float4* __restrict__ vset) {
+    extern __shared__ uint4 gs_smem[];
+    if (st->status != 0) return;
+    const int M = st->M;
+    const int nl = st->n_levels;
+    if ((size_t)32 * M + 4 * ((size_t)nl + 2) + 2 * (size_t)M * nbk + 2 * (size_t)M + 64 > (size_t)GS_SMEM_BUDGET) {
+        if (threadIdx.x == 0) st->status = OSEP_ERR_CAPACITY;
+        return;
+    }
+    // carve: sold[M] snew[M] (float4) | soff[nl+1] (int) | ssurf[M*nbk] slist[M] (ushort)
+    float4* sold = reinterpret_cast<float4*>(gs_smem);
+    float4* snew = sold + M;
+    int* soff = reinterpret_cast<int*>(snew + M);
+    unsigned short* ssurf = reinterpret_cast<unsigned short*>(soff + nl + 1);
+    unsigned short* slist = ssurf + (size_t)M * nbk;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) { float4 v = vnew[i]; v.w = vvar[i]; sold[i] = v; snew[i] = v; }
+    for (int i = threadIdx.x; i <= nl; i += blockDim.x) soff[i] = level_off[i];
+    for (int i = threadIdx.x; i < M * nbk; i += blockDim.x) { const int j = surf[i]; ssurf[i] = (unsigned short)(j < 0 ? 0 : j); }
+    for (int i = threadIdx.x; i < M; i += blockDim.x) slist[i] = (unsigned short)level_pts[i];
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    const int k_eff = min(nbk, M);
+    const bool fast10 = (nbk == 10 && k_eff == 10);
+    for (int l = 0; l < nl; ++l) {
+        const int b = soff[l], e = soff[l + 1];
+        for (int t = b + lane; t < e; t += 32) {
+            const int p = slist[t];
+            snew[p] = fast10 ? gs_point<10>(p, sold, snew, ssurf, nbk, k_eff) : gs_point<0>(p, sold, snew, ssurf, nbk, k_eff);
+        }
+        __syncwarp();
+    }
+    for (int i = lane; i < M; i += 32) { float4 v = snew[i]; v.w = 0.0f; vset[i] = v; }
+}
+
+// ------------------------------------------------------------------------------------------
+static size_t gs_smem_bytes(int M, int nbk) { return (size_t)32 * M + 4 * ((size_t)M + 2) + 2 * (size_t)M * nbk + 2 * (size_t)M + 64; }
+
+void drosa_set_attributes() {
+    cudaFuncSetAttribute(k_drosa_seed<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEED_SMEM_BUDGET + 1024);
+    cudaFuncSetAttribute(k_drosa_seed<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEED_SMEM_BUDGET + 1024);
+    cudaFuncSetAttribute(k_drosa_smooth2, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_SMEM_BUDGET);
+    cudaFuncSetAttribute(k_gs_levels2, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_SMEM_BUDGET);
+}
+
+// R13 level schedule + R14-R18; `sms` = number of SMs (one seed CTA per SM)
+void launch_drosa(osep_rosa_impl* h, int sms) {
+    RosaDev& d = h->d;
+    cudaStream_t s = h->stream;
+    const osep_rosa_config& c = h->cfg;
+    // largest M the all-shared smoothing kernel accepts with this nb_knn (checked against Mcap at create)
+    k_normal_prep<<<div_up(d.Mcap, 128), 128, 0, s>>>(d.st, d.nrms, d.nraw, d.vnd);
+    k_gs_levels2<<<1, 1024, sizeof(int) * (2 * d.Mcap + 2) + sizeof(unsigned short) * d.Mcap * d.nbk, s>>>(d.st, d.surf, d.nbk, d.level, d.level_off, d.level_pts);
+    stage_mark(h, SM_SURF);
+    stage_mark(h, SM_DROSA_ORIENT);
+    SeedOut o; o.vnew = d.vnew; o.vvar = d.vvar; o.pset = d.pset; o.good = d.good; o.centers = d.centers; o.active_size = d.active_size;
+    o.max_proj_range = c.max_proj_range;
+    cudaMemsetAsync(d.vnew, 0, sizeof(float4) * d.Mcap, s);        // vnew = Zero (rosa.cpp:272)
+    const size_t gs_bytes = gs_smem_bytes(d.Mcap, d.nbk) <= (size_t)GS_SMEM_BUDGET ? gs_smem_bytes(d.Mcap, d.nbk) : (size_t)GS_SMEM_BUDGET;
+    for (int it = 0; it < c.niter_drosa; ++it) {
+        k_drosa_seed<0><<<sms, SEED_WARPS * 32, SEED_SMEM_BUDGET, s>>>(d.st, d.pts, d.nraw, d.vnd, d.pset, d.vset, d.simi_bits, d.W, o);
+        k_drosa_smooth2<<<1, GS_THREADS, gs_bytes, s>>>(d.st, d.vnew, d.vvar, d.surf, d.nbk, d.level_off, d.level_pts, d.vset);
+        if (h->debug && d.vset_iters) cudaMemcpyAsync(d.vset_iters + (size_t)it * d.Mcap, d.vset, sizeof(float4) * d.Mcap, cudaMemcpyDeviceToDevice, s);
+    }
+    stage_mark(h, SM_DROSA_SMOOTH);
+    k_drosa_seed<1><<<sms, SEED_WARPS * 32, SEED_SMEM_BUDGET, s>>>(d.st, d.pts, d.nraw, d.vnd, d.pset, d.vset, d.simi_bits, d.W, o);
+    h->n_launches += 2 + 2 * c.niter_drosa + 1;
+}
+
+}  // namespace osep

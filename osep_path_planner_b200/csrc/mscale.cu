@@ -98,7 +98,8 @@ __device__ __forceinline__ float similarity_metric(const f3& p1, const f3& v1, c
 // summation order of dcrosa, rosa.cpp:395-397, 804-813).
 template <bool FILL>
 __global__ void k_simi(FrameState* st, const float4* __restrict__ pts, const float4* __restrict__ nrms,
-                       int* simi_off, int* __restrict__ simi_idx, int* __restrict__ tmp_j, float* __restrict__ tmp_d) {
+                       int* simi_off, int* __restrict__ simi_idx, int* __restrict__ tmp_j, float* __restrict__ tmp_d,
+                       unsigned* __restrict__ simi_bits, int W) {
     if (st->status != 0) return;
     const int M = st->M;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -129,11 +130,16 @@ __global__ void k_simi(FrameState* st, const float4* __restrict__ pts, const flo
                 }
             }
             const unsigned m = __ballot_sync(FULL, keep);
+            if (!FILL && lane == 0) simi_bits[(size_t)i * W + (j0 >> 5)] = m;      // bit row i of the similarity graph (drosa.cu)
             if (FILL && keep) { const int pos = base + cnt + __popc(m & ((1u << lane) - 1u)); tmp_j[pos] = j; tmp_d[pos] = d2; }
             cnt += __popc(m);
         }
     }
-    if (!FILL) { if (lane == 0) simi_off[i] = cnt; return; }
+    if (!FILL) {
+        if (!n1ok) for (int w = lane; w < ((M + 31) >> 5); w += 32) simi_bits[(size_t)i * W + w] = 0u;
+        if (lane == 0) simi_off[i] = cnt;
+        return;
+    }
     __syncwarp();
     for (int e = lane; e < cnt; e += 32) {
         const float d = tmp_d[base + e]; const int j = tmp_j[base + e];
@@ -185,289 +191,6 @@ __global__ void k_surf_knn(const FrameState* __restrict__ st, const float4* __re
     const int k_eff = min(k_req, M);
 #pragma unroll
     for (int u = 0; u < K; ++u) if (u < k_req) surf[p * k_req + u] = (u < k_eff) ? tk.id[u] : -1;
-}
-
-// dependency levels of the in-place smoothing pass (rosa.cpp:295-308): point p reads the
-// already-updated orientation of every surf neighbour j < p.  level[p] = 1 + max level[j<p].
-// One warp; then points are bucketed by level (order inside a level is irrelevant).
-__global__ void k_gs_levels(FrameState* st, const int* __restrict__ surf, int nbk, int* level, int* level_off, int* level_pts) {
-    extern __shared__ int lv[];          // M ints
-    if (st->status != 0) return;
-    const int M = st->M;
-    const int lane = threadIdx.x;
-    int maxlv = 0;
-    int jn = (lane < nbk && M > 0) ? surf[lane] : -1;
-    for (int p = 0; p < M; ++p) {
-        const int j = jn;
-        if (p + 1 < M) jn = (lane < nbk) ? surf[(p + 1) * nbk + lane] : -1;
-        int v = 0;
-        if (j >= 0 && j < p) v = lv[j];
-        v = __reduce_max_sync(FULL, v) + 1;
-        if (lane == 0) lv[p] = v;
-        maxlv = max(maxlv, v);
-        __syncwarp();
-    }
-    // bucket by level: level_off has maxlv + 1 entries (levels are 1..maxlv)
-    for (int l = lane; l <= maxlv; l += 32) level_off[l] = 0;
-    __syncwarp();
-    for (int p = lane; p < M; p += 32) { level[p] = lv[p]; atomicAdd(&level_off[lv[p] - 1], 1); }
-    __syncwarp();
-    // exclusive scan over maxlv+1 entries (single warp, tiles of 32)
-    int carry = 0;
-    for (int b = 0; b <= maxlv; b += 32) {
-        const int l = b + lane;
-        const int v = (l <= maxlv) ? level_off[l] : 0;
-        int incl = v;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += t; }
-        if (l <= maxlv) level_off[l] = carry + incl - v;
-        carry += __shfl_sync(FULL, incl, 31);
-    }
-    __syncwarp();
-    // fill (reuse lv[] as per-level cursors is not possible: use atomics on a copy kept in level[] high bits)
-    for (int p = lane; p < M; p += 32) lv[p] = 0;     // lv now: cursor per level index
-    __syncwarp();
-    for (int p = lane; p < M; p += 32) {
-        const int l = level[p] - 1;
-        const int pos = level_off[l] + atomicAdd(&lv[l], 1);
-        level_pts[pos] = p;
-    }
-    if (lane == 0) st->n_levels = maxlv;
-}
-
-// ------------------------------------------------------------------------------------------
-// R14: active samples of one seed = component of the seed in the similarity graph restricted
-// to the slab |n.(p-q)| < leaf (rosa.cpp:653-683), as a bitmask in shared memory.
-// Returns the number of members (0 when the seed itself is outside the slab).
-__device__ __forceinline__ int active_bfs(int seed, const f3& p, const f3& n, float leaf, int M, int Wn,
-                                          const float4* __restrict__ pts, const int* __restrict__ simi_off,
-                                          const int* __restrict__ simi_idx, unsigned* slab, unsigned* vis, unsigned* front, unsigned* next) {
-    const int lane = threadIdx.x & 31;
-    for (int w = 0; w < Wn; ++w) {
-        const int i = w * 32 + lane;
-        bool in = false;
-        if (i < M) {
-            const float4 q = pts[i];
-            const float d = n.x * (p.x - q.x) + n.y * (p.y - q.y) + n.z * (p.z - q.z);
-            in = fabsf(d) < leaf;
-        }
-        const unsigned word = __ballot_sync(FULL, in);
-        if (lane == 0) { slab[w] = word; vis[w] = 0u; front[w] = 0u; next[w] = 0u; }
-    }
-    __syncwarp();
-    const unsigned sbit = 1u << (seed & 31);
-    if (!(slab[seed >> 5] & sbit)) return 0;
-    __syncwarp();
-    if (lane == 0) { vis[seed >> 5] = sbit; front[seed >> 5] = sbit; }
-    __syncwarp();
-    while (true) {
-        for (int w = 0; w < Wn; ++w) {
-            unsigned fw = front[w];
-            while (fw) {
-                const int b = __ffs(fw) - 1; fw &= fw - 1;
-                const int cur = w * 32 + b;
-                const int rs = simi_off[cur], re = simi_off[cur + 1];
-                for (int e = rs + lane; e < re; e += 32) {
-                    const int nb = simi_idx[e];
-                    const unsigned bit = 1u << (nb & 31); const int ww = nb >> 5;
-                    if ((slab[ww] & bit) && !(vis[ww] & bit)) { atomicOr(&vis[ww], bit); atomicOr(&next[ww], bit); }
-                }
-            }
-        }
-        __syncwarp();
-        unsigned any = 0u;
-        for (int w = lane; w < Wn; w += 32) { const unsigned f = next[w]; front[w] = f; next[w] = 0u; any |= f; }
-        __syncwarp();
-        if (!__any_sync(FULL, any != 0u)) break;
-    }
-    int m = 0;
-    for (int w = lane; w < Wn; w += 32) m += __popc(vis[w]);
-    m = __reduce_add_sync(FULL, m);
-    return m;
-}
-
-// unit normals as written in the reference: double literal 1e-20 at rosa.cpp:695,741; float
-// literal at :341,:718; double division at :765
-__device__ __forceinline__ f3 unit_normal_d(const f3& v) { const float s2 = sqn3(v); const float il = ((double)s2 > 1e-20) ? 1.0f / sqrtf(s2) : 0.0f; return mul3(v, il); }
-__device__ __forceinline__ f3 unit_normal_f(const f3& v) { const float s2 = sqn3(v); const float il = (s2 > 1e-20f) ? 1.0f / sqrtf(s2) : 0.0f; return mul3(v, il); }
-
-// canonical reduction C4: lane l owns the members whose 32-index word w satisfies w % 32 == l,
-// adds them in ascending index, then xor butterfly.
-template <class F> __device__ __forceinline__ void for_owned(const unsigned* vis, int Wn, int lane, F body) {
-    for (int w = lane; w < Wn; w += 32) {
-        unsigned bits = vis[w];
-        while (bits) { const int i = w * 32 + (__ffs(bits) - 1); bits &= bits - 1; body(i); }
-    }
-}
-
-__device__ __forceinline__ void normal_cov_sums(const unsigned* vis, int Wn, int lane, const float4* __restrict__ nrms, float (&s)[9]) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) s[k] = 0.0f;
-    for_owned(vis, Wn, lane, [&](int i) {
-        const f3 vn = unit_normal_d(ld3(nrms, i));
-        s[0] += vn.x; s[1] += vn.y; s[2] += vn.z;
-        s[3] += vn.x * vn.x; s[4] += vn.y * vn.x; s[5] += vn.y * vn.y;
-        s[6] += vn.z * vn.x; s[7] += vn.z * vn.y; s[8] += vn.z * vn.z;
-    });
-    butterfly<9>(s);
-}
-// covariance = sum_outer * inv_m - mu mu^T (rosa.cpp:701-703, 747-749), lower triangle
-__device__ __forceinline__ Eig3 normal_cov_eig(const float (&s)[9], float inv_m) {
-    const float mx = s[0] * inv_m, my = s[1] * inv_m, mz = s[2] * inv_m;
-    const float c00 = s[3] * inv_m - mx * mx;
-    const float c10 = s[4] * inv_m - my * mx;
-    const float c11 = s[5] * inv_m - my * my;
-    const float c20 = s[6] * inv_m - mz * mx;
-    const float c21 = s[7] * inv_m - mz * my;
-    const float c22 = s[8] * inv_m - mz * mz;
-    return eig3_sym(c00, c10, c11, c20, c21, c22);
-}
-
-// R15-R17 Jacobi half of one drosa iteration: one warp per seed.
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_drosa_orient(FrameState* st, const float4* __restrict__ pts, const float4* __restrict__ nrms, const float4* __restrict__ pset,
-               const float4* __restrict__ vset, const int* __restrict__ simi_off, const int* __restrict__ simi_idx,
-               float4* __restrict__ vnew, float* __restrict__ vvar, int W) {
-    extern __shared__ unsigned smem_u[];
-    if (st->status != 0) return;
-    const int M = st->M;
-    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int seed = blockIdx.x * WARPS_PER_BLOCK + wib;
-    if (seed >= M) return;
-    unsigned* slab = smem_u + (size_t)wib * 4 * W; unsigned* vis = slab + W; unsigned* front = vis + W; unsigned* next = front + W;
-    const int Wn = (M + 31) >> 5;
-    const f3 p = ld3(pset, seed), n = ld3(vset, seed);
-    const int m = active_bfs(seed, p, n, st->leaf_size, M, Wn, pts, simi_off, simi_idx, slab, vis, front, next);
-    if (m == 0) { if (lane == 0) vvar[seed] = 1.0f / (0.0f + 1e-5f); return; }   // vvar = 0 -> 1/(0^4 + eps), vnew keeps its row (rosa.cpp:285-287)
-    // compute_symmetrynormal (rosa.cpp:685-706)
-    float s[9];
-    normal_cov_sums(vis, Wn, lane, nrms, s);
-    const float inv_m = 1.0f / (float)m;
-    const Eig3 E = normal_cov_eig(s, inv_m);
-    const f3 sym = eig_col(E, 0);
-    // symmnormal_variance (rosa.cpp:708-732)
-    float a2[2] = {0.0f, 0.0f};
-    for_owned(vis, Wn, lane, [&](int i) {
-        const f3 v = ld3(nrms, i);
-        const float s2 = sqn3(v);
-        const float il = (s2 > 1e-20f) ? 1.0f / sqrtf(s2) : 0.0f;
-        const float a = dot3(v, sym) * il;
-        a2[0] += a; a2[1] += a * a;
-    });
-    butterfly<2>(a2);
-    const float mu = a2[0] * inv_m;
-    float var = a2[1] * inv_m - mu * mu;
-    if (m > 1) var *= (float)m / (float)(m - 1);
-    if (lane == 0) {
-        st3(vnew, seed, sym);
-        // vvar = 1 / (vvar^4 + 1e-5)   (rosa.cpp:291-292)
-        float a = var * var; a = a * a;
-        vvar[seed] = 1.0f / (a + 1e-5f);
-    }
-}
-
-// R17 smoothing half: the in-place pass of rosa.cpp:295-308 with the reference's sequential
-// (Gauss-Seidel) semantics: point p reads the UPDATED orientation of neighbours j < p and the
-// OLD one of neighbours j >= p (itself included).  Old and new orientations are kept in two
-// shared-memory arrays, so only the true dependencies (j < p) order the work: points are
-// processed level by level of that DAG.  One warp.
-__global__ void k_drosa_smooth(FrameState* st, const float4* __restrict__ vnew, const float* __restrict__ vvar,
-                               const int* __restrict__ surf, int nbk, const int* __restrict__ level_off,
-                               const int* __restrict__ level_pts, float4* __restrict__ vset, int Mcap) {
-    extern __shared__ float4 sv[];       // [0, Mcap): old (xyz, w = weight); [Mcap, 2 Mcap): new
-    if (st->status != 0) return;
-    const int M = st->M;
-    float4* sold = sv; float4* snew = sv + Mcap;
-    const int lane = threadIdx.x;
-    for (int i = lane; i < M; i += 32) { float4 v = vnew[i]; v.w = vvar[i]; sold[i] = v; snew[i] = v; }     // vset = vnew (rosa.cpp:289)
-    __syncwarp();
-    const int nl = st->n_levels;
-    const int k_eff = min(nbk, M);
-    for (int l = 0; l < nl; ++l) {
-        const int b = level_off[l], e = level_off[l + 1];
-        for (int t = b + lane; t < e; t += 32) {
-            const int p = level_pts[t];
-            float m00 = 0, m10 = 0, m11 = 0, m20 = 0, m21 = 0, m22 = 0;
-            for (int u = 0; u < k_eff; ++u) {
-                const int j = surf[p * nbk + u];
-                const float4 v = (j < p) ? snew[j] : sold[j];
-                const float wx = v.x * v.w, wy = v.y * v.w, wz = v.z * v.w;     // (w * v) v^T, lower triangle
-                m00 += wx * v.x; m10 += wy * v.x; m11 += wy * v.y; m20 += wz * v.x; m21 += wz * v.y; m22 += wz * v.z;
-            }
-            const Eig3 E = eig3_sym(m00, m10, m11, m20, m21, m22);
-            const f3 d = normalize3(eig_col(E, 2));
-            snew[p] = make_float4(d.x, d.y, d.z, sold[p].w);
-        }
-        __syncwarp();
-    }
-    for (int i = lane; i < M; i += 32) { float4 v = snew[i]; v.w = 0.0f; vset[i] = v; }
-}
-
-// R18 position step: one warp per seed.
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_drosa_position(FrameState* st, const float4* __restrict__ pts, const float4* __restrict__ nrms, float4* pset,
-                 const float4* __restrict__ vset, const int* __restrict__ simi_off, const int* __restrict__ simi_idx,
-                 int* __restrict__ good, float4* __restrict__ centers, int* __restrict__ active_size, float max_proj_range, int W) {
-    extern __shared__ unsigned smem_u[];
-    if (st->status != 0) return;
-    const int M = st->M;
-    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int seed = blockIdx.x * WARPS_PER_BLOCK + wib;
-    if (seed >= M) return;
-    unsigned* slab = smem_u + (size_t)wib * 4 * W; unsigned* vis = slab + W; unsigned* front = vis + W; unsigned* next = front + W;
-    const int Wn = (M + 31) >> 5;
-    const f3 p = ld3(pset, seed), n = ld3(vset, seed);
-    const int m = active_bfs(seed, p, n, st->leaf_size, M, Wn, pts, simi_off, simi_idx, slab, vis, front, next);
-    if (lane == 0) active_size[seed] = m;
-    if (m == 0) { if (lane == 0) good[seed] = 0; return; }
-    // cov_eigs_from_normals (rosa.cpp:734-753)
-    float s[9];
-    normal_cov_sums(vis, Wn, lane, nrms, s);
-    const float inv_m = 1.0f / (float)m;
-    const Eig3 E = normal_cov_eig(s, inv_m);
-    const float planar_score = (E.ev[1] - E.ev[0]) / smax(E.ev[2], 1e-6f);
-    f3 center;
-    if (planar_score < 0.1f) {                                     // rosa.cpp:334-349
-        float t[6] = {0, 0, 0, 0, 0, 0};
-        for_owned(vis, Wn, lane, [&](int i) {
-            const f3 q = ld3(pts, i);
-            const f3 vn = unit_normal_f(ld3(nrms, i));
-            t[0] += q.x; t[1] += q.y; t[2] += q.z; t[3] += vn.x; t[4] += vn.y; t[5] += vn.z;
-        });
-        butterfly<6>(t);
-        const f3 mean_p{t[0] * inv_m, t[1] * inv_m, t[2] * inv_m};
-        const f3 mean_n{t[3] * inv_m, t[4] * inv_m, t[5] * inv_m};
-        center = sub3(mean_p, mul3(mean_n, 0.5f * max_proj_range));
-    } else {                                                       // closest_projection_point (rosa.cpp:755-791)
-        float t[12];
-#pragma unroll
-        for (int k = 0; k < 12; ++k) t[k] = 0.0f;
-        for_owned(vis, Wn, lane, [&](int i) {
-            const f3 q = ld3(pts, i);
-            const f3 v = ld3(nrms, i);
-            const float s2 = sqn3(v);
-            const float il = (s2 > 1e-20f) ? (float)(1.0 / (double)sqrtf(s2)) : 0.0f;
-            const f3 vn = mul3(v, il);
-            const float P00 = 1.0f - vn.x * vn.x, P01 = 0.0f - vn.x * vn.y, P02 = 0.0f - vn.x * vn.z;
-            const float P10 = 0.0f - vn.y * vn.x, P11 = 1.0f - vn.y * vn.y, P12 = 0.0f - vn.y * vn.z;
-            const float P20 = 0.0f - vn.z * vn.x, P21 = 0.0f - vn.z * vn.y, P22 = 1.0f - vn.z * vn.z;
-            t[0] += P00; t[1] += P01; t[2] += P02; t[3] += P10; t[4] += P11; t[5] += P12; t[6] += P20; t[7] += P21; t[8] += P22;
-            t[9] += sum3(P00 * q.x, P01 * q.y, P02 * q.z);
-            t[10] += sum3(P10 * q.x, P11 * q.y, P12 * q.z);
-            t[11] += sum3(P20 * q.x, P21 * q.y, P22 * q.z);
-        });
-        butterfly<12>(t);
-        const float tr = sum3(t[0], t[4], t[8]);
-        const float reg = 1e-6f * smax(tr, 1e-6f);
-        float Mm[9] = {t[0] + reg, t[1], t[2], t[3], t[4] + reg, t[5], t[6], t[7], t[8] + reg};
-        const f3 B{t[9], t[10], t[11]};
-        if (!llt3_solve(Mm, B, center)) { if (!ldlt3_solve(Mm, B, center)) center = {1e8f, 1e8f, 1e8f}; }
-    }
-    const bool ok = fin3(center) && (norm3(sub3(center, p)) < max_proj_range);
-    if (lane == 0) {
-        good[seed] = ok ? 1 : 0;
-        if (ok) { st3(pset, seed, center, 1.0f); st3(centers, seed, center, 1.0f); }
-    }
 }
 
 // R19 part 1 (single block): compact goodCenters, list poor points in ascending index.
@@ -750,9 +473,9 @@ template <int K> static void launch_surf(osep_rosa_impl* h) {
     k_surf_knn<K><<<div_up(d.Mcap, 128), 128, 0, h->stream>>>(d.st, d.pts, d.surf, d.nbk);
 }
 
-void mscale_set_attributes(int Mcap) {
-    cudaFuncSetAttribute(k_drosa_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(float4) * Mcap));
-}
+void drosa_set_attributes();
+void launch_drosa(osep_rosa_impl* h, int sms);
+void mscale_set_attributes(int Mcap) { (void)Mcap; drosa_set_attributes(); }
 
 void launch_mscale(osep_rosa_impl* h) {
     RosaDev& d = h->d;
@@ -763,27 +486,13 @@ void launch_mscale(osep_rosa_impl* h) {
     const int tblocks = div_up(d.Mcap, 128);
     k_mscale_begin<<<1, 1, 0, s>>>(d.st);
     // R12
-    k_simi<false><<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.nrms, d.simi_off, d.simi_idx, nullptr, nullptr);
+    k_simi<false><<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.nrms, d.simi_off, d.simi_idx, nullptr, nullptr, d.simi_bits, d.W);
     k_simi_scan<<<1, 1024, 0, s>>>(d.st, d.simi_off, d.Scap);
-    k_simi<true><<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.nrms, d.simi_off, d.simi_idx, d.rv1, (float*)d.rk1);
+    k_simi<true><<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.nrms, d.simi_off, d.simi_idx, d.rv1, (float*)d.rk1, d.simi_bits, d.W);
     stage_mark(h, SM_SIMI);
     // R13 + level schedule
     if (d.nbk <= 10) launch_surf<10>(h); else if (d.nbk <= 16) launch_surf<16>(h); else if (d.nbk <= 32) launch_surf<32>(h); else launch_surf<64>(h);
-    k_gs_levels<<<1, 32, sizeof(int) * d.Mcap, s>>>(d.st, d.surf, d.nbk, d.level, d.level_off, d.level_pts);
-    stage_mark(h, SM_SURF);
-    stage_mark(h, SM_DROSA_ORIENT);
-    // R14-R17
-    const size_t bfs_smem = (size_t)WARPS_PER_BLOCK * 4 * d.W * sizeof(unsigned);
-    cudaMemsetAsync(d.vnew, 0, sizeof(float4) * d.Mcap, s);        // vnew = Zero (rosa.cpp:272)
-    for (int it = 0; it < c.niter_drosa; ++it) {
-        k_drosa_orient<<<warp_blocks, tb, bfs_smem, s>>>(d.st, d.pts, d.nrms, d.pset, d.vset, d.simi_off, d.simi_idx, d.vnew, d.vvar, d.W);
-        k_drosa_smooth<<<1, 32, 2 * sizeof(float4) * d.Mcap, s>>>(d.st, d.vnew, d.vvar, d.surf, d.nbk, d.level_off, d.level_pts, d.vset, d.Mcap);
-        if (h->debug && d.vset_iters) cudaMemcpyAsync(d.vset_iters + (size_t)it * d.Mcap, d.vset, sizeof(float4) * d.Mcap, cudaMemcpyDeviceToDevice, s);
-    }
-    stage_mark(h, SM_DROSA_SMOOTH);
-    // R18-R19
-    k_drosa_position<<<warp_blocks, tb, bfs_smem, s>>>(d.st, d.pts, d.nrms, d.pset, d.vset, d.simi_off, d.simi_idx, d.good, d.centers,
-                                                      d.active_size, c.max_proj_range, d.W);
+    launch_drosa(h, h->sms);
     k_poor_prepare<<<1, 1024, 0, s>>>(d.st, d.good, d.good_rank, d.centers, d.pset2, d.poor_idx, nullptr);
     k_poor_fix<<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.good, d.pset2, d.poor_idx, d.pset);
     if (h->debug) cudaMemcpyAsync(d.centers, d.pset, sizeof(float4) * d.Mcap, cudaMemcpyDeviceToDevice, s);   // tap: pset after drosa
@@ -805,7 +514,7 @@ void launch_mscale(osep_rosa_impl* h) {
     k_vertex_smooth<<<1, 1024, 0, s>>>(d.st, d.skel, d.skel2, d.vtmp, d.vs_off, d.vs_idx, d.rv1, (float*)d.rk1, d.Scap,
                                        c.radius_smooth, c.alpha_recenter, c.niter_smooth);
     stage_mark(h, SM_VSMOOTH);
-    h->n_launches += 1 + 3 + 1 + 1 + 2 * c.niter_drosa + 1 + 2 + 2 * c.niter_dcrosa + 5 + 1;
+    h->n_launches += 1 + 3 + 1 + 2 + 2 * c.niter_dcrosa + 5 + 1;   // + launch_drosa
 }
 
 }  // namespace osep

@@ -38,6 +38,8 @@ struct RosaDev {
     float4* pts = nullptr; float4* nrms = nullptr;
     float4* pset = nullptr; float4* pset2 = nullptr; float4* vset = nullptr; float4* vnew = nullptr;
     float* vvar = nullptr;
+    unsigned* simi_bits = nullptr;     // Mcap x W bit matrix of the similarity graph
+    float4* nraw = nullptr; float4* vnd = nullptr;   // hoisted per-point normal quantities (drosa.cu)
     int* surf = nullptr;               // Mcap * nbk
     int* simi_off = nullptr; int* simi_idx = nullptr;
     int* level = nullptr; int* level_off = nullptr; int* level_pts = nullptr;
@@ -54,6 +56,7 @@ struct RosaDev {
 struct osep_rosa_impl {
     osep_rosa_config cfg;
     int device = 0;
+    int sms = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     RosaDev d;
