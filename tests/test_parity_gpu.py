@@ -264,3 +264,20 @@ def test_full_size_properties_turbine100k(mods):
     dd = ((pc[seeds][:, None, :] - pc[seeds][None, :, :]) ** 2).sum(-1) + np.eye(len(seeds)) * 1e9
     assert dd.min() >= R2 * 0.999                                                        # no seed lies inside another seed's cover
     r.close()
+
+
+def test_cpp_shim_demo_node_runs(mods):
+    """The C++ look-alike classes (host/rosa.hpp, host/gskel.hpp) drive the library exactly like the
+    reference's process_tick functions and print the reference's stdout protocol."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "osep_path_planner_b200", "host", "demo_node")
+    out = subprocess.run([exe, "20000", "5"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.splitlines()
+    assert "PointCloud size before downsampling: 20000" in lines
+    for name in ["preprocess", "rosa_init", "similarity_neighbor_extraction", "drosa", "dcrosa", "vertex_sampling", "vertex_smooth"]:
+        assert "[SUCCESS] " + name in lines
+    assert any(l.startswith("Number of vertices: ") for l in lines) and any(l.startswith("[ROSA] Time Elapsed:") for l in lines)
+    assert any(l.startswith("[FAILED] increment_skeleton") or l.startswith("[SUCCESS] increment_skeleton") for l in lines)
+    assert any(l.startswith("global skeleton:") or "[FAILED] vertex_merge" in l for l in lines)
