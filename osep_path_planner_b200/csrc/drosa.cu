@@ -21,6 +21,7 @@ constexpr int SEED_WARPS = 8;
 constexpr int SEED_SMEM_BUDGET = 200 * 1024;
 constexpr int GS_THREADS = 256;
 constexpr int GS_SMEM_BUDGET = 200 * 1024;
+constexpr int MAX_FUSED_ITERS = 8;
 
 __device__ __forceinline__ f3 ld3f(const float4* a, int i) { const float4 v = a[i]; return {v.x, v.y, v.z}; }
 
@@ -151,6 +152,8 @@ __device__ __forceinline__ Eig3 normal_cov_eig(const float (&s)[9], float inv_m)
 
 struct SeedOut {
     float4* vnew; float* vvar;                                    // orientation pass
+    const float4* prev;                                           // fused path: previous iteration's vnew row (kept when the active set is empty)
+    int pack_w;                                                   // fused path: weight travels in vnew[].w, no vvar array
     float4* pset; int* good; float4* centers; int* active_size;   // position pass
     float max_proj_range;
 };
@@ -163,7 +166,13 @@ __device__ __forceinline__ void seed_body(const SeedCtx& c, int seed, const f3& 
     unsigned vis[WPL];
     const int m = active_set<WPL>(c, seed, p, n, vis);
     if (MODE == 0) {
-        if (m == 0) { if (lane == 0) o.vvar[seed] = 1.0f / (0.0f + 1e-5f); return; }   // vvar = 0 (rosa.cpp:285-287) -> 1/(0^4+eps); vnew row kept
+        if (m == 0) {                                     // vvar = 0 (rosa.cpp:285-287) -> 1/(0^4+eps); vnew row kept
+            if (lane == 0) {
+                if (o.pack_w) { float4 pv = o.prev ? __ldcg(o.prev + seed) : make_float4(0.f, 0.f, 0.f, 0.f); pv.w = 1.0f / (0.0f + 1e-5f); o.vnew[seed] = pv; }
+                else o.vvar[seed] = 1.0f / (0.0f + 1e-5f);
+            }
+            return;
+        }
         float s[9];
         normal_cov_sums<WPL>(c, vis, s);
         const float inv_m = 1.0f / (float)m;
@@ -181,9 +190,10 @@ __device__ __forceinline__ void seed_body(const SeedCtx& c, int seed, const f3& 
         float var = a2[1] * inv_m - mu * mu;
         if (m > 1) var *= (float)m / (float)(m - 1);
         if (lane == 0) {
-            o.vnew[seed] = make_float4(sym.x, sym.y, sym.z, 0.0f);
             float a = var * var; a = a * a;
-            o.vvar[seed] = 1.0f / (a + 1e-5f);                                          // rosa.cpp:291-292
+            const float wgt = 1.0f / (a + 1e-5f);                                       // rosa.cpp:291-292
+            if (o.pack_w) o.vnew[seed] = make_float4(sym.x, sym.y, sym.z, wgt);
+            else { o.vnew[seed] = make_float4(sym.x, sym.y, sym.z, 0.0f); o.vvar[seed] = wgt; }
         }
     } else {
         if (lane == 0) o.active_size[seed] = m;
@@ -395,6 +405,184 @@ k_drosa_smooth2(FrameState* st, const float4* __restrict__ vnew, const float* __
     for (int i = lane; i < M; i += 32) { float4 v = snew[i]; v.w = 0.0f; vset[i] = v; }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Fused drosa: ONE persistent cooperative kernel for the niter_drosa orientation iterations and
+// the position step.  The reference's loop (rosa.cpp:274-309) is
+//     for it: { Jacobi: O(it,p) for all p ;  Gauss-Seidel: G(it,p) in index order }
+// and O(it+1,p) reads only G(it,p) (its own orientation), while G(it,p) reads O(it,j) of its surf
+// neighbours and G(it,j<p).  So the six Gauss-Seidel chains (each ~230 dependent eigen solves) do
+// not have to run back to back: they run as overlapping WAVEFRONTS, iteration it+1 trailing
+// iteration it by a few levels.  Results are bit-identical (same operands, same operations).
+//   CTA it < nit   : chain walker of iteration it (warp 0) + prefetch warps (stage O(it,*) results
+//                    from L2 into shared memory as they appear) + publish warp (G(it,p) -> L2 + flag)
+//   other CTAs     : workers; warps pull tasks (it, p) from one queue ordered by (it, level(p)),
+//                    wait for flagG[it-1][p], run the active-set kernel body, publish flagO[it][p].
+// Deadlock freedom: tasks are taken in queue order, so everything a waiting warp depends on has
+// already been taken by a running warp; all CTAs are co-resident (cooperative launch).
+struct FusedArgs {
+    FrameState* st;
+    const float4* pts; const float4* nraw; const float4* vnd; float4* pset;
+    const unsigned* bits; int W;
+    float4* vset_it;       // [nit+1][Mcap]  vset_it[0] = rosa_init orientation, vset_it[it+1] = after iteration it
+    float4* vnew_it;       // [nit][Mcap]    xyz = symmetry normal, w = weight 1/(var^4+eps)
+    int* flagO; int* flagG; int* qctr;
+    int Mcap; int nit;
+    const int* surf; int nbk; const int* level_off; const int* level_pts;
+    int* good; float4* centers; int* active_size; float max_proj_range;
+};
+
+__device__ __forceinline__ int ld_vol(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+__device__ __forceinline__ void st_vol(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
+
+__device__ __forceinline__ void fused_worker(const FusedArgs& a, uint4* smem, int M) {
+    const int Wn = (M + 31) >> 5;
+    const size_t small_bytes = (size_t)3 * 16 * M;
+    const bool small_in = small_bytes <= (size_t)SEED_SMEM_BUDGET;
+    const bool mat_in = small_in && (small_bytes + (size_t)4 * M * Wn <= (size_t)SEED_SMEM_BUDGET);
+    float4* s_pts = reinterpret_cast<float4*>(smem);
+    float4* s_nraw = s_pts + M; float4* s_vnd = s_nraw + M;
+    unsigned* s_bits = reinterpret_cast<unsigned*>(s_vnd + M);
+    if (small_in) for (int i = threadIdx.x; i < M; i += blockDim.x) { s_pts[i] = a.pts[i]; s_nraw[i] = a.nraw[i]; s_vnd[i] = a.vnd[i]; }
+    if (mat_in) {
+        for (int r = threadIdx.x >> 5; r < M; r += (blockDim.x >> 5)) {
+            const unsigned* src = a.bits + (size_t)r * a.W; unsigned* dst = s_bits + (size_t)r * Wn;
+            for (int w = threadIdx.x & 31; w < Wn; w += 32) dst[w] = src[w];
+        }
+    }
+    __syncthreads();
+    SeedCtx c;
+    c.pts = small_in ? s_pts : a.pts; c.nraw = small_in ? s_nraw : a.nraw; c.vnd = small_in ? s_vnd : a.vnd;
+    c.bits = mat_in ? s_bits : a.bits; c.bstride = mat_in ? Wn : a.W;
+    c.M = M; c.Wn = Wn; c.leaf = a.st->leaf_size;
+    const int lane = threadIdx.x & 31;
+    const int total = (a.nit + 1) * M;
+    SeedOut o; o.vvar = nullptr; o.pack_w = 1; o.pset = a.pset; o.good = a.good; o.centers = a.centers; o.active_size = a.active_size;
+    o.max_proj_range = a.max_proj_range;
+    while (true) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(a.qctr, 1);
+        t = __shfl_sync(FULLM, t, 0);
+        if (t >= total) break;
+        const int it = t / M;
+        const int p = a.level_pts[t - it * M];
+        if (it > 0) {
+            const int* f = a.flagG + (size_t)(it - 1) * a.Mcap + p;
+            if (lane == 0) while (ld_vol(f) == 0) __nanosleep(64);
+            __syncwarp();
+            __threadfence();
+        }
+        const float4 n4 = __ldcg(a.vset_it + (size_t)it * a.Mcap + p);
+        const float4 p4 = __ldcg(a.pset + p);
+        const f3 pp{p4.x, p4.y, p4.z}, nn{n4.x, n4.y, n4.z};
+        if (it < a.nit) {
+            o.vnew = a.vnew_it + (size_t)it * a.Mcap;
+            o.prev = it > 0 ? a.vnew_it + (size_t)(it - 1) * a.Mcap : nullptr;
+            if (Wn <= 32) seed_body<0, 1>(c, p, pp, nn, o);
+            else if (Wn <= 64) seed_body<0, 2>(c, p, pp, nn, o);
+            else seed_body<0, 4>(c, p, pp, nn, o);
+            __syncwarp();
+            if (lane == 0) { __threadfence(); st_vol(a.flagO + (size_t)it * a.Mcap + p, 1); }
+        } else {
+            if (Wn <= 32) seed_body<1, 1>(c, p, pp, nn, o);
+            else if (Wn <= 64) seed_body<1, 2>(c, p, pp, nn, o);
+            else seed_body<1, 4>(c, p, pp, nn, o);
+        }
+    }
+}
+
+__device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int M, int it) {
+    const int nl = a.st->n_levels;
+    const int nbk = a.nbk;
+    float4* sold = reinterpret_cast<float4*>(smem);
+    float4* snew = sold + M;
+    int* s_ready = reinterpret_cast<int*>(snew + M);
+    int* s_done = s_ready + M;
+    int* soff = s_done + M;
+    unsigned short* ssurf = reinterpret_cast<unsigned short*>(soff + nl + 1);
+    unsigned short* slist = ssurf + (size_t)M * nbk;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) { s_ready[i] = 0; s_done[i] = 0; slist[i] = (unsigned short)a.level_pts[i]; }
+    for (int i = threadIdx.x; i <= nl; i += blockDim.x) soff[i] = a.level_off[i];
+    for (int i = threadIdx.x; i < M * nbk; i += blockDim.x) { const int j = a.surf[i]; ssurf[i] = (unsigned short)(j < 0 ? 0 : j); }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int k_eff = min(nbk, M);
+    const int* fO = a.flagO + (size_t)it * a.Mcap;
+    const float4* vn = a.vnew_it + (size_t)it * a.Mcap;
+    if (warp == 0) {
+        // ---- chain walker (rosa.cpp:295-308, Gauss-Seidel semantics through the level schedule)
+        const bool fast10 = (nbk == 10 && k_eff == 10);
+        for (int l = 0; l < nl; ++l) {
+            const int b = soff[l], e = soff[l + 1];
+            for (int t0 = b; t0 < e; t0 += 32) {
+                const int t = t0 + lane;
+                const bool act = t < e;
+                const int p = act ? slist[t] : 0;
+                bool ok;
+                do {
+                    ok = !act || ld_vol(s_ready + p) != 0;           // own weight (and own old orientation if p is in its list)
+                    if (act) for (int u = 0; u < k_eff; ++u) { const int j = ssurf[p * nbk + u]; if (j >= p && ld_vol(s_ready + j) == 0) ok = false; }
+                } while (!__all_sync(FULLM, ok));
+                __threadfence_block();
+                float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (act) out = fast10 ? gs_point<10>(p, sold, snew, ssurf, nbk, k_eff) : gs_point<0>(p, sold, snew, ssurf, nbk, k_eff);
+                if (act) snew[p] = out;
+                __syncwarp();
+                if (act) { __threadfence_block(); st_vol(s_done + p, 1); }
+            }
+        }
+    } else if (warp == nw - 1) {
+        // ---- publisher: G(it,p) -> vset_it[it+1][p] in L2, then the flag the workers of iteration it+1 wait on
+        float4* dst = a.vset_it + (size_t)(it + 1) * a.Mcap;
+        int* fG = a.flagG + (size_t)it * a.Mcap;
+        int idx = lane;
+        while (__any_sync(FULLM, idx < M)) {
+            if (idx < M) {
+                const int p = slist[idx];
+                if (ld_vol(s_done + p) != 0) {
+                    __threadfence_block();
+                    float4 v = snew[p]; v.w = 0.0f;
+                    dst[p] = v;
+                    __threadfence();
+                    st_vol(fG + p, 1);
+                    idx += 32;
+                }
+            }
+        }
+    } else {
+        // ---- prefetchers: stage O(it,p) = (symmetry normal, weight) into shared memory as soon as its flag is up
+        const int npf = nw - 2;
+        const int stride = npf * 32;
+        const int first = (warp - 1) * 32 + lane;
+        unsigned pend = 0u;
+        for (int k = 0; k < 32; ++k) if (first + k * stride < M) pend |= 1u << k;
+        while (__any_sync(FULLM, pend != 0u)) {
+            unsigned scan = pend;
+            while (scan) {
+                const int k = __ffs(scan) - 1; scan &= scan - 1;
+                const int p = slist[first + k * stride];
+                if (ld_vol(fO + p) != 0) {
+                    __threadfence();
+                    const float4 v = __ldcg(vn + p);
+                    sold[p] = v;
+                    __threadfence_block();
+                    st_vol(s_ready + p, 1);
+                    pend &= ~(1u << k);
+                }
+            }
+            if (pend) __nanosleep(100);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SEED_WARPS * 32) k_drosa_fused(const __grid_constant__ FusedArgs a) {
+    extern __shared__ uint4 fused_smem[];
+    if (a.st->status != 0) return;
+    const int M = a.st->M;
+    if ((int)blockIdx.x < a.nit) fused_chain(a, fused_smem, M, (int)blockIdx.x);
+    else fused_worker(a, fused_smem, M);
+}
+
 // ------------------------------------------------------------------------------------------
 static size_t gs_smem_bytes(int M, int nbk) { return (size_t)32 * M + 4 * ((size_t)M + 2) + 2 * (size_t)M * nbk + 2 * (size_t)M + 64; }
 
@@ -403,6 +591,7 @@ void drosa_set_attributes() {
     cudaFuncSetAttribute(k_drosa_seed<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEED_SMEM_BUDGET + 1024);
     cudaFuncSetAttribute(k_drosa_smooth2, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_SMEM_BUDGET);
     cudaFuncSetAttribute(k_gs_levels2, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_SMEM_BUDGET);
+    cudaFuncSetAttribute(k_drosa_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, SEED_SMEM_BUDGET);
 }
 
 // R13 level schedule + R14-R18; `sms` = number of SMs (one seed CTA per SM)
@@ -415,8 +604,30 @@ void launch_drosa(osep_rosa_impl* h, int sms) {
     k_gs_levels2<<<1, 1024, sizeof(int) * (2 * d.Mcap + 2) + sizeof(unsigned short) * d.Mcap * d.nbk, s>>>(d.st, d.surf, d.nbk, d.level, d.level_off, d.level_pts);
     stage_mark(h, SM_SURF);
     stage_mark(h, SM_DROSA_ORIENT);
-    SeedOut o; o.vnew = d.vnew; o.vvar = d.vvar; o.pset = d.pset; o.good = d.good; o.centers = d.centers; o.active_size = d.active_size;
+    SeedOut o; o.vnew = d.vnew; o.vvar = d.vvar; o.prev = nullptr; o.pack_w = 0; o.pset = d.pset; o.good = d.good; o.centers = d.centers; o.active_size = d.active_size;
     o.max_proj_range = c.max_proj_range;
+    if (h->fused && c.niter_drosa <= MAX_FUSED_ITERS) {
+        // capacity of the chain CTA's shared memory: 62 bytes per point (+ level offsets)
+        cudaMemsetAsync(d.fused_flags, 0, sizeof(int) * ((size_t)2 * MAX_FUSED_ITERS * d.Mcap + 16), s);
+        cudaMemcpyAsync(d.vset_it, d.vset, sizeof(float4) * d.Mcap, cudaMemcpyDeviceToDevice, s);
+        FusedArgs a;
+        a.st = d.st; a.pts = d.pts; a.nraw = d.nraw; a.vnd = d.vnd; a.pset = d.pset; a.bits = d.simi_bits; a.W = d.W;
+        a.vset_it = d.vset_it; a.vnew_it = d.vnew_it;
+        a.flagO = d.fused_flags; a.flagG = d.fused_flags + (size_t)MAX_FUSED_ITERS * d.Mcap; a.qctr = d.fused_flags + (size_t)2 * MAX_FUSED_ITERS * d.Mcap;
+        a.Mcap = d.Mcap; a.nit = c.niter_drosa; a.surf = d.surf; a.nbk = d.nbk; a.level_off = d.level_off; a.level_pts = d.level_pts;
+        a.good = d.good; a.centers = d.centers; a.active_size = d.active_size; a.max_proj_range = c.max_proj_range;
+        int grid = h->fused_grid > 0 ? h->fused_grid : sms;
+        if (grid < c.niter_drosa + 1) grid = c.niter_drosa + 1;
+        void* args[] = {(void*)&a};
+        cudaLaunchCooperativeKernel((const void*)k_drosa_fused, dim3(grid), dim3(SEED_WARPS * 32), args, (size_t)SEED_SMEM_BUDGET, s);
+        cudaMemcpyAsync(d.vset, d.vset_it + (size_t)c.niter_drosa * d.Mcap, sizeof(float4) * d.Mcap, cudaMemcpyDeviceToDevice, s);
+        if (h->debug && d.vset_iters)
+            for (int it = 0; it < c.niter_drosa; ++it)
+                cudaMemcpyAsync(d.vset_iters + (size_t)it * d.Mcap, d.vset_it + (size_t)(it + 1) * d.Mcap, sizeof(float4) * d.Mcap, cudaMemcpyDeviceToDevice, s);
+        stage_mark(h, SM_DROSA_SMOOTH);
+        h->n_launches += 2 + 1;
+        return;
+    }
     cudaMemsetAsync(d.vnew, 0, sizeof(float4) * d.Mcap, s);        // vnew = Zero (rosa.cpp:272)
     const size_t gs_bytes = gs_smem_bytes(d.Mcap, d.nbk) <= (size_t)GS_SMEM_BUDGET ? gs_smem_bytes(d.Mcap, d.nbk) : (size_t)GS_SMEM_BUDGET;
     for (int it = 0; it < c.niter_drosa; ++it) {

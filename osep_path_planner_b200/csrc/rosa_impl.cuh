@@ -40,6 +40,7 @@ struct RosaDev {
     float* vvar = nullptr;
     unsigned* simi_bits = nullptr;     // Mcap x W bit matrix of the similarity graph
     float4* nraw = nullptr; float4* vnd = nullptr;   // hoisted per-point normal quantities (drosa.cu)
+    float4* vset_it = nullptr; float4* vnew_it = nullptr; int* fused_flags = nullptr;   // fused drosa (drosa.cu): per-iteration state + flags
     int* surf = nullptr;               // Mcap * nbk
     int* simi_off = nullptr; int* simi_idx = nullptr;
     int* level = nullptr; int* level_off = nullptr; int* level_pts = nullptr;
@@ -61,6 +62,8 @@ struct osep_rosa_impl {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     RosaDev d;
     bool debug = false;
+    bool fused = true;                 // drosa as one persistent cooperative kernel (OSEP_DROSA_UNFUSED=1 disables)
+    int fused_grid = 0;                // CTAs of the fused kernel (0 = one per SM)
     bool profile = false;              // record a CUDA event after every stage group (osep_rosa_set_profile)
     static constexpr int NSTAGE_EV = 16;
     cudaEvent_t stage_ev[NSTAGE_EV] = {};
