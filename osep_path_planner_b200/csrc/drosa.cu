@@ -288,7 +288,8 @@ k_drosa_seed(FrameState* st, const float4* __restrict__ pts, const float4* __res
 // parallel relaxation in shared memory (one cheap round per level of depth, ~230 rounds), then
 // points are bucketed by level (order inside a level is irrelevant: they are independent).
 __global__ void __launch_bounds__(1024) k_gs_levels2(FrameState* st, const int* __restrict__ surf, int nbk, int* __restrict__ level,
-                                                     int* __restrict__ level_off, int* __restrict__ level_pts) {
+                                                     int* __restrict__ level_off, int* __restrict__ level_pts,
+                                                     int* __restrict__ rev_off, unsigned short* __restrict__ rev_idx, int* __restrict__ need0) {
     extern __shared__ int lsm[];          // lv[M] | cnt[M+1] | surf as ushort [M*nbk]
     if (st->status != 0) return;
     const int M = st->M;
@@ -335,6 +336,36 @@ __global__ void __launch_bounds__(1024) k_gs_levels2(FrameState* st, const int* 
     __syncthreads();
     for (int p = threadIdx.x; p < M; p += blockDim.x) { const int pos = atomicAdd(&cnt[lv[p] - 1], 1); level_pts[pos] = p; }
     if (threadIdx.x == 0) st->n_levels = nl;
+    __syncthreads();
+    // reverse dependency lists for the dataflow chain walker (fused kernel): rev[j] = { q : j in deps(q) },
+    // deps(q) = surf[q] plus q itself (its own weight); need0[q] = |deps(q)| + #{ j in surf[q] : j < q }.
+    for (int l = threadIdx.x; l <= M; l += blockDim.x) cnt[l] = 0;
+    __syncthreads();
+    for (int q = threadIdx.x; q < M; q += blockDim.x) {
+        bool self = false; int lower = 0;
+        for (int u = 0; u < k_eff; ++u) { const int j = ss[q * nbk + u]; atomicAdd(&cnt[j], 1); self |= (j == q); lower += (j < q) ? 1 : 0; }
+        if (!self) atomicAdd(&cnt[q], 1);
+        need0[q] = k_eff + (self ? 0 : 1) + lower;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {               // exclusive scan of cnt[0..M] by one warp
+        int carry = 0;
+        for (int b = 0; b <= M; b += 32) {
+            const int l = b + threadIdx.x;
+            const int v = (l <= M) ? cnt[l] : 0;
+            int incl = v;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(FULLM, incl, off); if ((int)threadIdx.x >= off) incl += t; }
+            if (l <= M) { cnt[l] = carry + incl - v; rev_off[l] = carry + incl - v; }
+            carry += __shfl_sync(FULLM, incl, 31);
+        }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < M; q += blockDim.x) {
+        bool self = false;
+        for (int u = 0; u < k_eff; ++u) { const int j = ss[q * nbk + u]; rev_idx[atomicAdd(&cnt[j], 1)] = (unsigned short)q; self |= (j == q); }
+        if (!self) rev_idx[atomicAdd(&cnt[q], 1)] = (unsigned short)q;
+    }
 }
 
 // R17 smoothing half, level by level.  All operands in shared memory; one warp walks the chain.
@@ -429,6 +460,7 @@ struct FusedArgs {
     int* flagO; int* flagG; int* qctr;
     int Mcap; int nit;
     const int* surf; int nbk; const int* level_off; const int* level_pts;
+    const int* rev_off; const unsigned short* rev_idx; const int* need0;
     int* good; float4* centers; int* active_size; float max_proj_range;
 };
 
@@ -492,44 +524,55 @@ __device__ __forceinline__ void fused_worker(const FusedArgs& a, uint4* smem, in
 }
 
 __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int M, int it) {
-    const int nl = a.st->n_levels;
+    // Dataflow walker of the Gauss-Seidel pass of iteration `it` (rosa.cpp:295-308).  Point q may be
+    // rewritten once (a) the Jacobi results O(it,j) of all its surf neighbours (and its own) are staged and
+    // (b) every neighbour j < q has been rewritten.  need[q] counts the open dependencies; whoever closes the
+    // last one pushes q on the ready queue; the walker warp pops up to 32 ready points per step.  Any
+    // order that respects the dependencies produces the same bits (every operand is fixed by them).
     const int nbk = a.nbk;
     float4* sold = reinterpret_cast<float4*>(smem);
     float4* snew = sold + M;
-    int* s_ready = reinterpret_cast<int*>(snew + M);
-    int* s_done = s_ready + M;
-    int* soff = s_done + M;
-    unsigned short* ssurf = reinterpret_cast<unsigned short*>(soff + nl + 1);
-    unsigned short* slist = ssurf + (size_t)M * nbk;
-    for (int i = threadIdx.x; i < M; i += blockDim.x) { s_ready[i] = 0; s_done[i] = 0; slist[i] = (unsigned short)a.level_pts[i]; }
-    for (int i = threadIdx.x; i <= nl; i += blockDim.x) soff[i] = a.level_off[i];
+    int* need = reinterpret_cast<int*>(snew + M);
+    int* rq = need + M;                                   // ready queue, entries q+1, 0 = not written yet
+    int* srev_off = rq + M;                               // M+1
+    int* s_ctl = srev_off + M + 1;                        // [0] tail, [1] done_upto
+    unsigned short* ssurf = reinterpret_cast<unsigned short*>(s_ctl + 2);
+    unsigned short* srev = ssurf + (size_t)M * nbk;       // up to M*(nbk+1)
+    const int nrev = a.rev_off[M];
+    for (int i = threadIdx.x; i < M; i += blockDim.x) { need[i] = a.need0[i]; rq[i] = 0; }
+    for (int i = threadIdx.x; i <= M; i += blockDim.x) srev_off[i] = a.rev_off[i];
     for (int i = threadIdx.x; i < M * nbk; i += blockDim.x) { const int j = a.surf[i]; ssurf[i] = (unsigned short)(j < 0 ? 0 : j); }
+    for (int i = threadIdx.x; i < nrev; i += blockDim.x) srev[i] = a.rev_idx[i];
+    if (threadIdx.x < 2) s_ctl[threadIdx.x] = 0;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const int k_eff = min(nbk, M);
     const int* fO = a.flagO + (size_t)it * a.Mcap;
     const float4* vn = a.vnew_it + (size_t)it * a.Mcap;
     if (warp == 0) {
-        // ---- chain walker (rosa.cpp:295-308, Gauss-Seidel semantics through the level schedule)
+        // ---- chain walker
         const bool fast10 = (nbk == 10 && k_eff == 10);
-        for (int l = 0; l < nl; ++l) {
-            const int b = soff[l], e = soff[l + 1];
-            for (int t0 = b; t0 < e; t0 += 32) {
-                const int t = t0 + lane;
-                const bool act = t < e;
-                const int p = act ? slist[t] : 0;
-                bool ok;
-                do {
-                    ok = !act || ld_vol(s_ready + p) != 0;           // own weight (and own old orientation if p is in its list)
-                    if (act) for (int u = 0; u < k_eff; ++u) { const int j = ssurf[p * nbk + u]; if (j >= p && ld_vol(s_ready + j) == 0) ok = false; }
-                } while (!__all_sync(FULLM, ok));
-                __threadfence_block();
-                float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (act) out = fast10 ? gs_point<10>(p, sold, snew, ssurf, nbk, k_eff) : gs_point<0>(p, sold, snew, ssurf, nbk, k_eff);
-                if (act) snew[p] = out;
-                __syncwarp();
-                if (act) { __threadfence_block(); st_vol(s_done + p, 1); }
+        int head = 0;
+        while (head < M) {
+            const int e = (head + lane < M) ? ld_vol(rq + head + lane) : 0;
+            const unsigned got = __ballot_sync(FULLM, e != 0);
+            const int take = (got == FULLM) ? 32 : (__ffs(~got) - 1);
+            if (take == 0) continue;
+            const bool act = lane < take;
+            const int p = act ? e - 1 : 0;
+            __threadfence_block();
+            if (act) snew[p] = fast10 ? gs_point<10>(p, sold, snew, ssurf, nbk, k_eff) : gs_point<0>(p, sold, snew, ssurf, nbk, k_eff);
+            __syncwarp();
+            __threadfence_block();
+            if (act) {
+                for (int r = srev_off[p]; r < srev_off[p + 1]; ++r) {
+                    const int q = srev[r];
+                    if (q > p && atomicSub(need + q, 1) == 1) { const int slot = atomicAdd(s_ctl, 1); st_vol(rq + slot, q + 1); }
+                }
             }
+            head += take;
+            __syncwarp();
+            if (lane == 0) st_vol(s_ctl + 1, head);
         }
     } else if (warp == nw - 1) {
         // ---- publisher: G(it,p) -> vset_it[it+1][p] in L2, then the flag the workers of iteration it+1 wait on
@@ -537,20 +580,19 @@ __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int
         int* fG = a.flagG + (size_t)it * a.Mcap;
         int idx = lane;
         while (__any_sync(FULLM, idx < M)) {
-            if (idx < M) {
-                const int p = slist[idx];
-                if (ld_vol(s_done + p) != 0) {
-                    __threadfence_block();
-                    float4 v = snew[p]; v.w = 0.0f;
-                    dst[p] = v;
-                    __threadfence();
-                    st_vol(fG + p, 1);
-                    idx += 32;
-                }
+            const int upto = ld_vol(s_ctl + 1);
+            if (idx < upto) {
+                __threadfence_block();
+                const int p = ld_vol(rq + idx) - 1;
+                float4 v = snew[p]; v.w = 0.0f;
+                dst[p] = v;
+                __threadfence();
+                st_vol(fG + p, 1);
+                idx += 32;
             }
         }
     } else {
-        // ---- prefetchers: stage O(it,p) = (symmetry normal, weight) into shared memory as soon as its flag is up
+        // ---- prefetchers: stage O(it,j) = (symmetry normal, weight) as soon as its flag is up, release dependents
         const int npf = nw - 2;
         const int stride = npf * 32;
         const int first = (warp - 1) * 32 + lane;
@@ -560,17 +602,19 @@ __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int
             unsigned scan = pend;
             while (scan) {
                 const int k = __ffs(scan) - 1; scan &= scan - 1;
-                const int p = slist[first + k * stride];
-                if (ld_vol(fO + p) != 0) {
+                const int j = a.level_pts[first + k * stride];
+                if (ld_vol(fO + j) != 0) {
                     __threadfence();
-                    const float4 v = __ldcg(vn + p);
-                    sold[p] = v;
+                    sold[j] = __ldcg(vn + j);
                     __threadfence_block();
-                    st_vol(s_ready + p, 1);
+                    for (int r = srev_off[j]; r < srev_off[j + 1]; ++r) {
+                        const int q = srev[r];
+                        if (atomicSub(need + q, 1) == 1) { const int slot = atomicAdd(s_ctl, 1); st_vol(rq + slot, q + 1); }
+                    }
                     pend &= ~(1u << k);
                 }
             }
-            if (pend) __nanosleep(100);
+            if (pend) __nanosleep(64);
         }
     }
 }
@@ -579,6 +623,12 @@ __global__ void __launch_bounds__(SEED_WARPS * 32) k_drosa_fused(const __grid_co
     extern __shared__ uint4 fused_smem[];
     if (a.st->status != 0) return;
     const int M = a.st->M;
+    // shared-memory footprint of a chain CTA (see fused_chain); evaluated identically by every CTA
+    const size_t chain_bytes = (size_t)44 * M + 16 + (size_t)2 * M * a.nbk + (size_t)2 * M * (a.nbk + 1) + 64;
+    if (chain_bytes > (size_t)SEED_SMEM_BUDGET) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.st->status = OSEP_ERR_CAPACITY;
+        return;
+    }
     if ((int)blockIdx.x < a.nit) fused_chain(a, fused_smem, M, (int)blockIdx.x);
     else fused_worker(a, fused_smem, M);
 }
@@ -601,7 +651,7 @@ void launch_drosa(osep_rosa_impl* h, int sms) {
     const osep_rosa_config& c = h->cfg;
     // largest M the all-shared smoothing kernel accepts with this nb_knn (checked against Mcap at create)
     k_normal_prep<<<div_up(d.Mcap, 128), 128, 0, s>>>(d.st, d.nrms, d.nraw, d.vnd);
-    k_gs_levels2<<<1, 1024, sizeof(int) * (2 * d.Mcap + 2) + sizeof(unsigned short) * d.Mcap * d.nbk, s>>>(d.st, d.surf, d.nbk, d.level, d.level_off, d.level_pts);
+    k_gs_levels2<<<1, 1024, sizeof(int) * (2 * d.Mcap + 2) + sizeof(unsigned short) * d.Mcap * d.nbk, s>>>(d.st, d.surf, d.nbk, d.level, d.level_off, d.level_pts, d.rev_off, d.rev_idx, d.need0);
     stage_mark(h, SM_SURF);
     stage_mark(h, SM_DROSA_ORIENT);
     SeedOut o; o.vnew = d.vnew; o.vvar = d.vvar; o.prev = nullptr; o.pack_w = 0; o.pset = d.pset; o.good = d.good; o.centers = d.centers; o.active_size = d.active_size;
@@ -615,6 +665,7 @@ void launch_drosa(osep_rosa_impl* h, int sms) {
         a.vset_it = d.vset_it; a.vnew_it = d.vnew_it;
         a.flagO = d.fused_flags; a.flagG = d.fused_flags + (size_t)MAX_FUSED_ITERS * d.Mcap; a.qctr = d.fused_flags + (size_t)2 * MAX_FUSED_ITERS * d.Mcap;
         a.Mcap = d.Mcap; a.nit = c.niter_drosa; a.surf = d.surf; a.nbk = d.nbk; a.level_off = d.level_off; a.level_pts = d.level_pts;
+        a.rev_off = d.rev_off; a.rev_idx = d.rev_idx; a.need0 = d.need0;
         a.good = d.good; a.centers = d.centers; a.active_size = d.active_size; a.max_proj_range = c.max_proj_range;
         int grid = h->fused_grid > 0 ? h->fused_grid : sms;
         if (grid < c.niter_drosa + 1) grid = c.niter_drosa + 1;
