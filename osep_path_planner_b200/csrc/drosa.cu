@@ -457,13 +457,15 @@ struct FusedArgs {
     const unsigned* bits; int W;
     float4* vset_it;       // [nit+1][Mcap]  vset_it[0] = rosa_init orientation, vset_it[it+1] = after iteration it
     float4* vnew_it;       // [nit][Mcap]    xyz = symmetry normal, w = weight 1/(var^4+eps)
-    int* flagO; int* flagG; int* qctr;
+    int* flagO; int* taskq; int* qctr;      // qctr[0] = claim counter, qctr[1] = publish counter
     int Mcap; int nit;
     const int* surf; int nbk; const int* level_off; const int* level_pts;
     const int* rev_off; const unsigned short* rev_idx; const int* need0;
     int* good; float4* centers; int* active_size; float max_proj_range;
+    long long* dbg;        // per chain: [t_begin, t_first_step, t_end, steps, spins, points] (globaltimer ns)
 };
 
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ int ld_vol(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 __device__ __forceinline__ void st_vol(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
 
@@ -492,17 +494,20 @@ __device__ __forceinline__ void fused_worker(const FusedArgs& a, uint4* smem, in
     SeedOut o; o.vvar = nullptr; o.pack_w = 1; o.pset = a.pset; o.good = a.good; o.centers = a.centers; o.active_size = a.active_size;
     o.max_proj_range = a.max_proj_range;
     while (true) {
+        // claim the next slot of the ready queue: slots [0, M) are the iteration-0 tasks (ready at start, low
+        // levels first), later slots are filled by the chain publishers as orientations get final
         int t = 0;
         if (lane == 0) t = atomicAdd(a.qctr, 1);
         t = __shfl_sync(FULLM, t, 0);
         if (t >= total) break;
-        const int it = t / M;
-        const int p = a.level_pts[t - it * M];
-        if (it > 0) {
-            const int* f = a.flagG + (size_t)(it - 1) * a.Mcap + p;
-            if (lane == 0) while (ld_vol(f) == 0) __nanosleep(64);
-            __syncwarp();
+        int it = 0, p = 0;
+        if (t < M) p = a.level_pts[t];
+        else {
+            int e = 0;
+            if (lane == 0) { const int* q = a.taskq + (t - M); while ((e = ld_vol(q)) == 0) __nanosleep(32); }
+            e = __shfl_sync(FULLM, e, 0) - 1;
             __threadfence();
+            it = e / a.Mcap; p = e - it * a.Mcap;
         }
         const float4 n4 = __ldcg(a.vset_it + (size_t)it * a.Mcap + p);
         const float4 p4 = __ldcg(a.pset + p);
@@ -553,31 +558,42 @@ __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int
         // ---- chain walker
         const bool fast10 = (nbk == 10 && k_eff == 10);
         int head = 0;
+        long long t_begin = gtime(), t_first = 0; int steps = 0, spins = 0;
+        long long c_comp = 0, c_rel = 0, c_pts = 0;
         while (head < M) {
             const int e = (head + lane < M) ? ld_vol(rq + head + lane) : 0;
             const unsigned got = __ballot_sync(FULLM, e != 0);
             const int take = (got == FULLM) ? 32 : (__ffs(~got) - 1);
-            if (take == 0) continue;
+            if (take == 0) { ++spins; continue; }
+            if (steps == 0) t_first = gtime();
+            ++steps;
             const bool act = lane < take;
             const int p = act ? e - 1 : 0;
             __threadfence_block();
+            const long long c0 = clock64();
             if (act) snew[p] = fast10 ? gs_point<10>(p, sold, snew, ssurf, nbk, k_eff) : gs_point<0>(p, sold, snew, ssurf, nbk, k_eff);
             __syncwarp();
-            __threadfence_block();
-            if (act) {
-                for (int r = srev_off[p]; r < srev_off[p + 1]; ++r) {
+            const long long c1 = clock64();
+            c_comp += c1 - c0; c_pts += take;
+            // release the dependents of the points just rewritten: all 32 lanes work on one point's list at a time
+            for (int src = 0; src < take; ++src) {
+                const int pj = __shfl_sync(FULLM, p, src);
+                const int rb = srev_off[pj], re = srev_off[pj + 1];
+                for (int r = rb + lane; r < re; r += 32) {
                     const int q = srev[r];
-                    if (q > p && atomicSub(need + q, 1) == 1) { const int slot = atomicAdd(s_ctl, 1); st_vol(rq + slot, q + 1); }
+                    if (q > pj && atomicSub(need + q, 1) == 1) { const int slot = atomicAdd(s_ctl, 1); st_vol(rq + slot, q + 1); }
                 }
             }
             head += take;
             __syncwarp();
+            __threadfence_block();
             if (lane == 0) st_vol(s_ctl + 1, head);
+            c_rel += clock64() - c1;
         }
+        if (lane == 0 && a.dbg) { long long* g = a.dbg + it * 8; g[0] = t_begin; g[1] = t_first; g[2] = gtime(); g[3] = steps; g[4] = spins; g[5] = M; g[6] = c_comp; g[7] = c_rel; }
     } else if (warp == nw - 1) {
-        // ---- publisher: G(it,p) -> vset_it[it+1][p] in L2, then the flag the workers of iteration it+1 wait on
+        // ---- publisher: G(it,p) -> vset_it[it+1][p] in L2, then task (it+1, p) goes on the workers' ready queue
         float4* dst = a.vset_it + (size_t)(it + 1) * a.Mcap;
-        int* fG = a.flagG + (size_t)it * a.Mcap;
         int idx = lane;
         while (__any_sync(FULLM, idx < M)) {
             const int upto = ld_vol(s_ctl + 1);
@@ -587,7 +603,8 @@ __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int
                 float4 v = snew[p]; v.w = 0.0f;
                 dst[p] = v;
                 __threadfence();
-                st_vol(fG + p, 1);
+                const int slot = atomicAdd(a.qctr + 1, 1);
+                st_vol(a.taskq + slot, (it + 1) * a.Mcap + p + 1);
                 idx += 32;
             }
         }
@@ -663,10 +680,11 @@ void launch_drosa(osep_rosa_impl* h, int sms) {
         FusedArgs a;
         a.st = d.st; a.pts = d.pts; a.nraw = d.nraw; a.vnd = d.vnd; a.pset = d.pset; a.bits = d.simi_bits; a.W = d.W;
         a.vset_it = d.vset_it; a.vnew_it = d.vnew_it;
-        a.flagO = d.fused_flags; a.flagG = d.fused_flags + (size_t)MAX_FUSED_ITERS * d.Mcap; a.qctr = d.fused_flags + (size_t)2 * MAX_FUSED_ITERS * d.Mcap;
+        a.flagO = d.fused_flags; a.taskq = d.fused_flags + (size_t)MAX_FUSED_ITERS * d.Mcap; a.qctr = d.fused_flags + (size_t)2 * MAX_FUSED_ITERS * d.Mcap;
         a.Mcap = d.Mcap; a.nit = c.niter_drosa; a.surf = d.surf; a.nbk = d.nbk; a.level_off = d.level_off; a.level_pts = d.level_pts;
         a.rev_off = d.rev_off; a.rev_idx = d.rev_idx; a.need0 = d.need0;
         a.good = d.good; a.centers = d.centers; a.active_size = d.active_size; a.max_proj_range = c.max_proj_range;
+        a.dbg = d.fused_dbg;
         int grid = h->fused_grid > 0 ? h->fused_grid : sms;
         if (grid < c.niter_drosa + 1) grid = c.niter_drosa + 1;
         void* args[] = {(void*)&a};

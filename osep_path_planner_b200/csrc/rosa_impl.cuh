@@ -40,7 +40,7 @@ struct RosaDev {
     float* vvar = nullptr;
     unsigned* simi_bits = nullptr;     // Mcap x W bit matrix of the similarity graph
     float4* nraw = nullptr; float4* vnd = nullptr;   // hoisted per-point normal quantities (drosa.cu)
-    float4* vset_it = nullptr; float4* vnew_it = nullptr; int* fused_flags = nullptr;   // fused drosa (drosa.cu): per-iteration state + flags
+    float4* vset_it = nullptr; float4* vnew_it = nullptr; int* fused_flags = nullptr; long long* fused_dbg = nullptr;   // fused drosa (drosa.cu): per-iteration state + flags
     int* surf = nullptr;               // Mcap * nbk
     int* simi_off = nullptr; int* simi_idx = nullptr;
     int* level = nullptr; int* level_off = nullptr; int* level_pts = nullptr;
