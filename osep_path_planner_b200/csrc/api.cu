@@ -34,7 +34,7 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
     d.W = d.Mcap / 32;
     d.Scap = d.Mcap * 128;
     d.T = 1; while (d.T < 2 * d.Ncap) d.T <<= 1;
-    d.nchunks = div_up(d.Ncap, 512);
+    d.nchunks = div_up(d.Ncap, 2048);
     d.knn = c.ne_knn; d.nbk = c.nb_knn;
     const size_t N = d.Ncap, M = d.Mcap, T = d.T;
     const size_t tmpcap = std::max<size_t>(N, d.Scap);

@@ -301,11 +301,13 @@ __global__ void __launch_bounds__(1024) k_gs_levels2(FrameState* st, const int* 
     __syncthreads();
     while (true) {
         int changed = 0;
-        for (int p = threadIdx.x; p < M; p += blockDim.x) {
-            int v = 0;
-            for (int u = 0; u < k_eff; ++u) { const int j = ss[p * nbk + u]; if (j < p) v = max(v, lv[j]); }
-            v += 1;
-            if (v != lv[p]) { lv[p] = v; changed = 1; }       // monotone: racing reads only delay convergence
+        for (int sweep = 0; sweep < 8; ++sweep) {         // several chaotic sweeps per barrier (levels only grow towards the fixpoint)
+            for (int p = threadIdx.x; p < M; p += blockDim.x) {
+                int v = 0;
+                for (int u = 0; u < k_eff; ++u) { const int j = ss[p * nbk + u]; if (j < p) v = max(v, ((volatile int*)lv)[j]); }
+                v += 1;
+                if (v != lv[p]) { ((volatile int*)lv)[p] = v; changed = 1; }
+            }
         }
         if (!__syncthreads_or(changed)) break;
     }

@@ -179,18 +179,50 @@ template <int K> struct TopKM {
     }
 };
 
-template <int K>
-__global__ void k_surf_knn(const FrameState* __restrict__ st, const float4* __restrict__ pts, int* __restrict__ surf, int k_req) {
+// One warp per point.  Candidates inside an adaptive radius are compacted into a small shared list
+// (ballot + popc), which is then rank-sorted by (d2, index); the radius grows until the list holds at
+// least k points (then the k nearest are all inside it: exact) and shrinks if it overflows the list.
+constexpr int SURF_LIST = 128;
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_surf_knn(FrameState* st, const float4* __restrict__ pts, int* __restrict__ surf, int k_req) {
+    __shared__ float s_d[WARPS_PER_BLOCK][SURF_LIST];
+    __shared__ int s_j[WARPS_PER_BLOCK][SURF_LIST];
     if (st->status != 0) return;
     const int M = st->M;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * WARPS_PER_BLOCK + wib;
     if (p >= M) return;
-    const f3 q = ld3(pts, p);
-    TopKM<K> tk; tk.init();
-    for (int j = 0; j < M; ++j) { const f3 c = ld3(pts, j); tk.push(dist2(q, c), j); }
     const int k_eff = min(k_req, M);
-#pragma unroll
-    for (int u = 0; u < K; ++u) if (u < k_req) surf[p * k_req + u] = (u < k_eff) ? tk.id[u] : -1;
+    const f3 q = ld3(pts, p);
+    float r = 2.5f * st->leaf_used;
+    if (!(r > 0.0f) || !fin(r)) r = 1.0f;
+    float lo = 0.0f, hi = __int_as_float(0x7f800000);      // radii known to be too small / too large
+    int cnt = 0;
+    for (int attempt = 0; attempt < 64; ++attempt) {
+        const float r2 = (M <= SURF_LIST) ? __int_as_float(0x7f800000) : r * r;
+        cnt = 0;
+        for (int j0 = 0; j0 < M; j0 += 32) {
+            const int j = j0 + lane;
+            float d2 = 0.0f; bool in = false;
+            if (j < M) { d2 = dist2(q, ld3(pts, j)); in = d2 < r2; }
+            const unsigned m = __ballot_sync(FULL, in);
+            const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+            if (in && pos < SURF_LIST) { s_d[wib][pos] = d2; s_j[wib][pos] = j; }
+            cnt += __popc(m);
+        }
+        if (cnt >= k_eff && cnt <= SURF_LIST) break;
+        if (cnt < k_eff) { lo = r; r = (hi < 3.0e38f) ? 0.5f * (lo + hi) : r * 1.6f; }
+        else { hi = r; r = 0.5f * (lo + hi); }
+    }
+    __syncwarp();
+    if (cnt < k_eff || cnt > SURF_LIST) { if (lane == 0) st->status = OSEP_ERR_CAPACITY; return; }    // > 128 coincident points
+    for (int e = lane; e < cnt; e += 32) {
+        const float d = s_d[wib][e]; const int j = s_j[wib][e];
+        int rank = 0;
+        for (int f = 0; f < cnt; ++f) rank += nb_less(s_d[wib][f], s_j[wib][f], d, j) ? 1 : 0;
+        if (rank < k_eff) surf[p * k_req + rank] = j;
+    }
+    for (int u = k_eff + lane; u < k_req; u += 32) surf[p * k_req + u] = -1;
 }
 
 // R19 part 1 (single block): compact goodCenters, list poor points in ascending index.
@@ -468,11 +500,6 @@ __global__ void k_vertex_smooth(FrameState* st, float4* skel, float4* skel2, flo
 }
 
 // ------------------------------------------------------------------------------------------
-template <int K> static void launch_surf(osep_rosa_impl* h) {
-    RosaDev& d = h->d;
-    k_surf_knn<K><<<div_up(d.Mcap, 128), 128, 0, h->stream>>>(d.st, d.pts, d.surf, d.nbk);
-}
-
 void drosa_set_attributes();
 void launch_drosa(osep_rosa_impl* h, int sms);
 void mscale_set_attributes(int Mcap) { (void)Mcap; drosa_set_attributes(); }
@@ -491,7 +518,7 @@ void launch_mscale(osep_rosa_impl* h) {
     k_simi<true><<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.nrms, d.simi_off, d.simi_idx, d.rv1, (float*)d.rk1, d.simi_bits, d.W);
     stage_mark(h, SM_SIMI);
     // R13 + level schedule
-    if (d.nbk <= 10) launch_surf<10>(h); else if (d.nbk <= 16) launch_surf<16>(h); else if (d.nbk <= 32) launch_surf<32>(h); else launch_surf<64>(h);
+    k_surf_knn<<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.surf, d.nbk);
     launch_drosa(h, h->sms);
     k_poor_prepare<<<1, 1024, 0, s>>>(d.st, d.good, d.good_rank, d.centers, d.pset2, d.poor_idx, nullptr);
     k_poor_fix<<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.good, d.pset2, d.poor_idx, d.pset);

@@ -21,7 +21,7 @@
 namespace osep {
 
 constexpr int NT = 256;                 // threads per block for N-scale kernels
-constexpr int RADIX_CH = 512;           // elements per warp-chunk in the stable radix sort
+constexpr int RADIX_CH = 2048;          // elements per warp-chunk in the stable radix sort
 constexpr int RADIX_WARPS = 4;          // warps per block in the radix kernels
 
 // ------------------------------------------------------------------------------------------
@@ -545,46 +545,61 @@ __global__ void k_radix_scatter(const unsigned* __restrict__ keys, const int* __
     }
 }
 
-// per-voxel centroid (pcl::CentroidPoint<PointNormal>), then R10 + R11 fused
-__global__ void k_vox_reduce(FrameState* st, const int* __restrict__ sorted_idx, const int* __restrict__ vox_off,
-                             const float4* __restrict__ P, const float4* __restrict__ Nrm,
-                             float4* __restrict__ pts, float4* __restrict__ nrms, float4* __restrict__ pset, float4* __restrict__ vset) {
+// per-voxel centroid (pcl::CentroidPoint<PointNormal>), then R10 + R11 fused.
+// One CTA per voxel: all threads stage the voxel's points + normals into shared memory (many gathers in
+// flight), then ONE thread adds them in ascending point index -- the float sums stay strictly sequential
+// (canonical order C3), only the memory latency is parallelised.  Voxels hold ~100 points (max > 1000).
+constexpr int VOX_CHUNK = 512;
+__global__ void __launch_bounds__(128)
+k_vox_reduce(FrameState* st, const int* __restrict__ sorted_idx, const int* __restrict__ vox_off,
+             const float4* __restrict__ P, const float4* __restrict__ Nrm,
+             float4* __restrict__ pts, float4* __restrict__ nrms, float4* __restrict__ pset, float4* __restrict__ vset) {
+    __shared__ float4 sp[VOX_CHUNK];
+    __shared__ float4 sn[VOX_CHUNK];
     if (st->status != 0) return;
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
     const int M = st->M;
-    if (v >= M) return;
-    const int b = vox_off[v], e = vox_off[v + 1];
-    float sx = 0, sy = 0, sz = 0, n0 = 0, n1 = 0, n2 = 0, n3 = 0;
-    for (int t = b; t < e; ++t) {
-        const int i = sorted_idx[t];
-        const float4 p = P[i]; const float4 nn = Nrm[i];
-        sx += p.x; sy += p.y; sz += p.z;
-        n0 += nn.x; n1 += nn.y; n2 += nn.z; n3 += 0.0f;
+    for (int v = blockIdx.x; v < M; v += gridDim.x) {
+        const int b = vox_off[v], e = vox_off[v + 1];
+        float sx = 0, sy = 0, sz = 0, n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+        for (int c0 = b; c0 < e; c0 += VOX_CHUNK) {
+            const int cn = min(VOX_CHUNK, e - c0);
+            __syncthreads();
+            for (int t = threadIdx.x; t < cn; t += blockDim.x) { const int i = sorted_idx[c0 + t]; sp[t] = P[i]; sn[t] = Nrm[i]; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int t = 0; t < cn; ++t) {
+                    const float4 p = sp[t]; const float4 nn = sn[t];
+                    sx += p.x; sy += p.y; sz += p.z;
+                    n0 += nn.x; n1 += nn.y; n2 += nn.z; n3 += 0.0f;
+                }
+            }
+        }
+        if (threadIdx.x != 0) continue;
+        const float cnt = (float)(e - b);
+        const float px = sx / cnt, py = sy / cnt, pz = sz / cnt;
+        // AccumulatorNormal::get: Vector4f::normalized(); squaredNorm is packet-reduced (a0+a2)+(a1+a3)
+        const float zz = (n0 * n0 + n2 * n2) + (n1 * n1 + n3 * n3);
+        f3 nv{n0, n1, n2};
+        if (zz > 0.0f) { const float r = sqrtf(zz); nv = {n0 / r, n1 / r, n2 / r}; }
+        // R10 (rosa.cpp:156-165)
+        const float L = norm3(nv);
+        if (L > 1e-6f) nv = div3(nv, L); else nv = {0.0f, 0.0f, 0.0f};
+        pts[v] = make_float4(px, py, pz, 1.0f);
+        nrms[v] = make_float4(nv.x, nv.y, nv.z, 0.0f);
+        // R11 (rosa.cpp:183-199, rosa.hpp:112-128): pset = pts, vset = column 0 of the orthonormal frame
+        pset[v] = make_float4(px, py, pz, 1.0f);
+        f3 vs;
+        const float nn_ = norm3(nv);
+        if (nn_ == 0.0f) vs = {1.0f, 0.0f, 0.0f};
+        else {
+            const f3 z = div3(nv, nn_);
+            const bool use_x = (double)fabsf(z.x) < 0.9;
+            const f3 a = use_x ? f3{1.0f, 0.0f, 0.0f} : f3{0.0f, 1.0f, 0.0f};
+            const float az = dot3(a, z);
+            vs = normalize3(sub3(a, mul3(z, az)));
+        }
+        vset[v] = make_float4(vs.x, vs.y, vs.z, 0.0f);
     }
-    const float cnt = (float)(e - b);
-    const float px = sx / cnt, py = sy / cnt, pz = sz / cnt;
-    // AccumulatorNormal::get: Vector4f::normalized(); squaredNorm is packet-reduced (a0+a2)+(a1+a3)
-    const float zz = (n0 * n0 + n2 * n2) + (n1 * n1 + n3 * n3);
-    f3 nv{n0, n1, n2};
-    if (zz > 0.0f) { const float r = sqrtf(zz); nv = {n0 / r, n1 / r, n2 / r}; }
-    // R10 (rosa.cpp:156-165)
-    const float L = norm3(nv);
-    if (L > 1e-6f) nv = div3(nv, L); else nv = {0.0f, 0.0f, 0.0f};
-    pts[v] = make_float4(px, py, pz, 1.0f);
-    nrms[v] = make_float4(nv.x, nv.y, nv.z, 0.0f);
-    // R11 (rosa.cpp:183-199, rosa.hpp:112-128): pset = pts, vset = column 0 of the orthonormal frame
-    pset[v] = make_float4(px, py, pz, 1.0f);
-    f3 vs;
-    const float nn_ = norm3(nv);
-    if (nn_ == 0.0f) vs = {1.0f, 0.0f, 0.0f};
-    else {
-        const f3 z = div3(nv, nn_);
-        const bool use_x = (double)fabsf(z.x) < 0.9;
-        const f3 a = use_x ? f3{1.0f, 0.0f, 0.0f} : f3{0.0f, 1.0f, 0.0f};
-        const float az = dot3(a, z);
-        vs = normalize3(sub3(a, mul3(z, az)));
-    }
-    vset[v] = make_float4(vs.x, vs.y, vs.z, 0.0f);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -645,7 +660,7 @@ void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int strid
         std::swap(ka, kb); std::swap(va, vb);
     }
     // even number of passes: sorted data is back in rk0 / rv0
-    k_vox_reduce<<<div_up(d.Mcap, 128), 128, 0, s>>>(d.st, va, d.vox_cnt, d.P, d.Nrm, d.pts, d.nrms, d.pset, d.vset);
+    k_vox_reduce<<<1024, 128, 0, s>>>(d.st, va, d.vox_cnt, d.P, d.Nrm, d.pts, d.nrms, d.pset, d.vset);
     stage_mark(h, SM_VOXEL);
     h->n_launches += 1 + 3 + (2 * LEAF_MAX_ITERS + 1) + 4 + 1 + 4 + 3 * passes + 1;
 }
