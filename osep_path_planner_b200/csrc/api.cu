@@ -42,7 +42,7 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
     CK(dalloc(&d.in, N * 4));
     CK(dalloc(&d.P, N)); CK(dalloc(&d.filt_idx, N)); CK(dalloc(&d.blk_cnt, N / 256 + 2));
     { unsigned* g3; CK(dalloc(&g3, 3 * T)); d.gtab = (unsigned long long*)g3; d.g_cnt = (int*)(g3 + T); d.g_fill = (int*)(g3 + 2 * T); }
-    CK(dalloc(&d.g_start, T)); CK(dalloc(&d.p_slot, N)); CK(dalloc(&d.Pc, N)); CK(dalloc(&d.Nrm, N));
+    CK(dalloc(&d.g_start, T)); CK(dalloc(&d.units, N + N / 8 + 8)); CK(dalloc(&d.slow_list, N)); CK(dalloc(&d.over_list, N + N / 8 + 8)); CK(dalloc(&d.knn_full, N * (size_t)d.knn)); CK(dalloc(&d.p_slot, N)); CK(dalloc(&d.Pc, N)); CK(dalloc(&d.Nrm, N));
     CK(dalloc(&d.vtab, T)); CK(cudaMemset(d.vtab, 0, T * sizeof(unsigned long long)));
     CK(dalloc(&d.vkeys, M)); CK(dalloc(&d.vid, N)); CK(dalloc(&d.vox_cnt, M + 2));
     CK(dalloc(&d.rk0, tmpcap)); CK(dalloc(&d.rk1, tmpcap)); CK(dalloc(&d.rv0, tmpcap)); CK(dalloc(&d.rv1, tmpcap));
@@ -70,7 +70,7 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
 
 static void rosa_free(osep_rosa_impl* h) {
     RosaDev& d = h->d;
-    void* ptrs[] = {d.st, d.in, d.P, d.filt_idx, d.blk_cnt, d.gtab, d.g_start, d.p_slot, d.Pc, d.Nrm, d.knn_full, d.vtab, d.vkeys, d.vid,
+    void* ptrs[] = {d.st, d.in, d.P, d.filt_idx, d.blk_cnt, d.gtab, d.g_start, d.units, d.slow_list, d.over_list, d.p_slot, d.Pc, d.Nrm, d.knn_full, d.vtab, d.vkeys, d.vid,
                     d.vox_cnt, d.rk0, d.rk1, d.rv0, d.rv1, d.rhist, d.pts, d.nrms, d.pset, d.pset2, d.vset, d.vnew, d.vvar, d.surf,
                     d.simi_off, d.simi_idx, d.simi_bits, d.nraw, d.vnd, d.vset_it, d.vnew_it, d.fused_flags, d.fused_dbg, d.level, d.level_off, d.level_pts, d.rev_off, d.rev_idx, d.need0, d.good, d.centers, d.good_rank, d.poor_idx, d.active_size,
                     d.pcloud, d.adj_bits, d.seeds, d.corresp, d.skel, d.skel2, d.skel_sampled, d.vtmp, d.vs_off, d.vs_idx, d.vset_iters};
@@ -182,8 +182,7 @@ int osep_rosa_set_debug(osep_rosa* h, int enable) {
     osep_rosa_impl& I = h->impl;
     CK(cudaSetDevice(I.device));
     I.debug = enable != 0;
-    if (I.debug && !I.d.knn_full) {
-        CK(dalloc(&I.d.knn_full, (size_t)I.d.Ncap * I.d.knn));
+    if (I.debug && !I.d.vset_iters) {
         CK(dalloc(&I.d.vset_iters, (size_t)I.d.Mcap * std::max(1, I.cfg.niter_drosa)));
     }
     return OSEP_OK;
@@ -320,6 +319,7 @@ long osep_rosa_get(osep_rosa* h, const char* name, void* dst, long cap) {
         return SM_COUNT;
     }
     if (nm == "fused_dbg") return tap_copy(dst, cap, d.fused_dbg, 64, 8) * 2;     // 64 int64 = 128 int32 words
+    if (nm == "knn_stats") { if (dst && cap >= 12) { ((int*)dst)[0] = s.n_units; ((int*)dst)[1] = s.n_slow; ((int*)dst)[2] = s.n_over; } return 3; }
     if (nm == "launches") { if (dst && cap >= 4) *(int*)dst = (int)I.n_launches; return 1; }
     return -1;
 }

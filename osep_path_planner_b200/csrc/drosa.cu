@@ -289,7 +289,8 @@ k_drosa_seed(FrameState* st, const float4* __restrict__ pts, const float4* __res
 // points are bucketed by level (order inside a level is irrelevant: they are independent).
 __global__ void __launch_bounds__(1024) k_gs_levels2(FrameState* st, const int* __restrict__ surf, int nbk, int* __restrict__ level,
                                                      int* __restrict__ level_off, int* __restrict__ level_pts,
-                                                     int* __restrict__ rev_off, unsigned short* __restrict__ rev_idx, int* __restrict__ need0) {
+                                                     int* __restrict__ rev_off, unsigned short* __restrict__ rev_idx, int* __restrict__ need0,
+                                                     int want_levels) {
     extern __shared__ int lsm[];          // lv[M] | cnt[M+1] | surf as ushort [M*nbk]
     if (st->status != 0) return;
     const int M = st->M;
@@ -299,7 +300,9 @@ __global__ void __launch_bounds__(1024) k_gs_levels2(FrameState* st, const int* 
     for (int p = threadIdx.x; p < M; p += blockDim.x) lv[p] = 1;
     for (int i = threadIdx.x; i < M * nbk; i += blockDim.x) { const int j = surf[i]; ss[i] = (unsigned short)(j < 0 ? 0xffff : j); }
     __syncthreads();
-    while (true) {
+    // the level relaxation is only needed by the unfused (level-synchronous) smoothing kernel; the fused
+    // dataflow walker needs just the reverse lists below, so all points stay at level 1 there.
+    while (want_levels) {
         int changed = 0;
         for (int sweep = 0; sweep < 8; ++sweep) {         // several chaotic sweeps per barrier (levels only grow towards the fixpoint)
             for (int p = threadIdx.x; p < M; p += blockDim.x) {
@@ -670,7 +673,8 @@ void launch_drosa(osep_rosa_impl* h, int sms) {
     const osep_rosa_config& c = h->cfg;
     // largest M the all-shared smoothing kernel accepts with this nb_knn (checked against Mcap at create)
     k_normal_prep<<<div_up(d.Mcap, 128), 128, 0, s>>>(d.st, d.nrms, d.nraw, d.vnd);
-    k_gs_levels2<<<1, 1024, sizeof(int) * (2 * d.Mcap + 2) + sizeof(unsigned short) * d.Mcap * d.nbk, s>>>(d.st, d.surf, d.nbk, d.level, d.level_off, d.level_pts, d.rev_off, d.rev_idx, d.need0);
+    k_gs_levels2<<<1, 1024, sizeof(int) * (2 * d.Mcap + 2) + sizeof(unsigned short) * d.Mcap * d.nbk, s>>>(d.st, d.surf, d.nbk, d.level, d.level_off, d.level_pts, d.rev_off, d.rev_idx, d.need0,
+                                                                                     (h->fused && c.niter_drosa <= MAX_FUSED_ITERS) ? 0 : 1);
     stage_mark(h, SM_SURF);
     stage_mark(h, SM_DROSA_ORIENT);
     SeedOut o; o.vnew = d.vnew; o.vvar = d.vvar; o.prev = nullptr; o.pack_w = 0; o.pset = d.pset; o.good = d.good; o.centers = d.centers; o.active_size = d.active_size;

@@ -265,7 +265,7 @@ __global__ void k_grid_params(FrameState* st, int target_ppc) {
         if (dim < 1) dim = 1; if (dim > 1023) dim = 1023;
         st->g_dim[d] = dim;
     }
-    st->g_cells_used = 0;
+    st->g_cells_used = 0; st->n_units = 0; st->n_slow = 0; st->n_over = 0; st->unit_ctr = 0; st->over_ctr = 0;
 }
 
 __device__ __forceinline__ void cell_of(const FrameState* st, float x, float y, float z, int& cx, int& cy, int& cz) {
@@ -294,12 +294,18 @@ __global__ void k_grid_insert(const float4* __restrict__ P, const FrameState* __
     atomicAdd(&g_cnt[s], 1);
     p_slot[i] = (int)s;
 }
-__global__ void k_grid_alloc(FrameState* st, const int* __restrict__ g_cnt, int* __restrict__ g_start, int T) {
+constexpr int QCH = 8;            // queries per kNN work unit
+__global__ void k_grid_alloc(FrameState* st, const int* __restrict__ g_cnt, int* __restrict__ g_start, int T, int2* __restrict__ units) {
     if (st->status != 0) return;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= T) return;
     const int c = g_cnt[s];
-    if (c > 0) g_start[s] = atomicAdd(&st->g_cells_used, c);
+    if (c > 0) {
+        g_start[s] = atomicAdd(&st->g_cells_used, c);
+        const int nu = (c + QCH - 1) / QCH;
+        const int ub = atomicAdd(&st->n_units, nu);
+        for (int u = 0; u < nu; ++u) units[ub + u] = make_int2(s, u * QCH);
+    }
 }
 __global__ void k_grid_scatter(const float4* __restrict__ P, const FrameState* __restrict__ st, const int* __restrict__ p_slot,
                                const int* __restrict__ g_start, int* g_fill, float4* __restrict__ Pc) {
@@ -332,97 +338,315 @@ template <int K> struct TopK {
     }
 };
 
-// R5: one thread per query (queries in cell order => neighbouring threads scan the same cells).
-// Exact kNN: scan the (2R+1)^3 block of cells; accept when the K-th distance is strictly below
-// the distance to the block boundary (minus a float safety margin), otherwise grow R; beyond
-// R = 3 scan everything.  Then PCL computeMeanAndCovarianceMatrix (shifted by the nearest
-// neighbour, sums in neighbour order) -> smallest eigenvector -> flip towards the viewpoint.
+// PCL computeMeanAndCovarianceMatrix (float, shifted by the nearest neighbour, sums in neighbour order)
+// -> smallest eigenvector -> flipNormalTowardsViewpoint(point, 0,0,0) (PCL NormalEstimation::computeFeature)
+template <class IDX>
+__device__ __forceinline__ float4 normal_from_neighbours(const float4* __restrict__ P, const float4& q, IDX idx, int k_eff) {
+    const float qnan = __int_as_float(0x7fc00000);
+    if (k_eff < 3) return make_float4(qnan, qnan, qnan, 0.0f);
+    const float4 Kp = P[idx(0)];
+    float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;
+    for (int u = 0; u < k_eff; ++u) {
+        const float4 c = P[idx(u)];
+        const float x = c.x - Kp.x, y = c.y - Kp.y, z = c.z - Kp.z;
+        a0 += x * x; a1 += x * y; a2 += x * z; a3 += y * y; a4 += y * z; a5 += z * z; a6 += x; a7 += y; a8 += z;
+    }
+    const float cnt = (float)k_eff;
+    a0 /= cnt; a1 /= cnt; a2 /= cnt; a3 /= cnt; a4 /= cnt; a5 /= cnt; a6 /= cnt; a7 /= cnt; a8 /= cnt;
+    const float c00 = a0 - a6 * a6, c01 = a1 - a6 * a7, c02 = a2 - a6 * a8;
+    const float c11 = a3 - a7 * a7, c12 = a4 - a7 * a8, c22 = a5 - a8 * a8;
+    const Eig3 E = eig3_sym(c00, c01, c11, c02, c12, c22);
+    f3 nv = eig_col(E, 0);
+    const float vx = 0.0f - q.x, vy = 0.0f - q.y, vz = 0.0f - q.z;
+    const float cos_theta = (vx * nv.x + vy * nv.y + vz * nv.z);
+    if (cos_theta < 0.0f) { nv.x *= -1.0f; nv.y *= -1.0f; nv.z *= -1.0f; }
+    return make_float4(nv.x, nv.y, nv.z, 0.0f);
+}
+
+// distance from q to the faces of the scanned cell block [x0..x1]x[y0..y1]x[z0..z1] that still have unscanned
+// cells behind them, minus a float-safety margin: every point closer than this is inside the block.
+__device__ __forceinline__ float block_bound(const FrameState* st, float rx, float ry, float rz, int x0, int x1, int y0, int y1, int z0, int z1) {
+    const float h = st->g_h;
+    float bound = 3.0e38f;
+    if (x0 > 0) bound = fminf(bound, rx - (float)x0 * h);
+    if (x1 < st->g_dim[0] - 1) bound = fminf(bound, (float)(x1 + 1) * h - rx);
+    if (y0 > 0) bound = fminf(bound, ry - (float)y0 * h);
+    if (y1 < st->g_dim[1] - 1) bound = fminf(bound, (float)(y1 + 1) * h - ry);
+    if (z0 > 0) bound = fminf(bound, rz - (float)z0 * h);
+    if (z1 < st->g_dim[2] - 1) bound = fminf(bound, (float)(z1 + 1) * h - rz);
+    return bound - 1e-3f * h;
+}
+
+// R5 slow path: one thread per query, exact kNN by ring expansion (R = 1, 2, 3, then everything) with a
+// register-resident sorted top-K.  Handles whatever the cell-cooperative kernel below could not certify.
 template <int K>
-__global__ void __launch_bounds__(128) k_knn_normals(const float4* __restrict__ Pc, const float4* __restrict__ P,
-                                                     const FrameState* __restrict__ st,
-                                                     const unsigned* __restrict__ gtab, const int* __restrict__ g_cnt,
-                                                     const int* __restrict__ g_start, unsigned mask, float4* __restrict__ Nrm,
-                                                     int* __restrict__ knn_out, int k_req) {
+__global__ void __launch_bounds__(128) k_knn_exact(const float4* __restrict__ Pc, const FrameState* __restrict__ st,
+                                                   const unsigned* __restrict__ gtab, const int* __restrict__ g_cnt,
+                                                   const int* __restrict__ g_start, unsigned mask,
+                                                   int* __restrict__ knn_idx, int k_req, const int* __restrict__ slow_list) {
     if (st->status != 0) return;
     const int n = st->n_filt;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const float4 q = Pc[t];
-    const int qi = __float_as_int(q.w);
-    const int k_eff = min(k_req, n);
-    const int dimx = st->g_dim[0], dimy = st->g_dim[1], dimz = st->g_dim[2];
-    const float h = st->g_h;
-    int cx, cy, cz; cell_of(st, q.x, q.y, q.z, cx, cy, cz);
-    const float rx = q.x - st->bmin[0], ry = q.y - st->bmin[1], rz = q.z - st->bmin[2];
-
-    TopK<K> tk;
-    for (int R = 1;; ++R) {
-        tk.init();
-        const bool all = (R > 3);
-        if (all) {
-            for (int e = 0; e < n; ++e) { const float4 c = Pc[e]; tk.push(dist2(q.x, q.y, q.z, c.x, c.y, c.z), __float_as_int(c.w)); }
-            break;
+    const int nwork = st->n_slow;
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < nwork; w += gridDim.x * blockDim.x) {
+        const int t = slow_list[w];
+        const float4 q = Pc[t];
+        const int qi = __float_as_int(q.w);
+        const int k_eff = min(k_req, n);
+        const int dimx = st->g_dim[0], dimy = st->g_dim[1], dimz = st->g_dim[2];
+        int cx, cy, cz; cell_of(st, q.x, q.y, q.z, cx, cy, cz);
+        const float rx = q.x - st->bmin[0], ry = q.y - st->bmin[1], rz = q.z - st->bmin[2];
+        TopK<K> tk;
+        for (int R = 1;; ++R) {
+            tk.init();
+            if (R > 3) {
+                for (int e = 0; e < n; ++e) { const float4 c = Pc[e]; tk.push(dist2(q.x, q.y, q.z, c.x, c.y, c.z), __float_as_int(c.w)); }
+                break;
+            }
+            const int x0 = max(cx - R, 0), x1 = min(cx + R, dimx - 1);
+            const int y0 = max(cy - R, 0), y1 = min(cy + R, dimy - 1);
+            const int z0 = max(cz - R, 0), z1 = min(cz + R, dimz - 1);
+            for (int z = z0; z <= z1; ++z) for (int y = y0; y <= y1; ++y) for (int x = x0; x <= x1; ++x) {
+                const unsigned key1 = (unsigned)((z * dimy + y) * dimx + x) + 1u;
+                unsigned s = hash_u32(key1) & mask;
+                unsigned cur;
+                while ((cur = gtab[s]) != key1 && cur != 0u) s = (s + 1) & mask;
+                if (cur == 0u) continue;
+                const int b = g_start[s], c = g_cnt[s];
+                for (int e = b; e < b + c; ++e) { const float4 cc = Pc[e]; tk.push(dist2(q.x, q.y, q.z, cc.x, cc.y, cc.z), __float_as_int(cc.w)); }
+            }
+            if (x0 == 0 && y0 == 0 && z0 == 0 && x1 == dimx - 1 && y1 == dimy - 1 && z1 == dimz - 1) break;
+            const float bound = block_bound(st, rx, ry, rz, x0, x1, y0, y1, z0, z1);
+            float wd = 0.0f; int wi = 0x7fffffff;
+#pragma unroll
+            for (int u = 0; u < K; ++u) if (u == k_eff - 1) { wd = tk.d[u]; wi = tk.id[u]; }
+            if (bound > 0.0f && wi != 0x7fffffff && wd < bound * bound) break;
         }
-        const int x0 = max(cx - R, 0), x1 = min(cx + R, dimx - 1);
-        const int y0 = max(cy - R, 0), y1 = min(cy + R, dimy - 1);
-        const int z0 = max(cz - R, 0), z1 = min(cz + R, dimz - 1);
-        for (int z = z0; z <= z1; ++z) for (int y = y0; y <= y1; ++y) for (int x = x0; x <= x1; ++x) {
-            const unsigned key1 = (unsigned)((z * dimy + y) * dimx + x) + 1u;
-            unsigned s = hash_u32(key1) & mask;
-            unsigned cur;
-            while ((cur = gtab[s]) != key1 && cur != 0u) s = (s + 1) & mask;
-            if (cur == 0u) continue;
-            const int b = g_start[s], c = g_cnt[s];
-            for (int e = b; e < b + c; ++e) { const float4 cc = Pc[e]; tk.push(dist2(q.x, q.y, q.z, cc.x, cc.y, cc.z), __float_as_int(cc.w)); }
-        }
-        // whole grid covered?
-        if (x0 == 0 && y0 == 0 && z0 == 0 && x1 == dimx - 1 && y1 == dimy - 1 && z1 == dimz - 1) break;
-        // distance from q to the faces of the scanned block that have unscanned cells behind them
-        float bound = 3.0e38f;
-        if (x0 > 0) bound = fminf(bound, rx - (float)x0 * h);
-        if (x1 < dimx - 1) bound = fminf(bound, (float)(x1 + 1) * h - rx);
-        if (y0 > 0) bound = fminf(bound, ry - (float)y0 * h);
-        if (y1 < dimy - 1) bound = fminf(bound, (float)(y1 + 1) * h - ry);
-        if (z0 > 0) bound = fminf(bound, rz - (float)z0 * h);
-        if (z1 < dimz - 1) bound = fminf(bound, (float)(z1 + 1) * h - rz);
-        bound -= 1e-3f * h;
-        float wd = 0.0f; int wi = 0x7fffffff;
 #pragma unroll
-        for (int u = 0; u < K; ++u) if (u == k_eff - 1) { wd = tk.d[u]; wi = tk.id[u]; }
-        if (bound > 0.0f && wi != 0x7fffffff && wd < bound * bound) break;
+        for (int u = 0; u < K; ++u) if (u < k_eff) knn_idx[(size_t)qi * k_eff + u] = tk.id[u];
     }
+}
 
-    if (knn_out) {
+// R5 fast path: one WARP per work unit = up to QCH queries of one grid cell.  The queries of a cell share
+// their candidate cells: the (start, count) table of the non-empty cells of the (2R+1)^3 block is built
+// once per unit (lanes probe the hash table in parallel) and the candidate points are STAGED in shared
+// memory with coalesced float4 loads (STAGED = true; units with more than KNN_STAGE candidates are
+// re-run with STAGED = false, reading the cells from L1/L2).  Per query the warp
+//   1. counts the candidates inside 4 nested radii (bound^2 / 1,2,4,8) with ballots (skipped when the
+//      radius that worked for the previous query of the cell works again),
+//   2. compacts the candidates of the smallest radius that still holds >= k points (exact: every point
+//      closer than `bound` is inside the scanned block, and the k nearest by (d2, index) are all inside
+//      any radius that holds >= k points),
+//   3. sorts them as packed (d2, index) keys with a register bitonic network.
+// Queries that cannot be certified within R <= 2 (isolated points) go to k_knn_exact.
+constexpr int KNN_LIST = 64;
+constexpr int KNN_TAB = 125;
+constexpr int KNN_WARPS = 4;
+constexpr int KNN_STAGE = 384;
+
+// ascending bitonic sort of 64 packed keys (d2 bits << 32 | index; d2 >= 0 so the bit pattern orders like the
+// float and the packed compare is exactly the canonical (d2, index) order), two keys per lane: element r*32+lane.
+__device__ __forceinline__ void bitonic64(unsigned long long& a0, unsigned long long& a1) {
+    const int lane = threadIdx.x & 31;
 #pragma unroll
-        for (int u = 0; u < K; ++u) if (u < k_eff) knn_out[(size_t)qi * k_eff + u] = tk.id[u];
-    }
-    const float qnan = __int_as_float(0x7fc00000);
-    float4 out = make_float4(qnan, qnan, qnan, 0.0f);
-    if (k_eff >= 3) {
-        // PCL computeMeanAndCovarianceMatrix, float, shifted by the first neighbour
-        const float4 Kp = P[tk.id[0]];
-        float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;
+    for (int k = 2; k <= 64; k <<= 1) {
 #pragma unroll
-        for (int u = 0; u < K; ++u) {
-            if (u < k_eff) {
-                const float4 c = P[tk.id[u]];
-                const float x = c.x - Kp.x, y = c.y - Kp.y, z = c.z - Kp.z;
-                a0 += x * x; a1 += x * y; a2 += x * z; a3 += y * y; a4 += y * z; a5 += z * z; a6 += x; a7 += y; a8 += z;
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j == 32) {                       // partner = other register of the same lane (k == 64: ascending)
+                const unsigned long long lo = a0 < a1 ? a0 : a1, hi = a0 < a1 ? a1 : a0;
+                a0 = lo; a1 = hi;
+            } else {
+                const unsigned long long b0 = __shfl_xor_sync(0xffffffffu, a0, j), b1 = __shfl_xor_sync(0xffffffffu, a1, j);
+                const bool lower = (lane & j) == 0;
+                const bool up0 = ((lane & k) == 0) || (k == 64);
+                const bool up1 = (k == 64) ? true : (((lane + 32) & k) == 0);
+                const bool keepmin0 = (lower == up0), keepmin1 = (lower == up1);
+                a0 = keepmin0 ? (a0 < b0 ? a0 : b0) : (a0 < b0 ? b0 : a0);
+                a1 = keepmin1 ? (a1 < b1 ? a1 : b1) : (a1 < b1 ? b1 : a1);
             }
         }
-        const float cnt = (float)k_eff;
-        a0 /= cnt; a1 /= cnt; a2 /= cnt; a3 /= cnt; a4 /= cnt; a5 /= cnt; a6 /= cnt; a7 /= cnt; a8 /= cnt;
-        const float c00 = a0 - a6 * a6, c01 = a1 - a6 * a7, c02 = a2 - a6 * a8;
-        const float c11 = a3 - a7 * a7, c12 = a4 - a7 * a8, c22 = a5 - a8 * a8;
-        const Eig3 E = eig3_sym(c00, c01, c11, c02, c12, c22);
-        f3 nv = eig_col(E, 0);
-        // flipNormalTowardsViewpoint(point, 0, 0, 0, nx, ny, nz)
-        const float vx = 0.0f - q.x, vy = 0.0f - q.y, vz = 0.0f - q.z;
-        const float cos_theta = (vx * nv.x + vy * nv.y + vz * nv.z);
-        if (cos_theta < 0.0f) { nv.x *= -1.0f; nv.y *= -1.0f; nv.z *= -1.0f; }
-        out = make_float4(nv.x, nv.y, nv.z, 0.0f);
     }
-    Nrm[qi] = out;
+}
+
+template <int K, bool STAGED>
+__global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __restrict__ Pc, FrameState* st,
+                                                             const unsigned* __restrict__ gtab, const int* __restrict__ g_cnt,
+                                                             const int* __restrict__ g_start, unsigned mask, const int2* __restrict__ units,
+                                                             int* __restrict__ knn_idx, int k_req, int* __restrict__ slow_list,
+                                                             int* __restrict__ over_list) {
+    __shared__ int2 tab[KNN_WARPS][KNN_TAB];
+    __shared__ unsigned long long keys[KNN_WARPS][KNN_LIST];
+    __shared__ float4 stage[STAGED ? KNN_WARPS : 1][STAGED ? KNN_STAGE : 1];
+    if (st->status != 0) return;
+    const int n = st->n_filt;
+    const int k_eff = min(k_req, n);
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int dimx = st->g_dim[0], dimy = st->g_dim[1], dimz = st->g_dim[2];
+    const float h = st->g_h;
+    const float diag2 = ((float)dimx * h) * ((float)dimx * h) + ((float)dimy * h) * ((float)dimy * h) + ((float)dimz * h) * ((float)dimz * h);
+    const int n_work = STAGED ? st->n_units : st->n_over;
+    int* ctr = STAGED ? &st->unit_ctr : &st->over_ctr;
+    const unsigned long long KINF = ~0ull;
+    while (true) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(ctr, 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= n_work) break;
+        const int unit = STAGED ? w : over_list[w];
+        const int2 un = units[unit];
+        const int cstart = g_start[un.x], ccnt = g_cnt[un.x];
+        const int q0 = un.y;
+        const int nq = min(QCH, ccnt - q0);
+        int cx, cy, cz;
+        { const float4 f = Pc[cstart]; cell_of(st, f.x, f.y, f.z, cx, cy, cz); }
+        unsigned todo = (1u << nq) - 1u;
+        bool overflow = false;
+        for (int R = 1; R <= 2 && todo && !overflow; ++R) {
+            const int x0 = max(cx - R, 0), x1 = min(cx + R, dimx - 1);
+            const int y0 = max(cy - R, 0), y1 = min(cy + R, dimy - 1);
+            const int z0 = max(cz - R, 0), z1 = min(cz + R, dimz - 1);
+            const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, nz = z1 - z0 + 1;
+            const int ncell = nx * ny * nz;
+            const bool whole = (x0 == 0 && y0 == 0 && z0 == 0 && x1 == dimx - 1 && y1 == dimy - 1 && z1 == dimz - 1);
+            int nt = 0, total = 0;
+            __syncwarp();
+            for (int c0 = 0; c0 < ncell; c0 += 32) {
+                const int c = c0 + lane;
+                int2 e = make_int2(0, 0);
+                if (c < ncell) {
+                    const int x = x0 + c % nx, y = y0 + (c / nx) % ny, z = z0 + c / (nx * ny);
+                    const unsigned key1 = (unsigned)((z * dimy + y) * dimx + x) + 1u;
+                    unsigned s = hash_u32(key1) & mask;
+                    unsigned cur;
+                    while ((cur = gtab[s]) != key1 && cur != 0u) s = (s + 1) & mask;
+                    if (cur != 0u) e = make_int2(g_start[s], g_cnt[s]);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, e.y > 0);
+                if (e.y > 0) tab[wib][nt + __popc(m & lt)] = e;
+                nt += __popc(m);
+                total += __reduce_add_sync(0xffffffffu, e.y);
+            }
+            __syncwarp();
+            const float4* base = Pc;
+            if (STAGED) {
+                if (total > KNN_STAGE) { overflow = true; break; }
+                // stage: flat copy of every candidate cell (independent loads, many in flight)
+                int off = 0;
+                for (int ti = 0; ti < nt; ++ti) {
+                    const int2 e = tab[wib][ti];
+                    for (int t = lane; t < e.y; t += 32) stage[wib][off + t] = Pc[e.x + t];
+                    off += e.y;
+                }
+                __syncwarp();
+                if (lane == 0) tab[wib][0] = make_int2(0, total);
+                nt = 1;
+                base = stage[wib];
+                __syncwarp();
+            }
+            float guess = 0.0f;                               // radius^2 that worked for the previous query of this cell
+            for (int qi = 0; qi < nq; ++qi) {
+                if (!((todo >> qi) & 1u)) continue;
+                const float4 q = Pc[cstart + q0 + qi];
+                float b2;
+                if (whole) b2 = 4.0f * diag2 + 1.0f;
+                else {
+                    const float bound = block_bound(st, q.x - st->bmin[0], q.y - st->bmin[1], q.z - st->bmin[2], x0, x1, y0, y1, z0, z1);
+                    b2 = bound > 0.0f ? bound * bound : 0.0f;
+                }
+                unsigned long long k0 = KINF, k1 = KINF;
+                auto collect = [&](float thr) -> int {
+                    int ln = 0;
+                    for (int ti = 0; ti < nt; ++ti) {
+                        const int2 e = tab[wib][ti];
+                        for (int o = 0; o < e.y; o += 32) {
+                            const int t = o + lane;
+                            float d2 = 3.0e38f; int id = 0;
+                            if (t < e.y) { const float4 c = base[e.x + t]; d2 = dist2(q.x, q.y, q.z, c.x, c.y, c.z); id = __float_as_int(c.w); }
+                            const bool in = d2 < thr;
+                            const unsigned m = __ballot_sync(0xffffffffu, in);
+                            const int pos = ln + __popc(m & lt);
+                            if (in && pos < KNN_LIST) keys[wib][pos] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)id;
+                            ln += __popc(m);
+                        }
+                    }
+                    __syncwarp();
+                    k0 = (lane < ln && lane < KNN_LIST) ? keys[wib][lane] : KINF;
+                    k1 = (lane + 32 < ln && lane + 32 < KNN_LIST) ? keys[wib][lane + 32] : KINF;
+                    __syncwarp();
+                    return ln;
+                };
+                auto population = [&](float thr) -> int {
+                    int cm = 0;
+                    for (int ti = 0; ti < nt; ++ti) {
+                        const int2 e = tab[wib][ti];
+                        for (int o = 0; o < e.y; o += 32) {
+                            const int t = o + lane;
+                            float d2 = 3.0e38f;
+                            if (t < e.y) { const float4 c = base[e.x + t]; d2 = dist2(q.x, q.y, q.z, c.x, c.y, c.z); }
+                            cm += __popc(__ballot_sync(0xffffffffu, d2 < thr));
+                        }
+                    }
+                    return cm;
+                };
+                int ln = -1; float hi = 0.0f;
+                if (guess > 0.0f && guess < b2) { hi = guess; ln = collect(hi); if (ln < k_eff || ln > KNN_LIST) ln = -1; }
+                if (ln < 0) {
+                    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;       // population of 4 nested radii
+                    const float t1 = b2 * 0.5f, t2 = b2 * 0.25f, t3 = b2 * 0.125f;
+                    for (int ti = 0; ti < nt; ++ti) {
+                        const int2 e = tab[wib][ti];
+                        for (int o = 0; o < e.y; o += 32) {
+                            const int t = o + lane;
+                            float d2 = 3.0e38f;
+                            if (t < e.y) { const float4 c = base[e.x + t]; d2 = dist2(q.x, q.y, q.z, c.x, c.y, c.z); }
+                            c0 += __popc(__ballot_sync(0xffffffffu, d2 < b2));
+                            c1 += __popc(__ballot_sync(0xffffffffu, d2 < t1));
+                            c2 += __popc(__ballot_sync(0xffffffffu, d2 < t2));
+                            c3 += __popc(__ballot_sync(0xffffffffu, d2 < t3));
+                        }
+                    }
+                    if (c0 < k_eff) continue;                 // not certifiable at this R
+                    float lo; int cnt;
+                    if (c3 >= k_eff) { hi = t3; lo = 0.0f; cnt = c3; }
+                    else if (c2 >= k_eff) { hi = t2; lo = t3; cnt = c2; }
+                    else if (c1 >= k_eff) { hi = t1; lo = t2; cnt = c1; }
+                    else { hi = b2; lo = t1; cnt = c0; }
+                    int guardc = 0;
+                    while (cnt > KNN_LIST && guardc < 48) {   // bisection: population(hi) >= k > population(lo)
+                        const float mid = 0.5f * (lo + hi);
+                        if (!(mid > lo && mid < hi)) break;
+                        const int cm = population(mid);
+                        if (cm >= k_eff) { hi = mid; cnt = cm; } else lo = mid;
+                        ++guardc;
+                    }
+                    if (cnt > KNN_LIST) continue;             // > 64 candidates tie at the k-th distance: slow path
+                    ln = collect(hi);
+                }
+                guess = hi * 1.25f;
+                bitonic64(k0, k1);
+                const int qidx = __float_as_int(q.w);
+                if (lane < k_eff) knn_idx[(size_t)qidx * k_eff + lane] = (int)(unsigned)(k0 & 0xffffffffull);
+                if (lane + 32 < k_eff) knn_idx[(size_t)qidx * k_eff + lane + 32] = (int)(unsigned)(k1 & 0xffffffffull);
+                todo &= ~(1u << qi);
+            }
+        }
+        __syncwarp();
+        if (STAGED && overflow) { if (lane == 0) over_list[atomicAdd(&st->n_over, 1)] = unit; }
+        else if (lane < nq && ((todo >> lane) & 1u)) slow_list[atomicAdd(&st->n_slow, 1)] = cstart + q0 + lane;
+        __syncwarp();
+    }
+}
+
+// normals: one thread per point, neighbours from knn_idx (k_eff per point, canonical order)
+__global__ void __launch_bounds__(128) k_normals(const float4* __restrict__ P, const FrameState* __restrict__ st,
+                                                 const int* __restrict__ knn_idx, int k_req, float4* __restrict__ Nrm) {
+    if (st->status != 0) return;
+    const int n = st->n_filt;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int k_eff = min(k_req, n);
+    const int* row = knn_idx + (size_t)i * k_eff;
+    Nrm[i] = normal_from_neighbours(P, P[i], [&](int u) { return row[u]; }, k_eff);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -606,8 +830,14 @@ k_vox_reduce(FrameState* st, const int* __restrict__ sorted_idx, const int* __re
 template <int K>
 static void launch_knn(osep_rosa_impl* h, int n, int k_req) {
     RosaDev& d = h->d;
-    k_knn_normals<K><<<div_up(n, 128), 128, 0, h->stream>>>(d.Pc, d.P, d.st, (const unsigned*)d.gtab, d.g_cnt, d.g_start,
-                                                           (unsigned)(d.T - 1), d.Nrm, h->debug ? d.knn_full : nullptr, k_req);
+    cudaStream_t s = h->stream;
+    const unsigned mask = (unsigned)(d.T - 1);
+    k_knn_cells<K, true><<<h->sms * 6, KNN_WARPS * 32, 0, s>>>(d.Pc, d.st, (const unsigned*)d.gtab, d.g_cnt, d.g_start, mask, d.units,
+                                                              d.knn_full, k_req, d.slow_list, d.over_list);
+    k_knn_cells<K, false><<<h->sms * 2, KNN_WARPS * 32, 0, s>>>(d.Pc, d.st, (const unsigned*)d.gtab, d.g_cnt, d.g_start, mask, d.units,
+                                                               d.knn_full, k_req, d.slow_list, d.over_list);
+    k_knn_exact<K><<<64, 128, 0, s>>>(d.Pc, d.st, (const unsigned*)d.gtab, d.g_cnt, d.g_start, mask, d.knn_full, k_req, d.slow_list);
+    k_normals<<<div_up(n, 128), 128, 0, s>>>(d.P, d.st, d.knn_full, k_req, d.Nrm);
 }
 
 void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int stride) {
@@ -631,9 +861,9 @@ void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int strid
     stage_mark(h, SM_LEAF);
     // R5: grid + kNN normals
     cudaMemsetAsync(d.gtab, 0, sizeof(unsigned) * 3 * (size_t)d.T, s);   // gtab | g_cnt | g_fill are contiguous
-    k_grid_params<<<1, 1, 0, s>>>(d.st, 10);
+    k_grid_params<<<1, 1, 0, s>>>(d.st, 16);
     k_grid_insert<<<nb, NT, 0, s>>>(d.P, d.st, (unsigned*)d.gtab, d.g_cnt, d.p_slot, (unsigned)(d.T - 1));
-    k_grid_alloc<<<div_up(d.T, NT), NT, 0, s>>>(d.st, d.g_cnt, d.g_start, d.T);
+    k_grid_alloc<<<div_up(d.T, NT), NT, 0, s>>>(d.st, d.g_cnt, d.g_start, d.T, d.units);
     k_grid_scatter<<<nb, NT, 0, s>>>(d.P, d.st, d.p_slot, d.g_start, d.g_fill, d.Pc);
     stage_mark(h, SM_GRID);
     const int k = c.ne_knn;
@@ -662,7 +892,7 @@ void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int strid
     // even number of passes: sorted data is back in rk0 / rv0
     k_vox_reduce<<<1024, 128, 0, s>>>(d.st, va, d.vox_cnt, d.P, d.Nrm, d.pts, d.nrms, d.pset, d.vset);
     stage_mark(h, SM_VOXEL);
-    h->n_launches += 1 + 3 + (2 * LEAF_MAX_ITERS + 1) + 4 + 1 + 4 + 3 * passes + 1;
+    h->n_launches += 1 + 3 + (2 * LEAF_MAX_ITERS + 1) + 4 + 4 + 4 + 3 * passes + 1;
 }
 
 }  // namespace osep

@@ -25,9 +25,10 @@ struct RosaDev {
     unsigned long long* gtab = nullptr;  // kNN grid: (epoch<<32 | cell key)
     int* g_cnt = nullptr; int* g_start = nullptr; int* g_fill = nullptr;
     int* p_slot = nullptr;
+    int2* units = nullptr; int* slow_list = nullptr; int* over_list = nullptr;   // kNN work units (cell, first query) and slow-path query list
     float4* Pc = nullptr;              // points in cell order, w = filtered index (int bits)
     float4* Nrm = nullptr;             // normals of the filtered cloud
-    int* knn_full = nullptr;           // debug tap (Ncap * knn) or null
+    int* knn_full = nullptr;           // kNN indices of the filtered cloud (Ncap * ne_knn), canonical order
     unsigned long long* vtab = nullptr;  // voxel set: (epoch<<32 | voxel key)
     unsigned* vkeys = nullptr;         // distinct voxel keys, sorted
     int* vid = nullptr;                // voxel id per filtered point

@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import RosaConfig, RosaResult, GraphView, OsepError, ROSA_STAGES
 
 _INT_TAPS = {"filt_idx", "knn_full", "nvox_hist", "vox_count", "surf_off", "surf_idx", "simi_off", "simi_idx",
-             "poor_idx", "active_size", "corresp", "seeds", "levels", "launches"}
+             "poor_idx", "active_size", "corresp", "seeds", "levels", "launches", "knn_stats"}
 _U32_TAPS = {"vox_keys"}
 _V3_TAPS = {"filtered", "normals_full", "pts", "nrms", "vset", "vset_iters", "pset", "pset_drosa", "skelver_sampled", "skelver"}
 

@@ -17,3 +17,6 @@ for it in range(6):
     print("      compute cycles/step %.0f  release cycles/step %.0f" % (d[it, 6] / max(1, steps), d[it, 7] / max(1, steps)))
     print("it %d: begin +%.1f us first_step +%.1f us end +%.1f us | steps %d spins %d | busy per step %.2f us" % (it, (b - t0) / 1e3, (f - t0) / 1e3, (e - t0) / 1e3, steps, spins, (e - f) / 1e3 / max(1, steps)))
 print(r.stage_ms())
+
+print("knn_stats [units, slow, overflow]", r.tap("knn_stats"))
+
