@@ -50,6 +50,7 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
     CK(dalloc(&d.pts, M)); CK(dalloc(&d.nrms, M)); CK(dalloc(&d.pset, M)); CK(dalloc(&d.pset2, M)); CK(dalloc(&d.vset, M)); CK(dalloc(&d.vnew, M));
     CK(dalloc(&d.vvar, M)); CK(dalloc(&d.simi_bits, M * (size_t)d.W)); CK(dalloc(&d.nraw, M)); CK(dalloc(&d.vnd, M));
     CK(dalloc(&d.vset_it, M * 9)); CK(dalloc(&d.vnew_it, M * 8)); CK(dalloc(&d.fused_flags, M * 16 + 16)); CK(dalloc(&d.fused_dbg, 64)); CK(cudaMemset(d.fused_dbg, 0, 64 * 8));
+    { const char* e = getenv("OSEP_KNN_PPC"); if (e && atoi(e) > 0) h->knn_ppc = atoi(e); }
     { const char* e = getenv("OSEP_DROSA_UNFUSED"); if (e && e[0] == '1') h->fused = false;
       int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device); if (!coop) h->fused = false; }
     { int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device)); h->sms = sms > 0 ? sms : 148; } CK(dalloc(&d.surf, M * (size_t)std::max(d.nbk, 1)));

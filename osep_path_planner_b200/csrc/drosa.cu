@@ -580,13 +580,27 @@ __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int
             __syncwarp();
             const long long c1 = clock64();
             c_comp += c1 - c0; c_pts += take;
-            // release the dependents of the points just rewritten: all 32 lanes work on one point's list at a time
-            for (int src = 0; src < take; ++src) {
-                const int pj = __shfl_sync(FULLM, p, src);
-                const int rb = srev_off[pj], re = srev_off[pj + 1];
-                for (int r = rb + lane; r < re; r += 32) {
-                    const int q = srev[r];
-                    if (q > pj && atomicSub(need + q, 1) == 1) { const int slot = atomicAdd(s_ctl, 1); st_vol(rq + slot, q + 1); }
+            // release the dependents of the points just rewritten, flattened over the warp: entry t of the
+            // concatenated reverse lists belongs to the source lane whose degree prefix covers t
+            {
+                const int rb = act ? srev_off[p] : 0;
+                const int deg = act ? srev_off[p + 1] - rb : 0;
+                int incl = deg;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(FULLM, incl, off); if (lane >= off) incl += v; }
+                const int total = __shfl_sync(FULLM, incl, 31);
+                for (int t0 = 0; t0 < total; t0 += 32) {          // uniform trip count: every lane takes part in the shuffles
+                    const int t = t0 + lane;
+                    // smallest source lane whose inclusive prefix exceeds t (prefixes are monotone: 5-step search)
+                    int src = 0;
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1) { const int probe = __shfl_sync(FULLM, incl, src + step - 1); if (probe <= t) src += step; }
+                    const int s_incl = __shfl_sync(FULLM, incl, src), s_deg = __shfl_sync(FULLM, deg, src);
+                    const int s_rb = __shfl_sync(FULLM, rb, src), s_p = __shfl_sync(FULLM, p, src);
+                    if (t < total) {
+                        const int q = srev[s_rb + (t - (s_incl - s_deg))];
+                        if (q > s_p && atomicSub(need + q, 1) == 1) { const int slot = atomicAdd(s_ctl, 1); st_vol(rq + slot, q + 1); }
+                    }
                 }
             }
             head += take;

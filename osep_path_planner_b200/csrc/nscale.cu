@@ -861,7 +861,7 @@ void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int strid
     stage_mark(h, SM_LEAF);
     // R5: grid + kNN normals
     cudaMemsetAsync(d.gtab, 0, sizeof(unsigned) * 3 * (size_t)d.T, s);   // gtab | g_cnt | g_fill are contiguous
-    k_grid_params<<<1, 1, 0, s>>>(d.st, 16);
+    k_grid_params<<<1, 1, 0, s>>>(d.st, h->knn_ppc);
     k_grid_insert<<<nb, NT, 0, s>>>(d.P, d.st, (unsigned*)d.gtab, d.g_cnt, d.p_slot, (unsigned)(d.T - 1));
     k_grid_alloc<<<div_up(d.T, NT), NT, 0, s>>>(d.st, d.g_cnt, d.g_start, d.T, d.units);
     k_grid_scatter<<<nb, NT, 0, s>>>(d.P, d.st, d.p_slot, d.g_start, d.g_fill, d.Pc);
