@@ -42,13 +42,13 @@ def algorithmic_bytes(n_in, n_filt, L, M, V):
 
 
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         self.rows = []
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -57,7 +57,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.p.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([time.time()] + [x.strip() for x in line.split(",")][1:])
+
+    def mark(self):
+        """start of the timed region: only samples taken after this call are reported"""
+        self.t_mark = time.time()
 
     def stop(self):
         if self.p is None:
@@ -70,7 +74,9 @@ class ClockSampler:
             self.p.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t_mark = getattr(self, "t_mark", 0.0)
+        rows = [r[1:] for r in self.rows if r[0] >= t_mark] or [r[1:] for r in self.rows]
+        for r in rows:
             if len(r) < 7:
                 continue
             try:
@@ -154,6 +160,7 @@ def run_ours(args, rank, world, local_rank):
     def step_device():
         r.run_device(dev.data_ptr(), n, 4)
 
+    clocks = ClockSampler(local_rank)      # started early (nvidia-smi takes a while to come up); samples before mark() are dropped
     # ---- warm-up
     for _ in range(args.warmup):
         step_device(); assert r.finish(), "frame failed: status %d" % r.result.status
@@ -164,7 +171,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- timed: device-resident input, CUDA events on the library's stream, L2 flushed between steps
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     stage_acc = None
-    clocks = ClockSampler(local_rank)
+    clocks.mark()
     barrier()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
@@ -225,6 +232,24 @@ def run_ours(args, rank, world, local_rank):
                                        "frac": (knn_bytes / (knn_ms * 1e-3) / 1e9) / peak if knn_ms > 0 else None},
                 "note": "a single frame is latency-bound (SURVEY.md H3): 26 MB of compulsory traffic = 4 us at peak; the fraction is reported, not a target"}
 
+    # ---- extra (not the headline): batched independent frames on this GPU (BASELINE.json configs[3] in miniature)
+    batched = None
+    if args.batch > 0:
+        nb = args.batch
+        r.set_lanes(args.lanes)
+        devs = [torch.from_numpy(fx.to_xyz4(fx.batch_frame(rank * nb + b, n=args.points))).cuda() for b in range(min(nb, 16))]
+        ptrs = [devs[b % len(devs)].data_ptr() for b in range(nb)]
+        cnts = [devs[b % len(devs)].shape[0] for b in range(nb)]
+        r.run_batch(ptrs[:args.lanes * 2], device_ptrs=True, counts=cnts[:args.lanes * 2])      # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        bres, _ = r.run_batch(ptrs, device_ptrs=True, counts=cnts)
+        barrier()
+        bt = shard.max_over_ranks(time.perf_counter() - t0)
+        assert all(x.status == 0 for x in bres)
+        batched = {"frames": nb * world, "lanes_per_gpu": args.lanes, "frames_per_s": nb * world / bt, "ms_per_frame_amortised": 1e3 * bt / nb,
+                   "distinct_frames": len(devs), "note": "device-resident frames, %d streams per GPU, wall clock around osep_rosa_run_batch_device" % args.lanes}
+        r.set_lanes(1)
     if world > 1:
         counts, _ = shard.gather_frame_results({rank: np.ascontiguousarray(r.output_vertices())}, world, cap=1024)
     cpu_baseline = None
@@ -242,7 +267,7 @@ def run_ours(args, rank, world, local_rank):
                            "parallelism": "1 frame per GPU per step; ranks = independent frames (no collective on the data path)"},
                 "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": 1e3 * e2e_s / args.steps, "h2d_bytes_per_step": int(n * 16), "d2h_bytes_per_step": d2h},
-                "gpu_launches": int(launches), "stage_ms": stage_ms, "clocks": clk, "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps}
+                "gpu_launches": int(launches), "stage_ms": stage_ms, "clocks": clk, "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps, "batched": batched}
         print(json.dumps(line), flush=True)
     r.close()
     if world > 1:
@@ -258,6 +283,8 @@ def main():
     ap.add_argument("--points", type=int, default=100000)
     ap.add_argument("--cpu-frames", type=int, default=20, help="frames of the bounded CPU-baseline sample (~0.4 s each)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--batch", type=int, default=64, help="frames of the extra batched-throughput measurement (0 = skip)")
+    ap.add_argument("--lanes", type=int, default=8, help="concurrent frames (streams) per GPU in the batched measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
