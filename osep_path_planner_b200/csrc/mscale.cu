@@ -18,6 +18,7 @@
 //   * the greedy radius cover keeps the sequential semantics on one warp over precomputed
 //     adjacency bit rows.
 #include "rosa_impl.cuh"
+#include <cooperative_groups.h>
 
 namespace osep {
 
@@ -318,6 +319,87 @@ __global__ void k_dcrosa_line(const FrameState* __restrict__ st, const float4* _
     } else pout[i] = self4;
 }
 
+// R20 fused: all niter_dcrosa iterations (two Jacobi passes each) in ONE launch on a thread-block CLUSTER of
+// 8 CTAs.  Every CTA keeps a full copy of the pset ping-pong in its shared memory (16 B x M x 2); a thread owns
+// one point, gathers its similarity neighbours from the local copy (sums in list order, as rosa.cpp:395-397 and
+// :804-813), and broadcasts its result to the 8 copies through distributed shared memory; cluster.sync()
+// separates the Jacobi passes.  One SM alone is shared-memory-bandwidth bound on the random gathers; 8 SMs
+// with replicated operands are not, and no pass goes back to L2.
+constexpr int DC_CLUSTER = 8;
+constexpr int DC_THREADS = 128;
+constexpr int DC_SMEM_BUDGET = 200 * 1024;
+
+__global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS)
+k_dcrosa_cluster(const FrameState* __restrict__ st, float4* pset, const int* __restrict__ simi_off, const int* __restrict__ simi_idx, int niter) {
+    extern __shared__ float4 dcs[];
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    if (st->status != 0) return;                       // uniform over the cluster
+    const int M = st->M;
+    float4* pa = dcs; float4* pb = dcs + M;
+    const unsigned rank = cluster.block_rank();
+    for (int i = threadIdx.x; i < M; i += blockDim.x) pa[i] = pset[i];
+    __syncthreads();
+    float4* pa_r[DC_CLUSTER]; float4* pb_r[DC_CLUSTER];
+#pragma unroll
+    for (int r = 0; r < DC_CLUSTER; ++r) { pa_r[r] = cluster.map_shared_rank(pa, r); pb_r[r] = cluster.map_shared_rank(pb, r); }
+    cluster.sync();
+    const int per = (M + DC_CLUSTER - 1) / DC_CLUSTER;
+    const int lo = (int)rank * per, hi = min(M, lo + per);
+    for (int it = 0; it < niter; ++it) {
+        for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {          // neighbour mean (rosa.cpp:388-399)
+            const int b = simi_off[i], e = simi_off[i + 1];
+            float4 out = pa[i];
+            if (e > b) {
+                f3 acc{0.0f, 0.0f, 0.0f};
+                for (int t = b; t < e; ++t) { const float4 v = pa[simi_idx[t]]; acc = add3(acc, f3{v.x, v.y, v.z}); }
+                const f3 mth = div3(acc, (float)(e - b));
+                out = make_float4(mth.x, mth.y, mth.z, 1.0f);
+            }
+#pragma unroll
+            for (int r = 0; r < DC_CLUSTER; ++r) pb_r[r][i] = out;
+        }
+        cluster.sync();
+        for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {          // local_line_fit + projection (rosa.cpp:402-418, 793-841)
+            const int b = simi_off[i], e = simi_off[i + 1];
+            const int m = e - b;
+            const float4 self4 = pb[i];
+            float4 out = self4;
+            if (m >= 3) {
+                f3 mean{0.0f, 0.0f, 0.0f};
+                for (int t = b; t < e; ++t) { const float4 v = pb[simi_idx[t]]; mean = add3(mean, f3{v.x, v.y, v.z}); }
+                mean = div3(mean, (float)m);
+                float c00 = 0, c10 = 0, c11 = 0, c20 = 0, c21 = 0, c22 = 0;
+                for (int t = b; t < e; ++t) {
+                    const float4 v = pb[simi_idx[t]];
+                    const f3 q = sub3(f3{v.x, v.y, v.z}, mean);
+                    c00 += q.x * q.x; c10 += q.y * q.x; c11 += q.y * q.y; c20 += q.z * q.x; c21 += q.z * q.y; c22 += q.z * q.z;
+                }
+                const float fm = (float)m;
+                c00 /= fm; c10 /= fm; c11 /= fm; c20 /= fm; c21 /= fm; c22 /= fm;
+                const Eig3 E = eig3_sym(c00, c10, c11, c20, c21, c22);
+                if (E.ok) {
+                    const float denom = smax(1e-6f, sum3(E.ev[0], E.ev[1], E.ev[2]));
+                    f3 dir = eig_col(E, 2);
+                    const float nrm = norm3(dir);
+                    if (nrm > 1e-6f) dir = div3(dir, nrm); else dir = {1.0f, 0.0f, 0.0f};
+                    const float conf = E.ev[2] / denom;
+                    if (conf > 0.5f) {
+                        const f3 x{self4.x, self4.y, self4.z};
+                        const float t = dot3(dir, sub3(x, mean));
+                        const f3 pr = add3(mean, mul3(dir, t));
+                        out = make_float4(pr.x, pr.y, pr.z, 1.0f);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < DC_CLUSTER; ++r) pa_r[r][i] = out;
+        }
+        cluster.sync();
+    }
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) pset[i] = pa[i];
+}
+
 // ------------------------------------------------------------------------------------------
 // R21 vertex_sampling (rosa.cpp:424-532)
 __global__ void k_vs_compact(FrameState* st, const float4* __restrict__ pset, float4* __restrict__ pcloud, int* scratch) {
@@ -353,60 +435,102 @@ __global__ void k_vs_adj(const FrameState* __restrict__ st, const float4* __rest
         if (lane == 0) adj[(size_t)i * W + w] = word;
     }
 }
-// greedy cover with the reference's sequential semantics (lowest uncovered index becomes the
-// next vertex, rosa.cpp:462-502); one warp, covered set in shared memory.
-__global__ void k_vs_greedy(FrameState* st, const unsigned* __restrict__ adj, int W, int* __restrict__ seeds) {
-    extern __shared__ unsigned cov[];
+// greedy cover with the reference's sequential semantics (lowest uncovered index becomes the next vertex,
+// rosa.cpp:462-502).  The cover bit matrix is staged in shared memory by the whole block; warp 0 then walks:
+// each lane keeps its words of the covered set in registers, a step = ffs + warp min + one row OR.
+constexpr int VS_SMEM_BUDGET = 200 * 1024;
+__global__ void __launch_bounds__(256) k_vs_greedy(FrameState* st, const unsigned* __restrict__ adj, int W, int* __restrict__ seeds) {
+    extern __shared__ unsigned vs_rows[];
     if (st->status != 0) return;
     const int Mc = st->Mc;
-    const int lane = threadIdx.x;
     const int Wn = (Mc + 31) >> 5;
-    for (int w = lane; w < Wn; w += 32) {
-        unsigned c = 0u;
-        const int rem = Mc - w * 32;
-        if (rem < 32) c = ~((1u << rem) - 1u);       // bits beyond Mc count as covered
-        cov[w] = c;
+    const bool in_smem = (size_t)4 * Mc * Wn <= (size_t)VS_SMEM_BUDGET;
+    if (in_smem) {
+        for (int r = threadIdx.x >> 5; r < Mc; r += (blockDim.x >> 5)) {
+            const unsigned* src = adj + (size_t)r * W; unsigned* dst = vs_rows + (size_t)r * Wn;
+            for (int w = threadIdx.x & 31; w < Wn; w += 32) dst[w] = src[w];
+        }
     }
-    __syncwarp();
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    const unsigned* rows = in_smem ? vs_rows : adj;
+    const int stride = in_smem ? Wn : W;
+    constexpr int WPL = 4;                      // up to 128 words = 4096 points
+    unsigned cov[WPL];
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) {
+        const int w = lane + 32 * k;
+        unsigned c = 0xffffffffu;               // words beyond Mc count as covered
+        if (w < Wn) { const int rem = Mc - w * 32; c = (rem >= 32) ? 0u : ~((1u << rem) - 1u); }
+        cov[k] = c;
+    }
     int V = 0;
     while (true) {
         int cand = 0x7fffffff;
-        for (int w = lane; w < Wn; w += 32) { const unsigned u = ~cov[w]; if (u) { cand = min(cand, w * 32 + __ffs(u) - 1); break; } }
+#pragma unroll
+        for (int k = WPL - 1; k >= 0; --k) { const unsigned u = ~cov[k]; if (u) cand = (lane + 32 * k) * 32 + __ffs(u) - 1; }
         const int seed = __reduce_min_sync(FULL, cand);
         if (seed == 0x7fffffff) break;
         if (lane == 0) seeds[V] = seed;
         ++V;
-        for (int w = lane; w < Wn; w += 32) cov[w] |= adj[(size_t)seed * W + w];
-        __syncwarp();
+        const unsigned* row = rows + (size_t)seed * stride;
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) { const int w = lane + 32 * k; if (w < Wn) cov[k] |= row[w]; }
     }
     if (lane == 0) st->V = V;
 }
-// corresp[idx] = vertex with the smallest d2 among those covering idx, first wins ties (rosa.cpp:490-496)
-__global__ void k_vs_corresp(const FrameState* __restrict__ st, const float4* __restrict__ pcloud, const int* __restrict__ seeds,
-                             int* __restrict__ corresp) {
+// corresp[idx] = vertex with the smallest d2 among those covering idx, first wins ties (rosa.cpp:490-496);
+// seed coordinates are staged in shared memory tile by tile
+__global__ void __launch_bounds__(128) k_vs_corresp(const FrameState* __restrict__ st, const float4* __restrict__ pcloud, const int* __restrict__ seeds,
+                                                    int* __restrict__ corresp) {
+    __shared__ float4 sseed[512];
+    __shared__ int sidx[512];
     if (st->status != 0) return;
+    const int Mc = st->Mc, V = st->V;
+    if ((int)(blockIdx.x * blockDim.x) >= Mc) return;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= st->Mc) return;
     const float R = st->leaf_size; const float R2 = R * R;
-    const f3 q = ld3(pcloud, idx);
-    const int V = st->V;
+    const f3 q = idx < Mc ? ld3(pcloud, idx) : f3{0.f, 0.f, 0.f};
     float mind2 = __int_as_float(0x7f800000); int best = -1;
-    for (int v = 0; v < V; ++v) {
-        const int s = seeds[v];
-        const float d2 = (s == idx) ? 0.0f : dist2(ld3(pcloud, s), q);
-        if ((s == idx || d2 < R2) && d2 < mind2) { mind2 = d2; best = v; }
+    for (int v0 = 0; v0 < V; v0 += 512) {
+        const int nv = min(512, V - v0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < nv; t += blockDim.x) { const int s = seeds[v0 + t]; sidx[t] = s; sseed[t] = pcloud[s]; }
+        __syncthreads();
+        if (idx < Mc) {
+            for (int t = 0; t < nv; ++t) {
+                const int s = sidx[t];
+                const float4 c = sseed[t];
+                const float d2 = (s == idx) ? 0.0f : dist2(f3{c.x, c.y, c.z}, q);
+                if ((s == idx || d2 < R2) && d2 < mind2) { mind2 = d2; best = v0 + t; }
+            }
+        }
     }
-    corresp[idx] = best;
+    if (idx < Mc) corresp[idx] = best;
 }
-// recentering (rosa.cpp:506-530): sums over pts_ in ascending point index
-__global__ void k_vs_recenter(FrameState* st, const float4* __restrict__ pts, const float4* __restrict__ pset, const int* __restrict__ seeds,
-                              const int* __restrict__ corresp, float alpha, float4* __restrict__ skel, float4* __restrict__ skel_sampled) {
+// recentering (rosa.cpp:506-530): one warp per vertex; the sum over pts_ stays in ascending point index
+// (lanes load 32 consecutive candidates, the matches are added in bit order)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_vs_recenter(FrameState* st, const float4* __restrict__ pts, const float4* __restrict__ pset, const int* __restrict__ seeds,
+              const int* __restrict__ corresp, float alpha, float4* __restrict__ skel, float4* __restrict__ skel_sampled) {
     if (st->status != 0) return;
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (v >= st->V) return;
     const int Mc = st->Mc;
     f3 sum{0.0f, 0.0f, 0.0f}; int cnt = 0;
-    for (int i = 0; i < Mc; ++i) if (corresp[i] == v) { sum = add3(sum, ld3(pts, i)); ++cnt; }
+    for (int i0 = 0; i0 < Mc; i0 += 32) {
+        const int i = i0 + lane;
+        bool hit = false; float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < Mc) { hit = (corresp[i] == v); if (hit) p = pts[i]; }
+        unsigned m = __ballot_sync(FULL, hit);
+        cnt += __popc(m);
+        while (m) {
+            const int b = __ffs(m) - 1; m &= m - 1;
+            sum.x += __shfl_sync(FULL, p.x, b); sum.y += __shfl_sync(FULL, p.y, b); sum.z += __shfl_sync(FULL, p.z, b);
+        }
+    }
+    if (lane != 0) return;
     f3 cur = ld3(pset, seeds[v]);                        // rosa.cpp:475 (uncompacted pset, compacted index)
     if (cnt > 0) {
         const f3 ec = div3(sum, (float)cnt);
@@ -502,7 +626,12 @@ __global__ void k_vertex_smooth(FrameState* st, float4* skel, float4* skel2, flo
 // ------------------------------------------------------------------------------------------
 void drosa_set_attributes();
 void launch_drosa(osep_rosa_impl* h, int sms);
-void mscale_set_attributes(int Mcap) { (void)Mcap; drosa_set_attributes(); }
+void mscale_set_attributes(int Mcap) {
+    (void)Mcap;
+    drosa_set_attributes();
+    cudaFuncSetAttribute(k_dcrosa_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, DC_SMEM_BUDGET);
+    cudaFuncSetAttribute(k_vs_greedy, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM_BUDGET);
+}
 
 void launch_mscale(osep_rosa_impl* h) {
     RosaDev& d = h->d;
@@ -525,17 +654,21 @@ void launch_mscale(osep_rosa_impl* h) {
     if (h->debug) cudaMemcpyAsync(d.centers, d.pset, sizeof(float4) * d.Mcap, cudaMemcpyDeviceToDevice, s);   // tap: pset after drosa
     stage_mark(h, SM_POSITION);
     // R20
-    for (int it = 0; it < c.niter_dcrosa; ++it) {
-        k_dcrosa_mean<<<tblocks, 128, 0, s>>>(d.st, d.pset, d.pset2, d.simi_off, d.simi_idx);
-        k_dcrosa_line<<<tblocks, 128, 0, s>>>(d.st, d.pset2, d.pset, d.simi_off, d.simi_idx);
+    if ((size_t)32 * d.Mcap <= (size_t)DC_SMEM_BUDGET) {
+        k_dcrosa_cluster<<<DC_CLUSTER, DC_THREADS, (size_t)32 * d.Mcap, s>>>(d.st, d.pset, d.simi_off, d.simi_idx, c.niter_dcrosa);
+    } else {
+        for (int it = 0; it < c.niter_dcrosa; ++it) {
+            k_dcrosa_mean<<<tblocks, 128, 0, s>>>(d.st, d.pset, d.pset2, d.simi_off, d.simi_idx);
+            k_dcrosa_line<<<tblocks, 128, 0, s>>>(d.st, d.pset2, d.pset, d.simi_off, d.simi_idx);
+        }
     }
     stage_mark(h, SM_DCROSA);
     // R21
     k_vs_compact<<<1, 1024, 0, s>>>(d.st, d.pset, d.pcloud, d.good_rank);
     k_vs_adj<<<warp_blocks, tb, 0, s>>>(d.st, d.pcloud, d.adj_bits, d.W);
-    k_vs_greedy<<<1, 32, sizeof(unsigned) * d.W, s>>>(d.st, d.adj_bits, d.W, d.seeds);
+    k_vs_greedy<<<1, 256, VS_SMEM_BUDGET, s>>>(d.st, d.adj_bits, d.W, d.seeds);
     k_vs_corresp<<<tblocks, 128, 0, s>>>(d.st, d.pcloud, d.seeds, d.corresp);
-    k_vs_recenter<<<tblocks, 128, 0, s>>>(d.st, d.pts, d.pset, d.seeds, d.corresp, c.alpha_recenter, d.skel, d.skel_sampled);
+    k_vs_recenter<<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.pset, d.seeds, d.corresp, c.alpha_recenter, d.skel, d.skel_sampled);
     stage_mark(h, SM_VSAMPLE);
     // R22
     k_vertex_smooth<<<1, 1024, 0, s>>>(d.st, d.skel, d.skel2, d.vtmp, d.vs_off, d.vs_idx, d.rv1, (float*)d.rk1, d.Scap,
