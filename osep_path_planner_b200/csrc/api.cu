@@ -44,7 +44,7 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
     { unsigned* g3; CK(dalloc(&g3, 3 * T)); d.gtab = (unsigned long long*)g3; d.g_cnt = (int*)(g3 + T); d.g_fill = (int*)(g3 + 2 * T); }
     CK(dalloc(&d.g_start, T)); CK(dalloc(&d.units, N + N / 8 + 8)); CK(dalloc(&d.slow_list, N)); CK(dalloc(&d.over_list, N + N / 8 + 8)); CK(dalloc(&d.knn_full, N * (size_t)d.knn)); CK(dalloc(&d.p_slot, N)); CK(dalloc(&d.Pc, N)); CK(dalloc(&d.Nrm, N));
     CK(dalloc(&d.vtab, T)); CK(cudaMemset(d.vtab, 0, T * sizeof(unsigned long long)));
-    CK(dalloc(&d.vkeys, M)); CK(dalloc(&d.vid, N)); CK(dalloc(&d.vox_cnt, M + 2));
+    CK(dalloc(&d.vkeys, M)); CK(dalloc(&d.vid, N)); CK(dalloc(&d.vox_cnt, M + 2)); CK(dalloc(&d.vox_fill, M + 2));
     CK(dalloc(&d.rk0, tmpcap)); CK(dalloc(&d.rk1, tmpcap)); CK(dalloc(&d.rv0, tmpcap)); CK(dalloc(&d.rv1, tmpcap));
     CK(dalloc(&d.rhist, (size_t)256 * d.nchunks + 1024));
     CK(dalloc(&d.pts, M)); CK(dalloc(&d.nrms, M)); CK(dalloc(&d.pset, M)); CK(dalloc(&d.pset2, M)); CK(dalloc(&d.vset, M)); CK(dalloc(&d.vnew, M));
@@ -72,7 +72,7 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
 static void rosa_free(osep_rosa_impl* h) {
     RosaDev& d = h->d;
     void* ptrs[] = {d.st, d.in, d.P, d.filt_idx, d.blk_cnt, d.gtab, d.g_start, d.units, d.slow_list, d.over_list, d.p_slot, d.Pc, d.Nrm, d.knn_full, d.vtab, d.vkeys, d.vid,
-                    d.vox_cnt, d.rk0, d.rk1, d.rv0, d.rv1, d.rhist, d.pts, d.nrms, d.pset, d.pset2, d.vset, d.vnew, d.vvar, d.surf,
+                    d.vox_cnt, d.vox_fill, d.rk0, d.rk1, d.rv0, d.rv1, d.rhist, d.pts, d.nrms, d.pset, d.pset2, d.vset, d.vnew, d.vvar, d.surf,
                     d.simi_off, d.simi_idx, d.simi_bits, d.nraw, d.vnd, d.vset_it, d.vnew_it, d.fused_flags, d.fused_dbg, d.level, d.level_off, d.level_pts, d.rev_off, d.rev_idx, d.need0, d.good, d.centers, d.good_rank, d.poor_idx, d.active_size,
                     d.pcloud, d.adj_bits, d.seeds, d.corresp, d.skel, d.skel2, d.skel_sampled, d.vtmp, d.vs_off, d.vs_idx, d.vset_iters};
     for (void* p : ptrs) if (p) cudaFree(p);

@@ -769,26 +769,71 @@ __global__ void k_radix_scatter(const unsigned* __restrict__ keys, const int* __
     }
 }
 
+// group the point indices by voxel: slot = vox_off[v] + atomic cursor (order inside a voxel is fixed later)
+__global__ void k_vox_scatter(const FrameState* __restrict__ st, const unsigned* __restrict__ vid, const int* __restrict__ vox_off,
+                              int* fill, int* __restrict__ grouped) {
+    if (st->status != 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st->n_filt) return;
+    const int v = (int)vid[i];
+    grouped[vox_off[v] + atomicAdd(&fill[v], 1)] = i;
+}
+
 // per-voxel centroid (pcl::CentroidPoint<PointNormal>), then R10 + R11 fused.
-// One CTA per voxel: all threads stage the voxel's points + normals into shared memory (many gathers in
-// flight), then ONE thread adds them in ascending point index -- the float sums stay strictly sequential
-// (canonical order C3), only the memory latency is parallelised.  Voxels hold ~100 points (max > 1000).
-constexpr int VOX_CHUNK = 512;
+// One CTA per voxel: (1) the voxel's point indices are sorted ascending in shared memory (bitonic; lists
+// longer than VOX_SORT are rank-sorted through global memory) -- this restores the canonical order C3 that a
+// stable sort of (key, index) would give; (2) all threads stage points + normals in that order (many gathers
+// in flight); (3) ONE thread adds them, so the float sums stay strictly sequential in ascending point index.
+constexpr int VOX_SORT = 2048;
+constexpr int VOX_CHUNK = 256;
 __global__ void __launch_bounds__(128)
-k_vox_reduce(FrameState* st, const int* __restrict__ sorted_idx, const int* __restrict__ vox_off,
+k_vox_reduce(FrameState* st, int* grouped, int* __restrict__ scratch, const int* __restrict__ vox_off,
              const float4* __restrict__ P, const float4* __restrict__ Nrm,
              float4* __restrict__ pts, float4* __restrict__ nrms, float4* __restrict__ pset, float4* __restrict__ vset) {
+    __shared__ int sidx[VOX_SORT];
     __shared__ float4 sp[VOX_CHUNK];
     __shared__ float4 sn[VOX_CHUNK];
     if (st->status != 0) return;
     const int M = st->M;
     for (int v = blockIdx.x; v < M; v += gridDim.x) {
         const int b = vox_off[v], e = vox_off[v + 1];
-        float sx = 0, sy = 0, sz = 0, n0 = 0, n1 = 0, n2 = 0, n3 = 0;
-        for (int c0 = b; c0 < e; c0 += VOX_CHUNK) {
-            const int cn = min(VOX_CHUNK, e - c0);
+        const int cnt = e - b;
+        const int* order;
+        __syncthreads();
+        if (cnt <= VOX_SORT) {
+            int P2 = 1; while (P2 < cnt) P2 <<= 1;
+            for (int t = threadIdx.x; t < P2; t += blockDim.x) sidx[t] = (t < cnt) ? grouped[b + t] : 0x7fffffff;
             __syncthreads();
-            for (int t = threadIdx.x; t < cn; t += blockDim.x) { const int i = sorted_idx[c0 + t]; sp[t] = P[i]; sn[t] = Nrm[i]; }
+            for (int k = 2; k <= P2; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int i = threadIdx.x; i < P2; i += blockDim.x) {
+                        const int ixj = i ^ j;
+                        if (ixj > i) {
+                            const int x = sidx[i], y = sidx[ixj];
+                            const bool up = ((i & k) == 0);
+                            if ((x > y) == up) { sidx[i] = y; sidx[ixj] = x; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            order = sidx;
+        } else {
+            // rank sort (indices are distinct): O(cnt^2), only for voxels with more than VOX_SORT points
+            for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
+                const int x = grouped[b + t];
+                int rank = 0;
+                for (int f = 0; f < cnt; ++f) rank += (grouped[b + f] < x) ? 1 : 0;
+                scratch[b + rank] = x;
+            }
+            __syncthreads();
+            order = scratch + b;
+        }
+        float sx = 0, sy = 0, sz = 0, n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+        for (int c0 = 0; c0 < cnt; c0 += VOX_CHUNK) {
+            const int cn = min(VOX_CHUNK, cnt - c0);
+            __syncthreads();
+            for (int t = threadIdx.x; t < cn; t += blockDim.x) { const int i = order[c0 + t]; sp[t] = P[i]; sn[t] = Nrm[i]; }
             __syncthreads();
             if (threadIdx.x == 0) {
                 for (int t = 0; t < cn; ++t) {
@@ -799,8 +844,8 @@ k_vox_reduce(FrameState* st, const int* __restrict__ sorted_idx, const int* __re
             }
         }
         if (threadIdx.x != 0) continue;
-        const float cnt = (float)(e - b);
-        const float px = sx / cnt, py = sy / cnt, pz = sz / cnt;
+        const float cntf = (float)cnt;
+        const float px = sx / cntf, py = sy / cntf, pz = sz / cntf;
         // AccumulatorNormal::get: Vector4f::normalized(); squaredNorm is packet-reduced (a0+a2)+(a1+a3)
         const float zz = (n0 * n0 + n2 * n2) + (n1 * n1 + n3 * n3);
         f3 nv{n0, n1, n2};
@@ -879,20 +924,12 @@ void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int strid
     k_vox_sortkeys<<<1, 1024, sizeof(unsigned) * P2, s>>>(d.st, d.vkeys, d.Mcap, d.vox_cnt);
     k_vox_assign<<<nb, NT, 0, s>>>(d.P, d.st, d.vkeys, d.rk0, d.rv0, d.vox_cnt);
     k_scan_counts<<<1, 1024, 0, s>>>(d.st, d.vox_cnt, 0);
-    const int nch = div_up(n, RADIX_CH);
-    const int rb = div_up(nch, RADIX_WARPS);
-    int passes = 1; { int bits = 0; while ((1 << bits) < d.Mcap) ++bits; passes = div_up(bits, 8); if (passes < 1) passes = 1; if (passes & 1) ++passes; }
-    unsigned* ka = d.rk0; unsigned* kb = d.rk1; int* va = d.rv0; int* vb = d.rv1;
-    for (int p = 0; p < passes; ++p) {
-        k_radix_hist<<<rb, RADIX_WARPS * 32, 0, s>>>(ka, d.st, p * 8, d.rhist, nch);
-        k_radix_scan<<<1, 1024, 0, s>>>(d.st, d.rhist, 256 * nch);
-        k_radix_scatter<<<rb, RADIX_WARPS * 32, 0, s>>>(ka, va, d.st, p * 8, d.rhist, nch, kb, vb);
-        std::swap(ka, kb); std::swap(va, vb);
-    }
-    // even number of passes: sorted data is back in rk0 / rv0
-    k_vox_reduce<<<1024, 128, 0, s>>>(d.st, va, d.vox_cnt, d.P, d.Nrm, d.pts, d.nrms, d.pset, d.vset);
+    // group by voxel with atomics, then fix the order inside every voxel in the reduce kernel (no global sort)
+    cudaMemsetAsync(d.vox_fill, 0, sizeof(int) * (d.Mcap + 2), s);
+    k_vox_scatter<<<nb, NT, 0, s>>>(d.st, d.rk0, d.vox_cnt, d.vox_fill, d.rv0);
+    k_vox_reduce<<<1024, 128, 0, s>>>(d.st, d.rv0, d.rv1, d.vox_cnt, d.P, d.Nrm, d.pts, d.nrms, d.pset, d.vset);
     stage_mark(h, SM_VOXEL);
-    h->n_launches += 1 + 3 + (2 * LEAF_MAX_ITERS + 1) + 4 + 4 + 4 + 3 * passes + 1;
+    h->n_launches += 1 + 3 + (2 * LEAF_MAX_ITERS + 1) + 4 + 4 + 4 + 2;
 }
 
 }  // namespace osep

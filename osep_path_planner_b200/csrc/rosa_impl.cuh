@@ -32,7 +32,7 @@ struct RosaDev {
     unsigned long long* vtab = nullptr;  // voxel set: (epoch<<32 | voxel key)
     unsigned* vkeys = nullptr;         // distinct voxel keys, sorted
     int* vid = nullptr;                // voxel id per filtered point
-    int* vox_cnt = nullptr; int* vox_off = nullptr;
+    int* vox_cnt = nullptr; int* vox_off = nullptr; int* vox_fill = nullptr;
     unsigned* rk0 = nullptr; unsigned* rk1 = nullptr; int* rv0 = nullptr; int* rv1 = nullptr;
     int* rhist = nullptr;
     // M-scale
