@@ -262,12 +262,7 @@ k_drosa_seed(FrameState* st, const float4* __restrict__ pts, const float4* __res
     if (small_in) {
         for (int i = threadIdx.x; i < M; i += blockDim.x) { s_pts[i] = pts[i]; s_nraw[i] = nraw[i]; s_vnd[i] = vnd[i]; }
     }
-    if (mat_in) {
-        for (int r = threadIdx.x >> 5; r < M; r += (blockDim.x >> 5)) {
-            const unsigned* src = bits + (size_t)r * W; unsigned* dst = s_bits + (size_t)r * Wn;
-            for (int w = threadIdx.x & 31; w < Wn; w += 32) dst[w] = src[w];
-        }
-    }
+    if (mat_in) stage_bit_rows(s_bits, bits, M, Wn, W);
     __syncthreads();
     SeedCtx c;
     c.pts = small_in ? s_pts : pts; c.nraw = small_in ? s_nraw : nraw; c.vnd = small_in ? s_vnd : vnd;
@@ -483,12 +478,7 @@ __device__ __forceinline__ void fused_worker(const FusedArgs& a, uint4* smem, in
     float4* s_nraw = s_pts + M; float4* s_vnd = s_nraw + M;
     unsigned* s_bits = reinterpret_cast<unsigned*>(s_vnd + M);
     if (small_in) for (int i = threadIdx.x; i < M; i += blockDim.x) { s_pts[i] = a.pts[i]; s_nraw[i] = a.nraw[i]; s_vnd[i] = a.vnd[i]; }
-    if (mat_in) {
-        for (int r = threadIdx.x >> 5; r < M; r += (blockDim.x >> 5)) {
-            const unsigned* src = a.bits + (size_t)r * a.W; unsigned* dst = s_bits + (size_t)r * Wn;
-            for (int w = threadIdx.x & 31; w < Wn; w += 32) dst[w] = src[w];
-        }
-    }
+    if (mat_in) stage_bit_rows(s_bits, a.bits, M, Wn, a.W);
     __syncthreads();
     SeedCtx c;
     c.pts = small_in ? s_pts : a.pts; c.nraw = small_in ? s_nraw : a.nraw; c.vnd = small_in ? s_vnd : a.vnd;

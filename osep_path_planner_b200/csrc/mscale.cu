@@ -439,18 +439,13 @@ __global__ void k_vs_adj(const FrameState* __restrict__ st, const float4* __rest
 // rosa.cpp:462-502).  The cover bit matrix is staged in shared memory by the whole block; warp 0 then walks:
 // each lane keeps its words of the covered set in registers, a step = ffs + warp min + one row OR.
 constexpr int VS_SMEM_BUDGET = 200 * 1024;
-__global__ void __launch_bounds__(256) k_vs_greedy(FrameState* st, const unsigned* __restrict__ adj, int W, int* __restrict__ seeds) {
+__global__ void __launch_bounds__(1024) k_vs_greedy(FrameState* st, const unsigned* __restrict__ adj, int W, int* __restrict__ seeds) {
     extern __shared__ unsigned vs_rows[];
     if (st->status != 0) return;
     const int Mc = st->Mc;
     const int Wn = (Mc + 31) >> 5;
     const bool in_smem = (size_t)4 * Mc * Wn <= (size_t)VS_SMEM_BUDGET;
-    if (in_smem) {
-        for (int r = threadIdx.x >> 5; r < Mc; r += (blockDim.x >> 5)) {
-            const unsigned* src = adj + (size_t)r * W; unsigned* dst = vs_rows + (size_t)r * Wn;
-            for (int w = threadIdx.x & 31; w < Wn; w += 32) dst[w] = src[w];
-        }
-    }
+    if (in_smem) stage_bit_rows(vs_rows, adj, Mc, Wn, W);
     __syncthreads();
     if (threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
@@ -557,35 +552,56 @@ __global__ void k_vertex_smooth(FrameState* st, float4* skel, float4* skel2, flo
     for (int i = threadIdx.x; i < V; i += blockDim.x) { const float4 v = skel[i]; if (fin(v.x) && fin(v.y) && fin(v.z)) vtmp[vs_off[i]] = v; }
     __syncthreads();
     const float r2 = radius * radius;
-    // neighbour counts
-    for (int i = threadIdx.x; i < Vf; i += blockDim.x) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    // neighbour counts: one warp per vertex, ballots over 32 candidates at a time; `first` = smallest (d2, index)
+    for (int i = warp; i < Vf; i += nwarps) {
         const f3 q = ld3(vtmp, i);
         int c = 0; float bd = __int_as_float(0x7f800000); int bi = 0x7fffffff;
-        for (int j = 0; j < Vf; ++j) { const float d = dist2(q, ld3(vtmp, j)); if (d < r2) { ++c; if (nb_less(d, j, bd, bi)) { bd = d; bi = j; } } }
-        if (c == 0) c = 1; else if (bi != i) c += 1;
-        vs_off[i] = c;
+        for (int j0 = 0; j0 < Vf; j0 += 32) {
+            const int j = j0 + lane;
+            float d = 0.0f; bool in = false;
+            if (j < Vf) { d = dist2(q, ld3(vtmp, j)); in = d < r2; }
+            c += __popc(__ballot_sync(FULL, in));
+            if (in && nb_less(d, j, bd, bi)) { bd = d; bi = j; }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const float od = __shfl_xor_sync(FULL, bd, off); const int oi = __shfl_xor_sync(FULL, bi, off);
+            if (nb_less(od, oi, bd, bi)) { bd = od; bi = oi; }
+        }
+        if (c == 0) c = 1; else if (bi != i) c += 1;      // self forced first (rosa.cpp:567-573)
+        if (lane == 0) vs_off[i] = c;
     }
     if (threadIdx.x == 0) vs_off[Vf] = 0;
     __syncthreads();
     const int total = block_scan_inplace(vs_off, Vf + 1);
     __syncthreads();
     if (total > cap) { if (threadIdx.x == 0) st->status = OSEP_ERR_CAPACITY; return; }
-    for (int i = threadIdx.x; i < Vf; i += blockDim.x) {
+    for (int i = warp; i < Vf; i += nwarps) {
         const f3 q = ld3(vtmp, i);
         const int b = vs_off[i];
         int c = 0;
-        for (int j = 0; j < Vf; ++j) { const float d = dist2(q, ld3(vtmp, j)); if (d < r2) { tmp_j[b + c] = j; tmp_d[b + c] = d; ++c; } }
-        if (c == 0) { vs_idx[b] = i; continue; }
-        // rank sort; if the first sorted entry is not i, i is inserted in front (rosa.cpp:567-569)
-        int first = -1;
-        for (int e = 0; e < c; ++e) {
+        for (int j0 = 0; j0 < Vf; j0 += 32) {
+            const int j = j0 + lane;
+            float d = 0.0f; bool in = false;
+            if (j < Vf) { d = dist2(q, ld3(vtmp, j)); in = d < r2; }
+            const unsigned m = __ballot_sync(FULL, in);
+            if (in) { const int pos = b + c + __popc(m & ((1u << lane) - 1u)); tmp_j[pos] = j; tmp_d[pos] = d; }
+            c += __popc(m);
+        }
+        __syncwarp();
+        if (c == 0) { if (lane == 0) vs_idx[b] = i; continue; }
+        // rank sort by (d2, index); if the first sorted entry is not i, i is inserted in front (rosa.cpp:567-569)
+        int myfirst = 0x7fffffff;
+        for (int e = lane; e < c; e += 32) {
             int rank = 0;
             for (int f = 0; f < c; ++f) rank += nb_less(tmp_d[b + f], tmp_j[b + f], tmp_d[b + e], tmp_j[b + e]) ? 1 : 0;
-            if (rank == 0) first = tmp_j[b + e];
+            if (rank == 0) myfirst = tmp_j[b + e];
         }
+        const int first = __reduce_min_sync(FULL, myfirst);
         const int shift = (first != i) ? 1 : 0;
-        if (shift) vs_idx[b] = i;
-        for (int e = 0; e < c; ++e) {
+        if (shift && lane == 0) vs_idx[b] = i;
+        for (int e = lane; e < c; e += 32) {
             int rank = 0;
             for (int f = 0; f < c; ++f) rank += nb_less(tmp_d[b + f], tmp_j[b + f], tmp_d[b + e], tmp_j[b + e]) ? 1 : 0;
             vs_idx[b + shift + rank] = tmp_j[b + e];
@@ -666,7 +682,7 @@ void launch_mscale(osep_rosa_impl* h) {
     // R21
     k_vs_compact<<<1, 1024, 0, s>>>(d.st, d.pset, d.pcloud, d.good_rank);
     k_vs_adj<<<warp_blocks, tb, 0, s>>>(d.st, d.pcloud, d.adj_bits, d.W);
-    k_vs_greedy<<<1, 256, VS_SMEM_BUDGET, s>>>(d.st, d.adj_bits, d.W, d.seeds);
+    k_vs_greedy<<<1, 1024, VS_SMEM_BUDGET, s>>>(d.st, d.adj_bits, d.W, d.seeds);
     k_vs_corresp<<<tblocks, 128, 0, s>>>(d.st, d.pcloud, d.seeds, d.corresp);
     k_vs_recenter<<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.pset, d.seeds, d.corresp, c.alpha_recenter, d.skel, d.skel_sampled);
     stage_mark(h, SM_VSAMPLE);

@@ -141,8 +141,7 @@ __global__ void k_filter_scatter(const float* __restrict__ in, int n, int stride
 // R7 + R8: the leaf-size control law, one thread, no host round trip.
 // step p = 0..8: consume the voxel count of pass p-1 exactly as the body of the loop at
 // rosa.cpp:125-146 does, then (p < 8, not finished) set up pass p.
-__global__ void k_leaf_step(FrameState* st, int p, int max_points) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ void leaf_step(FrameState* st, int p, int max_points) {
     if (st->status != 0) return;
     const float tol = 0.05f, leaf_min = 1e-4f, leaf_max = 1e4f;
     if (p == 0) {
@@ -206,6 +205,11 @@ __global__ void k_leaf_step(FrameState* st, int p, int max_points) {
     }
 }
 
+__global__ void k_leaf_step(FrameState* st, int p, int max_points) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    leaf_step(st, p, max_points);
+}
+
 // voxel key of PCL VoxelGrid::applyFilter step 5
 __device__ __forceinline__ unsigned voxel_key(const float4& p, float inv, int mb0, int mb1, int mb2, int db0, int db1) {
     const int i0 = (int)(floorf(p.x * inv) - (float)mb0);
@@ -232,17 +236,26 @@ __device__ __forceinline__ bool vset_insert(unsigned long long* tab, unsigned ma
 }
 
 // count-only VoxelGrid pass: number of distinct voxel keys at the current leaf
-__global__ void k_vox_count(const float4* __restrict__ P, FrameState* st, unsigned long long* vtab, unsigned mask) {
-    if (st->status != 0 || !st->cnt0 || st->pass_overflow) return;
-    const int n = st->n_filt;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool isnew = false;
-    if (i < n) {
-        const unsigned key = voxel_key(P[i], st->inv_leaf, st->minb[0], st->minb[1], st->minb[2], st->divb[0], st->divb[1]);
-        isnew = vset_insert(vtab, mask, st->epoch, key);
+__global__ void k_vox_count(const float4* __restrict__ P, FrameState* st, unsigned long long* vtab, unsigned mask, int next_step, int max_points) {
+    if (st->status != 0) return;
+    if (st->cnt0 && !st->pass_overflow) {
+        const int n = st->n_filt;
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        bool isnew = false;
+        if (i < n) {
+            const unsigned key = voxel_key(P[i], st->inv_leaf, st->minb[0], st->minb[1], st->minb[2], st->divb[0], st->divb[1]);
+            isnew = vset_insert(vtab, mask, st->epoch, key);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, isnew);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&st->nvox, __popc(m));
     }
-    const unsigned m = __ballot_sync(0xffffffffu, isnew);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&st->nvox, __popc(m));
+    // the last block to finish runs the control law for the next pass (rosa.cpp:130-146): no extra launch
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1) == (int)gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) { st->ticket = 0; __threadfence(); leaf_step(st, next_step, max_points); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -898,11 +911,9 @@ void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int strid
     k_filter_scatter<<<nb, NT, 0, s>>>(xyz_dev, n, stride, r2, d.blk_cnt, d.P, d.filt_idx, d.st);
     stage_mark(h, SM_FILTER);
     // R7/R8: device-resident leaf loop (count-only passes)
-    for (int p = 0; p < LEAF_MAX_ITERS; ++p) {
-        k_leaf_step<<<1, 1, 0, s>>>(d.st, p, c.max_points);
-        k_vox_count<<<nb, NT, 0, s>>>(d.P, d.st, d.vtab, (unsigned)(d.T - 1));
-    }
-    k_leaf_step<<<1, 1, 0, s>>>(d.st, LEAF_MAX_ITERS, c.max_points);
+    k_leaf_step<<<1, 1, 0, s>>>(d.st, 0, c.max_points);
+    for (int p = 0; p < LEAF_MAX_ITERS; ++p)
+        k_vox_count<<<nb, NT, 0, s>>>(d.P, d.st, d.vtab, (unsigned)(d.T - 1), p + 1, c.max_points);
     stage_mark(h, SM_LEAF);
     // R5: grid + kNN normals
     cudaMemsetAsync(d.gtab, 0, sizeof(unsigned) * 3 * (size_t)d.T, s);   // gtab | g_cnt | g_fill are contiguous
@@ -929,7 +940,7 @@ void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int strid
     k_vox_scatter<<<nb, NT, 0, s>>>(d.st, d.rk0, d.vox_cnt, d.vox_fill, d.rv0);
     k_vox_reduce<<<1024, 128, 0, s>>>(d.st, d.rv0, d.rv1, d.vox_cnt, d.P, d.Nrm, d.pts, d.nrms, d.pset, d.vset);
     stage_mark(h, SM_VOXEL);
-    h->n_launches += 1 + 3 + (2 * LEAF_MAX_ITERS + 1) + 4 + 4 + 4 + 2;
+    h->n_launches += 1 + 3 + (LEAF_MAX_ITERS + 1) + 4 + 4 + 4 + 2;
 }
 
 }  // namespace osep

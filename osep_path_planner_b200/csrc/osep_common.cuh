@@ -54,6 +54,7 @@ struct FrameState {
     int n_good, n_poor;
     // ---- scratch counters
     int cnt0, cnt1;
+    int ticket;            // last-block detection
 };
 
 // ordered-int encoding of a float: monotone map so atomicMin/atomicMax(int) order floats
@@ -62,6 +63,14 @@ __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ unsigned hash_u32(unsigned k) { k *= 2654435761u; k ^= k >> 15; k *= 2246822519u; k ^= k >> 13; return k; }
+
+// stage `rows` bit rows (Wn words each, row stride W in the source) into a dense destination; flat index so
+// that every thread has many independent loads in flight
+__device__ __forceinline__ void stage_bit_rows(unsigned* __restrict__ dst, const unsigned* __restrict__ src, int rows, int Wn, int W) {
+    const int total = rows * Wn;
+#pragma unroll 8
+    for (int i = threadIdx.x; i < total; i += blockDim.x) { const int r = i / Wn; dst[i] = src[(size_t)r * W + (i - r * Wn)]; }
+}
 
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
