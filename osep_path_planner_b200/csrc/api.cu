@@ -34,7 +34,6 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
     d.W = d.Mcap / 32;
     d.Scap = d.Mcap * 128;
     d.T = 1; while (d.T < 2 * d.Ncap) d.T <<= 1;
-    d.nchunks = div_up(d.Ncap, 2048);
     d.knn = c.ne_knn; d.nbk = c.nb_knn;
     const size_t N = d.Ncap, M = d.Mcap, T = d.T;
     const size_t tmpcap = std::max<size_t>(N, d.Scap);
@@ -46,7 +45,6 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
     CK(dalloc(&d.vtab, T)); CK(cudaMemset(d.vtab, 0, T * sizeof(unsigned long long)));
     CK(dalloc(&d.vkeys, M)); CK(dalloc(&d.vid, N)); CK(dalloc(&d.vox_cnt, M + 2)); CK(dalloc(&d.vox_fill, M + 2));
     CK(dalloc(&d.rk0, tmpcap)); CK(dalloc(&d.rk1, tmpcap)); CK(dalloc(&d.rv0, tmpcap)); CK(dalloc(&d.rv1, tmpcap));
-    CK(dalloc(&d.rhist, (size_t)256 * d.nchunks + 1024));
     CK(dalloc(&d.pts, M)); CK(dalloc(&d.nrms, M)); CK(dalloc(&d.pset, M)); CK(dalloc(&d.pset2, M)); CK(dalloc(&d.vset, M)); CK(dalloc(&d.vnew, M));
     CK(dalloc(&d.vvar, M)); CK(dalloc(&d.simi_bits, M * (size_t)d.W)); CK(dalloc(&d.nraw, M)); CK(dalloc(&d.vnd, M));
     CK(dalloc(&d.vset_it, M * 9)); CK(dalloc(&d.vnew_it, M * 8)); CK(dalloc(&d.fused_flags, M * 16 + 16)); CK(dalloc(&d.fused_dbg, 64)); CK(cudaMemset(d.fused_dbg, 0, 64 * 8));
@@ -72,7 +70,7 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
 static void rosa_free(osep_rosa_impl* h) {
     RosaDev& d = h->d;
     void* ptrs[] = {d.st, d.in, d.P, d.filt_idx, d.blk_cnt, d.gtab, d.g_start, d.units, d.slow_list, d.over_list, d.p_slot, d.Pc, d.Nrm, d.knn_full, d.vtab, d.vkeys, d.vid,
-                    d.vox_cnt, d.vox_fill, d.rk0, d.rk1, d.rv0, d.rv1, d.rhist, d.pts, d.nrms, d.pset, d.pset2, d.vset, d.vnew, d.vvar, d.surf,
+                    d.vox_cnt, d.vox_fill, d.rk0, d.rk1, d.rv0, d.rv1, d.pts, d.nrms, d.pset, d.pset2, d.vset, d.vnew, d.vvar, d.surf,
                     d.simi_off, d.simi_idx, d.simi_bits, d.nraw, d.vnd, d.vset_it, d.vnew_it, d.fused_flags, d.fused_dbg, d.level, d.level_off, d.level_pts, d.rev_off, d.rev_idx, d.need0, d.good, d.centers, d.good_rank, d.poor_idx, d.active_size,
                     d.pcloud, d.adj_bits, d.seeds, d.corresp, d.skel, d.skel2, d.skel_sampled, d.vtmp, d.vs_off, d.vs_idx, d.vset_iters};
     for (void* p : ptrs) if (p) cudaFree(p);

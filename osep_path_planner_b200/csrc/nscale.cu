@@ -15,14 +15,12 @@
 // HBM layout: filtered cloud P as float4 AoS {x,y,z,1} (pcl::PointXYZ's own 16-byte layout:
 // one coalesced 16 B load per point); the kNN copy Pc is the same points regrouped by grid
 // cell with the filtered index in .w; normals Nrm float4 {nx,ny,nz,0}.  All tables (2 hash
-// tables, radix histograms) are L2 resident at 100k points (< 10 MB of the 126 MB L2).
+// tables, voxel groups) are L2 resident at 100k points (< 10 MB of the 126 MB L2).
 #include "rosa_impl.cuh"
 
 namespace osep {
 
 constexpr int NT = 256;                 // threads per block for N-scale kernels
-constexpr int RADIX_CH = 2048;          // elements per warp-chunk in the stable radix sort
-constexpr int RADIX_WARPS = 4;          // warps per block in the radix kernels
 
 // ------------------------------------------------------------------------------------------
 // single-block exclusive scan (in place) over n ints; returns the total to every thread.
@@ -663,8 +661,8 @@ __global__ void __launch_bounds__(128) k_normals(const float4* __restrict__ P, c
 }
 
 // ------------------------------------------------------------------------------------------
-// R9 final pass: distinct voxel keys -> sorted -> dense voxel ids -> stable radix sort of
-// (voxel id, point index) -> per-voxel sums in ascending point index.
+// R9 final pass: distinct voxel keys -> sorted -> dense voxel ids -> points grouped by voxel (atomic
+// cursors) -> per-voxel index sort + sums in ascending point index (k_vox_reduce).
 __global__ void k_vox_collect(FrameState* st, const unsigned long long* __restrict__ vtab, int T, unsigned* __restrict__ vkeys, int Mcap) {
     if (st->status != 0) return;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -725,61 +723,6 @@ __global__ void k_vox_assign(const float4* __restrict__ P, const FrameState* __r
 __global__ void k_scan_counts(const FrameState* __restrict__ st, int* data, int which /*0: M+1 entries*/) {
     if (st->status != 0) return;
     block_excl_scan(data, st->M + 1);
-}
-
-// ---- stable LSD radix sort, 8-bit digits; one warp owns RADIX_CH consecutive elements
-__global__ void k_radix_hist(const unsigned* __restrict__ keys, const FrameState* __restrict__ st, int shift, int* __restrict__ hist, int nchunks) {
-    __shared__ int cnt[RADIX_WARPS][256];
-    if (st->status != 0) return;
-    const int n = st->n_filt;
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int chunk = blockIdx.x * RADIX_WARPS + wid;
-    for (int d = lane; d < 256; d += 32) cnt[wid][d] = 0;
-    __syncwarp();
-    const int base = chunk * RADIX_CH;
-    if (chunk < nchunks && base < n) {
-        for (int it = 0; it < RADIX_CH / 32; ++it) {
-            const int i = base + it * 32 + lane;
-            const bool valid = i < n;
-            const unsigned dg = valid ? ((keys[i] >> shift) & 255u) : 256u + lane;
-            const unsigned peers = __match_any_sync(0xffffffffu, dg);
-            if (valid && (int)lane == __ffs(peers) - 1) cnt[wid][dg] += __popc(peers);
-            __syncwarp();
-        }
-    }
-    __syncwarp();
-    if (chunk < nchunks) for (int d = lane; d < 256; d += 32) hist[d * nchunks + chunk] = cnt[wid][d];
-}
-__global__ void k_radix_scan(const FrameState* __restrict__ st, int* hist, int total) {
-    if (st->status != 0) return;
-    block_excl_scan(hist, total);
-}
-__global__ void k_radix_scatter(const unsigned* __restrict__ keys, const int* __restrict__ vals, const FrameState* __restrict__ st, int shift,
-                                const int* __restrict__ hist, int nchunks, unsigned* __restrict__ keys_out, int* __restrict__ vals_out) {
-    __shared__ int base_s[RADIX_WARPS][256];
-    if (st->status != 0) return;
-    const int n = st->n_filt;
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int chunk = blockIdx.x * RADIX_WARPS + wid;
-    if (chunk >= nchunks) return;
-    const int base = chunk * RADIX_CH;
-    if (base >= n) return;
-    for (int d = lane; d < 256; d += 32) base_s[wid][d] = hist[d * nchunks + chunk];
-    __syncwarp();
-    for (int it = 0; it < RADIX_CH / 32; ++it) {
-        const int i = base + it * 32 + lane;
-        const bool valid = i < n;
-        unsigned k = 0; int v = 0;
-        if (valid) { k = keys[i]; v = vals[i]; }
-        const unsigned dg = valid ? ((k >> shift) & 255u) : 256u + lane;
-        const unsigned peers = __match_any_sync(0xffffffffu, dg);
-        int pos = 0;
-        if (valid) pos = base_s[wid][dg] + __popc(peers & ((1u << lane) - 1u));
-        __syncwarp();
-        if (valid && (int)lane == __ffs(peers) - 1) base_s[wid][dg] += __popc(peers);
-        __syncwarp();
-        if (valid) { keys_out[pos] = k; vals_out[pos] = v; }
-    }
 }
 
 // group the point indices by voxel: slot = vox_off[v] + atomic cursor (order inside a voxel is fixed later)

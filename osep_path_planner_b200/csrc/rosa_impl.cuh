@@ -13,7 +13,6 @@ struct RosaDev {
     int Scap = 0;          // similarity CSR entries
     int T = 0;             // hash table slots (power of two >= 2*Ncap)
     int W = 0;             // bitmask words per row = Mcap/32
-    int nchunks = 0;       // radix chunks of RADIX_CH elements
     int knn = 0, nbk = 0;  // ne_knn, nb_knn
 
     FrameState* st = nullptr;
@@ -34,7 +33,6 @@ struct RosaDev {
     int* vid = nullptr;                // voxel id per filtered point
     int* vox_cnt = nullptr; int* vox_off = nullptr; int* vox_fill = nullptr;
     unsigned* rk0 = nullptr; unsigned* rk1 = nullptr; int* rv0 = nullptr; int* rv1 = nullptr;
-    int* rhist = nullptr;
     // M-scale
     float4* pts = nullptr; float4* nrms = nullptr;
     float4* pset = nullptr; float4* pset2 = nullptr; float4* vset = nullptr; float4* vnew = nullptr;
