@@ -565,19 +565,43 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
                     b2 = bound > 0.0f ? bound * bound : 0.0f;
                 }
                 unsigned long long k0 = KINF, k1 = KINF;
+                // STAGED: the distances of this lane's candidates (slots r*32+lane of the staged list) live in
+                // registers for all passes of the query; unstaged units re-read the cells from L1/L2.
+                constexpr int RPL = KNN_STAGE / 32;
+                float dq[STAGED ? RPL : 1]; int iq[STAGED ? RPL : 1];
+                if constexpr (STAGED) {
+                    const int tot = tab[wib][0].y;
+#pragma unroll
+                    for (int r = 0; r < RPL; ++r) {
+                        const int t = r * 32 + lane;
+                        dq[r] = 3.0e38f; iq[r] = 0;
+                        if (t < tot) { const float4 c = base[t]; dq[r] = dist2(q.x, q.y, q.z, c.x, c.y, c.z); iq[r] = __float_as_int(c.w); }
+                    }
+                }
                 auto collect = [&](float thr) -> int {
                     int ln = 0;
-                    for (int ti = 0; ti < nt; ++ti) {
-                        const int2 e = tab[wib][ti];
-                        for (int o = 0; o < e.y; o += 32) {
-                            const int t = o + lane;
-                            float d2 = 3.0e38f; int id = 0;
-                            if (t < e.y) { const float4 c = base[e.x + t]; d2 = dist2(q.x, q.y, q.z, c.x, c.y, c.z); id = __float_as_int(c.w); }
-                            const bool in = d2 < thr;
+                    if constexpr (STAGED) {
+#pragma unroll
+                        for (int r = 0; r < RPL; ++r) {
+                            const bool in = dq[r] < thr;
                             const unsigned m = __ballot_sync(0xffffffffu, in);
                             const int pos = ln + __popc(m & lt);
-                            if (in && pos < KNN_LIST) keys[wib][pos] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)id;
+                            if (in && pos < KNN_LIST) keys[wib][pos] = ((unsigned long long)__float_as_uint(dq[r]) << 32) | (unsigned)iq[r];
                             ln += __popc(m);
+                        }
+                    } else {
+                        for (int ti = 0; ti < nt; ++ti) {
+                            const int2 e = tab[wib][ti];
+                            for (int o = 0; o < e.y; o += 32) {
+                                const int t = o + lane;
+                                float d2 = 3.0e38f; int id = 0;
+                                if (t < e.y) { const float4 c = base[e.x + t]; d2 = dist2(q.x, q.y, q.z, c.x, c.y, c.z); id = __float_as_int(c.w); }
+                                const bool in = d2 < thr;
+                                const unsigned m = __ballot_sync(0xffffffffu, in);
+                                const int pos = ln + __popc(m & lt);
+                                if (in && pos < KNN_LIST) keys[wib][pos] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)id;
+                                ln += __popc(m);
+                            }
                         }
                     }
                     __syncwarp();
@@ -588,32 +612,45 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
                 };
                 auto population = [&](float thr) -> int {
                     int cm = 0;
-                    for (int ti = 0; ti < nt; ++ti) {
-                        const int2 e = tab[wib][ti];
-                        for (int o = 0; o < e.y; o += 32) {
-                            const int t = o + lane;
-                            float d2 = 3.0e38f;
-                            if (t < e.y) { const float4 c = base[e.x + t]; d2 = dist2(q.x, q.y, q.z, c.x, c.y, c.z); }
-                            cm += __popc(__ballot_sync(0xffffffffu, d2 < thr));
+                    if constexpr (STAGED) {
+#pragma unroll
+                        for (int r = 0; r < RPL; ++r) cm += (dq[r] < thr) ? 1 : 0;
+                        return __reduce_add_sync(0xffffffffu, cm);
+                    } else {
+                        for (int ti = 0; ti < nt; ++ti) {
+                            const int2 e = tab[wib][ti];
+                            for (int o = 0; o < e.y; o += 32) {
+                                const int t = o + lane;
+                                float d2 = 3.0e38f;
+                                if (t < e.y) { const float4 c = base[e.x + t]; d2 = dist2(q.x, q.y, q.z, c.x, c.y, c.z); }
+                                cm += __popc(__ballot_sync(0xffffffffu, d2 < thr));
+                            }
                         }
+                        return cm;
                     }
-                    return cm;
                 };
                 int ln = -1; float hi = 0.0f;
                 if (guess > 0.0f && guess < b2) { hi = guess; ln = collect(hi); if (ln < k_eff || ln > KNN_LIST) ln = -1; }
                 if (ln < 0) {
                     int c0 = 0, c1 = 0, c2 = 0, c3 = 0;       // population of 4 nested radii
                     const float t1 = b2 * 0.5f, t2 = b2 * 0.25f, t3 = b2 * 0.125f;
-                    for (int ti = 0; ti < nt; ++ti) {
-                        const int2 e = tab[wib][ti];
-                        for (int o = 0; o < e.y; o += 32) {
-                            const int t = o + lane;
-                            float d2 = 3.0e38f;
-                            if (t < e.y) { const float4 c = base[e.x + t]; d2 = dist2(q.x, q.y, q.z, c.x, c.y, c.z); }
-                            c0 += __popc(__ballot_sync(0xffffffffu, d2 < b2));
-                            c1 += __popc(__ballot_sync(0xffffffffu, d2 < t1));
-                            c2 += __popc(__ballot_sync(0xffffffffu, d2 < t2));
-                            c3 += __popc(__ballot_sync(0xffffffffu, d2 < t3));
+                    if constexpr (STAGED) {
+#pragma unroll
+                        for (int r = 0; r < RPL; ++r) { c0 += (dq[r] < b2) ? 1 : 0; c1 += (dq[r] < t1) ? 1 : 0; c2 += (dq[r] < t2) ? 1 : 0; c3 += (dq[r] < t3) ? 1 : 0; }
+                        c0 = __reduce_add_sync(0xffffffffu, c0); c1 = __reduce_add_sync(0xffffffffu, c1);
+                        c2 = __reduce_add_sync(0xffffffffu, c2); c3 = __reduce_add_sync(0xffffffffu, c3);
+                    } else {
+                        for (int ti = 0; ti < nt; ++ti) {
+                            const int2 e = tab[wib][ti];
+                            for (int o = 0; o < e.y; o += 32) {
+                                const int t = o + lane;
+                                float d2 = 3.0e38f;
+                                if (t < e.y) { const float4 c = base[e.x + t]; d2 = dist2(q.x, q.y, q.z, c.x, c.y, c.z); }
+                                c0 += __popc(__ballot_sync(0xffffffffu, d2 < b2));
+                                c1 += __popc(__ballot_sync(0xffffffffu, d2 < t1));
+                                c2 += __popc(__ballot_sync(0xffffffffu, d2 < t2));
+                                c3 += __popc(__ballot_sync(0xffffffffu, d2 < t3));
+                            }
                         }
                     }
                     if (c0 < k_eff) continue;                 // not certifiable at this R
