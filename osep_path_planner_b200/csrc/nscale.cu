@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(128) k_knn_exact(const float4* __restrict__ Pc
 constexpr int KNN_LIST = 64;
 constexpr int KNN_TAB = 125;
 constexpr int KNN_WARPS = 4;
-constexpr int KNN_STAGE = 384;
+constexpr int KNN_STAGE = 512;
 
 // ascending bitonic sort of 64 packed keys (d2 bits << 32 | index; d2 >= 0 so the bit pattern orders like the
 // float and the packed compare is exactly the canonical (d2, index) order), two keys per lane: element r*32+lane.
@@ -474,6 +474,21 @@ __device__ __forceinline__ void bitonic64(unsigned long long& a0, unsigned long 
                 a0 = keepmin0 ? (a0 < b0 ? a0 : b0) : (a0 < b0 ? b0 : a0);
                 a1 = keepmin1 ? (a1 < b1 ? a1 : b1) : (a1 < b1 ? b1 : a1);
             }
+        }
+    }
+}
+
+// 32-key variant (one key per lane) for lists that fit one register
+__device__ __forceinline__ void bitonic32(unsigned long long& a0) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const unsigned long long b0 = __shfl_xor_sync(0xffffffffu, a0, j);
+            const bool lower = (lane & j) == 0;
+            const bool up = ((lane & k) == 0) || (k == 32);
+            a0 = (lower == up) ? (a0 < b0 ? a0 : b0) : (a0 < b0 ? b0 : a0);
         }
     }
 }
@@ -670,8 +685,8 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
                     if (cnt > KNN_LIST) continue;             // > 64 candidates tie at the k-th distance: slow path
                     ln = collect(hi);
                 }
-                guess = hi * 1.25f;
-                bitonic64(k0, k1);
+                guess = hi * 1.125f;
+                if (ln <= 32) bitonic32(k0); else bitonic64(k0, k1);
                 const int qidx = __float_as_int(q.w);
                 if (lane < k_eff) knn_idx[(size_t)qidx * k_eff + lane] = (int)(unsigned)(k0 & 0xffffffffull);
                 if (lane + 32 < k_eff) knn_idx[(size_t)qidx * k_eff + lane + 32] = (int)(unsigned)(k1 & 0xffffffffull);
