@@ -11,6 +11,7 @@
 namespace osep {
 
 void mscale_set_attributes(int Mcap);
+bool drosa_fused_supported(int sms);
 struct GraphHost;
 GraphHost* graph_create(int cap, int device, cudaStream_t stream);
 void graph_destroy(GraphHost* g);
@@ -64,6 +65,7 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
     CK(cudaMallocHost((void**)&h->skel_host, sizeof(float4) * M));
     memset(h->st_host, 0, sizeof(FrameState));
     mscale_set_attributes(d.Mcap);
+    if (h->fused && !drosa_fused_supported(h->sms)) h->fused = false;     // falls back to the per-iteration kernels (same results)
     return OSEP_OK;
 }
 

@@ -662,6 +662,13 @@ __global__ void __launch_bounds__(SEED_WARPS * 32) k_drosa_fused(const __grid_co
 // ------------------------------------------------------------------------------------------
 static size_t gs_smem_bytes(int M, int nbk) { return (size_t)32 * M + 4 * ((size_t)M + 2) + 2 * (size_t)M * nbk + 2 * (size_t)M + 64; }
 
+// can `grid` CTAs of the fused kernel be co-resident on this device? (cooperative launch requirement)
+bool drosa_fused_supported(int sms) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_drosa_fused, SEED_WARPS * 32, (size_t)SEED_SMEM_BUDGET) != cudaSuccess) { cudaGetLastError(); return false; }
+    return per_sm >= 1 && sms >= MAX_FUSED_ITERS + 1;
+}
+
 void drosa_set_attributes() {
     cudaFuncSetAttribute(k_drosa_seed<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEED_SMEM_BUDGET + 1024);
     cudaFuncSetAttribute(k_drosa_seed<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEED_SMEM_BUDGET + 1024);
@@ -698,6 +705,7 @@ void launch_drosa(osep_rosa_impl* h, int sms) {
         int grid = h->fused_grid > 0 ? h->fused_grid : sms;
         if (grid < c.niter_drosa + 1) grid = c.niter_drosa + 1;
         void* args[] = {(void*)&a};
+        if (grid > sms) grid = sms;
         cudaLaunchCooperativeKernel((const void*)k_drosa_fused, dim3(grid), dim3(SEED_WARPS * 32), args, (size_t)SEED_SMEM_BUDGET, s);
         cudaMemcpyAsync(d.vset, d.vset_it + (size_t)c.niter_drosa * d.Mcap, sizeof(float4) * d.Mcap, cudaMemcpyDeviceToDevice, s);
         if (h->debug && d.vset_iters)

@@ -281,3 +281,33 @@ def test_cpp_shim_demo_node_runs(mods):
     assert any(l.startswith("Number of vertices: ") for l in lines) and any(l.startswith("[ROSA] Time Elapsed:") for l in lines)
     assert any(l.startswith("[FAILED] increment_skeleton") or l.startswith("[SUCCESS] increment_skeleton") for l in lines)
     assert any(l.startswith("global skeleton:") or "[FAILED] vertex_merge" in l for l in lines)
+
+
+def test_tiled_map_per_tile_parity(mods):
+    """configs[4] in miniature on one GPU: a two-structure map split into 2 slabs + halo; every tile (tile + halo
+    input) must match the oracle bit-for-bit, and the seam graph over the union of owned vertices too."""
+    osep, po, fx = mods
+    from osep_path_planner_b200 import tiled
+    A = fx.turbine(40000, seed=3)
+    B = fx.cylinder(20000, seed=4, cx=15.0) + np.array([0, 40, 0], np.float32)
+    P = np.concatenate([A, B]).astype(np.float32)
+    axis, bounds = tiled.split_axis_and_bounds(P, 2)
+    halo = tiled.default_halo(P)
+    cfg_kw = dict(pts_dist_lim=1000.0)
+    r = osep.Rosa(osep.RosaConfig(**cfg_kw), capacity_points=len(P))
+    owned = []
+    for t in range(2):
+        own = tiled.slab_of(P, axis, bounds, t)
+        c = P[:, axis]
+        nb = P[((c >= bounds[t] - halo) & (c < bounds[t])) | ((c >= bounds[t + 1]) & (c < bounds[t + 1] + halo))]
+        tile = np.ascontiguousarray(np.concatenate([own, nb]))
+        r.set_input(tile); ok = r.rosa_run()
+        o = po.RosaOracle(po.RosaConfig.default(**cfg_kw)); ok_o = o.run(tile)
+        assert ok and ok_o
+        assert_bit_equal(np.ascontiguousarray(r.output_vertices()), o.tap("skelver"), "tile %d vertices" % t)
+        owned.append(tiled.owned_filter(o.tap("skelver"), axis, bounds[t], bounds[t + 1]))
+    allv = np.ascontiguousarray(np.concatenate(owned))
+    assert len(allv) > 20
+    g = osep.build_graph(allv, 3.0); go = po.GraphOracle(allv, 3.0)
+    assert_bit_equal(g["edges"].reshape(-1), go.tap("mst_edges"), "seam graph edges")
+    r.close()
