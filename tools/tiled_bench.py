@@ -23,8 +23,8 @@ for k, (ox, oy) in enumerate([(0, 0), (60, 0), (0, 60), (60, 60)]):
 P = np.concatenate(parts).astype(np.float32)
 axis, bounds = tiled.split_axis_and_bounds(P, world)
 own = np.ascontiguousarray(tiled.slab_of(P, axis, bounds, rank))
-halo = tiled.default_halo(P)
-r = osep.Rosa(osep.RosaConfig(pts_dist_lim=1.0e4), device=local, capacity_points=int(len(own) * 1.6) + 1024)
+halo = float(sys.argv[2]) if len(sys.argv) > 2 else 15.0     # ~10 x the converged per-tile leaf (similarity radius, rosa.cpp:212)
+r = osep.Rosa(osep.RosaConfig(pts_dist_lim=1.0e4), device=local, capacity_points=int(len(own) * 1.8) + 1024)
 info = {}
 
 def skeletonize(tile):
