@@ -827,15 +827,25 @@ k_vox_reduce(FrameState* st, int* grouped, int* __restrict__ scratch, const int*
             }
             order = sidx;
         } else {
-            // rank sort (indices are distinct): O(cnt^2), only for voxels with more than VOX_SORT points
-            for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
-                const int x = grouped[b + t];
-                int rank = 0;
-                for (int f = 0; f < cnt; ++f) rank += (grouped[b + f] < x) ? 1 : 0;
-                scratch[b + rank] = x;
+            // voxels with more than VOX_SORT points (large maps): bitonic network with all comparators ascending
+            // ("flip" first stage), which needs no power-of-two padding -- missing partners act as +inf -- in place
+            // in global memory (the segment is private to this CTA)
+            int* seg = grouped + b;
+            for (int k = 2; (k >> 1) < cnt; k <<= 1) {
+                for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+                    const int ixj = i ^ (k - 1);
+                    if (ixj > i && ixj < cnt) { const int x = seg[i], y = seg[ixj]; if (x > y) { seg[i] = y; seg[ixj] = x; } }
+                }
+                __syncthreads();
+                for (int j = k >> 2; j > 0; j >>= 1) {
+                    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+                        const int ixj = i ^ j;
+                        if (ixj > i && ixj < cnt) { const int x = seg[i], y = seg[ixj]; if (x > y) { seg[i] = y; seg[ixj] = x; } }
+                    }
+                    __syncthreads();
+                }
             }
-            __syncthreads();
-            order = scratch + b;
+            order = seg;
         }
         float sx = 0, sy = 0, sz = 0, n0 = 0, n1 = 0, n2 = 0, n3 = 0;
         for (int c0 = 0; c0 < cnt; c0 += VOX_CHUNK) {

@@ -311,3 +311,16 @@ def test_tiled_map_per_tile_parity(mods):
     g = osep.build_graph(allv, 3.0); go = po.GraphOracle(allv, 3.0)
     assert_bit_equal(g["edges"].reshape(-1), go.tap("mst_edges"), "seam graph edges")
     r.close()
+
+
+def test_large_voxels_global_sort_path(mods):
+    """max_points small relative to N => voxels with more than 2048 points (the in-place global bitonic path)."""
+    osep, po, fx = mods
+    o, ok_o, r, ok_g = run_both(mods, fx.cylinder(60000, seed=8), dict(max_points=20, min_points=10), debug=False)
+    assert ok_o == ok_g and r.result.status == o.failed_stage
+    assert r.tap("vox_count").max() > 2048
+    for tap in ["vox_keys", "vox_count", "pts", "nrms"]:
+        assert_bit_equal(r.tap(tap), o.tap(tap), tap)
+    if ok_o:
+        assert_bit_equal(r.tap("skelver"), o.tap("skelver"), "skelver")
+    r.close()

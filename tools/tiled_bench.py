@@ -25,12 +25,13 @@ axis, bounds = tiled.split_axis_and_bounds(P, world)
 own = np.ascontiguousarray(tiled.slab_of(P, axis, bounds, rank))
 halo = float(sys.argv[2]) if len(sys.argv) > 2 else 15.0     # ~10 x the converged per-tile leaf (similarity radius, rosa.cpp:212)
 r = osep.Rosa(osep.RosaConfig(pts_dist_lim=1.0e4), device=local, capacity_points=int(len(own) * 1.8) + 1024)
+r.set_profile(True)
 info = {}
 
 def skeletonize(tile):
     r.set_input(tile)
     ok = r.rosa_run()
-    info.update(ok=ok, status=r.result.status, M=r.result.n_downsampled, gpu_ms=r.result.gpu_ms, n=len(tile), leaf=r.result.leaf_size)
+    info.update(ok=ok, status=r.result.status, M=r.result.n_downsampled, gpu_ms=r.result.gpu_ms, n=len(tile), leaf=r.result.leaf_size, stage_ms={k: round(v, 3) for k, v in r.stage_ms().items()})
     return np.ascontiguousarray(r.output_vertices())
 
 def sync():
@@ -52,6 +53,6 @@ else:
 if rank == 0:
     print(json.dumps({"config": "tiled map, %d points, %d GPU(s), halo %.2f m along axis %d" % (len(P), world, halo, axis), "seconds_per_map": dt,
                       "points_per_s": len(P) / dt, "tile_points": [i["n"] for i in infos], "tile_gpu_ms": [i["gpu_ms"] for i in infos],
-                      "tile_ok": [i["ok"] for i in infos], "owned_vertices": [int(c) for c in res["counts"]], "seam_graph_edges": int(g["n_edges"])}))
+                      "tile_ok": [i["ok"] for i in infos], "stage_ms_rank0": infos[0]["stage_ms"], "owned_vertices": [int(c) for c in res["counts"]], "seam_graph_edges": int(g["n_edges"])}))
 if world > 1:
     dist.barrier(); dist.destroy_process_group()
