@@ -313,9 +313,11 @@ __global__ void k_grid_alloc(FrameState* st, const int* __restrict__ g_cnt, int*
     const int c = g_cnt[s];
     if (c > 0) {
         g_start[s] = atomicAdd(&st->g_cells_used, c);
-        const int nu = (c + QCH - 1) / QCH;
+        // dense cells have long candidate lists: fewer queries per unit there, so more warps share the work
+        const int chunk = (c >= 64) ? 2 : QCH;
+        const int nu = (c + chunk - 1) / chunk;
         const int ub = atomicAdd(&st->n_units, nu);
-        for (int u = 0; u < nu; ++u) units[ub + u] = make_int2(s, u * QCH);
+        for (int u = 0; u < nu; ++u) units[ub + u] = make_int2(s, (u * chunk) | (chunk << 24));
     }
 }
 __global__ void k_grid_scatter(const float4* __restrict__ P, const FrameState* __restrict__ st, const int* __restrict__ p_slot,
@@ -521,8 +523,8 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
         const int unit = STAGED ? w : over_list[w];
         const int2 un = units[unit];
         const int cstart = g_start[un.x], ccnt = g_cnt[un.x];
-        const int q0 = un.y;
-        const int nq = min(QCH, ccnt - q0);
+        const int q0 = un.y & 0xffffff;
+        const int nq = min(un.y >> 24, ccnt - q0);
         int cx, cy, cz;
         { const float4 f = Pc[cstart]; cell_of(st, f.x, f.y, f.z, cx, cy, cz); }
         unsigned todo = (1u << nq) - 1u;
@@ -794,7 +796,7 @@ __global__ void k_vox_scatter(const FrameState* __restrict__ st, const unsigned*
 // in flight); (3) ONE thread adds them, so the float sums stay strictly sequential in ascending point index.
 constexpr int VOX_SORT = 2048;
 constexpr int VOX_CHUNK = 256;
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_vox_reduce(FrameState* st, int* grouped, int* __restrict__ scratch, const int* __restrict__ vox_off,
              const float4* __restrict__ P, const float4* __restrict__ Nrm,
              float4* __restrict__ pts, float4* __restrict__ nrms, float4* __restrict__ pset, float4* __restrict__ vset) {
@@ -943,7 +945,7 @@ void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int strid
     // group by voxel with atomics, then fix the order inside every voxel in the reduce kernel (no global sort)
     cudaMemsetAsync(d.vox_fill, 0, sizeof(int) * (d.Mcap + 2), s);
     k_vox_scatter<<<nb, NT, 0, s>>>(d.st, d.rk0, d.vox_cnt, d.vox_fill, d.rv0);
-    k_vox_reduce<<<1024, 128, 0, s>>>(d.st, d.rv0, d.rv1, d.vox_cnt, d.P, d.Nrm, d.pts, d.nrms, d.pset, d.vset);
+    k_vox_reduce<<<1024, 256, 0, s>>>(d.st, d.rv0, d.rv1, d.vox_cnt, d.P, d.Nrm, d.pts, d.nrms, d.pset, d.vset);
     stage_mark(h, SM_VOXEL);
     h->n_launches += 1 + 3 + (LEAF_MAX_ITERS + 1) + 4 + 4 + 4 + 2;
 }
