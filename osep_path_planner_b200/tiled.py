@@ -13,7 +13,7 @@ it owns its halo, so the only data-path communication is
 
 Halo points take part as neighbours (normals, similarity, active sets) but a tile only EMITS the vertices
 that fall inside its own interval.  This is a new capability (the reference has no tiling): parity is defined
-per tile, against the oracle run on the identical tile + halo input (tests/test_parity_gpu.py).
+per tile, against the CPU restatement run on the identical tile + halo input (tests/test_parity_gpu.py).
 """
 import numpy as np
 import torch
