@@ -324,3 +324,39 @@ def test_large_voxels_global_sort_path(mods):
     if ok_o:
         assert_bit_equal(r.tap("skelver"), o.tap("skelver"), "skelver")
     r.close()
+
+
+def test_many_frames_bit_exact(mods):
+    """Breadth: different viewpoints / stand-offs / sizes (BASELINE configs[3]-style frames and stream frames)."""
+    osep, po, fx = mods
+    r = osep.Rosa(capacity_points=60000)
+    frames = [fx.batch_frame(b, n=30000) for b in range(8)] + [fx.stream_frame(f, n=25000)[0] for f in (0, 60, 125, 190)]
+    for k, P in enumerate(frames):
+        r.set_input(P); ok = r.rosa_run()
+        o = po.RosaOracle(); ok_o = o.run(P)
+        assert ok == ok_o and r.result.status == o.failed_stage, "frame %d" % k
+        assert r.result.flags == o.flags and r.result.n_downsampled == len(o.tap("pts"))
+        assert_bit_equal(np.ascontiguousarray(r.output_vertices()), o.tap("skelver"), "frame %d vertices" % k)
+        assert_bit_equal(r.tap("pset"), o.tap("pset"), "frame %d pset" % k)
+        assert_bit_equal(r.tap("vset"), o.tap("vset"), "frame %d vset" % k)
+    r.close()
+
+
+def test_fused_and_unfused_drosa_agree(mods):
+    """The persistent cooperative drosa kernel and the per-iteration fallback kernels give identical bits."""
+    osep, po, fx = mods
+    P = fx.turbine(50000, seed=9)
+    outs = []
+    for unfused in ("0", "1"):
+        os.environ["OSEP_DROSA_UNFUSED"] = unfused
+        try:
+            r = osep.Rosa(capacity_points=50000); r.set_debug(True)
+            r.set_input(P); assert r.rosa_run()
+            outs.append((r.tap("vset_iters"), r.tap("pset_drosa"), np.ascontiguousarray(r.output_vertices()).copy()))
+            r.close()
+        finally:
+            os.environ.pop("OSEP_DROSA_UNFUSED", None)
+    for a, b, what in zip(outs[0], outs[1], ["vset_iters", "pset_drosa", "vertices"]):
+        assert_bit_equal(a, b, what)
+    o = po.RosaOracle(); assert o.run(P)
+    assert_bit_equal(outs[0][2], o.tap("skelver"), "vertices vs oracle")
