@@ -58,19 +58,25 @@ OSEP_HD float eig_hypot(float x, float y) {
     return p * sqrtf(1.0f + qp * qp);
 }
 
-// Eigen JacobiRotation<float>::makeGivens (real)
+// Eigen JacobiRotation<float>::makeGivens (real).  Written branch-uniform (selects instead of a 4-way
+// branch) so that the lanes of a warp solving different matrices stay converged; every lane still performs
+// exactly the operations of its own case:
+//   |p| > |q| : t = q/p, u = +-sqrt(1+t^2) (sign of p), c = 1/u,  s = -t*c        = -(t * (1/u))
+//   otherwise : t = p/q, u = +-sqrt(1+t^2) (sign of q), s = -1/u, c = -t*s        =  (t * (1/u))
+//   q == 0    : c = sign(p), s = 0          p == 0 : c = 0, s = -sign(q)
 OSEP_HD void make_givens(float p, float q, float& c, float& s) {
-    if (q == 0.0f) { c = p < 0.0f ? -1.0f : 1.0f; s = 0.0f; }
-    else if (p == 0.0f) { c = 0.0f; s = q < 0.0f ? 1.0f : -1.0f; }
-    else if (fabsf(p) > fabsf(q)) {
-        const float t = q / p; float u = sqrtf(1.0f + t * t);
-        if (p < 0.0f) u = -u;
-        c = 1.0f / u; s = -t * c;
-    } else {
-        const float t = p / q; float u = sqrtf(1.0f + t * t);
-        if (q < 0.0f) u = -u;
-        s = -1.0f / u; c = -t * s;
-    }
+    const bool A = fabsf(p) > fabsf(q);
+    const float num = A ? q : p, den = A ? p : q;
+    const float t = num / den;
+    float u = sqrtf(1.0f + t * t);
+    if (den < 0.0f) u = -u;
+    const float inv = 1.0f / u;
+    const float tinv = t * inv;
+    float cc = A ? inv : tinv;
+    float ss = A ? -tinv : -inv;
+    if (p == 0.0f) { cc = 0.0f; ss = q < 0.0f ? 1.0f : -1.0f; }
+    if (q == 0.0f) { cc = p < 0.0f ? -1.0f : 1.0f; ss = 0.0f; }
+    c = cc; s = ss;
 }
 
 // Symmetric 3x3 eigen-decomposition = Eigen::SelfAdjointEigenSolver<Matrix3f>::compute
@@ -81,7 +87,9 @@ OSEP_HD void make_givens(float p, float q, float& c, float& s) {
 // arrays with compile-time indices only (the k-loops are fully unrolled over start/end).
 struct Eig3 { float ev[3]; float q[9]; bool ok; };
 
-OSEP_HD void eig3_qr_rot(float* diag, float* sub, float* q, int k, int start, int end, float& x, float& z) {
+// one Givens step of tridiagonal_qr_step at compile-time position k; `first` = (k == start), `last` = (k == end-1)
+template <int k>
+OSEP_HD void eig3_qr_rot(float* diag, float* sub, float* q, bool first, bool last, float& x, float& z) {
     float c, s;
     make_givens(x, z, c, s);
     const float sdk = s * diag[k] + c * sub[k];
@@ -89,9 +97,9 @@ OSEP_HD void eig3_qr_rot(float* diag, float* sub, float* q, int k, int start, in
     diag[k] = c * (c * diag[k] - s * sub[k]) - s * (c * sub[k] - s * diag[k + 1]);
     diag[k + 1] = s * sdk + c * dkp1;
     sub[k] = c * sdk - s * dkp1;
-    if (k > start) sub[k - 1] = c * sub[k - 1] - s * z;
+    if (k > 0) { if (!first) sub[k - 1] = c * sub[k - 1] - s * z; }
     x = sub[k];
-    if (k < end - 1) { z = -s * sub[k + 1]; sub[k + 1] = c * sub[k + 1]; }
+    if (k < 1) { if (!last) { z = -s * sub[k + 1]; sub[k + 1] = c * sub[k + 1]; } }
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         const float xi = q[r * 3 + k], yi = q[r * 3 + k + 1];
@@ -165,12 +173,10 @@ OSEP_HD Eig3 eig3_sym(float a00, float a10, float a11, float a20, float a21, flo
         }
         float x = ((start == 0) ? diag[0] : diag[1]) - mu;
         float z = (start == 0) ? sub[0] : sub[1];
-        if (start == 0) {
-            if (z != 0.0f) eig3_qr_rot(diag, sub, q, 0, 0, end, x, z);
-            if (end == 2 && z != 0.0f) eig3_qr_rot(diag, sub, q, 1, 0, end, x, z);
-        } else {
-            if (z != 0.0f) eig3_qr_rot(diag, sub, q, 1, 1, end, x, z);
-        }
+        // for (k = start; k < end && z != 0; ++k): one code copy per position, predicated, so lanes with
+        // different (start, end) stay converged
+        if (start == 0 && z != 0.0f) eig3_qr_rot<0>(diag, sub, q, true, end == 1, x, z);
+        if (end == 2 && z != 0.0f) eig3_qr_rot<1>(diag, sub, q, start == 1, true, x, z);
     }
     R.ok = iter <= 90;
     if (R.ok) {
