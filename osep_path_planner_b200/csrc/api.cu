@@ -82,6 +82,8 @@ static void rosa_free(osep_rosa_impl* h) {
     for (int i = 0; i < osep_rosa_impl::NSTAGE_EV; ++i) if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (int i = 0; i < 2; ++i) { if (h->ev_fork[i]) cudaEventDestroy(h->ev_fork[i]); if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]); }
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
 }
 
@@ -160,6 +162,8 @@ int osep_rosa_create(const osep_rosa_config* cfg, int device, int capacity_point
     do {
         if (cudaStreamCreateWithFlags(&h->impl.stream, cudaStreamNonBlocking) != cudaSuccess) { set_err("cudaStreamCreate failed"); rc = OSEP_ERR_CUDA; break; }
         cudaEventCreate(&h->impl.ev0); cudaEventCreate(&h->impl.ev1);
+        if (cudaStreamCreateWithFlags(&h->impl.stream2, cudaStreamNonBlocking) != cudaSuccess) { set_err("cudaStreamCreate failed"); rc = OSEP_ERR_CUDA; break; }
+        for (int i = 0; i < 2; ++i) { cudaEventCreateWithFlags(&h->impl.ev_fork[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&h->impl.ev_join[i], cudaEventDisableTiming); }
         rc = rosa_alloc(&h->impl, capacity_points);
     } while (0);
     if (rc != OSEP_OK) { rosa_free(&h->impl); delete h; return rc; }
@@ -194,6 +198,7 @@ int osep_rosa_set_profile(osep_rosa* h, int enable) {
     osep_rosa_impl& I = h->impl;
     CK(cudaSetDevice(I.device));
     I.profile = enable != 0;
+    I.overlap = !I.profile;
     if (I.profile) for (int i = 0; i < SM_COUNT; ++i) if (!I.stage_ev[i]) CK(cudaEventCreate(&I.stage_ev[i]));
     return OSEP_OK;
 }

@@ -657,13 +657,18 @@ void launch_mscale(osep_rosa_impl* h) {
     const int tb = WARPS_PER_BLOCK * 32;
     const int tblocks = div_up(d.Mcap, 128);
     k_mscale_begin<<<1, 1, 0, s>>>(d.st);
+    // two independent branches on the downsampled cloud: similarity lists (main stream) || surf kNN (side stream)
+    cudaStream_t sk = s;
+    if (h->overlap) { cudaEventRecord(h->ev_fork[1], s); sk = h->stream2; cudaStreamWaitEvent(sk, h->ev_fork[1], 0); }
+    // R13
+    k_surf_knn<<<warp_blocks, tb, 0, sk>>>(d.st, d.pts, d.surf, d.nbk);
+    if (h->overlap) cudaEventRecord(h->ev_join[1], sk);
     // R12
     k_simi<false><<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.nrms, d.simi_off, d.simi_idx, nullptr, nullptr, d.simi_bits, d.W);
     k_simi_scan<<<1, 1024, 0, s>>>(d.st, d.simi_off, d.Scap);
     k_simi<true><<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.nrms, d.simi_off, d.simi_idx, d.rv1, (float*)d.rk1, d.simi_bits, d.W);
     stage_mark(h, SM_SIMI);
-    // R13 + level schedule
-    k_surf_knn<<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.surf, d.nbk);
+    if (h->overlap) cudaStreamWaitEvent(s, h->ev_join[1], 0);
     launch_drosa(h, h->sms);
     k_poor_prepare<<<1, 1024, 0, s>>>(d.st, d.good, d.good_rank, d.centers, d.pset2, d.poor_idx, nullptr);
     k_poor_fix<<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.good, d.pset2, d.poor_idx, d.pset);

@@ -262,10 +262,10 @@ __global__ void k_grid_params(FrameState* st, int target_ppc) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (st->status != 0) return;
     const int n = st->n_filt;
-    const int nv = st->pass_overflow ? n : st->nvox;
-    // density estimate from the last VoxelGrid pass: nv occupied voxels of size leaf_used hold n points;
-    // for a surface-like cloud a cell of size h holds ~ (h/leaf)^2 * n/nv points.
-    float h = st->leaf_used * sqrtf((float)target_ppc * (float)(nv > 0 ? nv : 1) / (float)(n > 0 ? n : 1));
+    // density estimate from VoxelGrid pass 0 (leaf_hist[0], nvox_hist[0]): nv occupied voxels of that size hold n
+    // points; for a surface-like cloud a cell of size h holds ~ (h/leaf)^2 * n/nv points.
+    const int nv = st->nvox_hist[0];
+    float h = st->leaf_hist[0] * sqrtf((float)target_ppc * (float)(nv > 0 ? nv : 1) / (float)(n > 0 ? n : 1));
     if (!(h > 1e-6f) || !fin(h)) h = 1.0f;
     float ext = 0.0f;
     for (int d = 0; d < 3; ++d) ext = fmaxf(ext, st->bmax[d] - st->bmin[d]);
@@ -893,9 +893,8 @@ k_vox_reduce(FrameState* st, int* grouped, int* __restrict__ scratch, const int*
 
 // ------------------------------------------------------------------------------------------
 template <int K>
-static void launch_knn(osep_rosa_impl* h, int n, int k_req) {
+static void launch_knn(osep_rosa_impl* h, int n, int k_req, cudaStream_t s) {
     RosaDev& d = h->d;
-    cudaStream_t s = h->stream;
     const unsigned mask = (unsigned)(d.T - 1);
     k_knn_cells<K, true><<<h->sms * 6, KNN_WARPS * 32, 0, s>>>(d.Pc, d.st, (const unsigned*)d.gtab, d.g_cnt, d.g_start, mask, d.units,
                                                               d.knn_full, k_req, d.slow_list, d.over_list);
@@ -917,24 +916,30 @@ void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int strid
     k_filter_scan<<<1, 1024, 0, s>>>(d.blk_cnt, nb, d.st, c.min_points);
     k_filter_scatter<<<nb, NT, 0, s>>>(xyz_dev, n, stride, r2, d.blk_cnt, d.P, d.filt_idx, d.st);
     stage_mark(h, SM_FILTER);
-    // R7/R8: device-resident leaf loop (count-only passes)
+    // R7/R8: device-resident leaf loop (count-only passes).  The kNN grid is sized from the density seen by
+    // pass 0, so the whole normals branch (grid build + kNN + covariance/eigen) only depends on pass 0 and runs
+    // on the side stream while the remaining passes iterate the control law.
     k_leaf_step<<<1, 1, 0, s>>>(d.st, 0, c.max_points);
-    for (int p = 0; p < LEAF_MAX_ITERS; ++p)
+    k_vox_count<<<nb, NT, 0, s>>>(d.P, d.st, d.vtab, (unsigned)(d.T - 1), 1, c.max_points);
+    k_grid_params<<<1, 1, 0, s>>>(d.st, h->knn_ppc);
+    cudaStream_t sk = s;
+    if (h->overlap) { cudaEventRecord(h->ev_fork[0], s); sk = h->stream2; cudaStreamWaitEvent(sk, h->ev_fork[0], 0); }
+    for (int p = 1; p < LEAF_MAX_ITERS; ++p)
         k_vox_count<<<nb, NT, 0, s>>>(d.P, d.st, d.vtab, (unsigned)(d.T - 1), p + 1, c.max_points);
     stage_mark(h, SM_LEAF);
     // R5: grid + kNN normals
-    cudaMemsetAsync(d.gtab, 0, sizeof(unsigned) * 3 * (size_t)d.T, s);   // gtab | g_cnt | g_fill are contiguous
-    k_grid_params<<<1, 1, 0, s>>>(d.st, h->knn_ppc);
-    k_grid_insert<<<nb, NT, 0, s>>>(d.P, d.st, (unsigned*)d.gtab, d.g_cnt, d.p_slot, (unsigned)(d.T - 1));
-    k_grid_alloc<<<div_up(d.T, NT), NT, 0, s>>>(d.st, d.g_cnt, d.g_start, d.T, d.units);
-    k_grid_scatter<<<nb, NT, 0, s>>>(d.P, d.st, d.p_slot, d.g_start, d.g_fill, d.Pc);
+    cudaMemsetAsync(d.gtab, 0, sizeof(unsigned) * 3 * (size_t)d.T, sk);   // gtab | g_cnt | g_fill are contiguous
+    k_grid_insert<<<nb, NT, 0, sk>>>(d.P, d.st, (unsigned*)d.gtab, d.g_cnt, d.p_slot, (unsigned)(d.T - 1));
+    k_grid_alloc<<<div_up(d.T, NT), NT, 0, sk>>>(d.st, d.g_cnt, d.g_start, d.T, d.units);
+    k_grid_scatter<<<nb, NT, 0, sk>>>(d.P, d.st, d.p_slot, d.g_start, d.g_fill, d.Pc);
     stage_mark(h, SM_GRID);
     const int k = c.ne_knn;
-    if (k == 20) launch_knn<20>(h, n, k);
-    else if (k <= 10) launch_knn<10>(h, n, k);
-    else if (k <= 16) launch_knn<16>(h, n, k);
-    else if (k <= 32) launch_knn<32>(h, n, k);
-    else launch_knn<64>(h, n, k);
+    if (k == 20) launch_knn<20>(h, n, k, sk);
+    else if (k <= 10) launch_knn<10>(h, n, k, sk);
+    else if (k <= 16) launch_knn<16>(h, n, k, sk);
+    else if (k <= 32) launch_knn<32>(h, n, k, sk);
+    else launch_knn<64>(h, n, k, sk);
+    if (h->overlap) cudaEventRecord(h->ev_join[0], sk);
     stage_mark(h, SM_KNN);
     // R9 final pass
     k_vox_collect<<<div_up(d.T, NT), NT, 0, s>>>(d.st, d.vtab, d.T, d.vkeys, d.Mcap);
@@ -945,6 +950,7 @@ void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int strid
     // group by voxel with atomics, then fix the order inside every voxel in the reduce kernel (no global sort)
     cudaMemsetAsync(d.vox_fill, 0, sizeof(int) * (d.Mcap + 2), s);
     k_vox_scatter<<<nb, NT, 0, s>>>(d.st, d.rk0, d.vox_cnt, d.vox_fill, d.rv0);
+    if (h->overlap) cudaStreamWaitEvent(s, h->ev_join[0], 0);              // the reduce is the first consumer of the normals
     k_vox_reduce<<<1024, 256, 0, s>>>(d.st, d.rv0, d.rv1, d.vox_cnt, d.P, d.Nrm, d.pts, d.nrms, d.pset, d.vset);
     stage_mark(h, SM_VOXEL);
     h->n_launches += 1 + 3 + (LEAF_MAX_ITERS + 1) + 4 + 4 + 4 + 2;

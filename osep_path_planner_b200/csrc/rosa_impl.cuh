@@ -59,6 +59,9 @@ struct osep_rosa_impl {
     int device = 0;
     int sms = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;     // side stream: independent branches of one frame overlap (kNN normals || leaf passes; surf kNN || similarity)
+    cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
+    bool overlap = true;                // disabled while per-stage profiling is on (stage times stay sequential and attributable)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     RosaDev d;
     bool debug = false;
