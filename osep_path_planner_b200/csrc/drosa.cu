@@ -262,11 +262,12 @@ k_drosa_seed(FrameState* st, const float4* __restrict__ pts, const float4* __res
     if (small_in) {
         for (int i = threadIdx.x; i < M; i += blockDim.x) { s_pts[i] = pts[i]; s_nraw[i] = nraw[i]; s_vnd[i] = vnd[i]; }
     }
-    if (mat_in) stage_bit_rows(s_bits, bits, M, Wn, W);
+    if (mat_in) stage_bit_rows(s_bits, bits, M, Wn);
     __syncthreads();
     SeedCtx c;
     c.pts = small_in ? s_pts : pts; c.nraw = small_in ? s_nraw : nraw; c.vnd = small_in ? s_vnd : vnd;
-    c.bits = mat_in ? s_bits : bits; c.bstride = mat_in ? Wn : W;
+    c.bits = mat_in ? s_bits : bits; c.bstride = Wn;          // the matrix is dense (row stride Wn) in global memory too
+    (void)W;
     c.M = M; c.Wn = Wn; c.leaf = st->leaf_size;
     const int wib = threadIdx.x >> 5;
     for (int seed = blockIdx.x + gridDim.x * wib; seed < M; seed += gridDim.x * SEED_WARPS) {
@@ -478,11 +479,11 @@ __device__ __forceinline__ void fused_worker(const FusedArgs& a, uint4* smem, in
     float4* s_nraw = s_pts + M; float4* s_vnd = s_nraw + M;
     unsigned* s_bits = reinterpret_cast<unsigned*>(s_vnd + M);
     if (small_in) for (int i = threadIdx.x; i < M; i += blockDim.x) { s_pts[i] = a.pts[i]; s_nraw[i] = a.nraw[i]; s_vnd[i] = a.vnd[i]; }
-    if (mat_in) stage_bit_rows(s_bits, a.bits, M, Wn, a.W);
+    if (mat_in) stage_bit_rows(s_bits, a.bits, M, Wn);
     __syncthreads();
     SeedCtx c;
     c.pts = small_in ? s_pts : a.pts; c.nraw = small_in ? s_nraw : a.nraw; c.vnd = small_in ? s_vnd : a.vnd;
-    c.bits = mat_in ? s_bits : a.bits; c.bstride = mat_in ? Wn : a.W;
+    c.bits = mat_in ? s_bits : a.bits; c.bstride = Wn;
     c.M = M; c.Wn = Wn; c.leaf = a.st->leaf_size;
     const int lane = threadIdx.x & 31;
     const int total = (a.nit + 1) * M;

@@ -100,9 +100,11 @@ __device__ __forceinline__ float similarity_metric(const f3& p1, const f3& v1, c
 template <bool FILL>
 __global__ void k_simi(FrameState* st, const float4* __restrict__ pts, const float4* __restrict__ nrms,
                        int* simi_off, int* __restrict__ simi_idx, int* __restrict__ tmp_j, float* __restrict__ tmp_d,
-                       unsigned* __restrict__ simi_bits, int W) {
+                       unsigned* __restrict__ simi_bits, int W_cap) {
     if (st->status != 0) return;
     const int M = st->M;
+    const int W = (M + 31) >> 5;           // dense row stride of the bit matrix
+    (void)W_cap;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (i >= M) return;
@@ -330,7 +332,8 @@ constexpr int DC_THREADS = 128;
 constexpr int DC_SMEM_BUDGET = 200 * 1024;
 
 __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS)
-k_dcrosa_cluster(const FrameState* __restrict__ st, float4* pset, const int* __restrict__ simi_off, const int* __restrict__ simi_idx, int niter) {
+k_dcrosa_cluster(const FrameState* __restrict__ st, float4* pset, const int* __restrict__ simi_off, const int* __restrict__ simi_idx, int niter,
+                 unsigned smem_bytes) {
     extern __shared__ float4 dcs[];
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -345,14 +348,22 @@ k_dcrosa_cluster(const FrameState* __restrict__ st, float4* pset, const int* __r
     for (int r = 0; r < DC_CLUSTER; ++r) { pa_r[r] = cluster.map_shared_rank(pa, r); pb_r[r] = cluster.map_shared_rank(pb, r); }
     cluster.sync();
     const int per = (M + DC_CLUSTER - 1) / DC_CLUSTER;
-    const int lo = (int)rank * per, hi = min(M, lo + per);
+    const int lo = min(M, (int)rank * per), hi = min(M, lo + per);
+    // this CTA's slice of the similarity CSR, staged in shared memory when it fits
+    int* sidx = reinterpret_cast<int*>(dcs + 2 * (size_t)M);
+    const int seg_b = simi_off[lo], seg_e = simi_off[hi];
+    const bool csr_in = ((size_t)32 * M + 4 * (size_t)(seg_e - seg_b)) <= smem_bytes;
+    if (csr_in) for (int t = seg_b + threadIdx.x; t < seg_e; t += blockDim.x) sidx[t - seg_b] = simi_idx[t];
+    __syncthreads();
+    const int* nbr = csr_in ? (sidx - seg_b) : simi_idx;       // nbr[t] for t in [seg_b, seg_e)
     for (int it = 0; it < niter; ++it) {
         for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {          // neighbour mean (rosa.cpp:388-399)
             const int b = simi_off[i], e = simi_off[i + 1];
             float4 out = pa[i];
             if (e > b) {
                 f3 acc{0.0f, 0.0f, 0.0f};
-                for (int t = b; t < e; ++t) { const float4 v = pa[simi_idx[t]]; acc = add3(acc, f3{v.x, v.y, v.z}); }
+#pragma unroll 4
+                for (int t = b; t < e; ++t) { const float4 v = pa[nbr[t]]; acc = add3(acc, f3{v.x, v.y, v.z}); }
                 const f3 mth = div3(acc, (float)(e - b));
                 out = make_float4(mth.x, mth.y, mth.z, 1.0f);
             }
@@ -367,11 +378,13 @@ k_dcrosa_cluster(const FrameState* __restrict__ st, float4* pset, const int* __r
             float4 out = self4;
             if (m >= 3) {
                 f3 mean{0.0f, 0.0f, 0.0f};
-                for (int t = b; t < e; ++t) { const float4 v = pb[simi_idx[t]]; mean = add3(mean, f3{v.x, v.y, v.z}); }
+#pragma unroll 4
+                for (int t = b; t < e; ++t) { const float4 v = pb[nbr[t]]; mean = add3(mean, f3{v.x, v.y, v.z}); }
                 mean = div3(mean, (float)m);
                 float c00 = 0, c10 = 0, c11 = 0, c20 = 0, c21 = 0, c22 = 0;
+#pragma unroll 4
                 for (int t = b; t < e; ++t) {
-                    const float4 v = pb[simi_idx[t]];
+                    const float4 v = pb[nbr[t]];
                     const f3 q = sub3(f3{v.x, v.y, v.z}, mean);
                     c00 += q.x * q.x; c10 += q.y * q.x; c11 += q.y * q.y; c20 += q.z * q.x; c21 += q.z * q.y; c22 += q.z * q.z;
                 }
@@ -419,9 +432,11 @@ __global__ void k_vs_compact(FrameState* st, const float4* __restrict__ pset, fl
     if (threadIdx.x == 0) { st->Mc = Mc; st->V = 0; if (Mc != M) st->flags |= OSEP_FLAG_NONFINITE_PSET; }
 }
 // cover adjacency: bit j of row i = (d2(i,j) < R^2) or i == j; one warp per row
-__global__ void k_vs_adj(const FrameState* __restrict__ st, const float4* __restrict__ pcloud, unsigned* __restrict__ adj, int W) {
+__global__ void k_vs_adj(const FrameState* __restrict__ st, const float4* __restrict__ pcloud, unsigned* __restrict__ adj, int W_cap) {
     if (st->status != 0) return;
     const int Mc = st->Mc;
+    const int W = (Mc + 31) >> 5;          // dense row stride
+    (void)W_cap;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= Mc) return;
     const float R = st->leaf_size; const float R2 = R * R;
@@ -445,12 +460,13 @@ __global__ void __launch_bounds__(1024) k_vs_greedy(FrameState* st, const unsign
     const int Mc = st->Mc;
     const int Wn = (Mc + 31) >> 5;
     const bool in_smem = (size_t)4 * Mc * Wn <= (size_t)VS_SMEM_BUDGET;
-    if (in_smem) stage_bit_rows(vs_rows, adj, Mc, Wn, W);
+    if (in_smem) stage_bit_rows(vs_rows, adj, Mc, Wn);
+    (void)W;
     __syncthreads();
     if (threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
     const unsigned* rows = in_smem ? vs_rows : adj;
-    const int stride = in_smem ? Wn : W;
+    const int stride = Wn;
     constexpr int WPL = 4;                      // up to 128 words = 4096 points
     unsigned cov[WPL];
 #pragma unroll
@@ -676,7 +692,7 @@ void launch_mscale(osep_rosa_impl* h) {
     stage_mark(h, SM_POSITION);
     // R20
     if ((size_t)32 * d.Mcap <= (size_t)DC_SMEM_BUDGET) {
-        k_dcrosa_cluster<<<DC_CLUSTER, DC_THREADS, (size_t)32 * d.Mcap, s>>>(d.st, d.pset, d.simi_off, d.simi_idx, c.niter_dcrosa);
+        k_dcrosa_cluster<<<DC_CLUSTER, DC_THREADS, DC_SMEM_BUDGET, s>>>(d.st, d.pset, d.simi_off, d.simi_idx, c.niter_dcrosa, (unsigned)DC_SMEM_BUDGET);
     } else {
         for (int it = 0; it < c.niter_dcrosa; ++it) {
             k_dcrosa_mean<<<tblocks, 128, 0, s>>>(d.st, d.pset, d.pset2, d.simi_off, d.simi_idx);

@@ -64,12 +64,15 @@ __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ unsigned hash_u32(unsigned k) { k *= 2654435761u; k ^= k >> 15; k *= 2246822519u; k ^= k >> 13; return k; }
 
-// stage `rows` bit rows (Wn words each, row stride W in the source) into a dense destination; flat index so
-// that every thread has many independent loads in flight
-__device__ __forceinline__ void stage_bit_rows(unsigned* __restrict__ dst, const unsigned* __restrict__ src, int rows, int Wn, int W) {
+// stage a dense bit matrix (rows x Wn words, contiguous) into shared memory with 16-byte loads
+__device__ __forceinline__ void stage_bit_rows(unsigned* __restrict__ dst, const unsigned* __restrict__ src, int rows, int Wn) {
     const int total = rows * Wn;
-#pragma unroll 8
-    for (int i = threadIdx.x; i < total; i += blockDim.x) { const int r = i / Wn; dst[i] = src[(size_t)r * W + (i - r * Wn)]; }
+    const int n4 = total >> 2;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) d4[i] = s4[i];
+    for (int i = (n4 << 2) + threadIdx.x; i < total; i += blockDim.x) dst[i] = src[i];
 }
 
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
