@@ -500,7 +500,7 @@ __device__ __forceinline__ void fused_worker(const FusedArgs& a, uint4* smem, in
         if (t < M) p = a.level_pts[t];
         else {
             int e = 0;
-            if (lane == 0) { const int* q = a.taskq + (t - M); while ((e = ld_vol(q)) == 0) __nanosleep(32); }
+            if (lane == 0) { const int* q = a.taskq + (t - M); while ((e = ld_vol(q)) == 0) __nanosleep(20); }
             e = __shfl_sync(FULLM, e, 0) - 1;
             __threadfence();
             it = e / a.Mcap; p = e - it * a.Mcap;
@@ -641,7 +641,7 @@ __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int
                     pend &= ~(1u << k);
                 }
             }
-            if (pend) __nanosleep(64);
+            if (pend) __nanosleep(20);
         }
     }
 }
