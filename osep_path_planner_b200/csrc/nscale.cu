@@ -649,13 +649,21 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
                 int ln = -1; float hi = 0.0f;
                 if (guess > 0.0f && guess < b2) { hi = guess; ln = collect(hi); if (ln < k_eff || ln > KNN_LIST) ln = -1; }
                 if (ln < 0) {
-                    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;       // population of 4 nested radii
-                    const float t1 = b2 * 0.5f, t2 = b2 * 0.25f, t3 = b2 * 0.125f;
+                    // population of 8 nested radii b2 / 2^m: the smallest one that still holds >= k points usually holds
+                    // fewer than 2k (area halves per level), so the list fits without any bisection pass
+                    constexpr int NR = 8;
+                    int cr[NR];
+                    float tr[NR];
+#pragma unroll
+                    for (int m = 0; m < NR; ++m) { cr[m] = 0; tr[m] = b2 * (1.0f / (float)(1 << m)); }
                     if constexpr (STAGED) {
 #pragma unroll
-                        for (int r = 0; r < RPL; ++r) { c0 += (dq[r] < b2) ? 1 : 0; c1 += (dq[r] < t1) ? 1 : 0; c2 += (dq[r] < t2) ? 1 : 0; c3 += (dq[r] < t3) ? 1 : 0; }
-                        c0 = __reduce_add_sync(0xffffffffu, c0); c1 = __reduce_add_sync(0xffffffffu, c1);
-                        c2 = __reduce_add_sync(0xffffffffu, c2); c3 = __reduce_add_sync(0xffffffffu, c3);
+                        for (int r = 0; r < RPL; ++r) {
+#pragma unroll
+                            for (int m = 0; m < NR; ++m) cr[m] += (dq[r] < tr[m]) ? 1 : 0;
+                        }
+#pragma unroll
+                        for (int m = 0; m < NR; ++m) cr[m] = __reduce_add_sync(0xffffffffu, cr[m]);
                     } else {
                         for (int ti = 0; ti < nt; ++ti) {
                             const int2 e = tab[wib][ti];
@@ -663,19 +671,20 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
                                 const int t = o + lane;
                                 float d2 = 3.0e38f;
                                 if (t < e.y) { const float4 c = base[e.x + t]; d2 = dist2(q.x, q.y, q.z, c.x, c.y, c.z); }
-                                c0 += __popc(__ballot_sync(0xffffffffu, d2 < b2));
-                                c1 += __popc(__ballot_sync(0xffffffffu, d2 < t1));
-                                c2 += __popc(__ballot_sync(0xffffffffu, d2 < t2));
-                                c3 += __popc(__ballot_sync(0xffffffffu, d2 < t3));
+#pragma unroll
+                                for (int m = 0; m < NR; ++m) cr[m] += (d2 < tr[m]) ? 1 : 0;
                             }
                         }
+#pragma unroll
+                        for (int m = 0; m < NR; ++m) cr[m] = __reduce_add_sync(0xffffffffu, cr[m]);
                     }
-                    if (c0 < k_eff) continue;                 // not certifiable at this R
-                    float lo; int cnt;
-                    if (c3 >= k_eff) { hi = t3; lo = 0.0f; cnt = c3; }
-                    else if (c2 >= k_eff) { hi = t2; lo = t3; cnt = c2; }
-                    else if (c1 >= k_eff) { hi = t1; lo = t2; cnt = c1; }
-                    else { hi = b2; lo = t1; cnt = c0; }
+                    if (cr[0] < k_eff) continue;              // not certifiable at this R
+                    float lo = 0.0f; int cnt = cr[0];
+                    hi = tr[0];
+#pragma unroll
+                    for (int m = 1; m < NR; ++m) if (cr[m] >= k_eff) { hi = tr[m]; cnt = cr[m]; }
+#pragma unroll
+                    for (int m = 1; m < NR; ++m) if (cr[m] < k_eff && tr[m] > lo) lo = tr[m];   // largest radius known to hold < k
                     int guardc = 0;
                     while (cnt > KNN_LIST && guardc < 48) {   // bisection: population(hi) >= k > population(lo)
                         const float mid = 0.5f * (lo + hi);
