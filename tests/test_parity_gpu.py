@@ -86,7 +86,9 @@ def test_golden_fixture_against_gpu(mods):
 
 
 @pytest.mark.parametrize("cfgkw", [dict(ne_knn=10, nb_knn=6, max_points=500), dict(ne_knn=30, nb_knn=12, niter_drosa=3, niter_dcrosa=2, niter_smooth=1),
-                                   dict(ne_knn=16, max_points=1500, radius_smooth=3.0, alpha_recenter=0.5)])
+                                   dict(ne_knn=16, max_points=1500, radius_smooth=3.0, alpha_recenter=0.5),
+                                   dict(niter_drosa=0, niter_dcrosa=0, niter_smooth=0), dict(niter_drosa=8, nb_knn=4, ne_knn=5),
+                                   dict(niter_drosa=9, max_points=200)])
 def test_non_default_configs(mods, cfgkw):
     osep, po, fx = mods
     o, ok_o, r, ok_g = run_both(mods, fx.turbine(30000, seed=11), cfgkw)
