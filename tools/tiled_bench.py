@@ -24,11 +24,14 @@ P = np.concatenate(parts).astype(np.float32)
 axis, bounds = tiled.split_axis_and_bounds(P, world)
 own = np.ascontiguousarray(tiled.slab_of(P, axis, bounds, rank))
 halo = float(sys.argv[2]) if len(sys.argv) > 2 else 15.0     # ~10 x the converged per-tile leaf (similarity radius, rosa.cpp:212)
-r = osep.Rosa(osep.RosaConfig(pts_dist_lim=1.0e4), device=local, capacity_points=int(len(own) * 1.8) + 1024)
-r.set_profile(True)
+r = None
 info = {}
 
 def skeletonize(tile):
+    global r
+    if r is None:          # sized once the tile (own slab + halos) is known
+        r = osep.Rosa(osep.RosaConfig(pts_dist_lim=1.0e4), device=local, capacity_points=int(len(tile) * 1.05) + 1024)
+        r.set_profile(True)
     r.set_input(tile)
     ok = r.rosa_run()
     info.update(ok=ok, status=r.result.status, M=r.result.n_downsampled, gpu_ms=r.result.gpu_ms, n=len(tile), leaf=r.result.leaf_size, stage_ms={k: round(v, 3) for k, v in r.stage_ms().items()})
