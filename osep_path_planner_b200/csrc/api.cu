@@ -41,7 +41,7 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
     CK(dalloc(&d.st, 1)); CK(cudaMemset(d.st, 0, sizeof(FrameState)));
     CK(dalloc(&d.in, N * 4));
     CK(dalloc(&d.P, N)); CK(dalloc(&d.filt_idx, N)); CK(dalloc(&d.blk_cnt, N / 256 + 2));
-    { unsigned* g3; CK(dalloc(&g3, 3 * T)); d.gtab = (unsigned long long*)g3; d.g_cnt = (int*)(g3 + T); d.g_fill = (int*)(g3 + 2 * T); }
+    { unsigned* g4; CK(dalloc(&g4, 4 * T)); d.gtab = (unsigned long long*)g4; d.g_cnt = (int*)(g4 + 2 * T); d.g_fill = (int*)(g4 + 3 * T); }
     CK(dalloc(&d.g_start, T)); CK(dalloc(&d.units, N + 8)); CK(dalloc(&d.slow_list, N)); CK(dalloc(&d.over_list, N + 8)); CK(dalloc(&d.knn_full, N * (size_t)d.knn)); CK(dalloc(&d.p_slot, N)); CK(dalloc(&d.Pc, N)); CK(dalloc(&d.Nrm, N));
     CK(dalloc(&d.vtab, T)); CK(cudaMemset(d.vtab, 0, T * sizeof(unsigned long long)));
     CK(dalloc(&d.vkeys, M)); CK(dalloc(&d.vid, N)); CK(dalloc(&d.vox_cnt, M + 2)); CK(dalloc(&d.vox_fill, M + 2));

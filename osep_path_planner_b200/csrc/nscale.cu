@@ -258,6 +258,27 @@ __global__ void k_vox_count(const float4* __restrict__ P, FrameState* st, unsign
 
 // ------------------------------------------------------------------------------------------
 // kNN grid: sparse uniform grid in a hash table keyed by the linear cell id.
+__device__ void grid_set_h(FrameState* st, float h) {
+    if (!(h > 1e-6f) || !fin(h)) h = 1.0f;
+    float ext = 0.0f;
+    for (int d = 0; d < 3; ++d) ext = fmaxf(ext, st->bmax[d] - st->bmin[d]);
+    if (ext / h > 2.0e6f) h = ext / 2.0e6f;         // 21 bits per axis in the 64-bit cell key
+    st->g_h = h; st->g_inv_h = 1.0f / h;
+    for (int d = 0; d < 3; ++d) {
+        int dim = (int)floorf((st->bmax[d] - st->bmin[d]) * st->g_inv_h) + 1;
+        if (dim < 1) dim = 1; if (dim > 2097151) dim = 2097151;
+        st->g_dim[d] = dim;
+    }
+}
+
+__device__ __forceinline__ unsigned long long cell_key1(int x, int y, int z) {
+    return (((unsigned long long)z << 42) | ((unsigned long long)y << 21) | (unsigned long long)x) + 1ull;
+}
+__device__ __forceinline__ unsigned hash_u64(unsigned long long k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return (unsigned)k;
+}
+
 __global__ void k_grid_params(FrameState* st, int target_ppc) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (st->status != 0) return;
@@ -266,17 +287,29 @@ __global__ void k_grid_params(FrameState* st, int target_ppc) {
     // points; for a surface-like cloud a cell of size h holds ~ (h/leaf)^2 * n/nv points.
     const int nv = st->nvox_hist[0];
     float h = st->leaf_hist[0] * sqrtf((float)target_ppc * (float)(nv > 0 ? nv : 1) / (float)(n > 0 ? n : 1));
-    if (!(h > 1e-6f) || !fin(h)) h = 1.0f;
-    float ext = 0.0f;
-    for (int d = 0; d < 3; ++d) ext = fmaxf(ext, st->bmax[d] - st->bmin[d]);
-    if (ext / h > 1000.0f) h = ext / 1000.0f;       // keep the linear cell id inside 30 bits
-    st->g_h = h; st->g_inv_h = 1.0f / h;
-    for (int d = 0; d < 3; ++d) {
-        int dim = (int)floorf((st->bmax[d] - st->bmin[d]) * st->g_inv_h) + 1;
-        if (dim < 1) dim = 1; if (dim > 1023) dim = 1023;
-        st->g_dim[d] = dim;
-    }
+    grid_set_h(st, h);
     st->g_cells_used = 0; st->n_units = 0; st->n_slow = 0; st->n_over = 0; st->unit_ctr = 0; st->over_ctr = 0;
+    st->g_ncells = 0; st->g_redo = 0;
+}
+
+// After the first insertion pass the real occupancy is known: if the estimate was off (the surface-like scaling
+// breaks when leaf0 is larger than the structures, e.g. multi-structure maps), pick the cell size that would
+// give the target and ask for one rebuild.  Only the speed of the search depends on h, never its result.
+__global__ void k_grid_refine(FrameState* st, int target_ppc) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (st->status != 0) return;
+    const int n = st->n_filt, nc = st->g_ncells;
+    if (nc <= 0) return;
+    const float occ = (float)n / (float)nc;
+    if (occ > 1.4f * (float)target_ppc || occ < 0.6f * (float)target_ppc) {
+        grid_set_h(st, st->g_h * sqrtf((float)target_ppc / occ));
+        st->g_redo = 1; st->g_ncells = 0;
+    }
+}
+__global__ void k_grid_clear_if_redo(const FrameState* __restrict__ st, unsigned long long* gtab, int* g_cnt, int T) {
+    if (st->status != 0 || !st->g_redo) return;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < T) { gtab[s] = 0ull; g_cnt[s] = 0; }
 }
 
 __device__ __forceinline__ void cell_of(const FrameState* st, float x, float y, float z, int& cx, int& cy, int& cz) {
@@ -286,24 +319,30 @@ __device__ __forceinline__ void cell_of(const FrameState* st, float x, float y, 
     cx = max(0, min(cx, st->g_dim[0] - 1)); cy = max(0, min(cy, st->g_dim[1] - 1)); cz = max(0, min(cz, st->g_dim[2] - 1));
 }
 
-// gtab stores key+1 (0 = empty) so one memset clears keys, counts and fills together
-__global__ void k_grid_insert(const float4* __restrict__ P, const FrameState* __restrict__ st, unsigned* gtab, int* g_cnt,
-                              int* __restrict__ p_slot, unsigned mask) {
+// gtab stores key+1 (0 = empty) so one memset clears keys, counts and fills together.
+// pass 0 = first build; pass 1 = rebuild, runs only when k_grid_refine asked for it.
+__global__ void k_grid_insert(const float4* __restrict__ P, FrameState* st, unsigned long long* gtab, int* g_cnt,
+                              int* __restrict__ p_slot, unsigned mask, int pass) {
     if (st->status != 0) return;
+    if (pass == 1 && !st->g_redo) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= st->n_filt) return;
-    const float4 p = P[i];
-    int cx, cy, cz; cell_of(st, p.x, p.y, p.z, cx, cy, cz);
-    const unsigned key1 = (unsigned)((cz * st->g_dim[1] + cy) * st->g_dim[0] + cx) + 1u;
-    unsigned s = hash_u32(key1) & mask;
-    while (true) {
-        const unsigned cur = gtab[s];
-        if (cur == key1) break;
-        if (cur == 0u) { const unsigned old = atomicCAS(&gtab[s], 0u, key1); if (old == 0u || old == key1) break; }
-        s = (s + 1) & mask;
+    bool created = false;
+    if (i < st->n_filt) {
+        const float4 p = P[i];
+        int cx, cy, cz; cell_of(st, p.x, p.y, p.z, cx, cy, cz);
+        const unsigned long long key1 = cell_key1(cx, cy, cz);
+        unsigned s = hash_u64(key1) & mask;
+        while (true) {
+            const unsigned long long cur = gtab[s];
+            if (cur == key1) break;
+            if (cur == 0ull) { const unsigned long long old = atomicCAS(&gtab[s], 0ull, key1); if (old == 0ull) { created = true; break; } if (old == key1) break; }
+            s = (s + 1) & mask;
+        }
+        atomicAdd(&g_cnt[s], 1);
+        p_slot[i] = (int)s;
     }
-    atomicAdd(&g_cnt[s], 1);
-    p_slot[i] = (int)s;
+    const unsigned m = __ballot_sync(0xffffffffu, created);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&st->g_ncells, __popc(m));
 }
 constexpr int QCH = 8;            // queries per kNN work unit
 __global__ void k_grid_alloc(FrameState* st, const int* __restrict__ g_cnt, int* __restrict__ g_start, int T, int2* __restrict__ units) {
@@ -394,7 +433,7 @@ __device__ __forceinline__ float block_bound(const FrameState* st, float rx, flo
 // register-resident sorted top-K.  Handles whatever the cell-cooperative kernel below could not certify.
 template <int K>
 __global__ void __launch_bounds__(128) k_knn_exact(const float4* __restrict__ Pc, const FrameState* __restrict__ st,
-                                                   const unsigned* __restrict__ gtab, const int* __restrict__ g_cnt,
+                                                   const unsigned long long* __restrict__ gtab, const int* __restrict__ g_cnt,
                                                    const int* __restrict__ g_start, unsigned mask,
                                                    int* __restrict__ knn_idx, int k_req, const int* __restrict__ slow_list) {
     if (st->status != 0) return;
@@ -419,11 +458,11 @@ __global__ void __launch_bounds__(128) k_knn_exact(const float4* __restrict__ Pc
             const int y0 = max(cy - R, 0), y1 = min(cy + R, dimy - 1);
             const int z0 = max(cz - R, 0), z1 = min(cz + R, dimz - 1);
             for (int z = z0; z <= z1; ++z) for (int y = y0; y <= y1; ++y) for (int x = x0; x <= x1; ++x) {
-                const unsigned key1 = (unsigned)((z * dimy + y) * dimx + x) + 1u;
-                unsigned s = hash_u32(key1) & mask;
-                unsigned cur;
-                while ((cur = gtab[s]) != key1 && cur != 0u) s = (s + 1) & mask;
-                if (cur == 0u) continue;
+                const unsigned long long key1 = cell_key1(x, y, z);
+                unsigned s = hash_u64(key1) & mask;
+                unsigned long long cur;
+                while ((cur = gtab[s]) != key1 && cur != 0ull) s = (s + 1) & mask;
+                if (cur == 0ull) continue;
                 const int b = g_start[s], c = g_cnt[s];
                 for (int e = b; e < b + c; ++e) { const float4 cc = Pc[e]; tk.push(dist2(q.x, q.y, q.z, cc.x, cc.y, cc.z), __float_as_int(cc.w)); }
             }
@@ -497,7 +536,7 @@ __device__ __forceinline__ void bitonic32(unsigned long long& a0) {
 
 template <int K, bool STAGED>
 __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __restrict__ Pc, FrameState* st,
-                                                             const unsigned* __restrict__ gtab, const int* __restrict__ g_cnt,
+                                                             const unsigned long long* __restrict__ gtab, const int* __restrict__ g_cnt,
                                                              const int* __restrict__ g_start, unsigned mask, const int2* __restrict__ units,
                                                              int* __restrict__ knn_idx, int k_req, int* __restrict__ slow_list,
                                                              int* __restrict__ over_list) {
@@ -543,11 +582,11 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
                 int2 e = make_int2(0, 0);
                 if (c < ncell) {
                     const int x = x0 + c % nx, y = y0 + (c / nx) % ny, z = z0 + c / (nx * ny);
-                    const unsigned key1 = (unsigned)((z * dimy + y) * dimx + x) + 1u;
-                    unsigned s = hash_u32(key1) & mask;
-                    unsigned cur;
-                    while ((cur = gtab[s]) != key1 && cur != 0u) s = (s + 1) & mask;
-                    if (cur != 0u) e = make_int2(g_start[s], g_cnt[s]);
+                    const unsigned long long key1 = cell_key1(x, y, z);
+                    unsigned s = hash_u64(key1) & mask;
+                    unsigned long long cur;
+                    while ((cur = gtab[s]) != key1 && cur != 0ull) s = (s + 1) & mask;
+                    if (cur != 0ull) e = make_int2(g_start[s], g_cnt[s]);
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, e.y > 0);
                 if (e.y > 0) tab[wib][nt + __popc(m & lt)] = e;
@@ -905,11 +944,11 @@ template <int K>
 static void launch_knn(osep_rosa_impl* h, int n, int k_req, cudaStream_t s) {
     RosaDev& d = h->d;
     const unsigned mask = (unsigned)(d.T - 1);
-    k_knn_cells<K, true><<<h->sms * 6, KNN_WARPS * 32, 0, s>>>(d.Pc, d.st, (const unsigned*)d.gtab, d.g_cnt, d.g_start, mask, d.units,
+    k_knn_cells<K, true><<<h->sms * 6, KNN_WARPS * 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units,
                                                               d.knn_full, k_req, d.slow_list, d.over_list);
-    k_knn_cells<K, false><<<h->sms * 2, KNN_WARPS * 32, 0, s>>>(d.Pc, d.st, (const unsigned*)d.gtab, d.g_cnt, d.g_start, mask, d.units,
+    k_knn_cells<K, false><<<h->sms * 2, KNN_WARPS * 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units,
                                                                d.knn_full, k_req, d.slow_list, d.over_list);
-    k_knn_exact<K><<<64, 128, 0, s>>>(d.Pc, d.st, (const unsigned*)d.gtab, d.g_cnt, d.g_start, mask, d.knn_full, k_req, d.slow_list);
+    k_knn_exact<K><<<64, 128, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.knn_full, k_req, d.slow_list);
     k_normals<<<div_up(n, 128), 128, 0, s>>>(d.P, d.st, d.knn_full, k_req, d.Nrm);
 }
 
@@ -937,8 +976,11 @@ void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int strid
         k_vox_count<<<nb, NT, 0, s>>>(d.P, d.st, d.vtab, (unsigned)(d.T - 1), p + 1, c.max_points);
     stage_mark(h, SM_LEAF);
     // R5: grid + kNN normals
-    cudaMemsetAsync(d.gtab, 0, sizeof(unsigned) * 3 * (size_t)d.T, sk);   // gtab | g_cnt | g_fill are contiguous
-    k_grid_insert<<<nb, NT, 0, sk>>>(d.P, d.st, (unsigned*)d.gtab, d.g_cnt, d.p_slot, (unsigned)(d.T - 1));
+    cudaMemsetAsync(d.gtab, 0, sizeof(unsigned) * 4 * (size_t)d.T, sk);   // gtab (8 B) | g_cnt | g_fill are contiguous
+    k_grid_insert<<<nb, NT, 0, sk>>>(d.P, d.st, d.gtab, d.g_cnt, d.p_slot, (unsigned)(d.T - 1), 0);
+    k_grid_refine<<<1, 1, 0, sk>>>(d.st, h->knn_ppc);
+    k_grid_clear_if_redo<<<div_up(d.T, NT), NT, 0, sk>>>(d.st, d.gtab, d.g_cnt, d.T);
+    k_grid_insert<<<nb, NT, 0, sk>>>(d.P, d.st, d.gtab, d.g_cnt, d.p_slot, (unsigned)(d.T - 1), 1);
     k_grid_alloc<<<div_up(d.T, NT), NT, 0, sk>>>(d.st, d.g_cnt, d.g_start, d.T, d.units);
     k_grid_scatter<<<nb, NT, 0, sk>>>(d.P, d.st, d.p_slot, d.g_start, d.g_fill, d.Pc);
     stage_mark(h, SM_GRID);
@@ -962,7 +1004,7 @@ void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int strid
     if (h->overlap) cudaStreamWaitEvent(s, h->ev_join[0], 0);              // the reduce is the first consumer of the normals
     k_vox_reduce<<<1024, 256, 0, s>>>(d.st, d.rv0, d.rv1, d.vox_cnt, d.P, d.Nrm, d.pts, d.nrms, d.pset, d.vset);
     stage_mark(h, SM_VOXEL);
-    h->n_launches += 1 + 3 + (LEAF_MAX_ITERS + 1) + 4 + 4 + 4 + 2;
+    h->n_launches += 1 + 3 + (LEAF_MAX_ITERS + 1) + 7 + 4 + 4 + 2;
 }
 
 }  // namespace osep

@@ -35,6 +35,7 @@ struct FrameState {
     float g_inv_h, g_h;
     int g_dim[3];
     int g_cells_used;      // allocation cursor (points)
+    int g_ncells, g_redo;  // occupied cells of the current build; rebuild requested
     int n_units;           // kNN work units (cell, chunk of queries)
     int n_slow;            // queries handed to the exact slow path
     int n_over;            // units whose candidate set does not fit the shared-memory stage
