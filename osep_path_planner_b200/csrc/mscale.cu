@@ -163,24 +163,6 @@ __global__ void k_simi_scan(FrameState* st, int* simi_off, int Scap) {
 
 // ------------------------------------------------------------------------------------------
 // R13.  kNN(nb_knn) among the M points, brute force, canonical (d2, index) order, self first.
-template <int K> struct TopKM {
-    float d[K]; int id[K];
-    __device__ __forceinline__ void init() {
-#pragma unroll
-        for (int t = 0; t < K; ++t) { d[t] = __int_as_float(0x7f800000); id[t] = 0x7fffffff; }
-    }
-    __device__ __forceinline__ void push(float dd, int ii) {
-        if (!nb_less(dd, ii, d[K - 1], id[K - 1])) return;
-#pragma unroll
-        for (int t = K - 1; t > 0; --t) {
-            const bool lt_prev = nb_less(dd, ii, d[t - 1], id[t - 1]);
-            const bool lt_cur = nb_less(dd, ii, d[t], id[t]);
-            d[t] = lt_prev ? d[t - 1] : (lt_cur ? dd : d[t]);
-            id[t] = lt_prev ? id[t - 1] : (lt_cur ? ii : id[t]);
-        }
-        if (nb_less(dd, ii, d[0], id[0])) { d[0] = dd; id[0] = ii; }
-    }
-};
 
 // One warp per point.  Candidates inside an adaptive radius are compacted into a small shared list
 // (ballot + popc), which is then rank-sorted by (d2, index); the radius grows until the list holds at

@@ -192,7 +192,7 @@ __device__ void leaf_step(FrameState* st, int p, int max_points) {
         st->nvox = 0;
         st->epoch += 1;
     }
-    st->cnt0 = active;           // "pass active" flag read by k_vox_count
+    st->pass_active = active;           // "pass active" flag read by k_vox_count
     st->leaf = leaf;
     st->leaf_done = done;
     if (p == LEAF_MAX_ITERS || done) {
@@ -236,7 +236,7 @@ __device__ __forceinline__ bool vset_insert(unsigned long long* tab, unsigned ma
 // count-only VoxelGrid pass: number of distinct voxel keys at the current leaf
 __global__ void k_vox_count(const float4* __restrict__ P, FrameState* st, unsigned long long* vtab, unsigned mask, int next_step, int max_points) {
     if (st->status != 0) return;
-    if (st->cnt0 && !st->pass_overflow) {
+    if (st->pass_active && !st->pass_overflow) {
         const int n = st->n_filt;
         const int i = blockIdx.x * blockDim.x + threadIdx.x;
         bool isnew = false;
@@ -771,7 +771,7 @@ __global__ void k_vox_collect(FrameState* st, const unsigned long long* __restri
     if (s >= T) return;
     const unsigned long long e = vtab[s];
     if ((unsigned)(e >> 32) == st->epoch) {
-        const int pos = atomicAdd(&st->cnt1, 1);
+        const int pos = atomicAdd(&st->n_keys, 1);
         if (pos < Mcap) vkeys[pos] = (unsigned)e;
     }
 }
@@ -782,7 +782,7 @@ __global__ void k_vox_sortkeys(FrameState* st, unsigned* vkeys, int Mcap, int* v
     if (st->status != 0) return;
     __shared__ int sM;
     if (threadIdx.x == 0) {
-        int M = st->cnt1;
+        int M = st->n_keys;
         if (st->pass_overflow) { st->status = OSEP_ERR_CAPACITY; M = 0; }     // VoxelGrid output = input: not supported on device
         else if (M > Mcap) { st->status = OSEP_ERR_CAPACITY; M = 0; }
         st->M = M;

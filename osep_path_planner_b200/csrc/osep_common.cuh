@@ -53,8 +53,9 @@ struct FrameState {
     // ---- drosa bookkeeping
     int n_levels;
     int n_good, n_poor;
-    // ---- scratch counters
-    int cnt0, cnt1;
+    // ---- voxel passes
+    int pass_active;       // the VoxelGrid pass set up by leaf_step is live (loop not finished)
+    int n_keys;            // distinct voxel keys collected for the final pass
     int ticket;            // last-block detection
 };
 

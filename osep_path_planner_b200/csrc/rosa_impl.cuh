@@ -71,15 +71,12 @@ struct osep_rosa_impl {
     bool profile = false;              // record a CUDA event after every stage group (osep_rosa_set_profile)
     static constexpr int NSTAGE_EV = 16;
     cudaEvent_t stage_ev[NSTAGE_EV] = {};
-    int n_stage_ev = 0;
     long long n_launches = 0;          // kernels launched by this handle since create
     // host mirrors
     FrameState* st_host = nullptr;     // pinned
-    float* in_host = nullptr;          // pinned staging, Ncap*4 floats
     float4* skel_host = nullptr;       // pinned, Mcap
     std::vector<float> vertices_colmajor;
     int last_n = 0;
-    bool timed = false;
     // graph outputs (osep_rosa_graph)
     struct GraphHost* graph = nullptr;
     // batch
