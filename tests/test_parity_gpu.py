@@ -362,3 +362,61 @@ def test_fused_and_unfused_drosa_agree(mods):
         assert_bit_equal(a, b, what)
     o = po.RosaOracle(); assert o.run(P)
     assert_bit_equal(outs[0][2], o.tap("skelver"), "vertices vs oracle")
+
+
+def _weird_clouds(fx):
+    rng = np.random.default_rng(77)
+    out = {}
+    base = fx.cylinder(8000, seed=12)
+    # isolated outliers far from everything (kNN slow path: ring search beyond R = 2, brute force)
+    outl = rng.uniform(-40, 40, (12, 3)).astype(np.float32)
+    out["outliers"] = np.concatenate([base, outl])
+    # planar patch (normals all parallel -> planar branch of the position step, rosa.cpp:334)
+    pl = np.stack([rng.uniform(5, 15, 6000), rng.uniform(-5, 5, 6000), 0.01 * rng.normal(size=6000)], 1).astype(np.float32)
+    out["plane"] = pl
+    # thin line: 1-D structure, the leaf loop oscillates / runs out of passes
+    t = rng.uniform(0, 30, 5000)
+    out["line"] = np.stack([10 + 0.01 * rng.normal(size=5000), 0.01 * rng.normal(size=5000), t - 15], 1).astype(np.float32)
+    # two far-apart clusters (huge bbox, tiny occupied volume)
+    a = rng.normal(size=(3000, 3)).astype(np.float32) * 0.5 + np.array([10, -30, -20], np.float32)
+    b = rng.normal(size=(3000, 3)).astype(np.float32) * 0.5 + np.array([12, 30, 25], np.float32)
+    out["two_clusters"] = np.concatenate([a, b])
+    # heavy duplication: 400 distinct points, each repeated 10 times (distance ties everywhere)
+    d = fx.cylinder(400, seed=5)
+    out["duplicates"] = np.repeat(d, 10, axis=0)
+    # coarse lattice (many exactly equal distances)
+    g = np.stack(np.meshgrid(np.arange(10, 14, 0.25), np.arange(-3, 3, 0.25), np.arange(-4, 4, 0.25), indexing="ij"), -1).reshape(-1, 3)
+    out["lattice"] = g.astype(np.float32)
+    return out
+
+
+@pytest.mark.parametrize("name", ["outliers", "plane", "line", "two_clusters", "duplicates", "lattice"])
+def test_degenerate_geometries(mods, name):
+    """Shapes the reference never meets on a turbine: the CUDA path must agree with the oracle on the stage that
+    fails (RUN_STEP semantics) or on every bit of the result -- or fail loudly with a capacity error, never silently."""
+    osep, po, fx = mods
+    P = _weird_clouds(fx)[name]
+    o = po.RosaOracle(); ok_o = o.run(P)
+    r = osep.Rosa(capacity_points=len(P) + 64); r.set_debug(True)
+    r.set_input(P)
+    try:
+        ok_g = r.rosa_run()
+    except osep.OsepError as e:
+        assert "-3" in str(e), "only a capacity error may abort a degenerate frame: %s" % e
+        pytest.skip("capacity limit reached on %s (documented limit): %s" % (name, e))
+    st = r.result.status
+    if st < 0:
+        assert st == -3
+        pytest.skip("device-side capacity limit on %s" % name)
+    assert ok_g == ok_o and st == o.failed_stage, "%s: gpu status %d vs oracle stage %d" % (name, st, o.failed_stage)
+    for tap in ["filt_idx", "leaf_hist", "nvox_hist", "knn_full", "normals_full", "vox_keys", "pts", "nrms"]:
+        a, b = r.tap(tap), o.tap(tap)
+        if tap == "knn_full":
+            a, b = a.reshape(-1), b.reshape(-1)
+        assert_bit_equal(a, b, "%s %s" % (name, tap))
+    if ok_o:
+        assert_bit_equal(r.tap("simi_idx"), o.tap("simi_idx"), name + " simi")
+        assert_bit_equal(r.tap("pset"), o.tap("pset"), name + " pset")
+        assert_bit_equal(np.ascontiguousarray(r.output_vertices()), o.tap("skelver"), name + " vertices")
+        assert r.result.flags == o.flags
+    r.close()
