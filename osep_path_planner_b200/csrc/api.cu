@@ -55,7 +55,6 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
     { int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device)); h->sms = sms > 0 ? sms : 148; } CK(dalloc(&d.surf, M * (size_t)std::max(d.nbk, 1)));
     CK(dalloc(&d.simi_off, M + 2)); CK(dalloc(&d.simi_idx, (size_t)d.Scap));
     CK(dalloc(&d.level, M)); CK(dalloc(&d.level_off, M + 2)); CK(dalloc(&d.level_pts, M));
-    CK(dalloc(&d.rev_off, M + 2)); CK(dalloc(&d.rev_idx, M * (size_t)(d.nbk + 1))); CK(dalloc(&d.need0, M));
     CK(dalloc(&d.good, M)); CK(dalloc(&d.centers, M)); CK(dalloc(&d.good_rank, M + 2)); CK(dalloc(&d.poor_idx, M));
     CK(dalloc(&d.active_size, M)); CK(dalloc(&d.pcloud, M)); CK(dalloc(&d.adj_bits, M * (size_t)d.W));
     CK(dalloc(&d.seeds, M)); CK(dalloc(&d.corresp, M));
@@ -73,7 +72,7 @@ static void rosa_free(osep_rosa_impl* h) {
     RosaDev& d = h->d;
     void* ptrs[] = {d.st, d.in, d.P, d.filt_idx, d.blk_cnt, d.gtab, d.g_start, d.units, d.slow_list, d.over_list, d.p_slot, d.Pc, d.Nrm, d.knn_full, d.vtab, d.vkeys, d.vid,
                     d.vox_cnt, d.vox_fill, d.rk0, d.rk1, d.rv0, d.rv1, d.pts, d.nrms, d.pset, d.pset2, d.vset, d.vnew, d.vvar, d.surf,
-                    d.simi_off, d.simi_idx, d.simi_bits, d.nraw, d.vnd, d.vset_it, d.vnew_it, d.fused_flags, d.fused_dbg, d.level, d.level_off, d.level_pts, d.rev_off, d.rev_idx, d.need0, d.good, d.centers, d.good_rank, d.poor_idx, d.active_size,
+                    d.simi_off, d.simi_idx, d.simi_bits, d.nraw, d.vnd, d.vset_it, d.vnew_it, d.fused_flags, d.fused_dbg, d.level, d.level_off, d.level_pts, d.good, d.centers, d.good_rank, d.poor_idx, d.active_size,
                     d.pcloud, d.adj_bits, d.seeds, d.corresp, d.skel, d.skel2, d.skel_sampled, d.vtmp, d.vs_off, d.vs_idx, d.vset_iters};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->graph) graph_destroy(h->graph);

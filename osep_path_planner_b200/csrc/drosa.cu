@@ -279,94 +279,81 @@ k_drosa_seed(FrameState* st, const float4* __restrict__ pts, const float4* __res
 }
 
 // ------------------------------------------------------------------------------------------
-// Dependency levels of the in-place smoothing pass (rosa.cpp:295-308): p reads the updated
-// orientation of every surf neighbour j < p, so level[p] = 1 + max level[j < p].  Computed by
-// parallel relaxation in shared memory (one cheap round per level of depth, ~230 rounds), then
-// points are bucketed by level (order inside a level is irrelevant: they are independent).
-__global__ void __launch_bounds__(1024) k_gs_levels2(FrameState* st, const int* __restrict__ surf, int nbk, int* __restrict__ level,
-                                                     int* __restrict__ level_off, int* __restrict__ level_pts,
-                                                     int* __restrict__ rev_off, unsigned short* __restrict__ rev_idx, int* __restrict__ need0,
-                                                     int want_levels) {
-    extern __shared__ int lsm[];          // lv[M] | cnt[M+1] | surf as ushort [M*nbk]
-    if (st->status != 0) return;
-    const int M = st->M;
-    int* lv = lsm; int* cnt = lsm + M;
-    unsigned short* ss = reinterpret_cast<unsigned short*>(cnt + M + 1);
-    const int k_eff = min(nbk, M);
-    for (int p = threadIdx.x; p < M; p += blockDim.x) lv[p] = 1;
-    for (int i = threadIdx.x; i < M * nbk; i += blockDim.x) { const int j = surf[i]; ss[i] = (unsigned short)(j < 0 ? 0xffff : j); }
-    __syncthreads();
-    // the level relaxation is only needed by the unfused (level-synchronous) smoothing kernel; the fused
-    // dataflow walker needs just the reverse lists below, so all points stay at level 1 there.
-    while (want_levels) {
+// Dependency levels of the in-place smoothing pass (rosa.cpp:295-308) for the unfused, level-synchronous kernel:
+// p reads the updated orientation of every surf neighbour j < p, so level[p] = 1 + max level[j < p].  One block,
+// chaotic relaxation in shared memory (values only grow towards the fixpoint), then a counting sort by level.
+constexpr int SCHED_BINS = 4096;
+
+// val[p] = 1 + max(base[p], max_{j<p in nbs(p)} val[j]) to the fixpoint; returns with all threads synchronised
+template <int NBK>
+__device__ __forceinline__ void sched_relax(int M, int nbk, int k_eff, const unsigned short* ss, int* val, const int* base) {
+    while (true) {
         int changed = 0;
-        for (int sweep = 0; sweep < 8; ++sweep) {         // several chaotic sweeps per barrier (levels only grow towards the fixpoint)
+        for (int sweep = 0; sweep < 8; ++sweep) {
             for (int p = threadIdx.x; p < M; p += blockDim.x) {
-                int v = 0;
-                for (int u = 0; u < k_eff; ++u) { const int j = ss[p * nbk + u]; if (j < p) v = max(v, ((volatile int*)lv)[j]); }
+                int v = base ? base[p] : 0;
+                if (NBK > 0) {
+#pragma unroll
+                    for (int u = 0; u < NBK; ++u) { const int j = ss[p * NBK + u]; if (j < p) v = max(v, ((volatile int*)val)[j]); }
+                } else {
+                    for (int u = 0; u < k_eff; ++u) { const int j = ss[p * nbk + u]; if (j < p) v = max(v, ((volatile int*)val)[j]); }
+                }
                 v += 1;
-                if (v != lv[p]) { ((volatile int*)lv)[p] = v; changed = 1; }
+                if (v != val[p]) { ((volatile int*)val)[p] = v; changed = 1; }
             }
         }
         if (!__syncthreads_or(changed)) break;
     }
+}
+
+// counting sort of the points by key[p] >= 1 (ties in arbitrary order): order[] and optionally the bin offsets out
+__device__ __forceinline__ void sched_sort(int M, const int* key, int* hist, int* s_tot, int* __restrict__ order, int* __restrict__ off_out, int* n_bins_out) {
     int mx = 0;
-    for (int p = threadIdx.x; p < M; p += blockDim.x) mx = max(mx, lv[p]);
+    for (int p = threadIdx.x; p < M; p += blockDim.x) mx = max(mx, key[p]);
     mx = __reduce_max_sync(FULLM, mx);
-    __shared__ int s_mx;
-    if (threadIdx.x == 0) s_mx = 0;
+    if (threadIdx.x == 0) *s_tot = 0;
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) atomicMax(&s_mx, mx);
-    for (int l = threadIdx.x; l <= M; l += blockDim.x) cnt[l] = 0;
+    if ((threadIdx.x & 31) == 0) atomicMax(s_tot, mx);
     __syncthreads();
-    const int nl = s_mx;
-    for (int p = threadIdx.x; p < M; p += blockDim.x) { level[p] = lv[p]; atomicAdd(&cnt[lv[p] - 1], 1); }
+    const int nb = min(*s_tot, SCHED_BINS - 1);           // bin = key - 1; the clamp is never reached in practice (T < 8 * (depth + lag + 1))
+    for (int l = threadIdx.x; l <= nb; l += blockDim.x) hist[l] = 0;
     __syncthreads();
-    if (threadIdx.x < 32) {               // exclusive scan of cnt[0..nl] by one warp
+    for (int p = threadIdx.x; p < M; p += blockDim.x) atomicAdd(&hist[min(key[p], nb) - 1], 1);
+    __syncthreads();
+    if (threadIdx.x < 32) {               // exclusive scan of hist[0..nb] by one warp
         int carry = 0;
-        for (int b = 0; b <= nl; b += 32) {
+        for (int b = 0; b <= nb; b += 32) {
             const int l = b + threadIdx.x;
-            const int v = (l <= nl) ? cnt[l] : 0;
+            const int v = (l <= nb) ? hist[l] : 0;
             int incl = v;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(FULLM, incl, off); if ((int)threadIdx.x >= off) incl += t; }
-            if (l <= nl) { cnt[l] = carry + incl - v; level_off[l] = carry + incl - v; }
+            if (l <= nb) { hist[l] = carry + incl - v; if (off_out) off_out[l] = carry + incl - v; }
             carry += __shfl_sync(FULLM, incl, 31);
         }
     }
     __syncthreads();
-    for (int p = threadIdx.x; p < M; p += blockDim.x) { const int pos = atomicAdd(&cnt[lv[p] - 1], 1); level_pts[pos] = p; }
-    if (threadIdx.x == 0) st->n_levels = nl;
+    for (int p = threadIdx.x; p < M; p += blockDim.x) { const int pos = atomicAdd(&hist[min(key[p], nb) - 1], 1); order[pos] = p; }
+    if (n_bins_out && threadIdx.x == 0) *n_bins_out = nb;
     __syncthreads();
-    // reverse dependency lists for the dataflow chain walker (fused kernel): rev[j] = { q : j in deps(q) },
-    // deps(q) = surf[q] plus q itself (its own weight); need0[q] = |deps(q)| + #{ j in surf[q] : j < q }.
-    for (int l = threadIdx.x; l <= M; l += blockDim.x) cnt[l] = 0;
+}
+
+__global__ void __launch_bounds__(1024) k_gs_schedule(FrameState* st, const int* __restrict__ surf, int nbk, int* __restrict__ level,
+                                                      int* __restrict__ level_off, int* __restrict__ level_pts) {
+    extern __shared__ int lsm[];          // ta[M] | hist[SCHED_BINS] | surf as ushort [M*nbk]
+    __shared__ int s_tot;
+    if (st->status != 0) return;
+    const int M = st->M;
+    int* ta = lsm; int* hist = ta + M;
+    unsigned short* ss = reinterpret_cast<unsigned short*>(hist + SCHED_BINS);
+    const int k_eff = min(nbk, M);
+    const bool fast10 = (nbk == 10 && k_eff == 10);
+    for (int p = threadIdx.x; p < M; p += blockDim.x) ta[p] = 1;
+    for (int i = threadIdx.x; i < M * nbk; i += blockDim.x) { const int j = surf[i]; ss[i] = (unsigned short)(j < 0 ? 0xffff : j); }
     __syncthreads();
-    for (int q = threadIdx.x; q < M; q += blockDim.x) {
-        bool self = false; int lower = 0;
-        for (int u = 0; u < k_eff; ++u) { const int j = ss[q * nbk + u]; atomicAdd(&cnt[j], 1); self |= (j == q); lower += (j < q) ? 1 : 0; }
-        if (!self) atomicAdd(&cnt[q], 1);
-        need0[q] = k_eff + (self ? 0 : 1) + lower;
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {               // exclusive scan of cnt[0..M] by one warp
-        int carry = 0;
-        for (int b = 0; b <= M; b += 32) {
-            const int l = b + threadIdx.x;
-            const int v = (l <= M) ? cnt[l] : 0;
-            int incl = v;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(FULLM, incl, off); if ((int)threadIdx.x >= off) incl += t; }
-            if (l <= M) { cnt[l] = carry + incl - v; rev_off[l] = carry + incl - v; }
-            carry += __shfl_sync(FULLM, incl, 31);
-        }
-    }
-    __syncthreads();
-    for (int q = threadIdx.x; q < M; q += blockDim.x) {
-        bool self = false;
-        for (int u = 0; u < k_eff; ++u) { const int j = ss[q * nbk + u]; rev_idx[atomicAdd(&cnt[j], 1)] = (unsigned short)q; self |= (j == q); }
-        if (!self) rev_idx[atomicAdd(&cnt[q], 1)] = (unsigned short)q;
-    }
+    if (fast10) sched_relax<10>(M, nbk, k_eff, ss, ta, nullptr); else sched_relax<0>(M, nbk, k_eff, ss, ta, nullptr);
+    for (int p = threadIdx.x; p < M; p += blockDim.x) level[p] = ta[p];
+    sched_sort(M, ta, hist, &s_tot, level_pts, level_off, &st->n_levels);
 }
 
 // R17 smoothing half, level by level.  All operands in shared memory; one warp walks the chain.
@@ -460,8 +447,7 @@ struct FusedArgs {
     float4* vnew_it;       // [nit][Mcap]    xyz = symmetry normal, w = weight 1/(var^4+eps)
     int* flagO; int* taskq; int* qctr;      // qctr[0] = claim counter, qctr[1] = publish counter
     int Mcap; int nit;
-    const int* surf; int nbk; const int* level_off; const int* level_pts;
-    const int* rev_off; const unsigned short* rev_idx; const int* need0;
+    const int* surf; int nbk; int dbg_detail;
     int* good; float4* centers; int* active_size; float max_proj_range;
     long long* dbg;        // per chain: [t_begin, t_first_step, t_end, steps, spins, points] (globaltimer ns)
 };
@@ -497,7 +483,7 @@ __device__ __forceinline__ void fused_worker(const FusedArgs& a, uint4* smem, in
         t = __shfl_sync(FULLM, t, 0);
         if (t >= total) break;
         int it = 0, p = 0;
-        if (t < M) p = a.level_pts[t];
+        if (t < M) p = t;
         else {
             int e = 0;
             if (lane == 0) { const int* q = a.taskq + (t - M); while ((e = ld_vol(q)) == 0) __nanosleep(20); }
@@ -524,92 +510,232 @@ __device__ __forceinline__ void fused_worker(const FusedArgs& a, uint4* smem, in
     }
 }
 
+constexpr int O_LAG_STEPS = 3;            // modelled latency (walker steps) from G(k-1,j) to the staged O(k,j)
+
+__host__ __device__ __forceinline__ size_t fused_chain_bytes(int M, int nbk, int nit) {
+    return (size_t)32 * M + 64 + (size_t)2 * M * nbk + (size_t)4 * M + (size_t)M + 4 + (size_t)2 * M * nit + 4 + (size_t)4 * SCHED_BINS + 64;
+}
+
+// One pass of the schedule model (see fused_chain), run by ONE warp over index chunks of 32 points:
+//   w == 0: T_0(p) = 1 + max_{j<p in nbs(p)} T_0(j)                                   (the dependency level)
+//   w >= 1: T_w(p) = 1 + max( max_{j in nbs(p)+p} T_{w-1}(j) + lag, max_{j<p in nbs(p)} T_w(j) )
+// Dependencies below the chunk are final; the ones inside the chunk are resolved by a register fixpoint
+// (a shuffle per neighbour and round, about as many rounds as the chunk is deep).  Pass w trails pass w-1
+// through prog[]: it waits until every T_{w-1} it reads has been published.
+template <int NBK>
+__device__ __forceinline__ void chain_schedule_pass(int w, int M, int nbk, int k_eff, const unsigned short* ssurf,
+                                                    unsigned short* sT, volatile int* prog, volatile int* tmax) {
+    const int lane = threadIdx.x & 31;
+    unsigned short* Tc = sT + (size_t)w * M;
+    const unsigned short* Tp = sT + (size_t)(w > 0 ? w - 1 : 0) * M;
+    int vmax = 0;
+    for (int base = 0; base < M; base += 32) {
+        const int p = min(base + lane, M - 1);
+        const bool valid = base + lane < M;
+        int j[NBK > 0 ? NBK : 1];
+        int jmax = p;
+        if (NBK > 0) {
+#pragma unroll
+            for (int u = 0; u < NBK; ++u) { j[u] = ssurf[p * NBK + u]; jmax = max(jmax, j[u]); }
+        } else {
+            for (int u = 0; u < k_eff; ++u) jmax = max(jmax, (int)ssurf[p * nbk + u]);
+        }
+        int vext = 0;
+        if (w > 0) {
+            jmax = __reduce_max_sync(FULLM, jmax);
+            while (prog[w - 1] <= jmax) { }
+            __syncwarp();
+            int e = Tp[p];
+            if (NBK > 0) {
+#pragma unroll
+                for (int u = 0; u < NBK; ++u) e = max(e, (int)((const volatile unsigned short*)Tp)[j[u]]);
+            } else {
+                for (int u = 0; u < k_eff; ++u) e = max(e, (int)((const volatile unsigned short*)Tp)[ssurf[p * nbk + u]]);
+            }
+            vext = e + O_LAG_STEPS;
+        }
+        if (NBK > 0) {
+#pragma unroll
+            for (int u = 0; u < NBK; ++u) if (j[u] < base) vext = max(vext, (int)Tc[j[u]]);
+        } else {
+            for (int u = 0; u < k_eff; ++u) { const int jj = ssurf[p * nbk + u]; if (jj < base) vext = max(vext, (int)Tc[jj]); }
+        }
+        int v = vext + 1;
+        while (true) {
+            int nv = vext;
+            if (NBK > 0) {
+#pragma unroll
+                for (int u = 0; u < NBK; ++u) { const int tv = __shfl_sync(FULLM, v, j[u] & 31); if (j[u] >= base && j[u] < p) nv = max(nv, tv); }
+            } else {
+                for (int u = 0; u < k_eff; ++u) { const int jj = ssurf[p * nbk + u]; const int tv = __shfl_sync(FULLM, v, jj & 31); if (jj >= base && jj < p) nv = max(nv, tv); }
+            }
+            nv += 1;
+            const bool changed = nv != v;
+            v = nv;
+            if (!__any_sync(FULLM, changed)) break;
+        }
+        if (valid) { Tc[p] = (unsigned short)min(v, 65535); vmax = max(vmax, v); }
+        __syncwarp();
+        __threadfence_block();
+        if (lane == 0) prog[w] = min(base + 32, M);
+    }
+    vmax = __reduce_max_sync(FULLM, vmax);
+    if (lane == 0) *tmax = vmax;
+}
+
 __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int M, int it) {
-    // Dataflow walker of the Gauss-Seidel pass of iteration `it` (rosa.cpp:295-308).  Point q may be
-    // rewritten once (a) the Jacobi results O(it,j) of all its surf neighbours (and its own) are staged and
-    // (b) every neighbour j < q has been rewritten.  need[q] counts the open dependencies; whoever closes the
-    // last one pushes q on the ready queue; the walker warp pops up to 32 ready points per step.  Any
-    // order that respects the dependencies produces the same bits (every operand is fixed by them).
+    // Walker of the Gauss-Seidel pass of iteration `it` (rosa.cpp:295-308).  Point q may be rewritten once
+    // (a) the Jacobi results O(it,j) of all its surf neighbours (and its own) are staged and (b) every
+    // neighbour j < q has been rewritten.  The walker PULLS: each lane holds one candidate of a 32-point
+    // window over a topologically sorted point list and tests the candidate's dependencies against a
+    // per-point state byte in shared memory (bit 0 = O staged, bit 1 = G done); ready candidates are
+    // rewritten in the same step and their lanes refill from the list.  No counters, no atomics and no
+    // release phase on the critical path.  Any order that respects the dependencies produces the same
+    // bits (every operand is fixed by them).
+    //
+    // Window order.  Iteration 0 has every O available at once, so its order is the dependency level T_0.
+    // For it >= 1 the O results arrive as chain it-1 completes them, so the CTA first models its own
+    // schedule (chain_schedule_pass; warps 0..it run passes 0..it as a pipeline while the workers compute
+    // the first Jacobi results) and sorts the points by T_it.  T_it(p) > T_it(j) for every dependency
+    // j < p, so the order is topological (progress is guaranteed for any window size) and follows the
+    // arrival of the operands.
     const int nbk = a.nbk;
     float4* sold = reinterpret_cast<float4*>(smem);
     float4* snew = sold + M;
-    int* need = reinterpret_cast<int*>(snew + M);
-    int* rq = need + M;                                   // ready queue, entries q+1, 0 = not written yet
-    int* srev_off = rq + M;                               // M+1
-    int* s_ctl = srev_off + M + 1;                        // [0] tail, [1] done_upto
-    unsigned short* ssurf = reinterpret_cast<unsigned short*>(s_ctl + 2);
-    unsigned short* srev = ssurf + (size_t)M * nbk;       // up to M*(nbk+1)
-    const int nrev = a.rev_off[M];
-    for (int i = threadIdx.x; i < M; i += blockDim.x) { need[i] = a.need0[i]; rq[i] = 0; }
-    for (int i = threadIdx.x; i <= M; i += blockDim.x) srev_off[i] = a.rev_off[i];
+    int* s_ctl = reinterpret_cast<int*>(snew + M);        // [1] points rewritten (publisher progress) [2] max T  [4..12) pass progress
+    unsigned short* ssurf = reinterpret_cast<unsigned short*>(s_ctl + 16);
+    unsigned short* sorder = ssurf + (size_t)M * nbk;     // window order
+    unsigned short* solist = sorder + M;                  // completion order (what the publisher walks)
+    unsigned char* sstate = reinterpret_cast<unsigned char*>(solist + M);
+    unsigned short* sT = reinterpret_cast<unsigned short*>((reinterpret_cast<uintptr_t>(sstate + M) + 3) & ~(uintptr_t)3);   // (it+1) x M
+    int* shist = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(sT + (size_t)(it + 1) * M) + 3) & ~(uintptr_t)3);
+    for (int i = threadIdx.x; i < M; i += blockDim.x) sstate[i] = 0;
     for (int i = threadIdx.x; i < M * nbk; i += blockDim.x) { const int j = a.surf[i]; ssurf[i] = (unsigned short)(j < 0 ? 0 : j); }
-    for (int i = threadIdx.x; i < nrev; i += blockDim.x) srev[i] = a.rev_idx[i];
-    if (threadIdx.x < 2) s_ctl[threadIdx.x] = 0;
+    if (threadIdx.x < 16) s_ctl[threadIdx.x] = 0;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const int k_eff = min(nbk, M);
-    const int* fO = a.flagO + (size_t)it * a.Mcap;
-    const float4* vn = a.vnew_it + (size_t)it * a.Mcap;
-    if (warp == 0) {
-        // ---- chain walker
-        const bool fast10 = (nbk == 10 && k_eff == 10);
-        int head = 0;
-        long long t_begin = gtime(), t_first = 0; int steps = 0, spins = 0;
-        long long c_comp = 0, c_rel = 0, c_pts = 0;
-        while (head < M) {
-            const int e = (head + lane < M) ? ld_vol(rq + head + lane) : 0;
-            const unsigned got = __ballot_sync(FULLM, e != 0);
-            const int take = (got == FULLM) ? 32 : (__ffs(~got) - 1);
-            if (take == 0) { ++spins; continue; }
-            if (steps == 0) t_first = gtime();
-            ++steps;
-            const bool act = lane < take;
-            const int p = act ? e - 1 : 0;
-            __threadfence_block();
-            const long long c0 = clock64();
-            if (act) snew[p] = fast10 ? gs_point<10>(p, sold, snew, ssurf, nbk, k_eff) : gs_point<0>(p, sold, snew, ssurf, nbk, k_eff);
-            __syncwarp();
-            const long long c1 = clock64();
-            c_comp += c1 - c0; c_pts += take;
-            // release the dependents of the points just rewritten, flattened over the warp: entry t of the
-            // concatenated reverse lists belongs to the source lane whose degree prefix covers t
-            {
-                const int rb = act ? srev_off[p] : 0;
-                const int deg = act ? srev_off[p + 1] - rb : 0;
-                int incl = deg;
+    const bool fast10 = (nbk == 10 && k_eff == 10);
+    if (warp <= it) {
+        if (fast10) chain_schedule_pass<10>(warp, M, nbk, k_eff, ssurf, sT, s_ctl + 4, s_ctl + 2);
+        else chain_schedule_pass<0>(warp, M, nbk, k_eff, ssurf, sT, s_ctl + 4, s_ctl + 2);
+    }
+    __syncthreads();
+    {
+        // counting sort by T_it (ties in any order); a schedule deeper than the histogram falls back to the index order
+        const unsigned short* T = sT + (size_t)it * M;
+        const int nb = s_ctl[2];                          // written last by warp `it`
+        if (nb >= SCHED_BINS) {
+            for (int i = threadIdx.x; i < M; i += blockDim.x) sorder[i] = (unsigned short)i;
+        } else {
+            for (int l = threadIdx.x; l <= nb; l += blockDim.x) shist[l] = 0;
+            __syncthreads();
+            for (int p = threadIdx.x; p < M; p += blockDim.x) atomicAdd(&shist[T[p] - 1], 1);
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                int carry = 0;
+                for (int b = 0; b <= nb; b += 32) {
+                    const int l = b + threadIdx.x;
+                    const int v = (l <= nb) ? shist[l] : 0;
+                    int incl = v;
 #pragma unroll
-                for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(FULLM, incl, off); if (lane >= off) incl += v; }
-                const int total = __shfl_sync(FULLM, incl, 31);
-                for (int t0 = 0; t0 < total; t0 += 32) {          // uniform trip count: every lane takes part in the shuffles
-                    const int t = t0 + lane;
-                    // smallest source lane whose inclusive prefix exceeds t (prefixes are monotone: 5-step search)
-                    int src = 0;
-#pragma unroll
-                    for (int step = 16; step >= 1; step >>= 1) { const int probe = __shfl_sync(FULLM, incl, src + step - 1); if (probe <= t) src += step; }
-                    const int s_incl = __shfl_sync(FULLM, incl, src), s_deg = __shfl_sync(FULLM, deg, src);
-                    const int s_rb = __shfl_sync(FULLM, rb, src), s_p = __shfl_sync(FULLM, p, src);
-                    if (t < total) {
-                        const int q = srev[s_rb + (t - (s_incl - s_deg))];
-                        if (q > s_p && atomicSub(need + q, 1) == 1) { const int slot = atomicAdd(s_ctl, 1); st_vol(rq + slot, q + 1); }
-                    }
+                    for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(FULLM, incl, off); if ((int)threadIdx.x >= off) incl += t; }
+                    if (l <= nb) shist[l] = carry + incl - v;
+                    carry += __shfl_sync(FULLM, incl, 31);
                 }
             }
-            head += take;
+            __syncthreads();
+            for (int p = threadIdx.x; p < M; p += blockDim.x) sorder[atomicAdd(&shist[T[p] - 1], 1)] = (unsigned short)p;
+        }
+    }
+    __syncthreads();
+    const int* fO = a.flagO + (size_t)it * a.Mcap;
+    const float4* vn = a.vnew_it + (size_t)it * a.Mcap;
+    volatile unsigned char* vstate = sstate;
+    if (warp == 0) {
+        // ---- chain walker
+        const unsigned lt = (1u << lane) - 1u;
+        const bool detail = a.dbg_detail != 0;
+        int next = 32;
+        int cand = lane < M ? (int)sorder[lane] : -1;
+        unsigned nb[5] = {0u, 0u, 0u, 0u, 0u};             // fast path: the candidate's 10 neighbour indices, 2 per register
+        if (fast10 && cand >= 0) {
+            const unsigned* wsrc = reinterpret_cast<const unsigned*>(ssurf + cand * 10);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) nb[k] = wsrc[k];
+        }
+        int ndone = 0;
+        long long t_begin = gtime(), t_first = 0; int steps = 0, spins = 0;
+        long long c_comp = 0, c_rel = 0;
+        while (ndone < M) {
+            const long long c0 = detail ? clock64() : 0;
+            bool ready = false;
+            if (cand >= 0) {
+                unsigned ok = vstate[cand] & 1u;
+                if (fast10) {
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        const int j0 = (int)(nb[k] & 0xffffu), j1 = (int)(nb[k] >> 16);
+                        const unsigned s0 = vstate[j0], s1 = vstate[j1];
+                        ok &= s0 & ((j0 >= cand) ? 1u : (s0 >> 1));
+                        ok &= s1 & ((j1 >= cand) ? 1u : (s1 >> 1));
+                    }
+                } else {
+                    for (int u = 0; u < k_eff; ++u) {
+                        const int j = ssurf[cand * nbk + u];
+                        const unsigned sj = vstate[j];
+                        ok &= sj & ((j >= cand) ? 1u : (sj >> 1));
+                    }
+                }
+                ready = ok != 0u;
+            }
+            const unsigned rm = __ballot_sync(FULLM, ready);
+            if (rm == 0u) { ++spins; continue; }
+            if (steps == 0) t_first = gtime();
+            ++steps;
+            __threadfence_block();
+            const long long c1 = detail ? clock64() : 0;
+            // refill loads first: they do not depend on the solve below and hide behind it
+            const int r = __popc(rm & lt);
+            int ncand = cand;
+            unsigned nnb[5] = {nb[0], nb[1], nb[2], nb[3], nb[4]};
+            if (ready) {
+                const int pos = next + r;
+                ncand = pos < M ? (int)sorder[pos] : -1;
+                if (fast10 && ncand >= 0) {
+                    const unsigned* wsrc = reinterpret_cast<const unsigned*>(ssurf + ncand * 10);
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) nnb[k] = wsrc[k];
+                }
+                snew[cand] = fast10 ? gs_point<10>(cand, sold, snew, ssurf, nbk, k_eff) : gs_point<0>(cand, sold, snew, ssurf, nbk, k_eff);
+            }
+            __syncwarp();
+            const long long c2 = detail ? clock64() : 0;
+            if (ready) {
+                vstate[cand] = 3;
+                solist[ndone + r] = (unsigned short)cand;
+                cand = ncand;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) nb[k] = nnb[k];
+            }
+            const int c = __popc(rm);
+            ndone += c; next += c;
             __syncwarp();
             __threadfence_block();
-            if (lane == 0) st_vol(s_ctl + 1, head);
-            c_rel += clock64() - c1;
+            if (lane == 0) st_vol(s_ctl + 1, ndone);
+            if (detail) { c_comp += c2 - c1; c_rel += (c1 - c0) + (clock64() - c2); }
         }
         if (lane == 0 && a.dbg) { long long* g = a.dbg + it * 8; g[0] = t_begin; g[1] = t_first; g[2] = gtime(); g[3] = steps; g[4] = spins; g[5] = M; g[6] = c_comp; g[7] = c_rel; }
     } else if (warp == nw - 1) {
         // ---- publisher: G(it,p) -> vset_it[it+1][p] in L2, then task (it+1, p) goes on the workers' ready queue
         float4* dst = a.vset_it + (size_t)(it + 1) * a.Mcap;
+        const volatile unsigned short* vol = solist;
         int idx = lane;
         while (__any_sync(FULLM, idx < M)) {
             const int upto = ld_vol(s_ctl + 1);
             if (idx < upto) {
                 __threadfence_block();
-                const int p = ld_vol(rq + idx) - 1;
+                const int p = vol[idx];
                 float4 v = snew[p]; v.w = 0.0f;
                 dst[p] = v;
                 __threadfence();
@@ -619,7 +745,7 @@ __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int
             }
         }
     } else {
-        // ---- prefetchers: stage O(it,j) = (symmetry normal, weight) as soon as its flag is up, release dependents
+        // ---- prefetchers: stage O(it,j) = (symmetry normal, weight) as soon as its flag is up (window order)
         const int npf = nw - 2;
         const int stride = npf * 32;
         const int first = (warp - 1) * 32 + lane;
@@ -629,15 +755,12 @@ __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int
             unsigned scan = pend;
             while (scan) {
                 const int k = __ffs(scan) - 1; scan &= scan - 1;
-                const int j = a.level_pts[first + k * stride];
+                const int j = sorder[first + k * stride];
                 if (ld_vol(fO + j) != 0) {
                     __threadfence();
                     sold[j] = __ldcg(vn + j);
                     __threadfence_block();
-                    for (int r = srev_off[j]; r < srev_off[j + 1]; ++r) {
-                        const int q = srev[r];
-                        if (atomicSub(need + q, 1) == 1) { const int slot = atomicAdd(s_ctl, 1); st_vol(rq + slot, q + 1); }
-                    }
+                    vstate[j] = 1;
                     pend &= ~(1u << k);
                 }
             }
@@ -651,7 +774,7 @@ __global__ void __launch_bounds__(SEED_WARPS * 32) k_drosa_fused(const __grid_co
     if (a.st->status != 0) return;
     const int M = a.st->M;
     // shared-memory footprint of a chain CTA (see fused_chain); evaluated identically by every CTA
-    const size_t chain_bytes = (size_t)44 * M + 16 + (size_t)2 * M * a.nbk + (size_t)2 * M * (a.nbk + 1) + 64;
+    const size_t chain_bytes = fused_chain_bytes(M, a.nbk, a.nit);
     if (chain_bytes > (size_t)SEED_SMEM_BUDGET) {
         if (blockIdx.x == 0 && threadIdx.x == 0) a.st->status = OSEP_ERR_CAPACITY;
         return;
@@ -674,19 +797,29 @@ void drosa_set_attributes() {
     cudaFuncSetAttribute(k_drosa_seed<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEED_SMEM_BUDGET + 1024);
     cudaFuncSetAttribute(k_drosa_seed<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEED_SMEM_BUDGET + 1024);
     cudaFuncSetAttribute(k_drosa_smooth2, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_SMEM_BUDGET);
-    cudaFuncSetAttribute(k_gs_levels2, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_SMEM_BUDGET);
+    cudaFuncSetAttribute(k_gs_schedule, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_SMEM_BUDGET);
     cudaFuncSetAttribute(k_drosa_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, SEED_SMEM_BUDGET);
 }
 
-// R13 level schedule + R14-R18; `sms` = number of SMs (one seed CTA per SM)
+// hoisted normals + schedule of the smoothing pass: needs only the downsampled cloud and surf_nbs, so it runs on the
+// side stream next to the similarity stage
+void launch_drosa_prep(osep_rosa_impl* h, cudaStream_t sk) {
+    RosaDev& d = h->d;
+    const osep_rosa_config& c = h->cfg;
+    const bool fused = h->fused && c.niter_drosa <= MAX_FUSED_ITERS;
+    k_normal_prep<<<div_up(d.Mcap, 128), 128, 0, sk>>>(d.st, d.nrms, d.nraw, d.vnd);
+    if (!fused) {
+        k_gs_schedule<<<1, 1024, sizeof(int) * (d.Mcap + SCHED_BINS) + sizeof(unsigned short) * d.Mcap * d.nbk, sk>>>(d.st, d.surf, d.nbk, d.level, d.level_off, d.level_pts);
+        h->n_launches += 1;
+    }
+    h->n_launches += 1;
+}
+
+// R14-R18; `sms` = number of SMs (one seed CTA per SM)
 void launch_drosa(osep_rosa_impl* h, int sms) {
     RosaDev& d = h->d;
     cudaStream_t s = h->stream;
     const osep_rosa_config& c = h->cfg;
-    // largest M the all-shared smoothing kernel accepts with this nb_knn (checked against Mcap at create)
-    k_normal_prep<<<div_up(d.Mcap, 128), 128, 0, s>>>(d.st, d.nrms, d.nraw, d.vnd);
-    k_gs_levels2<<<1, 1024, sizeof(int) * (2 * d.Mcap + 2) + sizeof(unsigned short) * d.Mcap * d.nbk, s>>>(d.st, d.surf, d.nbk, d.level, d.level_off, d.level_pts, d.rev_off, d.rev_idx, d.need0,
-                                                                                     (h->fused && c.niter_drosa <= MAX_FUSED_ITERS) ? 0 : 1);
     stage_mark(h, SM_SURF);
     stage_mark(h, SM_DROSA_ORIENT);
     SeedOut o; o.vnew = d.vnew; o.vvar = d.vvar; o.prev = nullptr; o.pack_w = 0; o.pset = d.pset; o.good = d.good; o.centers = d.centers; o.active_size = d.active_size;
@@ -699,8 +832,7 @@ void launch_drosa(osep_rosa_impl* h, int sms) {
         a.st = d.st; a.pts = d.pts; a.nraw = d.nraw; a.vnd = d.vnd; a.pset = d.pset; a.bits = d.simi_bits; a.W = d.W;
         a.vset_it = d.vset_it; a.vnew_it = d.vnew_it;
         a.flagO = d.fused_flags; a.taskq = d.fused_flags + (size_t)MAX_FUSED_ITERS * d.Mcap; a.qctr = d.fused_flags + (size_t)2 * MAX_FUSED_ITERS * d.Mcap;
-        a.Mcap = d.Mcap; a.nit = c.niter_drosa; a.surf = d.surf; a.nbk = d.nbk; a.level_off = d.level_off; a.level_pts = d.level_pts;
-        a.rev_off = d.rev_off; a.rev_idx = d.rev_idx; a.need0 = d.need0;
+        a.Mcap = d.Mcap; a.nit = c.niter_drosa; a.surf = d.surf; a.nbk = d.nbk; a.dbg_detail = h->profile ? 1 : 0;
         a.good = d.good; a.centers = d.centers; a.active_size = d.active_size; a.max_proj_range = c.max_proj_range;
         a.dbg = d.fused_dbg;
         int grid = h->fused_grid > 0 ? h->fused_grid : sms;
@@ -713,7 +845,7 @@ void launch_drosa(osep_rosa_impl* h, int sms) {
             for (int it = 0; it < c.niter_drosa; ++it)
                 cudaMemcpyAsync(d.vset_iters + (size_t)it * d.Mcap, d.vset_it + (size_t)(it + 1) * d.Mcap, sizeof(float4) * d.Mcap, cudaMemcpyDeviceToDevice, s);
         stage_mark(h, SM_DROSA_SMOOTH);
-        h->n_launches += 2 + 1;
+        h->n_launches += 1;
         return;
     }
     cudaMemsetAsync(d.vnew, 0, sizeof(float4) * d.Mcap, s);        // vnew = Zero (rosa.cpp:272)
@@ -725,7 +857,7 @@ void launch_drosa(osep_rosa_impl* h, int sms) {
     }
     stage_mark(h, SM_DROSA_SMOOTH);
     k_drosa_seed<1><<<sms, SEED_WARPS * 32, SEED_SMEM_BUDGET, s>>>(d.st, d.pts, d.nraw, d.vnd, d.pset, d.vset, d.simi_bits, d.W, o);
-    h->n_launches += 2 + 2 * c.niter_drosa + 1;
+    h->n_launches += 2 * c.niter_drosa + 1;
 }
 
 }  // namespace osep

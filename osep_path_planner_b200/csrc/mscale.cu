@@ -640,6 +640,7 @@ __global__ void k_vertex_smooth(FrameState* st, float4* skel, float4* skel2, flo
 // ------------------------------------------------------------------------------------------
 void drosa_set_attributes();
 void launch_drosa(osep_rosa_impl* h, int sms);
+void launch_drosa_prep(osep_rosa_impl* h, cudaStream_t sk);
 void mscale_set_attributes(int Mcap) {
     (void)Mcap;
     drosa_set_attributes();
@@ -656,17 +657,23 @@ void launch_mscale(osep_rosa_impl* h) {
     const int tblocks = div_up(d.Mcap, 128);
     k_mscale_begin<<<1, 1, 0, s>>>(d.st);
     // two independent branches on the downsampled cloud: similarity lists (main stream) || surf kNN (side stream)
-    cudaStream_t sk = s;
-    if (h->overlap) { cudaEventRecord(h->ev_fork[1], s); sk = h->stream2; cudaStreamWaitEvent(sk, h->ev_fork[1], 0); }
-    // R13
-    k_surf_knn<<<warp_blocks, tb, 0, sk>>>(d.st, d.pts, d.surf, d.nbk);
-    if (h->overlap) cudaEventRecord(h->ev_join[1], sk);
+    if (h->overlap) {
+        cudaStream_t sk = h->stream2;
+        cudaEventRecord(h->ev_fork[1], s); cudaStreamWaitEvent(sk, h->ev_fork[1], 0);
+        k_surf_knn<<<warp_blocks, tb, 0, sk>>>(d.st, d.pts, d.surf, d.nbk);   // R13
+        launch_drosa_prep(h, sk);
+        cudaEventRecord(h->ev_join[1], sk);
+    }
     // R12
     k_simi<false><<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.nrms, d.simi_off, d.simi_idx, nullptr, nullptr, d.simi_bits, d.W);
     k_simi_scan<<<1, 1024, 0, s>>>(d.st, d.simi_off, d.Scap);
     k_simi<true><<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.nrms, d.simi_off, d.simi_idx, d.rv1, (float*)d.rk1, d.simi_bits, d.W);
     stage_mark(h, SM_SIMI);
     if (h->overlap) cudaStreamWaitEvent(s, h->ev_join[1], 0);
+    else {                                                                     // profiling: sequential, attributable
+        k_surf_knn<<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.surf, d.nbk);
+        launch_drosa_prep(h, s);
+    }
     launch_drosa(h, h->sms);
     k_poor_prepare<<<1, 1024, 0, s>>>(d.st, d.good, d.good_rank, d.centers, d.pset2, d.poor_idx, nullptr);
     k_poor_fix<<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.good, d.pset2, d.poor_idx, d.pset);

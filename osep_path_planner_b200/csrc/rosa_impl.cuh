@@ -43,7 +43,6 @@ struct RosaDev {
     int* surf = nullptr;               // Mcap * nbk
     int* simi_off = nullptr; int* simi_idx = nullptr;
     int* level = nullptr; int* level_off = nullptr; int* level_pts = nullptr;
-    int* rev_off = nullptr; unsigned short* rev_idx = nullptr; int* need0 = nullptr;   // reverse surf dependencies (fused drosa)
     int* good = nullptr; float4* centers = nullptr; int* good_rank = nullptr; int* poor_idx = nullptr;
     int* active_size = nullptr;
     float4* pcloud = nullptr;          // compacted finite pset (vertex_sampling)
