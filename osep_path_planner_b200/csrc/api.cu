@@ -51,6 +51,7 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
     CK(dalloc(&d.vset_it, M * 9)); CK(dalloc(&d.vnew_it, M * 8)); CK(dalloc(&d.fused_flags, M * 16 + 16)); CK(dalloc(&d.fused_dbg, 64)); CK(cudaMemset(d.fused_dbg, 0, 64 * 8));
     { const char* e = getenv("OSEP_KNN_PPC"); if (e && atoi(e) > 0) h->knn_ppc = atoi(e); }
     { const char* e = getenv("OSEP_DROSA_UNFUSED"); if (e && e[0] == '1') h->fused = false;
+      const char* e2 = getenv("OSEP_DROSA_LAG"); if (e2 && atoi(e2) >= 0) h->sched_lag = atoi(e2);
       int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device); if (!coop) h->fused = false; }
     { int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device)); h->sms = sms > 0 ? sms : 148; } CK(dalloc(&d.surf, M * (size_t)std::max(d.nbk, 1)));
     CK(dalloc(&d.simi_off, M + 2)); CK(dalloc(&d.simi_idx, (size_t)d.Scap));
@@ -298,7 +299,7 @@ long osep_rosa_get(osep_rosa* h, const char* name, void* dst, long cap) {
     if (nm == "surf_off") { if (dst && cap >= (long)((M + 1) * 4)) for (size_t i = 0; i <= M; ++i) ((int*)dst)[i] = (int)(i * d.nbk); return (long)M + 1; }
     if (nm == "simi_off") return tap_copy(dst, cap, d.simi_off, M + 1, 4);
     if (nm == "simi_idx") return tap_copy(dst, cap, d.simi_idx, (size_t)s.S, 4);
-    if (nm == "vset") return tap_f4_as_f3(dst, cap, d.vset, M);
+    if (nm == "vset") return tap_f4_as_f3(dst, cap, (I.fused && I.cfg.niter_drosa <= 8) ? d.vset_it + (size_t)I.cfg.niter_drosa * d.Mcap : d.vset, M);   // fused drosa keeps per-iteration rows
     if (nm == "vset_iters") {
         if (!d.vset_iters) return 0;
         const int nit = I.cfg.niter_drosa;

@@ -85,7 +85,7 @@ OSEP_HD void make_givens(float p, float q, float& c, float& s) {
 // Input: LOWER triangle (a00,a10,a11,a20,a21,a22).  Output: eigenvalues ascending in ev[],
 // eigenvectors in the columns of q (row-major q[r*3+c]).  Register resident: fixed-size
 // arrays with compile-time indices only (the k-loops are fully unrolled over start/end).
-struct Eig3 { float ev[3]; float q[9]; bool ok; };
+struct Eig3 { float ev[3]; float q[9]; bool ok; int iters; };
 
 // one Givens step of tridiagonal_qr_step at compile-time position k; `first` = (k == start), `last` = (k == end-1)
 template <int k>
@@ -179,6 +179,7 @@ OSEP_HD Eig3 eig3_sym(float a00, float a10, float a11, float a20, float a21, flo
         if (end == 2 && z != 0.0f) eig3_qr_rot<1>(diag, sub, q, start == 1, true, x, z);
     }
     R.ok = iter <= 90;
+    R.iters = iter;
     if (R.ok) {
         // selection sort ascending, swapping eigenvector columns (first minimum wins)
         {

@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(1024) k_gs_schedule(FrameState* st, const int*
 // sold = orientation after the Jacobi half (vset = vnew, rosa.cpp:289) with the weight in .w;
 // snew = orientations already rewritten by this pass.  p reads snew[j] for j < p, sold[j] otherwise.
 template <int NBK>
-__device__ __forceinline__ float4 gs_point(int p, const float4* sold, const float4* snew, const unsigned short* ssurf, int nbk, int k_eff) {
+__device__ __forceinline__ float4 gs_point(int p, const float4* sold, const float4* snew, const unsigned short* ssurf, int nbk, int k_eff, int* iters = nullptr) {
     float m00 = 0, m10 = 0, m11 = 0, m20 = 0, m21 = 0, m22 = 0;
     if (NBK > 0) {
         int j[NBK > 0 ? NBK : 1];
@@ -383,6 +383,7 @@ __device__ __forceinline__ float4 gs_point(int p, const float4* sold, const floa
         }
     }
     const Eig3 E = eig3_sym(m00, m10, m11, m20, m21, m22);
+    if (iters) *iters = E.iters;
     const f3 d = normalize3(eig_col(E, 2));                                                    // rosa.cpp:305-307
     return make_float4(d.x, d.y, d.z, sold[p].w);
 }
@@ -447,7 +448,7 @@ struct FusedArgs {
     float4* vnew_it;       // [nit][Mcap]    xyz = symmetry normal, w = weight 1/(var^4+eps)
     int* flagO; int* taskq; int* qctr;      // qctr[0] = claim counter, qctr[1] = publish counter
     int Mcap; int nit;
-    const int* surf; int nbk; int dbg_detail;
+    const int* surf; int nbk; int dbg_detail; int lag;
     int* good; float4* centers; int* active_size; float max_proj_range;
     long long* dbg;        // per chain: [t_begin, t_first_step, t_end, steps, spins, points] (globaltimer ns)
 };
@@ -524,7 +525,7 @@ __host__ __device__ __forceinline__ size_t fused_chain_bytes(int M, int nbk, int
 // through prog[]: it waits until every T_{w-1} it reads has been published.
 template <int NBK>
 __device__ __forceinline__ void chain_schedule_pass(int w, int M, int nbk, int k_eff, const unsigned short* ssurf,
-                                                    unsigned short* sT, volatile int* prog, volatile int* tmax) {
+                                                    unsigned short* sT, volatile int* prog, volatile int* tmax, int lag) {
     const int lane = threadIdx.x & 31;
     unsigned short* Tc = sT + (size_t)w * M;
     const unsigned short* Tp = sT + (size_t)(w > 0 ? w - 1 : 0) * M;
@@ -552,7 +553,7 @@ __device__ __forceinline__ void chain_schedule_pass(int w, int M, int nbk, int k
             } else {
                 for (int u = 0; u < k_eff; ++u) e = max(e, (int)((const volatile unsigned short*)Tp)[ssurf[p * nbk + u]]);
             }
-            vext = e + O_LAG_STEPS;
+            vext = e + lag;
         }
         if (NBK > 0) {
 #pragma unroll
@@ -617,8 +618,8 @@ __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int
     const int k_eff = min(nbk, M);
     const bool fast10 = (nbk == 10 && k_eff == 10);
     if (warp <= it) {
-        if (fast10) chain_schedule_pass<10>(warp, M, nbk, k_eff, ssurf, sT, s_ctl + 4, s_ctl + 2);
-        else chain_schedule_pass<0>(warp, M, nbk, k_eff, ssurf, sT, s_ctl + 4, s_ctl + 2);
+        if (fast10) chain_schedule_pass<10>(warp, M, nbk, k_eff, ssurf, sT, s_ctl + 4, s_ctl + 2, a.lag);
+        else chain_schedule_pass<0>(warp, M, nbk, k_eff, ssurf, sT, s_ctl + 4, s_ctl + 2, a.lag);
     }
     __syncthreads();
     {
@@ -666,7 +667,7 @@ __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int
         }
         int ndone = 0;
         long long t_begin = gtime(), t_first = 0; int steps = 0, spins = 0;
-        long long c_comp = 0, c_rel = 0;
+        long long c_comp = 0, c_rel = 0; int it_sum = 0, it_max = 0;
         while (ndone < M) {
             const long long c0 = detail ? clock64() : 0;
             bool ready = false;
@@ -697,7 +698,7 @@ __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int
             const long long c1 = detail ? clock64() : 0;
             // refill loads first: they do not depend on the solve below and hide behind it
             const int r = __popc(rm & lt);
-            int ncand = cand;
+            int ncand = cand; int my_it = 0;
             unsigned nnb[5] = {nb[0], nb[1], nb[2], nb[3], nb[4]};
             if (ready) {
                 const int pos = next + r;
@@ -707,10 +708,13 @@ __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int
 #pragma unroll
                     for (int k = 0; k < 5; ++k) nnb[k] = wsrc[k];
                 }
-                snew[cand] = fast10 ? gs_point<10>(cand, sold, snew, ssurf, nbk, k_eff) : gs_point<0>(cand, sold, snew, ssurf, nbk, k_eff);
+                int qi = 0;
+                snew[cand] = fast10 ? gs_point<10>(cand, sold, snew, ssurf, nbk, k_eff, &qi) : gs_point<0>(cand, sold, snew, ssurf, nbk, k_eff, &qi);
+                my_it = qi;
             }
             __syncwarp();
             const long long c2 = detail ? clock64() : 0;
+            if (detail) { it_sum += __reduce_add_sync(FULLM, ready ? my_it : 0); it_max += __reduce_max_sync(FULLM, ready ? my_it : 0); }
             if (ready) {
                 vstate[cand] = 3;
                 solist[ndone + r] = (unsigned short)cand;
@@ -725,7 +729,7 @@ __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int
             if (lane == 0) st_vol(s_ctl + 1, ndone);
             if (detail) { c_comp += c2 - c1; c_rel += (c1 - c0) + (clock64() - c2); }
         }
-        if (lane == 0 && a.dbg) { long long* g = a.dbg + it * 8; g[0] = t_begin; g[1] = t_first; g[2] = gtime(); g[3] = steps; g[4] = spins; g[5] = M; g[6] = c_comp; g[7] = c_rel; }
+        if (lane == 0 && a.dbg) { long long* g = a.dbg + it * 8; g[0] = t_begin; g[1] = t_first; g[2] = gtime(); g[3] = steps; g[4] = spins; g[5] = ((long long)it_sum << 32) | (unsigned)it_max; g[6] = c_comp; g[7] = c_rel; }
     } else if (warp == nw - 1) {
         // ---- publisher: G(it,p) -> vset_it[it+1][p] in L2, then task (it+1, p) goes on the workers' ready queue
         float4* dst = a.vset_it + (size_t)(it + 1) * a.Mcap;
@@ -808,6 +812,10 @@ void launch_drosa_prep(osep_rosa_impl* h, cudaStream_t sk) {
     const osep_rosa_config& c = h->cfg;
     const bool fused = h->fused && c.niter_drosa <= MAX_FUSED_ITERS;
     k_normal_prep<<<div_up(d.Mcap, 128), 128, 0, sk>>>(d.st, d.nrms, d.nraw, d.vnd);
+    if (fused) {                                           // flags + the rosa_init orientation as iteration-0 input: off the critical path
+        cudaMemsetAsync(d.fused_flags, 0, sizeof(int) * ((size_t)2 * MAX_FUSED_ITERS * d.Mcap + 16), sk);
+        cudaMemcpyAsync(d.vset_it, d.vset, sizeof(float4) * d.Mcap, cudaMemcpyDeviceToDevice, sk);
+    }
     if (!fused) {
         k_gs_schedule<<<1, 1024, sizeof(int) * (d.Mcap + SCHED_BINS) + sizeof(unsigned short) * d.Mcap * d.nbk, sk>>>(d.st, d.surf, d.nbk, d.level, d.level_off, d.level_pts);
         h->n_launches += 1;
@@ -826,13 +834,11 @@ void launch_drosa(osep_rosa_impl* h, int sms) {
     o.max_proj_range = c.max_proj_range;
     if (h->fused && c.niter_drosa <= MAX_FUSED_ITERS) {
         // capacity of the chain CTA's shared memory: 62 bytes per point (+ level offsets)
-        cudaMemsetAsync(d.fused_flags, 0, sizeof(int) * ((size_t)2 * MAX_FUSED_ITERS * d.Mcap + 16), s);
-        cudaMemcpyAsync(d.vset_it, d.vset, sizeof(float4) * d.Mcap, cudaMemcpyDeviceToDevice, s);
         FusedArgs a;
         a.st = d.st; a.pts = d.pts; a.nraw = d.nraw; a.vnd = d.vnd; a.pset = d.pset; a.bits = d.simi_bits; a.W = d.W;
         a.vset_it = d.vset_it; a.vnew_it = d.vnew_it;
         a.flagO = d.fused_flags; a.taskq = d.fused_flags + (size_t)MAX_FUSED_ITERS * d.Mcap; a.qctr = d.fused_flags + (size_t)2 * MAX_FUSED_ITERS * d.Mcap;
-        a.Mcap = d.Mcap; a.nit = c.niter_drosa; a.surf = d.surf; a.nbk = d.nbk; a.dbg_detail = h->profile ? 1 : 0;
+        a.Mcap = d.Mcap; a.nit = c.niter_drosa; a.surf = d.surf; a.nbk = d.nbk; a.dbg_detail = h->profile ? 1 : 0; a.lag = h->sched_lag;
         a.good = d.good; a.centers = d.centers; a.active_size = d.active_size; a.max_proj_range = c.max_proj_range;
         a.dbg = d.fused_dbg;
         int grid = h->fused_grid > 0 ? h->fused_grid : sms;
@@ -840,7 +846,7 @@ void launch_drosa(osep_rosa_impl* h, int sms) {
         void* args[] = {(void*)&a};
         if (grid > sms) grid = sms;
         cudaLaunchCooperativeKernel((const void*)k_drosa_fused, dim3(grid), dim3(SEED_WARPS * 32), args, (size_t)SEED_SMEM_BUDGET, s);
-        cudaMemcpyAsync(d.vset, d.vset_it + (size_t)c.niter_drosa * d.Mcap, sizeof(float4) * d.Mcap, cudaMemcpyDeviceToDevice, s);
+        if (h->debug) cudaMemcpyAsync(d.vset, d.vset_it + (size_t)c.niter_drosa * d.Mcap, sizeof(float4) * d.Mcap, cudaMemcpyDeviceToDevice, s);   // tap "vset"
         if (h->debug && d.vset_iters)
             for (int it = 0; it < c.niter_drosa; ++it)
                 cudaMemcpyAsync(d.vset_iters + (size_t)it * d.Mcap, d.vset_it + (size_t)(it + 1) * d.Mcap, sizeof(float4) * d.Mcap, cudaMemcpyDeviceToDevice, s);

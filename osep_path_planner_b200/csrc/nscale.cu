@@ -63,8 +63,7 @@ __device__ int block_excl_scan(int* data, int n) {
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void k_frame_init(FrameState* st, int n_in) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ __forceinline__ void frame_init(FrameState* st, int n_in) {
     const unsigned epoch = st->epoch;
     FrameState z;
     memset(&z, 0, sizeof(z));
@@ -92,7 +91,8 @@ __global__ void k_filter_count(const float* __restrict__ in, int n, int stride, 
 }
 
 // single block: scan the per-block counts; R4 gate (rosa.cpp:91-95)
-__global__ void k_filter_scan(int* blk_cnt, int nblk, FrameState* st, int min_points) {
+__global__ void k_filter_scan(int* blk_cnt, int nblk, FrameState* st, int min_points, int n_in) {
+    if (threadIdx.x == 0) frame_init(st, n_in);          // first writer of the frame state (k_filter_count does not touch it)
     const int total = block_excl_scan(blk_cnt, nblk);
     if (threadIdx.x == 0) {
         st->n_filt = total;
@@ -100,9 +100,11 @@ __global__ void k_filter_scan(int* blk_cnt, int nblk, FrameState* st, int min_po
     }
 }
 
+__device__ void leaf_step(FrameState* st, int p, int max_points);
 __global__ void k_filter_scatter(const float* __restrict__ in, int n, int stride, float r2, const int* __restrict__ blk_off,
-                                 float4* __restrict__ P, int* __restrict__ filt_idx, FrameState* st) {
+                                 float4* __restrict__ P, int* __restrict__ filt_idx, FrameState* st, int max_points) {
     __shared__ int warp_cnt[NT / 32];
+    __shared__ int s_last;
     __shared__ int s_lo[3], s_hi[3];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -133,6 +135,12 @@ __global__ void k_filter_scatter(const float* __restrict__ in, int n, int stride
             atomicMax(&st->bb_hi[threadIdx.x], s_hi[threadIdx.x]);
         }
     }
+    // the last block sees the complete bounding box: R7 + set-up of VoxelGrid pass 0 here (no extra launch)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1) == (int)gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) { st->ticket = 0; __threadfence(); leaf_step(st, 0, max_points); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -203,11 +211,6 @@ __device__ void leaf_step(FrameState* st, int p, int max_points) {
     }
 }
 
-__global__ void k_leaf_step(FrameState* st, int p, int max_points) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    leaf_step(st, p, max_points);
-}
-
 // voxel key of PCL VoxelGrid::applyFilter step 5
 __device__ __forceinline__ unsigned voxel_key(const float4& p, float inv, int mb0, int mb1, int mb2, int db0, int db1) {
     const int i0 = (int)(floorf(p.x * inv) - (float)mb0);
@@ -234,7 +237,8 @@ __device__ __forceinline__ bool vset_insert(unsigned long long* tab, unsigned ma
 }
 
 // count-only VoxelGrid pass: number of distinct voxel keys at the current leaf
-__global__ void k_vox_count(const float4* __restrict__ P, FrameState* st, unsigned long long* vtab, unsigned mask, int next_step, int max_points) {
+__device__ void grid_params(FrameState* st, int target_ppc);
+__global__ void k_vox_count(const float4* __restrict__ P, FrameState* st, unsigned long long* vtab, unsigned mask, int next_step, int max_points, int target_ppc) {
     if (st->status != 0) return;
     if (st->pass_active && !st->pass_overflow) {
         const int n = st->n_filt;
@@ -253,7 +257,10 @@ __global__ void k_vox_count(const float4* __restrict__ P, FrameState* st, unsign
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1) == (int)gridDim.x - 1) ? 1 : 0;
     __syncthreads();
-    if (s_last && threadIdx.x == 0) { st->ticket = 0; __threadfence(); leaf_step(st, next_step, max_points); }
+    if (s_last && threadIdx.x == 0) {
+        st->ticket = 0; __threadfence(); leaf_step(st, next_step, max_points);
+        if (next_step == 1) grid_params(st, target_ppc);      // pass 0 supplies the density estimate that sizes the kNN grid
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -279,8 +286,7 @@ __device__ __forceinline__ unsigned hash_u64(unsigned long long k) {
     return (unsigned)k;
 }
 
-__global__ void k_grid_params(FrameState* st, int target_ppc) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ void grid_params(FrameState* st, int target_ppc) {
     if (st->status != 0) return;
     const int n = st->n_filt;
     // density estimate from VoxelGrid pass 0 (leaf_hist[0], nvox_hist[0]): nv occupied voxels of that size hold n
@@ -295,10 +301,8 @@ __global__ void k_grid_params(FrameState* st, int target_ppc) {
 // After the first insertion pass the real occupancy is known: if the estimate was off (the surface-like scaling
 // breaks when leaf0 is larger than the structures, e.g. multi-structure maps), pick the cell size that would
 // give the target and ask for one rebuild.  Only the speed of the search depends on h, never its result.
-__global__ void k_grid_refine(FrameState* st, int target_ppc) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (st->status != 0) return;
-    const int n = st->n_filt, nc = st->g_ncells;
+__device__ __forceinline__ void grid_refine(FrameState* st, int target_ppc) {
+    const int n = st->n_filt, nc = *(volatile int*)&st->g_ncells;
     if (nc <= 0) return;
     const float occ = (float)n / (float)nc;
     if (occ > 1.4f * (float)target_ppc || occ < 0.6f * (float)target_ppc) {
@@ -322,7 +326,8 @@ __device__ __forceinline__ void cell_of(const FrameState* st, float x, float y, 
 // gtab stores key+1 (0 = empty) so one memset clears keys, counts and fills together.
 // pass 0 = first build; pass 1 = rebuild, runs only when k_grid_refine asked for it.
 __global__ void k_grid_insert(const float4* __restrict__ P, FrameState* st, unsigned long long* gtab, int* g_cnt,
-                              int* __restrict__ p_slot, unsigned mask, int pass) {
+                              int* __restrict__ p_slot, unsigned mask, int pass, int target_ppc) {
+    __shared__ int s_last;
     if (st->status != 0) return;
     if (pass == 1 && !st->g_redo) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -343,19 +348,32 @@ __global__ void k_grid_insert(const float4* __restrict__ P, FrameState* st, unsi
     }
     const unsigned m = __ballot_sync(0xffffffffu, created);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&st->g_ncells, __popc(m));
+    if (pass != 0) return;
+    // the last block of the first pass knows the real occupancy: decide about the rebuild here (no extra launch)
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); s_last = (atomicAdd(&st->ticket_grid, 1) == (int)gridDim.x - 1) ? 1 : 0; }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) { st->ticket_grid = 0; __threadfence(); grid_refine(st, target_ppc); }
 }
 constexpr int QCH = 8;            // queries per kNN work unit
 __global__ void k_grid_alloc(FrameState* st, const int* __restrict__ g_cnt, int* __restrict__ g_start, int T, int2* __restrict__ units) {
+    __shared__ int s_pts, s_units, b_pts, b_units;
     if (st->status != 0) return;
+    if (threadIdx.x == 0) { s_pts = 0; s_units = 0; }
+    __syncthreads();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= T) return;
-    const int c = g_cnt[s];
+    const int c = s < T ? g_cnt[s] : 0;
+    // dense cells have long candidate lists: fewer queries per unit there, so more warps share the work
+    const int chunk = (c >= 64) ? 2 : QCH;
+    const int nu = (c + chunk - 1) / chunk;
+    int op = 0, ou = 0;
+    if (c > 0) { op = atomicAdd(&s_pts, c); ou = atomicAdd(&s_units, nu); }     // block-local cursors: two global atomics per block
+    __syncthreads();
+    if (threadIdx.x == 0 && s_pts > 0) { b_pts = atomicAdd(&st->g_cells_used, s_pts); b_units = atomicAdd(&st->n_units, s_units); }
+    __syncthreads();
     if (c > 0) {
-        g_start[s] = atomicAdd(&st->g_cells_used, c);
-        // dense cells have long candidate lists: fewer queries per unit there, so more warps share the work
-        const int chunk = (c >= 64) ? 2 : QCH;
-        const int nu = (c + chunk - 1) / chunk;
-        const int ub = atomicAdd(&st->n_units, nu);
+        g_start[s] = b_pts + op;
+        const int ub = b_units + ou;
         for (int u = 0; u < nu; ++u) units[ub + u] = make_int2(s, (u * chunk) | (chunk << 24));
     }
 }
@@ -625,13 +643,15 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
                 // registers for all passes of the query; unstaged units re-read the cells from L1/L2.
                 constexpr int RPL = KNN_STAGE / 32;
                 float dq[STAGED ? RPL : 1]; int iq[STAGED ? RPL : 1];
+                int nr = 0;                                      // rounds of 32 staged candidates actually in use (uniform)
                 if constexpr (STAGED) {
                     const int tot = tab[wib][0].y;
+                    nr = (tot + 31) >> 5;
 #pragma unroll
                     for (int r = 0; r < RPL; ++r) {
                         const int t = r * 32 + lane;
                         dq[r] = 3.0e38f; iq[r] = 0;
-                        if (t < tot) { const float4 c = base[t]; dq[r] = dist2(q.x, q.y, q.z, c.x, c.y, c.z); iq[r] = __float_as_int(c.w); }
+                        if (r < nr && t < tot) { const float4 c = base[t]; dq[r] = dist2(q.x, q.y, q.z, c.x, c.y, c.z); iq[r] = __float_as_int(c.w); }
                     }
                 }
                 auto collect = [&](float thr) -> int {
@@ -639,6 +659,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
                     if constexpr (STAGED) {
 #pragma unroll
                         for (int r = 0; r < RPL; ++r) {
+                            if (r >= nr) break;
                             const bool in = dq[r] < thr;
                             const unsigned m = __ballot_sync(0xffffffffu, in);
                             const int pos = ln + __popc(m & lt);
@@ -670,7 +691,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
                     int cm = 0;
                     if constexpr (STAGED) {
 #pragma unroll
-                        for (int r = 0; r < RPL; ++r) cm += (dq[r] < thr) ? 1 : 0;
+                        for (int r = 0; r < RPL; ++r) if (r < nr) cm += (dq[r] < thr) ? 1 : 0;
                         return __reduce_add_sync(0xffffffffu, cm);
                     } else {
                         for (int ti = 0; ti < nt; ++ti) {
@@ -698,6 +719,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
                     if constexpr (STAGED) {
 #pragma unroll
                         for (int r = 0; r < RPL; ++r) {
+                            if (r >= nr) break;
 #pragma unroll
                             for (int m = 0; m < NR; ++m) cr[m] += (dq[r] < tr[m]) ? 1 : 0;
                         }
@@ -958,29 +980,30 @@ void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int strid
     const osep_rosa_config& c = h->cfg;
     const int nb = div_up(n, NT);
     const float r2 = c.pts_dist_lim * c.pts_dist_lim;
-    k_frame_init<<<1, 1, 0, s>>>(d.st, n);
+    cudaStream_t sk = s;
+    if (h->overlap) {                                      // the kNN grid tables are cleared while the filter runs
+        sk = h->stream2;
+        cudaEventRecord(h->ev_fork[0], s); cudaStreamWaitEvent(sk, h->ev_fork[0], 0);
+        cudaMemsetAsync(d.gtab, 0, sizeof(unsigned) * 4 * (size_t)d.T, sk);   // gtab (8 B) | g_cnt | g_fill are contiguous
+    }
     // R3/R4
     k_filter_count<<<nb, NT, 0, s>>>(xyz_dev, n, stride, r2, d.blk_cnt);
-    k_filter_scan<<<1, 1024, 0, s>>>(d.blk_cnt, nb, d.st, c.min_points);
-    k_filter_scatter<<<nb, NT, 0, s>>>(xyz_dev, n, stride, r2, d.blk_cnt, d.P, d.filt_idx, d.st);
+    k_filter_scan<<<1, 1024, 0, s>>>(d.blk_cnt, nb, d.st, c.min_points, n);
+    k_filter_scatter<<<nb, NT, 0, s>>>(xyz_dev, n, stride, r2, d.blk_cnt, d.P, d.filt_idx, d.st, c.max_points);
     stage_mark(h, SM_FILTER);
     // R7/R8: device-resident leaf loop (count-only passes).  The kNN grid is sized from the density seen by
     // pass 0, so the whole normals branch (grid build + kNN + covariance/eigen) only depends on pass 0 and runs
     // on the side stream while the remaining passes iterate the control law.
-    k_leaf_step<<<1, 1, 0, s>>>(d.st, 0, c.max_points);
-    k_vox_count<<<nb, NT, 0, s>>>(d.P, d.st, d.vtab, (unsigned)(d.T - 1), 1, c.max_points);
-    k_grid_params<<<1, 1, 0, s>>>(d.st, h->knn_ppc);
-    cudaStream_t sk = s;
-    if (h->overlap) { cudaEventRecord(h->ev_fork[0], s); sk = h->stream2; cudaStreamWaitEvent(sk, h->ev_fork[0], 0); }
+    k_vox_count<<<nb, NT, 0, s>>>(d.P, d.st, d.vtab, (unsigned)(d.T - 1), 1, c.max_points, h->knn_ppc);
+    if (h->overlap) { cudaEventRecord(h->ev_fork[0], s); cudaStreamWaitEvent(sk, h->ev_fork[0], 0); }
     for (int p = 1; p < LEAF_MAX_ITERS; ++p)
-        k_vox_count<<<nb, NT, 0, s>>>(d.P, d.st, d.vtab, (unsigned)(d.T - 1), p + 1, c.max_points);
+        k_vox_count<<<nb, NT, 0, s>>>(d.P, d.st, d.vtab, (unsigned)(d.T - 1), p + 1, c.max_points, h->knn_ppc);
     stage_mark(h, SM_LEAF);
     // R5: grid + kNN normals
-    cudaMemsetAsync(d.gtab, 0, sizeof(unsigned) * 4 * (size_t)d.T, sk);   // gtab (8 B) | g_cnt | g_fill are contiguous
-    k_grid_insert<<<nb, NT, 0, sk>>>(d.P, d.st, d.gtab, d.g_cnt, d.p_slot, (unsigned)(d.T - 1), 0);
-    k_grid_refine<<<1, 1, 0, sk>>>(d.st, h->knn_ppc);
+    if (!h->overlap) cudaMemsetAsync(d.gtab, 0, sizeof(unsigned) * 4 * (size_t)d.T, sk);
+    k_grid_insert<<<nb, NT, 0, sk>>>(d.P, d.st, d.gtab, d.g_cnt, d.p_slot, (unsigned)(d.T - 1), 0, h->knn_ppc);
     k_grid_clear_if_redo<<<div_up(d.T, NT), NT, 0, sk>>>(d.st, d.gtab, d.g_cnt, d.T);
-    k_grid_insert<<<nb, NT, 0, sk>>>(d.P, d.st, d.gtab, d.g_cnt, d.p_slot, (unsigned)(d.T - 1), 1);
+    k_grid_insert<<<nb, NT, 0, sk>>>(d.P, d.st, d.gtab, d.g_cnt, d.p_slot, (unsigned)(d.T - 1), 1, h->knn_ppc);
     k_grid_alloc<<<div_up(d.T, NT), NT, 0, sk>>>(d.st, d.g_cnt, d.g_start, d.T, d.units);
     k_grid_scatter<<<nb, NT, 0, sk>>>(d.P, d.st, d.p_slot, d.g_start, d.g_fill, d.Pc);
     stage_mark(h, SM_GRID);
@@ -1004,7 +1027,7 @@ void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int strid
     if (h->overlap) cudaStreamWaitEvent(s, h->ev_join[0], 0);              // the reduce is the first consumer of the normals
     k_vox_reduce<<<1024, 256, 0, s>>>(d.st, d.rv0, d.rv1, d.vox_cnt, d.P, d.Nrm, d.pts, d.nrms, d.pset, d.vset);
     stage_mark(h, SM_VOXEL);
-    h->n_launches += 1 + 3 + (LEAF_MAX_ITERS + 1) + 7 + 4 + 4 + 2;
+    h->n_launches += 3 + LEAF_MAX_ITERS + 5 + 4 + 4 + 2;
 }
 
 }  // namespace osep

@@ -56,7 +56,8 @@ struct FrameState {
     // ---- voxel passes
     int pass_active;       // the VoxelGrid pass set up by leaf_step is live (loop not finished)
     int n_keys;            // distinct voxel keys collected for the final pass
-    int ticket;            // last-block detection
+    int ticket;            // last-block detection (voxel count passes)
+    int ticket_grid;       // last-block detection (kNN grid build; runs concurrently with the voxel passes)
 };
 
 // ordered-int encoding of a float: monotone map so atomicMin/atomicMax(int) order floats
