@@ -355,7 +355,8 @@ int osep_rosa_set_lanes(osep_rosa* h, int lanes) {
     }
     while ((int)I.lanes.size() > lanes - 1) { osep_rosa_impl* l = I.lanes.back(); I.lanes.pop_back(); rosa_free(l); delete reinterpret_cast<osep_rosa*>(l); }
     // several frames in flight: give each frame's persistent drosa kernel a slice of the SMs so that `lanes` of them are co-resident
-    const int slice = lanes > 1 ? std::max(I.cfg.niter_drosa + 6, I.sms / lanes) : 0;
+    int slice = lanes > 1 ? std::max(I.cfg.niter_drosa + 6, I.sms / lanes) : 0;
+    { const char* e = getenv("OSEP_FUSED_SLICE"); if (e && lanes > 1 && atoi(e) > I.cfg.niter_drosa) slice = atoi(e); }   // tuning knob
     I.fused_grid = slice;
     for (osep_rosa_impl* l : I.lanes) l->fused_grid = slice;
     return OSEP_OK;
