@@ -51,6 +51,7 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
     CK(dalloc(&d.vset_it, M * 9)); CK(dalloc(&d.vnew_it, M * 8)); CK(dalloc(&d.fused_flags, M * 16 + 16)); CK(dalloc(&d.fused_dbg, 64)); CK(cudaMemset(d.fused_dbg, 0, 64 * 8));
     { const char* e = getenv("OSEP_KNN_PPC"); if (e && atoi(e) > 0) h->knn_ppc = atoi(e); }
     { const char* e = getenv("OSEP_DROSA_UNFUSED"); if (e && e[0] == '1') h->fused = false;
+      const char* e3 = getenv("OSEP_NO_GRAPH"); if (e3 && e3[0] == '1') h->use_graphs = false;
       const char* e2 = getenv("OSEP_DROSA_LAG"); if (e2 && atoi(e2) >= 0) h->sched_lag = atoi(e2);
       int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device); if (!coop) h->fused = false; }
     { int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device)); h->sms = sms > 0 ? sms : 148; } CK(dalloc(&d.surf, M * (size_t)std::max(d.nbk, 1)));
@@ -83,6 +84,7 @@ static void rosa_free(osep_rosa_impl* h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (int i = 0; i < 2; ++i) { if (h->ev_fork[i]) cudaEventDestroy(h->ev_fork[i]); if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]); }
+    if (h->fg.exec) cudaGraphExecDestroy(h->fg.exec);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
 }
@@ -91,10 +93,40 @@ static int rosa_enqueue(osep_rosa_impl* h, const float* xyz_dev, int n, int stri
     RosaDev& d = h->d;
     h->last_n = n;
     cudaEventRecord(h->ev0, h->stream);
-    launch_preprocess(h, xyz_dev, n, stride);
-    launch_mscale(h);
-    cudaMemcpyAsync(h->st_host, d.st, sizeof(FrameState), cudaMemcpyDeviceToHost, h->stream);
-    cudaMemcpyAsync(h->skel_host, d.skel, sizeof(float4) * d.Mcap / 4, cudaMemcpyDeviceToHost, h->stream);   // first Mcap/4 vertices; rest on demand
+    auto enqueue_all = [&]() {
+        launch_preprocess(h, xyz_dev, n, stride);
+        launch_mscale(h);
+        cudaMemcpyAsync(h->st_host, d.st, sizeof(FrameState), cudaMemcpyDeviceToHost, h->stream);
+        cudaMemcpyAsync(h->skel_host, d.skel, sizeof(float4) * d.Mcap / 4, cudaMemcpyDeviceToHost, h->stream);   // first Mcap/4 vertices; rest on demand
+    };
+    bool done = false;
+    if (h->use_graphs && !h->profile && !h->debug) {
+        osep_rosa_impl::FrameGraph& g = h->fg;
+        if (g.exec && g.xyz == xyz_dev && g.n == n && g.stride == stride && g.epoch == h->cfg_epoch) {
+            if (cudaGraphLaunch(g.exec, h->stream) == cudaSuccess) { h->n_launches += g.launches; done = true; }
+            else cudaGetLastError();
+        } else if (g.seen_xyz == xyz_dev && g.seen_n == n && g.seen_stride == stride && g.seen_epoch == h->cfg_epoch) {
+            if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+            const long long l0 = h->n_launches;
+            if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                enqueue_all();
+                cudaGraph_t graph = nullptr;
+                if (cudaStreamEndCapture(h->stream, &graph) == cudaSuccess && graph) {
+                    if (cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) g.exec = nullptr;
+                    cudaGraphDestroy(graph);
+                }
+                g.launches = h->n_launches - l0; h->n_launches = l0;
+                if (!g.exec) { cudaGetLastError(); h->use_graphs = false; }          // capture unsupported here: plain launches from now on
+                else {
+                    g.xyz = xyz_dev; g.n = n; g.stride = stride; g.epoch = h->cfg_epoch;
+                    if (cudaGraphLaunch(g.exec, h->stream) == cudaSuccess) { h->n_launches += g.launches; done = true; }
+                    else cudaGetLastError();
+                }
+            } else { cudaGetLastError(); h->use_graphs = false; }
+        }
+        g.seen_xyz = xyz_dev; g.seen_n = n; g.seen_stride = stride; g.seen_epoch = h->cfg_epoch;
+    }
+    if (!done) enqueue_all();
     cudaEventRecord(h->ev1, h->stream);
     CK(cudaGetLastError());
     return OSEP_OK;
@@ -186,7 +218,7 @@ int osep_rosa_set_debug(osep_rosa* h, int enable) {
     if (!h) return OSEP_ERR_ARG;
     osep_rosa_impl& I = h->impl;
     CK(cudaSetDevice(I.device));
-    I.debug = enable != 0;
+    I.debug = enable != 0; ++I.cfg_epoch;
     if (I.debug && !I.d.vset_iters) {
         CK(dalloc(&I.d.vset_iters, (size_t)I.d.Mcap * std::max(1, I.cfg.niter_drosa)));
     }
@@ -197,7 +229,7 @@ int osep_rosa_set_profile(osep_rosa* h, int enable) {
     if (!h) return OSEP_ERR_ARG;
     osep_rosa_impl& I = h->impl;
     CK(cudaSetDevice(I.device));
-    I.profile = enable != 0;
+    I.profile = enable != 0; ++I.cfg_epoch;
     I.overlap = !I.profile;
     if (I.profile) for (int i = 0; i < SM_COUNT; ++i) if (!I.stage_ev[i]) CK(cudaEventCreate(&I.stage_ev[i]));
     return OSEP_OK;
@@ -357,8 +389,8 @@ int osep_rosa_set_lanes(osep_rosa* h, int lanes) {
     // several frames in flight: give each frame's persistent drosa kernel a slice of the SMs so that `lanes` of them are co-resident
     int slice = lanes > 1 ? std::max(I.cfg.niter_drosa + 6, I.sms / lanes) : 0;
     { const char* e = getenv("OSEP_FUSED_SLICE"); if (e && lanes > 1 && atoi(e) > I.cfg.niter_drosa) slice = atoi(e); }   // tuning knob
-    I.fused_grid = slice;
-    for (osep_rosa_impl* l : I.lanes) l->fused_grid = slice;
+    I.fused_grid = slice; ++I.cfg_epoch;
+    for (osep_rosa_impl* l : I.lanes) { l->fused_grid = slice; ++l->cfg_epoch; }
     return OSEP_OK;
 }
 

@@ -72,6 +72,16 @@ struct osep_rosa_impl {
     static constexpr int NSTAGE_EV = 16;
     cudaEvent_t stage_ev[NSTAGE_EV] = {};
     long long n_launches = 0;          // kernels launched by this handle since create
+    // CUDA graph of one frame: a frame has no host decisions (osep_common.cuh), so the whole launch sequence of a
+    // repeated (buffer, n, stride) shape is captured on its second occurrence and replayed afterwards
+    struct FrameGraph {
+        cudaGraphExec_t exec = nullptr;
+        const float* xyz = nullptr; int n = -1, stride = 0, epoch = -1;
+        const float* seen_xyz = nullptr; int seen_n = -1, seen_stride = 0, seen_epoch = -1;
+        long long launches = 0;
+    } fg;
+    bool use_graphs = true;            // OSEP_NO_GRAPH=1 disables; also cleared when capture is not supported
+    int cfg_epoch = 0;                 // bumped by every setter that changes what a frame launches
     // host mirrors
     FrameState* st_host = nullptr;     // pinned
     float4* skel_host = nullptr;       // pinned, Mcap
