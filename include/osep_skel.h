@@ -117,6 +117,15 @@ int osep_rosa_destroy(osep_rosa* h);
  * cloud to the device, runs the 7 stages, copies the vertices back.  Returns res->status. */
 int osep_rosa_run(osep_rosa* h, const float* xyz_host, int n, int stride_floats, osep_rosa_result* res);
 
+/* pcl::fromROSMsg(*msg, rosa_->input_cloud()) + rosa_run() (rosa_node.cpp:129,136) without the host-side repack of
+ * the message: the raw sensor_msgs/PointCloud2 data block (n_points = width * height records of point_step bytes,
+ * little endian) is copied to the device as it is and the filter kernel reads x, y, z in place.
+ * Requires float32 fields x, y, z at the consecutive byte offsets off_x, off_x + 4, off_x + 8 -- the layout of every
+ * PointXYZ* message -- and off_x % 4 == 0, point_step % 4 == 0; anything else returns OSEP_ERR_ARG.  Like
+ * fromROSMsg, only x, y, z are used (the 4th float of pcl::PointXYZ is 1.0f). */
+int osep_rosa_run_pointcloud2(osep_rosa* h, const void* data_host, int n_points, int point_step, int off_x, int off_y, int off_z,
+                              osep_rosa_result* res);
+
 /* Same frame, DEVICE-resident input; enqueues on the handle's stream and returns without a
  * host synchronisation.  Follow with osep_rosa_finish() to wait and read the summary. */
 int osep_rosa_run_device(osep_rosa* h, const float* xyz_dev, int n, int stride_floats);
@@ -179,6 +188,11 @@ int osep_gskel_destroy(osep_gskel* h);
 /* input_vertices() write + gskel_run() (gskel_node.cpp:139-141).  cand_xyz: host, already in
  * the global frame (the TF transform, gskel_node.cpp:124-138, stays with the caller). */
 int osep_gskel_run(osep_gskel* h, const float* cand_xyz, int n, int stride_floats);
+/* tf2::doTransform(*msg, gmsg, T) + fromROSMsg + gskel_run() (gskel_node.cpp:137-142) in one call:
+ * cand_xyz are Rosa's vertices in the SENSOR frame; translation[3] / rotation_xyzw[4] are the float64 fields of the
+ * geometry_msgs/TransformStamped returned by lookupTransform(global_frame, sensor_frame).  The transform is applied
+ * with tf2_sensor_msgs' arithmetic (float32 Translation3f * Quaternionf, then linear * p + translation). */
+int osep_gskel_run_tf(osep_gskel* h, const float* cand_xyz, int n, int stride_floats, const double* translation, const double* rotation_xyzw);
 /* output_gskel() (gskel.hpp:112): G points, 16-byte {x,y,z,1} like pcl::PointXYZ. */
 int osep_gskel_vertices(osep_gskel* h, const float** xyz4, int* n_vertices);
 int osep_gskel_graph(osep_gskel* h, osep_graph_view* out);

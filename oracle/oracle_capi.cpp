@@ -168,6 +168,24 @@ int orc_ldlt3(const float* A9, const float* b3, float* x3) {
     bool ok = ldlt3_solve(A, {b3[0], b3[1], b3[2]}, x);
     x3[0] = x.x; x3[1] = x.y; x3[2] = x.z; return ok;
 }
+// gskel_node.cpp:137-138 tf2::doTransform(PointCloud2): float32 affine = Translation3f * Quaternionf (Eigen 3.4
+// Quaternion::toRotationMatrix), point = linear * p + translation with Eigen's 3-term reduction a + (b + c).
+void orc_tf_points(const float* xyz, int n, int stride, const double* trans, const double* rot_xyzw, float* out3) {
+    const float x = (float)rot_xyzw[0], y = (float)rot_xyzw[1], z = (float)rot_xyzw[2], w = (float)rot_xyzw[3];
+    const float tx = 2.0f * x, ty = 2.0f * y, tz = 2.0f * z;
+    const float twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    const float R[9] = {1.0f - (tyy + tzz), txy - twz, txz + twy,
+                        txy + twz, 1.0f - (txx + tzz), tyz - twx,
+                        txz - twy, tyz + twx, 1.0f - (txx + tyy)};
+    const float T[3] = {(float)trans[0], (float)trans[1], (float)trans[2]};
+    for (int i = 0; i < n; ++i) {
+        const float* p = xyz + (size_t)i * stride;
+        for (int r = 0; r < 3; ++r) {
+            const float a = R[3 * r] * p[0], b = R[3 * r + 1] * p[1], c = R[3 * r + 2] * p[2];
+            out3[3 * (size_t)i + r] = (a + (b + c)) + T[r];
+        }
+    }
+}
 // exact kNN / radius over a cloud (kd-tree), canonical (d2, idx) order
 void orc_knn(const float* xyz, int n, int stride, int k, int* out_idx /* n*k */) {
     std::vector<V3> p(n);

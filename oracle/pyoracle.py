@@ -191,6 +191,17 @@ class GSkelOracle:
         return _fetch(lib().orc_gskel_get, self._h, name)
 
 
+def tf_points(xyz, translation, rotation_xyzw):
+    """tf2::doTransform(PointCloud2) (gskel_node.cpp:137-138), float32 arithmetic of tf2_sensor_msgs."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    t = np.ascontiguousarray(translation, dtype=np.float64); q = np.ascontiguousarray(rotation_xyzw, dtype=np.float64)
+    out = np.zeros((xyz.shape[0], 3), np.float32)
+    L = lib()
+    L.orc_tf_points.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_tf_points(xyz.ctypes.data_as(C.c_void_p), xyz.shape[0], xyz.shape[1], t.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
 def eig3(A):
     A = np.ascontiguousarray(A, dtype=np.float32).reshape(3, 3)
     ev = np.zeros(3, np.float32); Q = np.zeros((3, 3), np.float32)

@@ -72,7 +72,7 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
 
 static void rosa_free(osep_rosa_impl* h) {
     RosaDev& d = h->d;
-    void* ptrs[] = {d.st, d.in, d.P, d.filt_idx, d.blk_cnt, d.gtab, d.g_start, d.units, d.slow_list, d.over_list, d.p_slot, d.Pc, d.Nrm, d.knn_full, d.vtab, d.vkeys, d.vid,
+    void* ptrs[] = {d.st, d.in, d.in_raw, d.P, d.filt_idx, d.blk_cnt, d.gtab, d.g_start, d.units, d.slow_list, d.over_list, d.p_slot, d.Pc, d.Nrm, d.knn_full, d.vtab, d.vkeys, d.vid,
                     d.vox_cnt, d.vox_fill, d.rk0, d.rk1, d.rv0, d.rv1, d.pts, d.nrms, d.pset, d.pset2, d.vset, d.vnew, d.vvar, d.surf,
                     d.simi_off, d.simi_idx, d.simi_bits, d.nraw, d.vnd, d.vset_it, d.vnew_it, d.fused_flags, d.fused_dbg, d.level, d.level_off, d.level_pts, d.good, d.centers, d.good_rank, d.poor_idx, d.active_size,
                     d.pcloud, d.adj_bits, d.seeds, d.corresp, d.skel, d.skel2, d.skel_sampled, d.vtmp, d.vs_off, d.vs_idx, d.vset_iters};
@@ -274,6 +274,34 @@ int osep_rosa_run(osep_rosa* h, const float* xyz_host, int n, int stride_floats,
     }
     rc = osep_rosa_run_device(h, I.d.in, n, stride_floats);
     if (rc) { if (res) { memset(res, 0, sizeof(*res)); res->status = rc; } return rc; }
+    return rosa_collect(&I, res);
+}
+
+int osep_rosa_run_pointcloud2(osep_rosa* h, const void* data_host, int n_points, int point_step, int off_x, int off_y, int off_z,
+                              osep_rosa_result* res) {
+    if (!h) return OSEP_ERR_ARG;
+    osep_rosa_impl& I = h->impl;
+    auto fail = [&](int rc) { if (res) { memset(res, 0, sizeof(*res)); res->status = rc; } return rc; };
+    if (n_points < 0 || point_step < 12 || (point_step & 3) || off_x < 0 || (off_x & 3) || off_y != off_x + 4 || off_z != off_x + 8 || off_z + 4 > point_step) {
+        set_err("PointCloud2 layout not supported: point_step=%d offsets x=%d y=%d z=%d (need consecutive 4-byte aligned float32 x,y,z)", point_step, off_x, off_y, off_z);
+        return fail(OSEP_ERR_ARG);
+    }
+    if (n_points > 0 && !data_host) return fail(OSEP_ERR_ARG);
+    int rc = check_frame(I, n_points, point_step / 4);
+    if (rc) return fail(rc);
+    CK(cudaSetDevice(I.device));
+    const size_t bytes = (size_t)n_points * point_step;
+    if (bytes > I.d.in_raw_bytes) {                      // sized for the widest record seen so far at full capacity
+        CK(cudaStreamSynchronize(I.stream));
+        if (I.d.in_raw) cudaFree(I.d.in_raw);
+        I.d.in_raw = nullptr; I.d.in_raw_bytes = 0;
+        const size_t want = (size_t)I.d.Ncap * point_step;
+        if (cudaMalloc((void**)&I.d.in_raw, want) != cudaSuccess) { cudaGetLastError(); set_err("cudaMalloc of %zu staging bytes failed", want); return fail(OSEP_ERR_CUDA); }
+        I.d.in_raw_bytes = want;
+    }
+    if (n_points > 0) CK(cudaMemcpyAsync(I.d.in_raw, data_host, bytes, cudaMemcpyHostToDevice, I.stream));
+    rc = osep_rosa_run_device(h, reinterpret_cast<const float*>(I.d.in_raw + off_x), n_points, point_step / 4);
+    if (rc) return fail(rc);
     return rosa_collect(&I, res);
 }
 

@@ -563,6 +563,29 @@ int osep_gskel_run(osep_gskel* h, const float* cand_xyz, int n, int stride_float
     return OSEP_OK;
 }
 
+// gskel_node.cpp:137-139: tf2::doTransform(PointCloud2) = Eigen::Translation3f(t) * Eigen::Quaternionf(w,x,y,z) applied to
+// every point in float32 (tf2_sensor_msgs.hpp); Quaternion::toRotationMatrix + (linear * p) + translation of Eigen 3.4.
+int osep_gskel_run_tf(osep_gskel* h, const float* cand_xyz, int n, int stride_floats, const double* translation, const double* rotation_xyzw) {
+    if (!h || n < 0 || stride_floats < 3 || (n > 0 && !cand_xyz) || !translation || !rotation_xyzw) return OSEP_ERR_ARG;
+    const float qx = (float)rotation_xyzw[0], qy = (float)rotation_xyzw[1], qz = (float)rotation_xyzw[2], qw = (float)rotation_xyzw[3];
+    const float t0 = (float)translation[0], t1 = (float)translation[1], t2 = (float)translation[2];
+    const float tx = 2.0f * qx, ty = 2.0f * qy, tz = 2.0f * qz;
+    const float twx = tx * qw, twy = ty * qw, twz = tz * qw;
+    const float txx = tx * qx, txy = ty * qx, txz = tz * qx;
+    const float tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+    const float r00 = 1.0f - (tyy + tzz), r01 = txy - twz, r02 = txz + twy;
+    const float r10 = txy + twz, r11 = 1.0f - (txx + tzz), r12 = tyz - twx;
+    const float r20 = txz - twy, r21 = tyz + twx, r22 = 1.0f - (txx + tyy);
+    std::vector<float> g((size_t)n * 3);
+    for (int i = 0; i < n; ++i) {
+        const float x = cand_xyz[(size_t)i * stride_floats], y = cand_xyz[(size_t)i * stride_floats + 1], z = cand_xyz[(size_t)i * stride_floats + 2];
+        g[3 * (size_t)i] = sum3(r00 * x, r01 * y, r02 * z) + t0;
+        g[3 * (size_t)i + 1] = sum3(r10 * x, r11 * y, r12 * z) + t1;
+        g[3 * (size_t)i + 2] = sum3(r20 * x, r21 * y, r22 * z) + t2;
+    }
+    return osep_gskel_run(h, g.data(), n, 3);
+}
+
 int osep_gskel_vertices(osep_gskel* h, const float** xyz4, int* n_vertices) {
     if (!h || !xyz4 || !n_vertices) return OSEP_ERR_ARG;
     GSkelImpl& S = h->impl;

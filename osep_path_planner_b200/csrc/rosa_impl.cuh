@@ -18,6 +18,7 @@ struct RosaDev {
     FrameState* st = nullptr;
     // N-scale
     float* in = nullptr;               // staged input (host-buffer path), Ncap * 4 floats
+    unsigned char* in_raw = nullptr; size_t in_raw_bytes = 0;   // staged raw PointCloud2 records (osep_rosa_run_pointcloud2), grown on demand
     float4* P = nullptr;               // filtered points (x,y,z,1)
     int* filt_idx = nullptr;
     int* blk_cnt = nullptr;

@@ -89,3 +89,23 @@ def to_xyz4(P):
     out = np.ones((P.shape[0], 4), dtype=np.float32)
     out[:, :3] = P
     return out
+
+
+def quat_xyzw_from_matrix(R):
+    """Unit quaternion (x, y, z, w) of a rotation matrix -- the rotation field of the geometry_msgs/TransformStamped a
+    TF lookup returns for the analytic sensor pose of stream_frame()."""
+    R = np.asarray(R, dtype=np.float64)
+    tr = R[0, 0] + R[1, 1] + R[2, 2]
+    if tr > 0:
+        s = 2.0 * np.sqrt(tr + 1.0); w = 0.25 * s
+        x = (R[2, 1] - R[1, 2]) / s; y = (R[0, 2] - R[2, 0]) / s; z = (R[1, 0] - R[0, 1]) / s
+    elif R[0, 0] > R[1, 1] and R[0, 0] > R[2, 2]:
+        s = 2.0 * np.sqrt(1.0 + R[0, 0] - R[1, 1] - R[2, 2]); x = 0.25 * s
+        w = (R[2, 1] - R[1, 2]) / s; y = (R[0, 1] + R[1, 0]) / s; z = (R[0, 2] + R[2, 0]) / s
+    elif R[1, 1] > R[2, 2]:
+        s = 2.0 * np.sqrt(1.0 + R[1, 1] - R[0, 0] - R[2, 2]); y = 0.25 * s
+        w = (R[0, 2] - R[2, 0]) / s; x = (R[0, 1] + R[1, 0]) / s; z = (R[1, 2] + R[2, 1]) / s
+    else:
+        s = 2.0 * np.sqrt(1.0 + R[2, 2] - R[0, 0] - R[1, 1]); z = 0.25 * s
+        w = (R[1, 0] - R[0, 1]) / s; x = (R[0, 2] + R[2, 0]) / s; y = (R[1, 2] + R[2, 1]) / s
+    return np.array([x, y, z, w], dtype=np.float64)

@@ -63,6 +63,19 @@ class GSkel:
                     break
         return self.running
 
+    def gskel_run_tf(self, translation, rotation_xyzw):
+        """tf2::doTransform + fromROSMsg + gskel_run (gskel_node.cpp:137-142): the candidates set with set_input() are in
+        the sensor frame; translation / rotation_xyzw are the TransformStamped fields (float64)."""
+        c = np.ascontiguousarray(self._cands, dtype=np.float32)
+        t = np.ascontiguousarray(translation, dtype=np.float64); q = np.ascontiguousarray(rotation_xyzw, dtype=np.float64)
+        rc = self._L.osep_gskel_run_tf(self._h, c.ctypes.data_as(C.c_void_p), c.shape[0], c.shape[1] if c.shape[0] else 4,
+                                       t.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p))
+        if rc < 0:
+            raise OsepError("osep_gskel_run_tf failed (%d): %s" % (rc, _lib.last_error()))
+        self.failed_stage = rc
+        self.running = rc == 0
+        return self.running
+
     def output_gskel(self):
         p = C.POINTER(C.c_float)(); n = C.c_int()
         self._L.osep_gskel_vertices(self._h, C.byref(p), C.byref(n))

@@ -41,11 +41,19 @@ public:
     ~GSkel() { if (h_) osep_gskel_destroy(h_); }
     GSkel(const GSkel&) = delete; GSkel& operator=(const GSkel&) = delete;
 
-    bool gskel_run() {           // gskel.cpp:21-38
+    bool gskel_run() { return run_impl(nullptr, nullptr); }           // gskel.cpp:21-38
+
+    // addition: tf2::doTransform + fromROSMsg + gskel_run (gskel_node.cpp:137-142) in one call; the
+    // candidates in input_vertices() are in the sensor frame, translation / rotation_xyzw come from lookupTransform.
+    bool gskel_run_tf(const double translation[3], const double rotation_xyzw[4]) { return run_impl(translation, rotation_xyzw); }
+
+private:
+    bool run_impl(const double* translation, const double* rotation_xyzw) {
         static const char* names[7] = {"increment_skeleton", "graph_adj", "mst", "vertex_merge", "prune", "smooth_vertex_positions", "extract_branches"};
         auto ts = std::chrono::high_resolution_clock::now();
         const int n = (int)new_cands_->points.size();
-        const int rc = osep_gskel_run(h_, n ? reinterpret_cast<const float*>(new_cands_->points.data()) : nullptr, n, 4);
+        const float* cands = n ? reinterpret_cast<const float*>(new_cands_->points.data()) : nullptr;
+        const int rc = translation ? osep_gskel_run_tf(h_, cands, n, 4, translation, rotation_xyzw) : osep_gskel_run(h_, cands, n, 4);
         if (rc < 0) { std::cerr << "[GSKEL] device error: " << osep_last_error() << std::endl; running = false; return false; }
         // the reference mutates the output cloud in place stage by stage; mirror the final state of this tick
         const float* xyz4 = nullptr; int G = 0;
@@ -63,6 +71,7 @@ public:
         std::cout << "[GSKEL] Time Elapsed: " << std::chrono::duration_cast<std::chrono::milliseconds>(te - ts).count() << " ms" << std::endl;
         return running;
     }
+public:
     osep::PointCloudXYZ& input_vertices() { return *new_cands_; }
     CloudPtr& output_gskel() { return global_vers_cloud_; }
 

@@ -80,13 +80,21 @@ public:
     ~Rosa() { if (h_) osep_rosa_destroy(h_); }
     Rosa(const Rosa&) = delete; Rosa& operator=(const Rosa&) = delete;
 
-    bool rosa_run() {            // rosa.cpp:36-55: same stdout protocol, RUN_STEP early exit
+    bool rosa_run() { return run_impl(nullptr, 0, 0, 0); }            // rosa.cpp:36-55: same stdout protocol, RUN_STEP early exit
+
+    // addition: rosa_run() straight from a sensor_msgs/PointCloud2 data block, replacing
+    // pcl::fromROSMsg + rosa_run (rosa_node.cpp:129,136).  x/y/z must be consecutive float32 fields at byte offset off_x.
+    bool rosa_run_pointcloud2(const void* data, int n_points, int point_step, int off_x = 0) { return run_impl(data, n_points, point_step, off_x); }
+
+private:
+    bool run_impl(const void* raw, int raw_n, int point_step, int off_x) {
         static const char* names[7] = {"preprocess", "rosa_init", "similarity_neighbor_extraction", "drosa", "dcrosa", "vertex_sampling", "vertex_smooth"};
         auto ts = std::chrono::high_resolution_clock::now();
-        const int n = (int)orig_.points.size();
+        const int n = raw ? raw_n : (int)orig_.points.size();
         std::cout << "PointCloud size before downsampling: " << n << std::endl;
         osep_rosa_result res;
-        const int rc = osep_rosa_run(h_, n ? reinterpret_cast<const float*>(orig_.points.data()) : nullptr, n, 4, &res);
+        const int rc = raw ? osep_rosa_run_pointcloud2(h_, raw, raw_n, point_step, off_x, off_x + 4, off_x + 8, &res)
+                           : osep_rosa_run(h_, n ? reinterpret_cast<const float*>(orig_.points.data()) : nullptr, n, 4, &res);
         last_ = res;
         if (rc < 0) { std::cerr << "[ROSA] device error: " << osep_last_error() << std::endl; running = false; skelver_.resize(0, 3); return false; }
         for (int s = 1; s <= 7; ++s) {
@@ -105,6 +113,7 @@ public:
         std::cout << "[ROSA] Time Elapsed: " << std::chrono::duration_cast<std::chrono::milliseconds>(te - ts).count() << " ms" << std::endl;
         return running;
     }
+public:
     osep::PointCloudXYZ& input_cloud() { return orig_; }
     osep::MatrixXf& output_vertices() { return skelver_; }
 

@@ -91,6 +91,20 @@ class Rosa:
             self._print_steps(rc)
         return self.running
 
+    def rosa_run_pointcloud2(self, data, n_points, point_step, off_x=0):
+        """rosa_run() straight from a sensor_msgs/PointCloud2 data block (bytes / uint8 array of n_points records of
+        point_step bytes; float32 x, y, z at byte offsets off_x, off_x + 4, off_x + 8) -- replaces
+        pcl::fromROSMsg + rosa_run (rosa_node.cpp:129,136) without the host-side repack."""
+        buf = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data.view(np.uint8).reshape(-1))
+        rc = self._L.osep_rosa_run_pointcloud2(self._h, buf.ctypes.data_as(C.c_void_p), n_points, point_step, off_x, off_x + 4, off_x + 8, C.byref(self.result))
+        if rc < 0:
+            raise OsepError("osep_rosa_run_pointcloud2 failed (%d): %s" % (rc, _lib.last_error()))
+        self._collect_vertices()
+        self.running = rc == 0
+        if self.verbose:
+            self._print_steps(rc)
+        return self.running
+
     def output_vertices(self):
         return self._vertices
 

@@ -195,3 +195,23 @@ def test_gskel_oracle_approves_on_third_update_and_respects_gnd_th():
     for _ in range(5):
         g2.run(pts)
     assert len(g2.tap("global")) == 0
+
+
+def test_tf_points_matches_float64_rigid_transform():
+    """orc_tf_points restates tf2::doTransform(PointCloud2) (gskel_node.cpp:137-138) in float32; against the float64
+    rigid transform of the same quaternion it may differ by rounding only."""
+    rng = np.random.default_rng(5)
+    for f in (0, 17, 113, 240):
+        P, R, t = fx.stream_frame(f, n=2000)
+        q = fx.quat_xyzw_from_matrix(R)
+        x, y, z, w = q
+        Rq = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                       [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                       [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        assert np.abs(Rq - R).max() < 1e-12
+        out = po.tf_points(P, t, q)
+        ref = P.astype(np.float64) @ R.T + t
+        assert out.dtype == np.float32 and np.abs(out - ref).max() < 2e-5
+    # identity transform returns the input bits
+    P = rng.normal(size=(100, 3)).astype(np.float32)
+    assert np.array_equal(po.tf_points(P, [0, 0, 0], [0, 0, 0, 1]), P)

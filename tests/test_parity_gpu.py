@@ -420,3 +420,66 @@ def test_degenerate_geometries(mods, name):
         assert_bit_equal(np.ascontiguousarray(r.output_vertices()), o.tap("skelver"), name + " vertices")
         assert r.result.flags == o.flags
     r.close()
+
+
+def test_frame_graph_replay_equals_plain_launches(mods):
+    """A repeated (buffer, n, stride) shape is captured into a CUDA graph on its second occurrence and replayed
+    afterwards (api.cu rosa_enqueue): replays, plain launches (debug mode disables the graph) and the oracle agree,
+    also when the content of the buffer or the number of points changes between replays."""
+    osep, po, fx = mods
+    A, B, Cc = fx.turbine(30000, seed=11), fx.turbine(30000, seed=12), fx.cylinder(18000, seed=13)
+    ref = {}
+    for name, P in (("A", A), ("B", B), ("C", Cc)):
+        o = po.RosaOracle(); assert o.run(P); ref[name] = o.tap("skelver")
+    r = osep.Rosa(capacity_points=30000)
+    seq = ["A", "A", "A", "B", "B", "C", "C", "C", "A", "A"]          # 3rd+ A and 2nd+ B / C are replays; C re-captures (n differs)
+    clouds = {"A": A, "B": B, "C": Cc}
+    for k, name in enumerate(seq):
+        r.set_input(clouds[name])
+        assert r.rosa_run()
+        assert_bit_equal(np.ascontiguousarray(r.output_vertices()), ref[name], "frame %d (%s)" % (k, name))
+    r.close()
+
+
+def test_pointcloud2_ingest_equals_packed_input(mods):
+    """osep_rosa_run_pointcloud2: raw PointCloud2 records (x,y,z at an offset inside a wider
+    point_step, e.g. x y z intensity ring time) give the same frame as the packed pcl::PointXYZ buffer."""
+    osep, po, fx = mods
+    P = fx.turbine(25000, seed=21)
+    o = po.RosaOracle(); assert o.run(P)
+    r = osep.Rosa(capacity_points=25000)
+    for point_step, off_x in ((16, 0), (32, 0), (48, 8), (12, 0)):
+        rec = np.zeros((P.shape[0], point_step), np.uint8)
+        rec[:] = 0xAB                                              # garbage in the other fields (incl. NaN-looking bytes)
+        rec[:, off_x:off_x + 12] = P.astype(np.float32).view(np.uint8).reshape(-1, 12)
+        assert r.rosa_run_pointcloud2(rec, P.shape[0], point_step, off_x)
+        assert_bit_equal(np.ascontiguousarray(r.output_vertices()), o.tap("skelver"), "point_step %d" % point_step)
+    L = osep.load(); import ctypes as C
+    res = osep.RosaResult(); rec = np.zeros(64, np.uint8)
+    assert L.osep_rosa_run_pointcloud2(r._h, rec.ctypes.data_as(C.c_void_p), 2, 18, 0, 4, 8, C.byref(res)) == -2      # point_step % 4
+    assert L.osep_rosa_run_pointcloud2(r._h, rec.ctypes.data_as(C.c_void_p), 2, 16, 0, 8, 4, C.byref(res)) == -2      # x,y,z not consecutive
+    r.close()
+
+
+def test_gskel_run_tf_equals_transform_then_run(mods):
+    """osep_gskel_run_tf (SURVEY.md 8f-3) = tf2::doTransform arithmetic + gskel_run, against the oracle's restatement."""
+    osep, po, fx = mods
+    from osep_path_planner_b200 import GSkel, GSkelConfig
+    cfg_kw = dict(gnd_th=-100.0)
+    gs = GSkel(GSkelConfig(**cfg_kw)); go = po.GSkelOracle(po.GSkelConfig.default(**cfg_kw))
+    r = osep.Rosa(capacity_points=32768)
+    for f in range(0, 12):
+        P, R, t = fx.stream_frame(f * 3, n=20000)
+        q = fx.quat_xyzw_from_matrix(R)
+        r.set_input(P)
+        if not r.rosa_run():
+            continue
+        v = np.ascontiguousarray(r.output_vertices())
+        gs.set_input(v)
+        ok_g = gs.gskel_run_tf(t, q)
+        ok_o = go.run(po.tf_points(v, t, q))
+        assert ok_g == ok_o and gs.failed_stage == go.failed_stage
+        assert_bit_equal(gs.output_gskel()[:, :3].copy(), go.tap("global"), "global vertices tick %d" % f)
+        assert_bit_equal(gs.tap("prelim"), go.tap("prelim"), "prelim vertices tick %d" % f)
+    assert len(go.tap("prelim")) > 5
+    gs.close(); r.close()
