@@ -355,7 +355,10 @@ __global__ void k_grid_insert(const float4* __restrict__ P, FrameState* st, unsi
     __syncthreads();
     if (s_last && threadIdx.x == 0) { st->ticket_grid = 0; __threadfence(); grid_refine(st, target_ppc); }
 }
-constexpr int QCH = 8;            // queries per kNN work unit
+#ifndef OSEP_QCH
+#define OSEP_QCH 12
+#endif
+constexpr int QCH = OSEP_QCH;            // queries per kNN work unit
 __global__ void k_grid_alloc(FrameState* st, const int* __restrict__ g_cnt, int* __restrict__ g_start, int T, int2* __restrict__ units) {
     __shared__ int s_pts, s_units, b_pts, b_units;
     if (st->status != 0) return;
@@ -512,6 +515,19 @@ constexpr int KNN_LIST = 64;
 constexpr int KNN_TAB = 125;
 constexpr int KNN_WARPS = 4;
 constexpr int KNN_STAGE = 512;
+#ifndef OSEP_KNN_GUESS
+#define OSEP_KNN_GUESS 1.35f
+#endif
+
+// flat candidate index t -> (cell entry, offset): largest ci with pre[ci] <= t (pre = exclusive prefix of the cell
+// counts, nt <= 125 entries => 7 halvings).  Lets the staging loops issue independent loads for 32 candidates per
+// round instead of walking the cells one after the other.
+__device__ __forceinline__ int flat_cell(const int* pre, int nt, int t) {
+    int lo = 0, hi = nt - 1;
+#pragma unroll
+    for (int step = 0; step < 7; ++step) { const int mid = (lo + hi + 1) >> 1; if (pre[mid] <= t) lo = mid; else hi = mid - 1; }
+    return lo;
+}
 
 // ascending bitonic sort of 64 packed keys (d2 bits << 32 | index; d2 >= 0 so the bit pattern orders like the
 // float and the packed compare is exactly the canonical (d2, index) order), two keys per lane: element r*32+lane.
@@ -559,6 +575,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
                                                              int* __restrict__ knn_idx, int k_req, int* __restrict__ slow_list,
                                                              int* __restrict__ over_list) {
     __shared__ int2 tab[KNN_WARPS][KNN_TAB];
+    __shared__ int pre[KNN_WARPS][KNN_TAB + 1];
     __shared__ unsigned long long keys[KNN_WARPS][KNN_LIST];
     __shared__ float4 stage[STAGED ? KNN_WARPS : 1][STAGED ? KNN_STAGE : 1];
     if (st->status != 0) return;
@@ -577,11 +594,14 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
         if (lane == 0) w = atomicAdd(ctr, 1);
         w = __shfl_sync(0xffffffffu, w, 0);
         if (w >= n_work) break;
-        const int unit = STAGED ? w : over_list[w];
+        // overflow work items are single queries (unit * 32 + query): one warp each, so a few oversized cells do not
+        // serialise 8-12 long queries on one warp at the end of the stage
+        const int code = STAGED ? 0 : over_list[w];
+        const int unit = STAGED ? w : (code >> 5);
         const int2 un = units[unit];
         const int cstart = g_start[un.x], ccnt = g_cnt[un.x];
-        const int q0 = un.y & 0xffffff;
-        const int nq = min(un.y >> 24, ccnt - q0);
+        const int q0 = (un.y & 0xffffff) + (STAGED ? 0 : (code & 31));
+        const int nq = STAGED ? min(un.y >> 24, ccnt - (un.y & 0xffffff)) : 1;
         int cx, cy, cz;
         { const float4 f = Pc[cstart]; cell_of(st, f.x, f.y, f.z, cx, cy, cz); }
         unsigned todo = (1u << nq) - 1u;
@@ -607,20 +627,22 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
                     if (cur != 0ull) e = make_int2(g_start[s], g_cnt[s]);
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, e.y > 0);
-                if (e.y > 0) tab[wib][nt + __popc(m & lt)] = e;
+                int incl = e.y;                                   // inclusive scan of the cell counts over the lanes
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                if (e.y > 0) { const int slot = nt + __popc(m & lt); tab[wib][slot] = e; pre[wib][slot] = total + incl - e.y; }
                 nt += __popc(m);
-                total += __reduce_add_sync(0xffffffffu, e.y);
+                total += __shfl_sync(0xffffffffu, incl, 31);
             }
             __syncwarp();
             const float4* base = Pc;
             if (STAGED) {
                 if (total > KNN_STAGE) { overflow = true; break; }
-                // stage: flat copy of every candidate cell (independent loads, many in flight)
-                int off = 0;
-                for (int ti = 0; ti < nt; ++ti) {
-                    const int2 e = tab[wib][ti];
-                    for (int t = lane; t < e.y; t += 32) stage[wib][off + t] = Pc[e.x + t];
-                    off += e.y;
+                // stage: flat copy of the candidate cells, 32 candidates per round, all rounds' loads independent
+#pragma unroll 4
+                for (int t0 = 0; t0 < total; t0 += 32) {
+                    const int t = t0 + lane;
+                    if (t < total) { const int ci = flat_cell(pre[wib], nt, t); stage[wib][t] = Pc[tab[wib][ci].x + (t - pre[wib][ci])]; }
                 }
                 __syncwarp();
                 if (lane == 0) tab[wib][0] = make_int2(0, total);
@@ -757,8 +779,13 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
                     if (cnt > KNN_LIST) continue;             // > 64 candidates tie at the k-th distance: slow path
                     ln = collect(hi);
                 }
-                guess = hi * 1.125f;
                 if (ln <= 32) bitonic32(k0); else bitonic64(k0, k1);
+                {   // next query of the cell: a radius^2 a little above this query's k-th distance usually holds k..32 points,
+                    // so it is accepted without counting and sorted with the one-register network
+                    const int kl = (k_eff - 1) & 31;
+                    const unsigned long long kth = __shfl_sync(0xffffffffu, (k_eff - 1) < 32 ? k0 : k1, kl);
+                    guess = __uint_as_float((unsigned)(kth >> 32)) * OSEP_KNN_GUESS;
+                }
                 const int qidx = __float_as_int(q.w);
                 if (lane < k_eff) knn_idx[(size_t)qidx * k_eff + lane] = (int)(unsigned)(k0 & 0xffffffffull);
                 if (lane + 32 < k_eff) knn_idx[(size_t)qidx * k_eff + lane + 32] = (int)(unsigned)(k1 & 0xffffffffull);
@@ -766,8 +793,146 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
             }
         }
         __syncwarp();
-        if (STAGED && overflow) { if (lane == 0) over_list[atomicAdd(&st->n_over, 1)] = unit; }
+        if (STAGED && overflow) { if (lane < nq && ((todo >> lane) & 1u)) over_list[atomicAdd(&st->n_over, 1)] = unit * 32 + lane; }
         else if (lane < nq && ((todo >> lane) & 1u)) slow_list[atomicAdd(&st->n_slow, 1)] = cstart + q0 + lane;
+        __syncwarp();
+    }
+}
+
+// R5 overflow path: queries whose candidate block does not fit the per-warp stage of k_knn_cells (dense spots: more
+// than KNN_STAGE points in 27 cells).  One WARP per QUERY, one warp per CTA: the (d2, index) pairs of all candidates
+// are computed once into a large shared-memory list (KNN_BIG entries), every selection pass then runs from shared
+// memory with full lane utilisation.  Same certification and the same canonical result as the fast path; what does
+// not fit or cannot be certified within R <= 2 goes to k_knn_exact.
+constexpr int KNN_BIG = 5120;
+template <int K>
+__global__ void __launch_bounds__(32) k_knn_big(const float4* __restrict__ Pc, FrameState* st,
+                                                const unsigned long long* __restrict__ gtab, const int* __restrict__ g_cnt,
+                                                const int* __restrict__ g_start, unsigned mask, const int2* __restrict__ units,
+                                                int* __restrict__ knn_idx, int k_req, int* __restrict__ slow_list,
+                                                const int* __restrict__ over_list) {
+    __shared__ int2 tab[KNN_TAB];
+    __shared__ int pre[KNN_TAB + 1];
+    __shared__ float sd[KNN_BIG];
+    __shared__ int si[KNN_BIG];
+    __shared__ unsigned long long keys[KNN_LIST];
+    if (st->status != 0) return;
+    const int n = st->n_filt;
+    const int k_eff = min(k_req, n);
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int dimx = st->g_dim[0], dimy = st->g_dim[1], dimz = st->g_dim[2];
+    const float h = st->g_h;
+    const float diag2 = ((float)dimx * h) * ((float)dimx * h) + ((float)dimy * h) * ((float)dimy * h) + ((float)dimz * h) * ((float)dimz * h);
+    const int n_work = st->n_over;
+    const unsigned long long KINF = ~0ull;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int code = over_list[w];
+        const int2 un = units[code >> 5];
+        const int cstart = g_start[un.x];
+        const int qpos = cstart + (un.y & 0xffffff) + (code & 31);
+        const float4 q = Pc[qpos];
+        int cx, cy, cz; cell_of(st, q.x, q.y, q.z, cx, cy, cz);
+        bool done = false;
+        for (int R = 1; R <= 2 && !done; ++R) {
+            const int x0 = max(cx - R, 0), x1 = min(cx + R, dimx - 1);
+            const int y0 = max(cy - R, 0), y1 = min(cy + R, dimy - 1);
+            const int z0 = max(cz - R, 0), z1 = min(cz + R, dimz - 1);
+            const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, nz = z1 - z0 + 1;
+            const int ncell = nx * ny * nz;
+            const bool whole = (x0 == 0 && y0 == 0 && z0 == 0 && x1 == dimx - 1 && y1 == dimy - 1 && z1 == dimz - 1);
+            int nt = 0, total = 0;
+            __syncwarp();
+            for (int c0 = 0; c0 < ncell; c0 += 32) {
+                const int c = c0 + lane;
+                int2 e = make_int2(0, 0);
+                if (c < ncell) {
+                    const int x = x0 + c % nx, y = y0 + (c / nx) % ny, z = z0 + c / (nx * ny);
+                    const unsigned long long key1 = cell_key1(x, y, z);
+                    unsigned s = hash_u64(key1) & mask;
+                    unsigned long long cur;
+                    while ((cur = gtab[s]) != key1 && cur != 0ull) s = (s + 1) & mask;
+                    if (cur != 0ull) e = make_int2(g_start[s], g_cnt[s]);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, e.y > 0);
+                int incl = e.y;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                if (e.y > 0) { const int slot = nt + __popc(m & lt); tab[slot] = e; pre[slot] = total + incl - e.y; }
+                nt += __popc(m);
+                total += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            __syncwarp();
+            if (total > KNN_BIG) break;                       // exact slow path
+            // every candidate's (d2, index) once, 32 candidates per round, all rounds' loads independent
+#pragma unroll 4
+            for (int t0 = 0; t0 < total; t0 += 32) {
+                const int t = t0 + lane;
+                if (t < total) {
+                    const int ci = flat_cell(pre, nt, t);
+                    const float4 c = Pc[tab[ci].x + (t - pre[ci])];
+                    sd[t] = dist2(q.x, q.y, q.z, c.x, c.y, c.z); si[t] = __float_as_int(c.w);
+                }
+            }
+            __syncwarp();
+            float b2;
+            if (whole) b2 = 4.0f * diag2 + 1.0f;
+            else {
+                const float bound = block_bound(st, q.x - st->bmin[0], q.y - st->bmin[1], q.z - st->bmin[2], x0, x1, y0, y1, z0, z1);
+                b2 = bound > 0.0f ? bound * bound : 0.0f;
+            }
+            auto population = [&](float thr) -> int {
+                int cm = 0;
+                for (int t = lane; t < total; t += 32) cm += (sd[t] < thr) ? 1 : 0;
+                return __reduce_add_sync(0xffffffffu, cm);
+            };
+            constexpr int NR = 8;
+            int cr[NR]; float tr[NR];
+#pragma unroll
+            for (int m = 0; m < NR; ++m) { cr[m] = 0; tr[m] = b2 * (1.0f / (float)(1 << m)); }
+            for (int t = lane; t < total; t += 32) {
+                const float d2 = sd[t];
+#pragma unroll
+                for (int m = 0; m < NR; ++m) cr[m] += (d2 < tr[m]) ? 1 : 0;
+            }
+#pragma unroll
+            for (int m = 0; m < NR; ++m) cr[m] = __reduce_add_sync(0xffffffffu, cr[m]);
+            if (cr[0] < k_eff) continue;                      // not certifiable at this R
+            float lo = 0.0f, hi = tr[0]; int cnt = cr[0];
+#pragma unroll
+            for (int m = 1; m < NR; ++m) if (cr[m] >= k_eff) { hi = tr[m]; cnt = cr[m]; }
+#pragma unroll
+            for (int m = 1; m < NR; ++m) if (cr[m] < k_eff && tr[m] > lo) lo = tr[m];
+            int guardc = 0;
+            while (cnt > KNN_LIST && guardc < 48) {           // bisection: population(hi) >= k > population(lo)
+                const float mid = 0.5f * (lo + hi);
+                if (!(mid > lo && mid < hi)) break;
+                const int cm = population(mid);
+                if (cm >= k_eff) { hi = mid; cnt = cm; } else lo = mid;
+                ++guardc;
+            }
+            if (cnt > KNN_LIST) break;                        // > 64 candidates tie at the k-th distance: slow path
+            int ln = 0;
+            for (int t0 = 0; t0 < total; t0 += 32) {
+                const int t = t0 + lane;
+                const float d2 = t < total ? sd[t] : 3.0e38f;
+                const bool in = d2 < hi;
+                const unsigned m = __ballot_sync(0xffffffffu, in);
+                const int pos = ln + __popc(m & lt);
+                if (in && pos < KNN_LIST) keys[pos] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)si[t];
+                ln += __popc(m);
+            }
+            __syncwarp();
+            unsigned long long k0 = (lane < ln) ? keys[lane] : KINF;
+            unsigned long long k1 = (lane + 32 < ln) ? keys[lane + 32] : KINF;
+            __syncwarp();
+            if (ln <= 32) bitonic32(k0); else bitonic64(k0, k1);
+            const int qidx = __float_as_int(q.w);
+            if (lane < k_eff) knn_idx[(size_t)qidx * k_eff + lane] = (int)(unsigned)(k0 & 0xffffffffull);
+            if (lane + 32 < k_eff) knn_idx[(size_t)qidx * k_eff + lane + 32] = (int)(unsigned)(k1 & 0xffffffffull);
+            done = true;
+        }
+        if (!done && lane == 0) slow_list[atomicAdd(&st->n_slow, 1)] = qpos;
         __syncwarp();
     }
 }
@@ -968,8 +1133,7 @@ static void launch_knn(osep_rosa_impl* h, int n, int k_req, cudaStream_t s) {
     const unsigned mask = (unsigned)(d.T - 1);
     k_knn_cells<K, true><<<h->sms * 6, KNN_WARPS * 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units,
                                                               d.knn_full, k_req, d.slow_list, d.over_list);
-    k_knn_cells<K, false><<<h->sms * 2, KNN_WARPS * 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units,
-                                                               d.knn_full, k_req, d.slow_list, d.over_list);
+    k_knn_big<K><<<h->sms * 4, 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units, d.knn_full, k_req, d.slow_list, d.over_list);
     k_knn_exact<K><<<64, 128, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.knn_full, k_req, d.slow_list);
     k_normals<<<div_up(n, 128), 128, 0, s>>>(d.P, d.st, d.knn_full, k_req, d.Nrm);
 }
