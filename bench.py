@@ -153,6 +153,7 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout = the one JSON line (NCCL prints its version banner to stdout)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
