@@ -285,6 +285,15 @@ __device__ __forceinline__ unsigned hash_u64(unsigned long long k) {
     k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
     return (unsigned)k;
 }
+// Home slot of a grid cell: the 4x4x4 block of cells is hashed, the position inside the block (6 bits) selects the
+// slot inside a 64-slot group.  Cells of one block are distinct slots of one group, so (a) the 27 cells a query block
+// touches sit in a few groups of the table and (b) the cell data, allocated in slot order, is spatially coherent:
+// neighbouring cells share cache lines and neighbouring work units share L2 lines (maps larger than L2: tiled path).
+__device__ __forceinline__ unsigned cell_slot(int x, int y, int z, unsigned mask) {
+    const unsigned fine = (unsigned)((x & 3) | ((y & 3) << 2) | ((z & 3) << 4));
+    const unsigned long long coarse = (((unsigned long long)(z >> 2) << 42) | ((unsigned long long)(y >> 2) << 21) | (unsigned long long)(x >> 2));
+    return ((hash_u64(coarse + 0x9e3779b97f4a7c15ull) << 6) | fine) & mask;
+}
 
 __device__ void grid_params(FrameState* st, int target_ppc) {
     if (st->status != 0) return;
@@ -336,7 +345,7 @@ __global__ void k_grid_insert(const float4* __restrict__ P, FrameState* st, unsi
         const float4 p = P[i];
         int cx, cy, cz; cell_of(st, p.x, p.y, p.z, cx, cy, cz);
         const unsigned long long key1 = cell_key1(cx, cy, cz);
-        unsigned s = hash_u64(key1) & mask;
+        unsigned s = cell_slot(cx, cy, cz, mask);
         while (true) {
             const unsigned long long cur = gtab[s];
             if (cur == key1) break;
@@ -480,7 +489,7 @@ __global__ void __launch_bounds__(128) k_knn_exact(const float4* __restrict__ Pc
             const int z0 = max(cz - R, 0), z1 = min(cz + R, dimz - 1);
             for (int z = z0; z <= z1; ++z) for (int y = y0; y <= y1; ++y) for (int x = x0; x <= x1; ++x) {
                 const unsigned long long key1 = cell_key1(x, y, z);
-                unsigned s = hash_u64(key1) & mask;
+                unsigned s = cell_slot(x, y, z, mask);
                 unsigned long long cur;
                 while ((cur = gtab[s]) != key1 && cur != 0ull) s = (s + 1) & mask;
                 if (cur == 0ull) continue;
@@ -621,7 +630,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
                 if (c < ncell) {
                     const int x = x0 + c % nx, y = y0 + (c / nx) % ny, z = z0 + c / (nx * ny);
                     const unsigned long long key1 = cell_key1(x, y, z);
-                    unsigned s = hash_u64(key1) & mask;
+                    unsigned s = cell_slot(x, y, z, mask);
                     unsigned long long cur;
                     while ((cur = gtab[s]) != key1 && cur != 0ull) s = (s + 1) & mask;
                     if (cur != 0ull) e = make_int2(g_start[s], g_cnt[s]);
@@ -849,7 +858,7 @@ __global__ void __launch_bounds__(32) k_knn_big(const float4* __restrict__ Pc, F
                 if (c < ncell) {
                     const int x = x0 + c % nx, y = y0 + (c / nx) % ny, z = z0 + c / (nx * ny);
                     const unsigned long long key1 = cell_key1(x, y, z);
-                    unsigned s = hash_u64(key1) & mask;
+                    unsigned s = cell_slot(x, y, z, mask);
                     unsigned long long cur;
                     while ((cur = gtab[s]) != key1 && cur != 0ull) s = (s + 1) & mask;
                     if (cur != 0ull) e = make_int2(g_start[s], g_cnt[s]);
