@@ -117,7 +117,16 @@ __global__ void k_simi(FrameState* st, const float4* __restrict__ pts, const flo
     const f3 v1 = normalize3(N1);
     const int base = FILL ? simi_off[i] : 0;
     int cnt = 0;
-    if (n1ok) {
+    if (n1ok && FILL) {
+        // second pass: the accepted set is the bit row the first pass wrote -- no second evaluation of the metric
+        for (int j0 = 0; j0 < M; j0 += 32) {
+            const int j = j0 + lane;
+            const unsigned m = simi_bits[(size_t)i * W + (j0 >> 5)];
+            const bool keep = (m >> lane) & 1u;
+            if (keep) { const int pos = base + cnt + __popc(m & ((1u << lane) - 1u)); tmp_j[pos] = j; tmp_d[pos] = dist2(P1, ld3(pts, j)); }
+            cnt += __popc(m);
+        }
+    } else if (n1ok) {
         for (int j0 = 0; j0 < M; j0 += 32) {
             const int j = j0 + lane;
             bool keep = false; float d2 = 0.0f;
