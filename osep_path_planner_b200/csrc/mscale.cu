@@ -67,10 +67,6 @@ __device__ int block_scan_inplace(int* data, int n) {
     return s_carry;
 }
 
-// stage gate: rosa_init always succeeds; similarity_neighbor_extraction fails on an empty cloud (rosa.cpp:205)
-__global__ void k_mscale_begin(FrameState* st) {
-    if (st->status == 0 && st->M == 0) st->status = OSEP_STAGE_3;
-}
 
 // ------------------------------------------------------------------------------------------
 // R12.  similarity_metric (rosa.cpp:625-651)
@@ -98,16 +94,9 @@ __device__ __forceinline__ float similarity_metric(const f3& p1, const f3& v1, c
 // ascending (d2, index) order (radiusSearch returns sorted results; the order is the
 // summation order of dcrosa, rosa.cpp:395-397, 804-813).
 template <bool FILL>
-__global__ void k_simi(FrameState* st, const float4* __restrict__ pts, const float4* __restrict__ nrms,
-                       int* simi_off, int* __restrict__ simi_idx, int* __restrict__ tmp_j, float* __restrict__ tmp_d,
-                       unsigned* __restrict__ simi_bits, int W_cap) {
-    if (st->status != 0) return;
-    const int M = st->M;
-    const int W = (M + 31) >> 5;           // dense row stride of the bit matrix
-    (void)W_cap;
-    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (i >= M) return;
+__device__ __forceinline__ void simi_row(FrameState* st, const float4* __restrict__ pts, const float4* __restrict__ nrms,
+                                         int* simi_off, int* __restrict__ simi_idx, int* __restrict__ tmp_j, float* __restrict__ tmp_d,
+                                         unsigned* __restrict__ simi_bits, int M, int W, int i, int lane) {
     const float leaf = st->leaf_size;
     const float radius_r = 10.0f * leaf;
     const float th_sim = 0.1f * leaf;
@@ -161,10 +150,26 @@ __global__ void k_simi(FrameState* st, const float4* __restrict__ pts, const flo
     }
 }
 
-__global__ void k_simi_scan(FrameState* st, int* simi_off, int Scap) {
+template <bool FILL>
+__global__ void k_simi(FrameState* st, const float4* __restrict__ pts, const float4* __restrict__ nrms,
+                       int* simi_off, int* __restrict__ simi_idx, int* __restrict__ tmp_j, float* __restrict__ tmp_d,
+                       unsigned* __restrict__ simi_bits, int Scap) {
     if (st->status != 0) return;
     const int M = st->M;
-    if (threadIdx.x == 0) simi_off[M] = 0;
+    const int W = (M + 31) >> 5;           // dense row stride of the bit matrix
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i < M) simi_row<FILL>(st, pts, nrms, simi_off, simi_idx, tmp_j, tmp_d, simi_bits, M, W, i, lane);
+    if (FILL) return;
+    // the last block of the count pass turns the counts into CSR offsets (no separate scan launch)
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket_m, 1) == (int)gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) { st->ticket_m = 0; simi_off[M] = 0; }
+    __threadfence();
     __syncthreads();
     const int total = block_scan_inplace(simi_off, M + 1);
     if (threadIdx.x == 0) { st->S = total; if (total > Scap) st->status = OSEP_ERR_CAPACITY; }
@@ -220,8 +225,8 @@ k_surf_knn(FrameState* st, const float4* __restrict__ pts, int* __restrict__ sur
 }
 
 // R19 part 1 (single block): compact goodCenters, list poor points in ascending index.
-__global__ void k_poor_prepare(FrameState* st, const int* __restrict__ good, int* good_rank, const float4* __restrict__ centers,
-                               float4* __restrict__ good_centers, int* __restrict__ poor_idx, int* scratch) {
+__global__ void k_poor_fixup(FrameState* st, const int* __restrict__ good, int* good_rank, const float4* __restrict__ centers,
+                             float4* __restrict__ good_centers, int* __restrict__ poor_idx, const float4* __restrict__ pts, float4* pset) {
     if (st->status != 0) return;
     const int M = st->M;
     for (int i = threadIdx.x; i < M; i += blockDim.x) good_rank[i] = good[i];
@@ -234,33 +239,30 @@ __global__ void k_poor_prepare(FrameState* st, const int* __restrict__ good, int
         else poor_idx[i - good_rank[i]] = i;
     }
     if (threadIdx.x == 0) { st->n_good = ng; st->n_poor = M - ng; }
-}
-// R19 part 2: one warp per poor point: nearest slot of tmp_pt_ (good slot = surface point, poor
-// slot = (0,0,0), rosa.cpp:314,359), then pset[poor] = goodCenters[gid] AS WRITTEN (rosa.cpp:374:
-// gid is a slot index applied to the compacted list).  Out of bounds = UB in the reference:
-// pset is left unchanged and OSEP_FLAG_POOR_FIXUP_OOB raised.
-__global__ void k_poor_fix(FrameState* st, const float4* __restrict__ pts, const int* __restrict__ good,
-                           const float4* __restrict__ good_centers, const int* __restrict__ poor_idx, float4* pset) {
-    if (st->status != 0) return;
-    const int M = st->M;
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= st->n_poor) return;
-    const int poor = poor_idx[w];
-    const f3 q = ld3(pts, poor);
-    float bd = __int_as_float(0x7f800000); int bi = 0x7fffffff;
-    for (int i = lane; i < M; i += 32) {
-        const f3 c = good[i] ? ld3(pts, i) : f3{0.0f, 0.0f, 0.0f};
-        const float d = dist2(q, c);
-        if (nb_less(d, i, bd, bi)) { bd = d; bi = i; }
-    }
+    __syncthreads();
+    // R19 part 2 (same block, no second launch): one warp per poor point: nearest slot of tmp_pt_ (good slot = surface
+    // point, poor slot = (0,0,0), rosa.cpp:314,359), then pset[poor] = goodCenters[gid] AS WRITTEN (rosa.cpp:374: gid is a
+    // slot index applied to the compacted list).  Out of bounds = UB in the reference: pset is left unchanged and
+    // OSEP_FLAG_POOR_FIXUP_OOB raised.  All fix-ups read pts / good / good_centers only, so they are independent.
+    const int lane = threadIdx.x & 31, n_poor = M - ng;
+    for (int w = threadIdx.x >> 5; w < n_poor; w += (int)(blockDim.x >> 5)) {
+        const int poor = poor_idx[w];
+        const f3 q = ld3(pts, poor);
+        float bd = __int_as_float(0x7f800000); int bi = 0x7fffffff;
+        for (int i = lane; i < M; i += 32) {
+            const f3 c = good[i] ? ld3(pts, i) : f3{0.0f, 0.0f, 0.0f};
+            const float d = dist2(q, c);
+            if (nb_less(d, i, bd, bi)) { bd = d; bi = i; }
+        }
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        const float od = __shfl_xor_sync(FULL, bd, off); const int oi = __shfl_xor_sync(FULL, bi, off);
-        if (nb_less(od, oi, bd, bi)) { bd = od; bi = oi; }
-    }
-    if (lane == 0 && bi != 0x7fffffff) {
-        if (bi < st->n_good) pset[poor] = good_centers[bi];
-        else atomicOr(&st->flags, (unsigned)OSEP_FLAG_POOR_FIXUP_OOB);
+        for (int off = 16; off >= 1; off >>= 1) {
+            const float od = __shfl_xor_sync(FULL, bd, off); const int oi = __shfl_xor_sync(FULL, bi, off);
+            if (nb_less(od, oi, bd, bi)) { bd = od; bi = oi; }
+        }
+        if (lane == 0 && bi != 0x7fffffff) {
+            if (bi < ng) pset[poor] = good_centers[bi];
+            else atomicOr(&st->flags, (unsigned)OSEP_FLAG_POOR_FIXUP_OOB);
+        }
     }
 }
 
@@ -664,7 +666,6 @@ void launch_mscale(osep_rosa_impl* h) {
     const int warp_blocks = div_up(d.Mcap, WARPS_PER_BLOCK);
     const int tb = WARPS_PER_BLOCK * 32;
     const int tblocks = div_up(d.Mcap, 128);
-    k_mscale_begin<<<1, 1, 0, s>>>(d.st);
     // two independent branches on the downsampled cloud: similarity lists (main stream) || surf kNN (side stream)
     if (h->overlap) {
         cudaStream_t sk = h->stream2;
@@ -674,9 +675,8 @@ void launch_mscale(osep_rosa_impl* h) {
         cudaEventRecord(h->ev_join[1], sk);
     }
     // R12
-    k_simi<false><<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.nrms, d.simi_off, d.simi_idx, nullptr, nullptr, d.simi_bits, d.W);
-    k_simi_scan<<<1, 1024, 0, s>>>(d.st, d.simi_off, d.Scap);
-    k_simi<true><<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.nrms, d.simi_off, d.simi_idx, d.rv1, (float*)d.rk1, d.simi_bits, d.W);
+    k_simi<false><<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.nrms, d.simi_off, d.simi_idx, nullptr, nullptr, d.simi_bits, d.Scap);   // count + bit rows; its last block scans
+    k_simi<true><<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.nrms, d.simi_off, d.simi_idx, d.rv1, (float*)d.rk1, d.simi_bits, d.Scap);
     stage_mark(h, SM_SIMI);
     if (h->overlap) cudaStreamWaitEvent(s, h->ev_join[1], 0);
     else {                                                                     // profiling: sequential, attributable
@@ -684,8 +684,7 @@ void launch_mscale(osep_rosa_impl* h) {
         launch_drosa_prep(h, s);
     }
     launch_drosa(h, h->sms);
-    k_poor_prepare<<<1, 1024, 0, s>>>(d.st, d.good, d.good_rank, d.centers, d.pset2, d.poor_idx, nullptr);
-    k_poor_fix<<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.good, d.pset2, d.poor_idx, d.pset);
+    k_poor_fixup<<<1, 1024, 0, s>>>(d.st, d.good, d.good_rank, d.centers, d.pset2, d.poor_idx, d.pts, d.pset);
     if (h->debug) cudaMemcpyAsync(d.centers, d.pset, sizeof(float4) * d.Mcap, cudaMemcpyDeviceToDevice, s);   // tap: pset after drosa
     stage_mark(h, SM_POSITION);
     // R20
@@ -709,7 +708,7 @@ void launch_mscale(osep_rosa_impl* h) {
     k_vertex_smooth<<<1, 1024, 0, s>>>(d.st, d.skel, d.skel2, d.vtmp, d.vs_off, d.vs_idx, d.rv1, (float*)d.rk1, d.Scap,
                                        c.radius_smooth, c.alpha_recenter, c.niter_smooth);
     stage_mark(h, SM_VSMOOTH);
-    h->n_launches += 1 + 3 + 1 + 2 + 2 * c.niter_dcrosa + 5 + 1;   // + launch_drosa
+    h->n_launches += 2 + 1 + 1 + 1 + 5 + 1;   // + launch_drosa (dcrosa = one cluster kernel in the common case)
 }
 
 }  // namespace osep

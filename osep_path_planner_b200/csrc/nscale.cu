@@ -982,6 +982,7 @@ __global__ void k_vox_sortkeys(FrameState* st, unsigned* vkeys, int Mcap, int* v
         if (st->pass_overflow) { st->status = OSEP_ERR_CAPACITY; M = 0; }     // VoxelGrid output = input: not supported on device
         else if (M > Mcap) { st->status = OSEP_ERR_CAPACITY; M = 0; }
         st->M = M;
+        if (M == 0 && st->status == 0) st->status = OSEP_STAGE_3;   // stage gate: rosa_init always succeeds, similarity_neighbor_extraction fails on an empty cloud (rosa.cpp:205)
         sM = M;
     }
     __syncthreads();

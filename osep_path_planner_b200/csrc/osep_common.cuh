@@ -57,6 +57,7 @@ struct FrameState {
     int pass_active;       // the VoxelGrid pass set up by leaf_step is live (loop not finished)
     int n_keys;            // distinct voxel keys collected for the final pass
     int ticket;            // last-block detection (voxel count passes)
+    int ticket_m;          // last-block detection (similarity count pass)
     int ticket_grid;       // last-block detection (kNN grid build; runs concurrently with the voxel passes)
 };
 
