@@ -303,7 +303,7 @@ __device__ void grid_params(FrameState* st, int target_ppc) {
     const int nv = st->nvox_hist[0];
     float h = st->leaf_hist[0] * sqrtf((float)target_ppc * (float)(nv > 0 ? nv : 1) / (float)(n > 0 ? n : 1));
     grid_set_h(st, h);
-    st->g_cells_used = 0; st->n_units = 0; st->n_slow = 0; st->n_over = 0; st->unit_ctr = 0; st->over_ctr = 0;
+    st->g_cells_used = 0; st->n_units = 0; st->n_slow = 0; st->n_over = 0; st->unit_ctr = 0;
     st->g_ncells = 0; st->g_redo = 0;
 }
 
@@ -510,11 +510,11 @@ __global__ void __launch_bounds__(128) k_knn_exact(const float4* __restrict__ Pc
 
 // R5 fast path: one WARP per work unit = up to QCH queries of one grid cell.  The queries of a cell share
 // their candidate cells: the (start, count) table of the non-empty cells of the (2R+1)^3 block is built
-// once per unit (lanes probe the hash table in parallel) and the candidate points are STAGED in shared
-// memory with coalesced float4 loads (STAGED = true; units with more than KNN_STAGE candidates are
-// re-run with STAGED = false, reading the cells from L1/L2).  Per query the warp
-//   1. counts the candidates inside 4 nested radii (bound^2 / 1,2,4,8) with ballots (skipped when the
-//      radius that worked for the previous query of the cell works again),
+// once per unit (lanes probe the hash table in parallel) and the candidate points are staged in shared
+// memory with coalesced float4 loads (units with more than KNN_STAGE candidates hand their queries to
+// k_knn_big).  Per query the warp keeps the distances of the staged candidates in registers and
+//   1. tries the radius just above the previous query's k-th distance, else counts the candidates inside
+//      8 nested radii (bound^2 / 2^m) with per-lane compares,
 //   2. compacts the candidates of the smallest radius that still holds >= k points (exact: every point
 //      closer than `bound` is inside the scanned block, and the k nearest by (d2, index) are all inside
 //      any radius that holds >= k points),
@@ -577,7 +577,7 @@ __device__ __forceinline__ void bitonic32(unsigned long long& a0) {
     }
 }
 
-template <int K, bool STAGED>
+template <int K>
 __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __restrict__ Pc, FrameState* st,
                                                              const unsigned long long* __restrict__ gtab, const int* __restrict__ g_cnt,
                                                              const int* __restrict__ g_start, unsigned mask, const int2* __restrict__ units,
@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
     __shared__ int2 tab[KNN_WARPS][KNN_TAB];
     __shared__ int pre[KNN_WARPS][KNN_TAB + 1];
     __shared__ unsigned long long keys[KNN_WARPS][KNN_LIST];
-    __shared__ float4 stage[STAGED ? KNN_WARPS : 1][STAGED ? KNN_STAGE : 1];
+    __shared__ float4 stage[KNN_WARPS][KNN_STAGE];
     if (st->status != 0) return;
     const int n = st->n_filt;
     const int k_eff = min(k_req, n);
@@ -595,22 +595,17 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
     const int dimx = st->g_dim[0], dimy = st->g_dim[1], dimz = st->g_dim[2];
     const float h = st->g_h;
     const float diag2 = ((float)dimx * h) * ((float)dimx * h) + ((float)dimy * h) * ((float)dimy * h) + ((float)dimz * h) * ((float)dimz * h);
-    const int n_work = STAGED ? st->n_units : st->n_over;
-    int* ctr = STAGED ? &st->unit_ctr : &st->over_ctr;
+    const int n_work = st->n_units;
     const unsigned long long KINF = ~0ull;
     while (true) {
-        int w = 0;
-        if (lane == 0) w = atomicAdd(ctr, 1);
-        w = __shfl_sync(0xffffffffu, w, 0);
-        if (w >= n_work) break;
-        // overflow work items are single queries (unit * 32 + query): one warp each, so a few oversized cells do not
-        // serialise 8-12 long queries on one warp at the end of the stage
-        const int code = STAGED ? 0 : over_list[w];
-        const int unit = STAGED ? w : (code >> 5);
+        int unit = 0;
+        if (lane == 0) unit = atomicAdd(&st->unit_ctr, 1);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= n_work) break;
         const int2 un = units[unit];
         const int cstart = g_start[un.x], ccnt = g_cnt[un.x];
-        const int q0 = (un.y & 0xffffff) + (STAGED ? 0 : (code & 31));
-        const int nq = STAGED ? min(un.y >> 24, ccnt - (un.y & 0xffffff)) : 1;
+        const int q0 = un.y & 0xffffff;
+        const int nq = min(un.y >> 24, ccnt - q0);
         int cx, cy, cz;
         { const float4 f = Pc[cstart]; cell_of(st, f.x, f.y, f.z, cx, cy, cz); }
         unsigned todo = (1u << nq) - 1u;
@@ -644,22 +639,17 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
                 total += __shfl_sync(0xffffffffu, incl, 31);
             }
             __syncwarp();
-            const float4* base = Pc;
-            if (STAGED) {
-                if (total > KNN_STAGE) { overflow = true; break; }
-                // stage: flat copy of the candidate cells, 32 candidates per round, all rounds' loads independent
+            if (total > KNN_STAGE) { overflow = true; break; }
+            // stage: flat copy of the candidate cells, 32 candidates per round, all rounds' loads independent
 #pragma unroll 4
-                for (int t0 = 0; t0 < total; t0 += 32) {
-                    const int t = t0 + lane;
-                    if (t < total) { const int ci = flat_cell(pre[wib], nt, t); stage[wib][t] = Pc[tab[wib][ci].x + (t - pre[wib][ci])]; }
-                }
-                __syncwarp();
-                if (lane == 0) tab[wib][0] = make_int2(0, total);
-                nt = 1;
-                base = stage[wib];
-                __syncwarp();
+            for (int t0 = 0; t0 < total; t0 += 32) {
+                const int t = t0 + lane;
+                if (t < total) { const int ci = flat_cell(pre[wib], nt, t); stage[wib][t] = Pc[tab[wib][ci].x + (t - pre[wib][ci])]; }
             }
-            float guess = 0.0f;                               // radius^2 that worked for the previous query of this cell
+            __syncwarp();
+            constexpr int RPL = KNN_STAGE / 32;
+            const int nr = (total + 31) >> 5;                   // rounds of 32 staged candidates actually in use (uniform)
+            float guess = 0.0f;                               // radius^2 just above the previous query's k-th distance
             for (int qi = 0; qi < nq; ++qi) {
                 if (!((todo >> qi) & 1u)) continue;
                 const float4 q = Pc[cstart + q0 + qi];
@@ -670,47 +660,25 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
                     b2 = bound > 0.0f ? bound * bound : 0.0f;
                 }
                 unsigned long long k0 = KINF, k1 = KINF;
-                // STAGED: the distances of this lane's candidates (slots r*32+lane of the staged list) live in
-                // registers for all passes of the query; unstaged units re-read the cells from L1/L2.
-                constexpr int RPL = KNN_STAGE / 32;
-                float dq[STAGED ? RPL : 1]; int iq[STAGED ? RPL : 1];
-                int nr = 0;                                      // rounds of 32 staged candidates actually in use (uniform)
-                if constexpr (STAGED) {
-                    const int tot = tab[wib][0].y;
-                    nr = (tot + 31) >> 5;
+                // the distances of this lane's candidates (slots r*32+lane of the staged list) live in registers for
+                // all passes of the query
+                float dq[RPL]; int iq[RPL];
 #pragma unroll
-                    for (int r = 0; r < RPL; ++r) {
-                        const int t = r * 32 + lane;
-                        dq[r] = 3.0e38f; iq[r] = 0;
-                        if (r < nr && t < tot) { const float4 c = base[t]; dq[r] = dist2(q.x, q.y, q.z, c.x, c.y, c.z); iq[r] = __float_as_int(c.w); }
-                    }
+                for (int r = 0; r < RPL; ++r) {
+                    const int t = r * 32 + lane;
+                    dq[r] = 3.0e38f; iq[r] = 0;
+                    if (r < nr && t < total) { const float4 c = stage[wib][t]; dq[r] = dist2(q.x, q.y, q.z, c.x, c.y, c.z); iq[r] = __float_as_int(c.w); }
                 }
                 auto collect = [&](float thr) -> int {
                     int ln = 0;
-                    if constexpr (STAGED) {
 #pragma unroll
-                        for (int r = 0; r < RPL; ++r) {
-                            if (r >= nr) break;
-                            const bool in = dq[r] < thr;
-                            const unsigned m = __ballot_sync(0xffffffffu, in);
-                            const int pos = ln + __popc(m & lt);
-                            if (in && pos < KNN_LIST) keys[wib][pos] = ((unsigned long long)__float_as_uint(dq[r]) << 32) | (unsigned)iq[r];
-                            ln += __popc(m);
-                        }
-                    } else {
-                        for (int ti = 0; ti < nt; ++ti) {
-                            const int2 e = tab[wib][ti];
-                            for (int o = 0; o < e.y; o += 32) {
-                                const int t = o + lane;
-                                float d2 = 3.0e38f; int id = 0;
-                                if (t < e.y) { const float4 c = base[e.x + t]; d2 = dist2(q.x, q.y, q.z, c.x, c.y, c.z); id = __float_as_int(c.w); }
-                                const bool in = d2 < thr;
-                                const unsigned m = __ballot_sync(0xffffffffu, in);
-                                const int pos = ln + __popc(m & lt);
-                                if (in && pos < KNN_LIST) keys[wib][pos] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)id;
-                                ln += __popc(m);
-                            }
-                        }
+                    for (int r = 0; r < RPL; ++r) {
+                        if (r >= nr) break;
+                        const bool in = dq[r] < thr;
+                        const unsigned m = __ballot_sync(0xffffffffu, in);
+                        const int pos = ln + __popc(m & lt);
+                        if (in && pos < KNN_LIST) keys[wib][pos] = ((unsigned long long)__float_as_uint(dq[r]) << 32) | (unsigned)iq[r];
+                        ln += __popc(m);
                     }
                     __syncwarp();
                     k0 = (lane < ln && lane < KNN_LIST) ? keys[wib][lane] : KINF;
@@ -720,22 +688,9 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
                 };
                 auto population = [&](float thr) -> int {
                     int cm = 0;
-                    if constexpr (STAGED) {
 #pragma unroll
-                        for (int r = 0; r < RPL; ++r) if (r < nr) cm += (dq[r] < thr) ? 1 : 0;
-                        return __reduce_add_sync(0xffffffffu, cm);
-                    } else {
-                        for (int ti = 0; ti < nt; ++ti) {
-                            const int2 e = tab[wib][ti];
-                            for (int o = 0; o < e.y; o += 32) {
-                                const int t = o + lane;
-                                float d2 = 3.0e38f;
-                                if (t < e.y) { const float4 c = base[e.x + t]; d2 = dist2(q.x, q.y, q.z, c.x, c.y, c.z); }
-                                cm += __popc(__ballot_sync(0xffffffffu, d2 < thr));
-                            }
-                        }
-                        return cm;
-                    }
+                    for (int r = 0; r < RPL; ++r) if (r < nr) cm += (dq[r] < thr) ? 1 : 0;
+                    return __reduce_add_sync(0xffffffffu, cm);
                 };
                 int ln = -1; float hi = 0.0f;
                 if (guess > 0.0f && guess < b2) { hi = guess; ln = collect(hi); if (ln < k_eff || ln > KNN_LIST) ln = -1; }
@@ -747,29 +702,14 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
                     float tr[NR];
 #pragma unroll
                     for (int m = 0; m < NR; ++m) { cr[m] = 0; tr[m] = b2 * (1.0f / (float)(1 << m)); }
-                    if constexpr (STAGED) {
 #pragma unroll
-                        for (int r = 0; r < RPL; ++r) {
-                            if (r >= nr) break;
+                    for (int r = 0; r < RPL; ++r) {
+                        if (r >= nr) break;
 #pragma unroll
-                            for (int m = 0; m < NR; ++m) cr[m] += (dq[r] < tr[m]) ? 1 : 0;
-                        }
-#pragma unroll
-                        for (int m = 0; m < NR; ++m) cr[m] = __reduce_add_sync(0xffffffffu, cr[m]);
-                    } else {
-                        for (int ti = 0; ti < nt; ++ti) {
-                            const int2 e = tab[wib][ti];
-                            for (int o = 0; o < e.y; o += 32) {
-                                const int t = o + lane;
-                                float d2 = 3.0e38f;
-                                if (t < e.y) { const float4 c = base[e.x + t]; d2 = dist2(q.x, q.y, q.z, c.x, c.y, c.z); }
-#pragma unroll
-                                for (int m = 0; m < NR; ++m) cr[m] += (d2 < tr[m]) ? 1 : 0;
-                            }
-                        }
-#pragma unroll
-                        for (int m = 0; m < NR; ++m) cr[m] = __reduce_add_sync(0xffffffffu, cr[m]);
+                        for (int m = 0; m < NR; ++m) cr[m] += (dq[r] < tr[m]) ? 1 : 0;
                     }
+#pragma unroll
+                    for (int m = 0; m < NR; ++m) cr[m] = __reduce_add_sync(0xffffffffu, cr[m]);
                     if (cr[0] < k_eff) continue;              // not certifiable at this R
                     float lo = 0.0f; int cnt = cr[0];
                     hi = tr[0];
@@ -802,7 +742,9 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
             }
         }
         __syncwarp();
-        if (STAGED && overflow) { if (lane < nq && ((todo >> lane) & 1u)) over_list[atomicAdd(&st->n_over, 1)] = unit * 32 + lane; }
+        // overflow work items are single queries (unit * 32 + query): k_knn_big gives each its own warp, so a few
+        // oversized blocks do not serialise 8-12 long queries on one warp at the end of the stage
+        if (overflow) { if (lane < nq && ((todo >> lane) & 1u)) over_list[atomicAdd(&st->n_over, 1)] = unit * 32 + lane; }
         else if (lane < nq && ((todo >> lane) & 1u)) slow_list[atomicAdd(&st->n_slow, 1)] = cstart + q0 + lane;
         __syncwarp();
     }
@@ -1141,7 +1083,7 @@ template <int K>
 static void launch_knn(osep_rosa_impl* h, int n, int k_req, cudaStream_t s) {
     RosaDev& d = h->d;
     const unsigned mask = (unsigned)(d.T - 1);
-    k_knn_cells<K, true><<<h->sms * 6, KNN_WARPS * 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units,
+    k_knn_cells<K><<<h->sms * 6, KNN_WARPS * 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units,
                                                               d.knn_full, k_req, d.slow_list, d.over_list);
     k_knn_big<K><<<h->sms * 4, 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units, d.knn_full, k_req, d.slow_list, d.over_list);
     k_knn_exact<K><<<64, 128, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.knn_full, k_req, d.slow_list);

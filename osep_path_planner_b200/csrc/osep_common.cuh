@@ -39,7 +39,7 @@ struct FrameState {
     int n_units;           // kNN work units (cell, chunk of queries)
     int n_slow;            // queries handed to the exact slow path
     int n_over;            // units whose candidate set does not fit the shared-memory stage
-    int unit_ctr, over_ctr;   // dynamic work counters of the kNN kernels
+    int unit_ctr;          // dynamic work counter of k_knn_cells
     // ---- leaf loop (rosa.cpp:118-148)
     float leaf, leaf_used, leaf_size;
     int leaf_done, n_pass, nvox;
