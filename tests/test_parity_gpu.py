@@ -483,3 +483,22 @@ def test_gskel_run_tf_equals_transform_then_run(mods):
         assert_bit_equal(gs.tap("prelim"), go.tap("prelim"), "prelim vertices tick %d" % f)
     assert len(go.tap("prelim")) > 5
     gs.close(); r.close()
+
+
+def test_knn_overflow_and_exact_paths_are_bit_exact(mods, monkeypatch):
+    """The kNN stage has three paths (k_knn_cells: <= 512 staged candidates; k_knn_big: one warp per query with a
+    5120-entry list; k_knn_exact: thread-per-query ring search).  A deliberately coarse grid (OSEP_KNN_PPC) pushes
+    most queries through the overflow paths; neighbour lists and normals stay bit-identical to the oracle."""
+    osep, po, fx = mods
+    P = fx.turbine(60000, seed=31)
+    o = po.RosaOracle(); assert o.run(P)
+    for ppc in ("40", "400"):
+        monkeypatch.setenv("OSEP_KNN_PPC", ppc)
+        r = osep.Rosa(capacity_points=60000); r.set_debug(True); r.set_input(P)
+        assert r.rosa_run()
+        st = r.tap("knn_stats")
+        assert st[2] > 0 or st[1] > 0, "the overflow paths were not exercised: %s" % (st,)
+        assert_bit_equal(r.tap("knn_full").reshape(-1), o.tap("knn_full").reshape(-1), "knn_full ppc=" + ppc)
+        assert_bit_equal(r.tap("normals_full"), o.tap("normals_full"), "normals ppc=" + ppc)
+        assert_bit_equal(np.ascontiguousarray(r.output_vertices()), o.tap("skelver"), "vertices ppc=" + ppc)
+        r.close()
