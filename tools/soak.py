@@ -1,0 +1,25 @@
+"""Developer script: race soak.  The same frame is run many times through the production path (CUDA graph replay,
+two streams, persistent cooperative drosa kernel); every run must reproduce the first run's vertices and frame
+summary bit for bit.  usage: python tools/soak.py [iterations]"""
+import sys, os, hashlib
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import osep_path_planner_b200 as osep
+from osep_path_planner_b200 import fixtures as fx
+
+iters = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+bad = 0
+for name, P in (("turbine100k", fx.turbine()), ("cyl20k", fx.cylinder()), ("stream50k_f300", fx.stream_frame(300, n=50000)[0]), ("turbine30k", fx.turbine(30000, seed=5))):
+    r = osep.Rosa(capacity_points=len(P))
+    r.set_input(P)
+    ref = None; mism = 0
+    for k in range(iters):
+        assert r.rosa_run()
+        h = hashlib.sha1(np.ascontiguousarray(r.output_vertices()).tobytes()).hexdigest() + "|%d|%d|%d" % (r.result.n_downsampled, r.result.n_simi, r.result.flags)
+        if ref is None: ref = h
+        elif h != ref: mism += 1
+    print("%-16s %d runs, %d mismatches, V=%d M=%d" % (name, iters, mism, r.result.n_vertices, r.result.n_downsampled))
+    bad += mism
+    r.close()
+print("SOAK", "OK" if bad == 0 else "FAILED")
+sys.exit(1 if bad else 0)
