@@ -321,7 +321,14 @@ __global__ void k_dcrosa_line(const FrameState* __restrict__ st, const float4* _
 // separates the Jacobi passes.  One SM alone is shared-memory-bandwidth bound on the random gathers; 8 SMs
 // with replicated operands are not, and no pass goes back to L2.
 constexpr int DC_CLUSTER = 8;
-constexpr int DC_THREADS = 128;
+#ifndef OSEP_DC_THREADS
+#define OSEP_DC_THREADS 256
+#endif
+#ifndef OSEP_DC_SPREAD
+#define OSEP_DC_SPREAD 2
+#endif
+constexpr int DC_THREADS = OSEP_DC_THREADS;
+constexpr int DC_SPREAD = OSEP_DC_SPREAD;       // every DC_SPREAD-th thread owns a point: fewer points per warp = shorter per-warp maximum of list length / eigen iterations
 constexpr int DC_SMEM_BUDGET = 200 * 1024;
 
 __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS)
@@ -350,7 +357,7 @@ k_dcrosa_cluster(const FrameState* __restrict__ st, float4* pset, const int* __r
     __syncthreads();
     const int* nbr = csr_in ? (sidx - seg_b) : simi_idx;       // nbr[t] for t in [seg_b, seg_e)
     for (int it = 0; it < niter; ++it) {
-        for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {          // neighbour mean (rosa.cpp:388-399)
+        for (int i = lo + (int)(threadIdx.x / DC_SPREAD); i < hi && (threadIdx.x % DC_SPREAD) == 0; i += (int)(blockDim.x / DC_SPREAD)) {          // neighbour mean (rosa.cpp:388-399)
             const int b = simi_off[i], e = simi_off[i + 1];
             float4 out = pa[i];
             if (e > b) {
@@ -364,7 +371,7 @@ k_dcrosa_cluster(const FrameState* __restrict__ st, float4* pset, const int* __r
             for (int r = 0; r < DC_CLUSTER; ++r) pb_r[r][i] = out;
         }
         cluster.sync();
-        for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {          // local_line_fit + projection (rosa.cpp:402-418, 793-841)
+        for (int i = lo + (int)(threadIdx.x / DC_SPREAD); i < hi && (threadIdx.x % DC_SPREAD) == 0; i += (int)(blockDim.x / DC_SPREAD)) {          // local_line_fit + projection (rosa.cpp:402-418, 793-841)
             const int b = simi_off[i], e = simi_off[i + 1];
             const int m = e - b;
             const float4 self4 = pb[i];
