@@ -1083,7 +1083,9 @@ template <int K>
 static void launch_knn(osep_rosa_impl* h, int n, int k_req, cudaStream_t s) {
     RosaDev& d = h->d;
     const unsigned mask = (unsigned)(d.T - 1);
-    k_knn_cells<K><<<h->sms * 6, KNN_WARPS * 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units,
+    // 3 CTAs per SM, not the 4 that fit: the register file would be full and the short kernels of the main stream (leaf
+    // passes, voxel grouping) could not co-run; the stage alone is 13 % slower, the frame 1 % faster
+    k_knn_cells<K><<<h->sms * h->knn_ctas_per_sm, KNN_WARPS * 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units,
                                                               d.knn_full, k_req, d.slow_list, d.over_list);
     k_knn_big<K><<<h->sms * 4, 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units, d.knn_full, k_req, d.slow_list, d.over_list);
     k_knn_exact<K><<<64, 128, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.knn_full, k_req, d.slow_list);
