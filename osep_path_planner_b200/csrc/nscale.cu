@@ -478,9 +478,12 @@ __global__ void __launch_bounds__(128) k_knn_exact(const float4* __restrict__ Pc
         int cx, cy, cz; cell_of(st, q.x, q.y, q.z, cx, cy, cz);
         const float rx = q.x - st->bmin[0], ry = q.y - st->bmin[1], rz = q.z - st->bmin[2];
         TopK<K> tk;
-        for (int R = 1;; ++R) {
+        // rings R = 1, 2, 3, 4, 6, 8, 12, 16, ... while scanning the (2R+1)^3 block is cheaper than scanning every point
+        // (isolated points of a large map must not cost O(N) each as long as a moderate block certifies them)
+        for (int R = 1;; R = (R < 4) ? R + 1 : R + (R >> 1)) {
             tk.init();
-            if (R > 3) {
+            const long long side = 2ll * R + 1;
+            if (R > 3 && side * side * side > (long long)n / 4) {
                 for (int e = 0; e < n; ++e) { const float4 c = Pc[e]; tk.push(dist2(q.x, q.y, q.z, c.x, c.y, c.z), __float_as_int(c.w)); }
                 break;
             }
@@ -751,22 +754,31 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
 }
 
 // R5 overflow path: queries whose candidate block does not fit the per-warp stage of k_knn_cells (dense spots: more
-// than KNN_STAGE points in 27 cells).  One WARP per QUERY, one warp per CTA: the (d2, index) pairs of all candidates
+// than KNN_STAGE points in 27 cells).  One WARP per QUERY: the (d2, index) pairs of all candidates
 // are computed once into a large shared-memory list (KNN_BIG entries), every selection pass then runs from shared
 // memory with full lane utilisation.  Same certification and the same canonical result as the fast path; what does
 // not fit or cannot be certified within R <= 2 goes to k_knn_exact.
-constexpr int KNN_BIG = 5120;
+#ifndef OSEP_KNN_BIG
+#define OSEP_KNN_BIG 1280
+#endif
+#ifndef OSEP_BIG_WARPS
+#define OSEP_BIG_WARPS 4
+#endif
+constexpr int KNN_BIG = OSEP_KNN_BIG;        // candidates per query (one warp); more go to k_knn_exact
+constexpr int BIG_WARPS = OSEP_BIG_WARPS;    // queries (warps) per CTA
 template <int K>
-__global__ void __launch_bounds__(32) k_knn_big(const float4* __restrict__ Pc, FrameState* st,
+__global__ void __launch_bounds__(BIG_WARPS * 32) k_knn_big(const float4* __restrict__ Pc, FrameState* st,
                                                 const unsigned long long* __restrict__ gtab, const int* __restrict__ g_cnt,
                                                 const int* __restrict__ g_start, unsigned mask, const int2* __restrict__ units,
                                                 int* __restrict__ knn_idx, int k_req, int* __restrict__ slow_list,
                                                 const int* __restrict__ over_list) {
-    __shared__ int2 tab[KNN_TAB];
-    __shared__ int pre[KNN_TAB + 1];
-    __shared__ float sd[KNN_BIG];
-    __shared__ int si[KNN_BIG];
-    __shared__ unsigned long long keys[KNN_LIST];
+    __shared__ int2 tab_[BIG_WARPS][KNN_TAB];
+    __shared__ int pre_[BIG_WARPS][KNN_TAB + 1];
+    __shared__ float sd_[BIG_WARPS][KNN_BIG];
+    __shared__ int si_[BIG_WARPS][KNN_BIG];
+    __shared__ unsigned long long keys_[BIG_WARPS][KNN_LIST];
+    const int wib = threadIdx.x >> 5;
+    int2* tab = tab_[wib]; int* pre = pre_[wib]; float* sd = sd_[wib]; int* si = si_[wib]; unsigned long long* keys = keys_[wib];
     if (st->status != 0) return;
     const int n = st->n_filt;
     const int k_eff = min(k_req, n);
@@ -777,7 +789,7 @@ __global__ void __launch_bounds__(32) k_knn_big(const float4* __restrict__ Pc, F
     const float diag2 = ((float)dimx * h) * ((float)dimx * h) + ((float)dimy * h) * ((float)dimy * h) + ((float)dimz * h) * ((float)dimz * h);
     const int n_work = st->n_over;
     const unsigned long long KINF = ~0ull;
-    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+    for (int w = blockIdx.x * BIG_WARPS + wib; w < n_work; w += gridDim.x * BIG_WARPS) {
         const int code = over_list[w];
         const int2 un = units[code >> 5];
         const int cstart = g_start[un.x];
@@ -1085,9 +1097,11 @@ static void launch_knn(osep_rosa_impl* h, int n, int k_req, cudaStream_t s) {
     const unsigned mask = (unsigned)(d.T - 1);
     // 3 CTAs per SM, not the 4 that fit: the register file would be full and the short kernels of the main stream (leaf
     // passes, voxel grouping) could not co-run; the stage alone is 13 % slower, the frame 1 % faster
-    k_knn_cells<K><<<h->sms * h->knn_ctas_per_sm, KNN_WARPS * 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units,
+    // (large maps: the stage is long, nothing competes for long, so the 4th CTA pays)
+    const int ctas_per_sm = (h->knn_ctas_per_sm > 0) ? h->knn_ctas_per_sm : (n > 400000 ? 4 : 3);
+    k_knn_cells<K><<<h->sms * ctas_per_sm, KNN_WARPS * 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units,
                                                               d.knn_full, k_req, d.slow_list, d.over_list);
-    k_knn_big<K><<<h->sms * 4, 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units, d.knn_full, k_req, d.slow_list, d.over_list);
+    k_knn_big<K><<<h->sms * 4, BIG_WARPS * 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units, d.knn_full, k_req, d.slow_list, d.over_list);
     k_knn_exact<K><<<64, 128, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.knn_full, k_req, d.slow_list);
     k_normals<<<div_up(n, 128), 128, 0, s>>>(d.P, d.st, d.knn_full, k_req, d.Nrm);
 }
@@ -1098,6 +1112,8 @@ void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int strid
     const osep_rosa_config& c = h->cfg;
     const int nb = div_up(n, NT);
     const float r2 = c.pts_dist_lim * c.pts_dist_lim;
+    // target points per kNN grid cell: large (dense, heavy-tailed) maps overflow the 512-point stage too often at 9
+    const int ppc = h->knn_ppc > 0 ? h->knn_ppc : (n > 400000 ? 6 : 9);
     cudaStream_t sk = s;
     if (h->overlap) {                                      // the kNN grid tables are cleared while the filter runs
         sk = h->stream2;
@@ -1112,16 +1128,16 @@ void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int strid
     // R7/R8: device-resident leaf loop (count-only passes).  The kNN grid is sized from the density seen by
     // pass 0, so the whole normals branch (grid build + kNN + covariance/eigen) only depends on pass 0 and runs
     // on the side stream while the remaining passes iterate the control law.
-    k_vox_count<<<nb, NT, 0, s>>>(d.P, d.st, d.vtab, (unsigned)(d.T - 1), 1, c.max_points, h->knn_ppc);
+    k_vox_count<<<nb, NT, 0, s>>>(d.P, d.st, d.vtab, (unsigned)(d.T - 1), 1, c.max_points, ppc);
     if (h->overlap) { cudaEventRecord(h->ev_fork[0], s); cudaStreamWaitEvent(sk, h->ev_fork[0], 0); }
     for (int p = 1; p < LEAF_MAX_ITERS; ++p)
-        k_vox_count<<<nb, NT, 0, s>>>(d.P, d.st, d.vtab, (unsigned)(d.T - 1), p + 1, c.max_points, h->knn_ppc);
+        k_vox_count<<<nb, NT, 0, s>>>(d.P, d.st, d.vtab, (unsigned)(d.T - 1), p + 1, c.max_points, ppc);
     stage_mark(h, SM_LEAF);
     // R5: grid + kNN normals
     if (!h->overlap) cudaMemsetAsync(d.gtab, 0, sizeof(unsigned) * 4 * (size_t)d.T, sk);
-    k_grid_insert<<<nb, NT, 0, sk>>>(d.P, d.st, d.gtab, d.g_cnt, d.p_slot, (unsigned)(d.T - 1), 0, h->knn_ppc);
+    k_grid_insert<<<nb, NT, 0, sk>>>(d.P, d.st, d.gtab, d.g_cnt, d.p_slot, (unsigned)(d.T - 1), 0, ppc);
     k_grid_clear_if_redo<<<div_up(d.T, NT), NT, 0, sk>>>(d.st, d.gtab, d.g_cnt, d.T);
-    k_grid_insert<<<nb, NT, 0, sk>>>(d.P, d.st, d.gtab, d.g_cnt, d.p_slot, (unsigned)(d.T - 1), 1, h->knn_ppc);
+    k_grid_insert<<<nb, NT, 0, sk>>>(d.P, d.st, d.gtab, d.g_cnt, d.p_slot, (unsigned)(d.T - 1), 1, ppc);
     k_grid_alloc<<<div_up(d.T, NT), NT, 0, sk>>>(d.st, d.g_cnt, d.g_start, d.T, d.units);
     k_grid_scatter<<<nb, NT, 0, sk>>>(d.P, d.st, d.p_slot, d.g_start, d.g_fill, d.Pc);
     stage_mark(h, SM_GRID);

@@ -34,7 +34,7 @@ def skeletonize(tile):
         r.set_profile(True)
     r.set_input(tile)
     ok = r.rosa_run()
-    info.update(ok=ok, status=r.result.status, M=r.result.n_downsampled, gpu_ms=r.result.gpu_ms, n=len(tile), leaf=r.result.leaf_size, stage_ms={k: round(v, 3) for k, v in r.stage_ms().items()})
+    info.update(ok=ok, status=r.result.status, M=r.result.n_downsampled, gpu_ms=r.result.gpu_ms, n=len(tile), leaf=r.result.leaf_size, stage_ms={k: round(v, 3) for k, v in r.stage_ms().items()}, knn_stats=[int(x) for x in r.tap("knn_stats")])
     return np.ascontiguousarray(r.output_vertices())
 
 def sync():
@@ -56,6 +56,6 @@ else:
 if rank == 0:
     print(json.dumps({"config": "tiled map, %d points, %d GPU(s), halo %.2f m along axis %d" % (len(P), world, halo, axis), "seconds_per_map": dt,
                       "points_per_s": len(P) / dt, "tile_points": [i["n"] for i in infos], "tile_gpu_ms": [i["gpu_ms"] for i in infos],
-                      "tile_ok": [i["ok"] for i in infos], "stage_ms_rank0": infos[0]["stage_ms"], "owned_vertices": [int(c) for c in res["counts"]], "seam_graph_edges": int(g["n_edges"])}))
+                      "tile_ok": [i["ok"] for i in infos], "stage_ms_rank0": infos[0]["stage_ms"], "stage_ms_all": [i["stage_ms"] for i in infos], "knn_stats_all": [i.get("knn_stats") for i in infos], "owned_vertices": [int(c) for c in res["counts"]], "seam_graph_edges": int(g["n_edges"])}))
 if world > 1:
     dist.barrier(); dist.destroy_process_group()
