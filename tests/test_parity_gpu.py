@@ -502,3 +502,27 @@ def test_knn_overflow_and_exact_paths_are_bit_exact(mods, monkeypatch):
         assert_bit_equal(r.tap("normals_full"), o.tap("normals_full"), "normals ppc=" + ppc)
         assert_bit_equal(np.ascontiguousarray(r.output_vertices()), o.tap("skelver"), "vertices ppc=" + ppc)
         r.close()
+
+
+@pytest.mark.parametrize("cfgkw,cloud", [
+    (dict(max_points=1500), ("turbine", 60000, 3)),            # M ~ 1560: bit matrix no longer fits the worker CTAs' shared memory
+    (dict(max_points=1536), ("cylinder", 40000, 4)),           # largest max_points the handle accepts
+    (dict(max_points=120, min_points=50), ("cylinder", 3000, 5)),
+    (dict(niter_drosa=8), ("cylinder", 20000, 7)),             # MAX_FUSED_ITERS chains
+    (dict(niter_drosa=1, niter_dcrosa=1, niter_smooth=0), ("cylinder", 20000, 8)),
+    (dict(nb_knn=20, ne_knn=40), ("turbine", 30000, 9)),       # generic (non-10) surf lists in the chain walker, K = 64 kNN variant
+])
+def test_configuration_edges_production_path(mods, cfgkw, cloud):
+    """Edges of the configuration space through the production path (CUDA graph replay on the third run, no debug taps)."""
+    osep, po, fx = mods
+    kind, n, seed = cloud
+    P = fx.turbine(n, seed=seed) if kind == "turbine" else fx.cylinder(n, seed=seed)
+    o = po.RosaOracle(po.RosaConfig.default(**cfgkw)); ok_o = o.run(P)
+    r = osep.Rosa(osep.RosaConfig(**cfgkw), capacity_points=n)
+    r.set_input(P)
+    for _ in range(3):
+        ok_g = r.rosa_run()
+        assert ok_g == ok_o
+        assert_bit_equal(np.ascontiguousarray(r.output_vertices()), o.tap("skelver"), "vertices %s" % (cfgkw,))
+    assert r.result.n_downsampled == len(o.tap("pts")) and r.result.n_simi == len(o.tap("simi_idx"))
+    r.close()
