@@ -21,5 +21,21 @@ for name, P in (("turbine100k", fx.turbine()), ("cyl20k", fx.cylinder()), ("stre
     print("%-16s %d runs, %d mismatches, V=%d M=%d" % (name, iters, mism, r.result.n_vertices, r.result.n_downsampled))
     bad += mism
     r.close()
+# batched frames in flight on several streams (BASELINE configs[3]): every frame must equal its single-frame result
+frames = [fx.batch_frame(b, n=40000) for b in range(12)]
+r = osep.Rosa(capacity_points=40000)
+single = []
+for P in frames:
+    r.set_input(P); assert r.rosa_run(); single.append(np.ascontiguousarray(r.output_vertices()).copy())
+r.set_lanes(5)
+mism = 0; rounds = max(1, iters // 100)
+for k in range(rounds):
+    order = [(b + k) % len(frames) for b in range(len(frames) * 2)]
+    res, outs = r.run_batch([fx.to_xyz4(frames[b]) for b in order])
+    for b, v in zip(order, outs):
+        if not np.array_equal(np.ascontiguousarray(v).view(np.uint32), single[b].view(np.uint32)): mism += 1
+print("batch            %d rounds x %d frames on 5 lanes, %d mismatches" % (rounds, 2 * len(frames), mism))
+bad += mism
+r.close()
 print("SOAK", "OK" if bad == 0 else "FAILED")
 sys.exit(1 if bad else 0)
