@@ -53,6 +53,7 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
     { const char* e = getenv("OSEP_KNN_CTAS"); if (e && atoi(e) > 0) h->knn_ctas_per_sm = atoi(e); }
     { const char* e = getenv("OSEP_DROSA_UNFUSED"); if (e && e[0] == '1') h->fused = false;
       const char* e3 = getenv("OSEP_NO_GRAPH"); if (e3 && e3[0] == '1') h->use_graphs = false;
+      const char* e4 = getenv("OSEP_FUSED_DETAIL"); if (e4 && e4[0] == '1') h->fused_detail = true;
       const char* e2 = getenv("OSEP_DROSA_LAG"); if (e2 && atoi(e2) >= 0) h->sched_lag = atoi(e2);
       int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device); if (!coop) h->fused = false; }
     { int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device)); h->sms = sms > 0 ? sms : 148; } CK(dalloc(&d.surf, M * (size_t)std::max(d.nbk, 1)));

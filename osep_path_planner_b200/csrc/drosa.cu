@@ -838,7 +838,7 @@ void launch_drosa(osep_rosa_impl* h, int sms) {
         a.st = d.st; a.pts = d.pts; a.nraw = d.nraw; a.vnd = d.vnd; a.pset = d.pset; a.bits = d.simi_bits; a.W = d.W;
         a.vset_it = d.vset_it; a.vnew_it = d.vnew_it;
         a.flagO = d.fused_flags; a.taskq = d.fused_flags + (size_t)MAX_FUSED_ITERS * d.Mcap; a.qctr = d.fused_flags + (size_t)2 * MAX_FUSED_ITERS * d.Mcap;
-        a.Mcap = d.Mcap; a.nit = c.niter_drosa; a.surf = d.surf; a.nbk = d.nbk; a.dbg_detail = h->profile ? 1 : 0; a.lag = h->sched_lag;
+        a.Mcap = d.Mcap; a.nit = c.niter_drosa; a.surf = d.surf; a.nbk = d.nbk; a.dbg_detail = h->fused_detail ? 1 : 0; a.lag = h->sched_lag;
         a.good = d.good; a.centers = d.centers; a.active_size = d.active_size; a.max_proj_range = c.max_proj_range;
         a.dbg = d.fused_dbg;
         int grid = h->fused_grid > 0 ? h->fused_grid : sms;

@@ -69,6 +69,7 @@ struct osep_rosa_impl {
     int knn_ctas_per_sm = 0;           // grid of the persistent kNN kernel in CTAs per SM; 0 = by frame size (OSEP_KNN_CTAS)
     int knn_ppc = 0;                   // target points per kNN grid cell; 0 = by frame size: 9, or 6 above 400k points (OSEP_KNN_PPC)
     int sched_lag = 3;                 // fused drosa schedule model: walker steps from G(k-1,j) to the staged O(k,j) (OSEP_DROSA_LAG)
+    bool fused_detail = false;         // per-step cycle counters in the chain walkers (OSEP_FUSED_DETAIL=1; costs ~4 % of the stage)
     int fused_grid = 0;                // CTAs of the fused kernel (0 = one per SM)
     bool profile = false;              // record a CUDA event after every stage group (osep_rosa_set_profile)
     static constexpr int NSTAGE_EV = 16;

@@ -1,4 +1,5 @@
 import sys, os
+os.environ.setdefault("OSEP_FUSED_DETAIL", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, ctypes as C
 import osep_path_planner_b200 as osep
