@@ -783,8 +783,11 @@ __global__ void __launch_bounds__(SEED_WARPS * 32) k_drosa_fused(const __grid_co
         if (blockIdx.x == 0 && threadIdx.x == 0) a.st->status = OSEP_ERR_CAPACITY;
         return;
     }
+    // detail mode (OSEP_FUSED_DETAIL=1): kernel entry / last exit stamps next to the per-chain records (tools/fused_dbg.py)
+    if (a.dbg_detail && threadIdx.x == 0) atomicMin(reinterpret_cast<unsigned long long*>(a.dbg + 56), (unsigned long long)gtime());
     if ((int)blockIdx.x < a.nit) fused_chain(a, fused_smem, M, (int)blockIdx.x);
     else fused_worker(a, fused_smem, M);
+    if (a.dbg_detail && threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long*>(a.dbg + 57), (unsigned long long)gtime());
 }
 
 // ------------------------------------------------------------------------------------------
@@ -841,6 +844,7 @@ void launch_drosa(osep_rosa_impl* h, int sms) {
         a.Mcap = d.Mcap; a.nit = c.niter_drosa; a.surf = d.surf; a.nbk = d.nbk; a.dbg_detail = h->fused_detail ? 1 : 0; a.lag = h->sched_lag;
         a.good = d.good; a.centers = d.centers; a.active_size = d.active_size; a.max_proj_range = c.max_proj_range;
         a.dbg = d.fused_dbg;
+        if (h->fused_detail) { cudaMemsetAsync(d.fused_dbg + 56, 0xff, 8, s); cudaMemsetAsync(d.fused_dbg + 57, 0, 8, s); }
         int grid = h->fused_grid > 0 ? h->fused_grid : sms;
         if (grid < c.niter_drosa + 1) grid = c.niter_drosa + 1;
         void* args[] = {(void*)&a};
