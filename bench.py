@@ -153,8 +153,14 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout = the one JSON line (NCCL prints its version banner to stdout)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # keep stdout = the one JSON line: NCCL prints its version banner to fd 1 when the communicator comes up
+        sys.stdout.flush()
+        saved = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier(); torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
 
     def barrier():
         if world > 1:
