@@ -581,7 +581,7 @@ __device__ __forceinline__ void chain_schedule_pass(int w, int M, int nbk, int k
         if (lane == 0) prog[w] = min(base + 32, M);
     }
     vmax = __reduce_max_sync(FULLM, vmax);
-    if (lane == 0) *tmax = vmax;
+    if (lane == 0 && tmax) *tmax = vmax;
 }
 
 __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int M, int it) {
@@ -618,14 +618,15 @@ __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int
     const int k_eff = min(nbk, M);
     const bool fast10 = (nbk == 10 && k_eff == 10);
     if (warp <= it) {
-        if (fast10) chain_schedule_pass<10>(warp, M, nbk, k_eff, ssurf, sT, s_ctl + 4, s_ctl + 2, a.lag);
-        else chain_schedule_pass<0>(warp, M, nbk, k_eff, ssurf, sT, s_ctl + 4, s_ctl + 2, a.lag);
+        int* tmax = (warp == it) ? s_ctl + 2 : nullptr;      // only the last pass reports its maximum (the sort's bin count)
+        if (fast10) chain_schedule_pass<10>(warp, M, nbk, k_eff, ssurf, sT, s_ctl + 4, tmax, a.lag);
+        else chain_schedule_pass<0>(warp, M, nbk, k_eff, ssurf, sT, s_ctl + 4, tmax, a.lag);
     }
     __syncthreads();
     {
         // counting sort by T_it (ties in any order); a schedule deeper than the histogram falls back to the index order
         const unsigned short* T = sT + (size_t)it * M;
-        const int nb = s_ctl[2];                          // written last by warp `it`
+        const int nb = s_ctl[2];                          // written by warp `it` only
         if (nb >= SCHED_BINS) {
             for (int i = threadIdx.x; i < M; i += blockDim.x) sorder[i] = (unsigned short)i;
         } else {
