@@ -445,14 +445,22 @@ static int run_batch(osep_rosa* h, const float* const* xyz, const int* n, int B,
         inflight[lane] = -1;
     };
     for (int b = 0; b < B; ++b) {
-        const int lane = b % nl;
+        // next lane: a free one, else the first whose frame has finished (frames take different times: M, leaf passes)
+        int lane = -1;
+        for (int k = 0; k < nl && lane < 0; ++k) if (inflight[k] < 0) lane = k;
+        while (lane < 0) {
+            for (int k = 0; k < nl && lane < 0; ++k) if (cudaStreamQuery(L[k]->stream) == cudaSuccess) lane = k;
+        }
         collect(lane);
         osep_rosa_impl* l = L[lane];
         int rc = check_frame(*l, n[b], stride);
         if (rc == OSEP_OK && n[b] == 0) rc = OSEP_STAGE_1;
         if (rc != OSEP_OK) { if (results) { memset(&results[b], 0, sizeof(osep_rosa_result)); results[b].status = rc; } if (rc < 0) worst = rc; continue; }
         const float* src = xyz[b];
+        // frames are staged in the lane's own input buffer (H2D, or D2D for device-resident frames: 1.6 MB, ~2 us), so the
+        // lane sees one (buffer, n, stride) shape and replays its CUDA graph instead of issuing ~40 launches per frame
         if (host) { cudaMemcpyAsync(l->d.in, xyz[b], sizeof(float) * (size_t)n[b] * stride, cudaMemcpyHostToDevice, l->stream); src = l->d.in; }
+        else if (stride <= 4) { cudaMemcpyAsync(l->d.in, xyz[b], sizeof(float) * (size_t)n[b] * stride, cudaMemcpyDeviceToDevice, l->stream); src = l->d.in; }
         rc = rosa_enqueue(l, src, n[b], stride);
         if (rc) return rc;
         inflight[lane] = b;
