@@ -330,7 +330,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--batch", type=int, default=64, help="frames of the extra batched-throughput measurement (0 = skip)")
     ap.add_argument("--prewarm", type=float, default=0.5, help="seconds of untimed frames before the W warm-up steps")
-    ap.add_argument("--lanes", type=int, default=5, help="concurrent frames (streams) per GPU in the batched measurement")
+    ap.add_argument("--lanes", type=int, default=12, help="concurrent frames (streams) per GPU in the batched measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)

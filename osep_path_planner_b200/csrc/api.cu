@@ -428,7 +428,7 @@ static int run_batch(osep_rosa* h, const float* const* xyz, const int* n, int B,
     if (!h || !xyz || !n || B < 0) return OSEP_ERR_ARG;
     osep_rosa_impl& I = h->impl;
     CK(cudaSetDevice(I.device));
-    if (I.lanes.empty()) { int rc = osep_rosa_set_lanes(h, 8); if (rc) return rc; }
+    if (I.lanes.empty()) { int rc = osep_rosa_set_lanes(h, 12); if (rc) return rc; }   // 12 lanes x 12 CTAs of the persistent drosa kernel fit 148 SMs
     std::vector<osep_rosa_impl*> L; L.push_back(&I); for (auto* l : I.lanes) L.push_back(l);
     const int nl = (int)L.size();
     I.batch_vertices.assign(B, {});
