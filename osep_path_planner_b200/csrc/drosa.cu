@@ -11,7 +11,9 @@
 // One warp per seed; float sums run in the canonical lane-owner order (C4): lane l owns the
 // members of words w = l (mod 32), ascending, then an xor butterfly.
 // The in-place smoothing pass (Gauss-Seidel, rosa.cpp:295-308) is a dependent chain: one warp
-// walks the levels of its dependency DAG with all operands in shared memory.
+// walks its dependency DAG with all operands in shared memory (k_drosa_fused: a pull-model
+// walker over a modelled schedule, six chains as overlapping wavefronts; k_drosa_smooth2: the
+// level-synchronous fallback).
 #include "rosa_impl.cuh"
 
 namespace osep {
@@ -436,10 +438,10 @@ k_drosa_smooth2(FrameState* st, const float4* __restrict__ vnew, const float* __
 // iteration it by a few levels.  Results are bit-identical (same operands, same operations).
 //   CTA it < nit   : chain walker of iteration it (warp 0) + prefetch warps (stage O(it,*) results
 //                    from L2 into shared memory as they appear) + publish warp (G(it,p) -> L2 + flag)
-//   other CTAs     : workers; warps pull tasks (it, p) from one queue ordered by (it, level(p)),
-//                    wait for flagG[it-1][p], run the active-set kernel body, publish flagO[it][p].
-// Deadlock freedom: tasks are taken in queue order, so everything a waiting warp depends on has
-// already been taken by a running warp; all CTAs are co-resident (cooperative launch).
+//   other CTAs     : workers; warps claim the next slot of one ready queue (slots [0, M) = the iteration-0
+//                    tasks, later slots are filled by the chain publishers as G(it,p) becomes final), run the
+//                    active-set body and publish flagO[it][p].
+// Deadlock freedom: only ready tasks are ever queued, and all CTAs are co-resident (cooperative launch).
 struct FusedArgs {
     FrameState* st;
     const float4* pts; const float4* nraw; const float4* vnd; float4* pset;
