@@ -59,3 +59,16 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) or f == "Makefile":
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in txt.lower().replace("# oracle", ""), "%s mentions the oracle" % os.path.join(dirpath, f)
+
+
+def test_header_is_plain_c_and_shims_compile(tmp_path):
+    """include/osep_skel.h must be consumable by a C compiler (cgo / JNI / ctypes-style bindings) and the C++ shim
+    classes must compile against it alone (no PCL / Eigen / ROS, no CUDA headers)."""
+    import subprocess
+    c = tmp_path / "abi.c"
+    c.write_text('#include "osep_skel.h"\nint main(void) { osep_rosa_config c; osep_rosa_default_config(&c); return (int)sizeof(osep_graph_view) == 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(c)])
+    cpp = tmp_path / "shim.cpp"
+    cpp.write_text('#include "rosa.hpp"\n#include "gskel.hpp"\nint main() { return 0; }\n')
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(ROOT, "osep_path_planner_b200", "host"), str(cpp)])
