@@ -149,7 +149,7 @@ __device__ __forceinline__ Eig3 normal_cov_eig(const float (&s)[9], float inv_m)
     const float c20 = s[6] * inv_m - mz * mx;
     const float c21 = s[7] * inv_m - mz * my;
     const float c22 = s[8] * inv_m - mz * mz;
-    return eig3_sym(c00, c10, c11, c20, c21, c22);
+    return eig3_sym_dev(c00, c10, c11, c20, c21, c22);
 }
 
 struct SeedOut {
@@ -384,9 +384,9 @@ __device__ __forceinline__ float4 gs_point(int p, const float4* sold, const floa
             m00 += wx * v.x; m10 += wy * v.x; m11 += wy * v.y; m20 += wz * v.x; m21 += wz * v.y; m22 += wz * v.z;
         }
     }
-    const Eig3 E = eig3_sym(m00, m10, m11, m20, m21, m22);
+    const Eig3 E = eig3_sym_dev(m00, m10, m11, m20, m21, m22);
     if (iters) *iters = E.iters;
-    const f3 d = normalize3(eig_col(E, 2));                                                    // rosa.cpp:305-307
+    const f3 d = normalize3_dev(eig_col(E, 2));                                                    // rosa.cpp:305-307
     return make_float4(d.x, d.y, d.z, sold[p].w);
 }
 

@@ -300,7 +300,7 @@ __global__ void k_dcrosa_line(const FrameState* __restrict__ st, const float4* _
     }
     const float fm = (float)m;
     c00 /= fm; c10 /= fm; c11 /= fm; c20 /= fm; c21 /= fm; c22 /= fm;
-    const Eig3 E = eig3_sym(c00, c10, c11, c20, c21, c22);
+    const Eig3 E = eig3_sym_dev(c00, c10, c11, c20, c21, c22);
     if (!E.ok) { pout[i] = self4; return; }
     const float denom = smax(1e-6f, sum3(E.ev[0], E.ev[1], E.ev[2]));
     f3 dir = eig_col(E, 2);
@@ -390,7 +390,7 @@ k_dcrosa_cluster(const FrameState* __restrict__ st, float4* pset, const int* __r
                 }
                 const float fm = (float)m;
                 c00 /= fm; c10 /= fm; c11 /= fm; c20 /= fm; c21 /= fm; c22 /= fm;
-                const Eig3 E = eig3_sym(c00, c10, c11, c20, c21, c22);
+                const Eig3 E = eig3_sym_dev(c00, c10, c11, c20, c21, c22);
                 if (E.ok) {
                     const float denom = smax(1e-6f, sum3(E.ev[0], E.ev[1], E.ev[2]));
                     f3 dir = eig_col(E, 2);
@@ -640,7 +640,7 @@ __global__ void k_vertex_smooth(FrameState* st, float4* skel, float4* skel2, flo
             }
             const float fn = (float)n;
             c00 /= fn; c10 /= fn; c11 /= fn; c20 /= fn; c21 /= fn; c22 /= fn;
-            const Eig3 E = eig3_sym(c00, c10, c11, c20, c21, c22);
+            const Eig3 E = eig3_sym_dev(c00, c10, c11, c20, c21, c22);
             const f3 dir = eig_col(E, 2);
             const f3 p = ld3(cur, i);
             const f3 delta = sub3(p, mean);

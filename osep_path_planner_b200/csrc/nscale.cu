@@ -437,7 +437,7 @@ __device__ __forceinline__ float4 normal_from_neighbours(const float4* __restric
     a0 /= cnt; a1 /= cnt; a2 /= cnt; a3 /= cnt; a4 /= cnt; a5 /= cnt; a6 /= cnt; a7 /= cnt; a8 /= cnt;
     const float c00 = a0 - a6 * a6, c01 = a1 - a6 * a7, c02 = a2 - a6 * a8;
     const float c11 = a3 - a7 * a7, c12 = a4 - a7 * a8, c22 = a5 - a8 * a8;
-    const Eig3 E = eig3_sym(c00, c01, c11, c02, c12, c22);
+    const Eig3 E = eig3_sym_dev(c00, c01, c11, c02, c12, c22);
     f3 nv = eig_col(E, 0);
     const float vx = 0.0f - q.x, vy = 0.0f - q.y, vz = 0.0f - q.z;
     const float cos_theta = (vx * nv.x + vy * nv.y + vz * nv.z);

@@ -7,6 +7,7 @@
 // launches (CUDA-graph capturable) and lets many frames overlap on many streams.
 #pragma once
 #include "dev_math.cuh"
+#include "eig_fast.cuh"
 #include "../../include/osep_skel.h"
 #include <cuda_runtime.h>
 #include <stdint.h>
