@@ -670,7 +670,73 @@ __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int
         }
         int ndone = 0;
         long long t_begin = gtime(), t_first = 0; int steps = 0, spins = 0;
-        long long c_comp = 0, c_rel = 0; int it_sum = 0, it_max = 0;
+        long long c_comp = 0, c_rel = 0, c_pre = 0; int it_sum = 0, it_max = 0;
+        // fast path (nb_knn = 10).  One poll = the 11 state bytes of the candidate AND, right behind them, its 10 operand
+        // rows (speculative: shared memory serves a warp's loads in order, so a row read after a state byte that says
+        // "final" is final) -- the dependency test, the ballot and the operand latency overlap instead of following one
+        // another, and the test is a tree instead of a chain.
+        while (fast10 && ndone < M) {
+            const long long c0 = detail ? clock64() : 0;
+            asm volatile("" ::: "memory");
+            unsigned ok = 0u; float4 v[10]; float wself = 0.0f;
+            if (cand >= 0) {
+                int j[10]; unsigned sj[10];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) { j[2 * k] = (int)(nb[k] & 0xffffu); j[2 * k + 1] = (int)(nb[k] >> 16); }
+                const unsigned sc = vstate[cand];
+#pragma unroll
+                for (int u = 0; u < 10; ++u) sj[u] = vstate[j[u]];
+                asm volatile("" ::: "memory");
+#pragma unroll
+                for (int u = 0; u < 10; ++u) v[u] = (j[u] < cand ? snew : sold)[j[u]];
+                wself = sold[cand].w;
+#pragma unroll
+                for (int u = 0; u < 10; ++u) sj[u] = (j[u] >= cand) ? sj[u] : (sj[u] >> 1);
+                ok = sc & ((sj[0] & sj[1]) & (sj[2] & sj[3])) & ((sj[4] & sj[5]) & (sj[6] & sj[7])) & (sj[8] & sj[9]) & 1u;
+            }
+            const bool ready = ok != 0u;
+            const unsigned rm = __ballot_sync(FULLM, ready);
+            if (rm == 0u) { ++spins; continue; }
+            if (steps == 0) t_first = gtime();
+            ++steps;
+            const long long c1 = detail ? clock64() : 0;
+            const int r = __popc(rm & lt);
+            int my_it = 0;
+            if (ready) {
+                // refill loads first: they do not depend on the solve below and hide behind it
+                const int pos = next + r;
+                const int ncand = pos < M ? (int)sorder[pos] : -1;
+                unsigned nnb[5] = {0u, 0u, 0u, 0u, 0u};
+                if (ncand >= 0) {
+                    const unsigned* wsrc = reinterpret_cast<const unsigned*>(ssurf + ncand * 10);
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) nnb[k] = wsrc[k];
+                }
+                float m00 = 0, m10 = 0, m11 = 0, m20 = 0, m21 = 0, m22 = 0;
+#pragma unroll
+                for (int u = 0; u < 10; ++u) {
+                    const float wx = v[u].x * v[u].w, wy = v[u].y * v[u].w, wz = v[u].z * v[u].w;      // (w v) v^T, lower triangle (rosa.cpp:300-304)
+                    m00 += wx * v[u].x; m10 += wy * v[u].x; m11 += wy * v[u].y; m20 += wz * v[u].x; m21 += wz * v[u].y; m22 += wz * v[u].z;
+                }
+                const Eig3 E = eig3_sym_dev(m00, m10, m11, m20, m21, m22);
+                my_it = E.iters;
+                const f3 d = normalize3_dev(eig_col(E, 2));                                         // rosa.cpp:305-307
+                snew[cand] = make_float4(d.x, d.y, d.z, wself);
+                vstate[cand] = 3;
+                solist[ndone + r] = (unsigned short)cand;
+                cand = ncand;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) nb[k] = nnb[k];
+            }
+            const long long c2 = detail ? clock64() : 0;
+            if (detail) { it_sum += __reduce_add_sync(FULLM, ready ? my_it : 0); it_max += __reduce_max_sync(FULLM, ready ? my_it : 0); }
+            const int c = __popc(rm);
+            ndone += c; next += c;
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) st_vol(s_ctl + 1, ndone);
+            if (detail) { c_comp += c2 - c1; c_rel += (c1 - c0) + (clock64() - c2); c_pre += c1 - c0; }
+        }
         while (ndone < M) {
             const long long c0 = detail ? clock64() : 0;
             bool ready = false;
@@ -730,9 +796,9 @@ __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int
             __syncwarp();
             __threadfence_block();
             if (lane == 0) st_vol(s_ctl + 1, ndone);
-            if (detail) { c_comp += c2 - c1; c_rel += (c1 - c0) + (clock64() - c2); }
+            if (detail) { c_comp += c2 - c1; c_rel += (c1 - c0) + (clock64() - c2); c_pre += c1 - c0; }
         }
-        if (lane == 0 && a.dbg) { long long* g = a.dbg + it * 8; g[0] = t_begin; g[1] = t_first; g[2] = gtime(); g[3] = steps; g[4] = spins; g[5] = ((long long)it_sum << 32) | (unsigned)it_max; g[6] = c_comp; g[7] = c_rel; }
+        if (lane == 0 && a.dbg) { long long* g = a.dbg + it * 8; g[0] = t_begin; g[1] = t_first; g[2] = gtime(); g[3] = steps; g[4] = detail ? -c_pre : spins; g[5] = ((long long)it_sum << 32) | (unsigned)it_max; g[6] = c_comp; g[7] = c_rel; }
     } else if (warp == nw - 1) {
         // ---- publisher: G(it,p) -> vset_it[it+1][p] in L2, then task (it+1, p) goes on the workers' ready queue
         float4* dst = a.vset_it + (size_t)(it + 1) * a.Mcap;

@@ -16,7 +16,7 @@ t0 = d[:6, 0].min()
 for it in range(6):
     b, f, e, steps, spins, M = d[it, :6]
     print("      QR iterations: mean per point %.2f, mean of per-step max %.2f" % ((int(M) >> 32) / 851.0, (int(M) & 0xffffffff) / max(1, steps)))
-    print("      compute cycles/step %.0f  release cycles/step %.0f" % (d[it, 6] / max(1, steps), d[it, 7] / max(1, steps)))
+    print("      compute cycles/step %.0f  release cycles/step %.0f (of which before the solve %.0f)" % (d[it, 6] / max(1, steps), d[it, 7] / max(1, steps), -spins / max(1, steps)))
     print("it %d: begin +%.1f us first_step +%.1f us end +%.1f us | steps %d spins %d | busy per step %.2f us" % (it, (b - t0) / 1e3, (f - t0) / 1e3, (e - t0) / 1e3, steps, spins, (e - f) / 1e3 / max(1, steps)))
 k0, k1 = int(d[7, 0]), int(d[7, 1])
 print("kernel: entry %+.1f us, last CTA exit %+.1f us (relative to the first chain's walker start)" % ((k0 - t0) / 1e3, (k1 - t0) / 1e3))
