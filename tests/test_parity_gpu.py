@@ -526,3 +526,79 @@ def test_configuration_edges_production_path(mods, cfgkw, cloud):
         assert_bit_equal(np.ascontiguousarray(r.output_vertices()), o.tap("skelver"), "vertices %s" % (cfgkw,))
     assert r.result.n_downsampled == len(o.tap("pts")) and r.result.n_simi == len(o.tap("simi_idx"))
     r.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The library against tests/pyref -- the independently written numpy / Python restatement of the reference (not the C++
+# oracle): discrete Rosa stages and the full stateful GSkel replay.
+def _pyref():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from pyref import gskel_ref, rosa_ref, scenarios
+    return gskel_ref, rosa_ref, scenarios
+
+
+@pytest.mark.parametrize("name", ["cyl20k", "turbine100k", "stream131"])
+def test_library_matches_pyref_on_the_discrete_rosa_stages(mods, name):
+    osep, po, fx = mods
+    _, rr, _ = _pyref()
+    P = {"cyl20k": fx.cylinder, "turbine100k": fx.turbine, "stream131": lambda: fx.stream_frame(131, n=30000)[0]}[name]()
+    ref = rr.RosaRef(); assert ref.run(P)
+    r = osep.Rosa(capacity_points=P.shape[0]); r.set_debug(True); r.set_input(P); assert r.rosa_run()
+    assert np.float32(r.result.leaf_size) == ref.leaf_size and np.float32(r.result.leaf_used) == ref.leaf_used
+    for tap in ["filt_idx", "filtered", "knn_full", "normals_full", "leaf_hist", "nvox_hist", "vox_keys", "vox_count", "pts", "nrms",
+                "surf_idx", "simi_off", "simi_idx"]:
+        a, b = r.tap(tap), ref.t[tap]
+        assert_bit_equal(a.reshape(-1), b.reshape(-1), "%s vs pyref on %s" % (tap, name))
+    r.close()
+
+
+def _compare_gskel_with_pyref(gs, ref, what):
+    assert_bit_equal(gs.output_gskel()[:, :3].copy(), ref.positions(), "global vertices " + what)
+    assert_bit_equal(gs.tap("prelim"), ref.prelim_positions(), "prelim vertices " + what)
+    off, idx = ref.csr(ref.adj)
+    assert_bit_equal(gs.tap("adj_off"), off, "adj_off " + what); assert_bit_equal(gs.tap("adj_idx"), idx, "adj_idx " + what)
+    off, idx = ref.csr(ref.branches)
+    assert_bit_equal(gs.tap("branch_off"), off, "branch_off " + what); assert_bit_equal(gs.tap("branch_idx"), idx, "branch_idx " + what)
+    for tap, val in [("joints", ref.joints), ("leafs", ref.leafs), ("new_idx", ref.new_idx), ("type", [v.type for v in ref.glob]),
+                     ("obs", [v.obs_count for v in ref.glob]), ("prelim_frozen", [int(v.frozen) for v in ref.prelim])]:
+        assert_bit_equal(gs.tap(tap), np.array(val, np.int32), tap + " " + what)
+
+
+def test_gskel_library_matches_pyref_over_70_ticks_with_merges_and_prunes(mods):
+    """G1-G10 against the independent Python state machine (tests/pyref/gskel_ref.py), every container every tick; the
+    scenario provably goes through merges, prunes, the > 50 % abort and ticks without an approval."""
+    from osep_path_planner_b200 import GSkel, GSkelConfig
+    gr, _, sc = _pyref()
+    cfg = dict(gnd_th=-100.0)
+    gs = GSkel(GSkelConfig(**cfg)); ref = gr.GSkelRef(**cfg)
+    stages = set()
+    for k, c in enumerate(sc.structure_ticks(70, seed=0, sigma=1.3, step=0.9)):
+        gs.set_input(c)
+        a, b = gs.gskel_run(), ref.run(c)
+        assert a == b and gs.failed_stage == ref.failed_stage, "tick %d: stage %d vs %d" % (k, gs.failed_stage, ref.failed_stage)
+        _compare_gskel_with_pyref(gs, ref, "tick %d" % k)
+        stages.add(ref.failed_stage)
+    assert ref.events["merged"] >= 10 and ref.events["pruned"] >= 10 and {0, 1, 4} <= stages, (ref.events, stages)
+    gs.close()
+
+
+def test_gskel_library_edge_cases_against_pyref(mods):
+    """empty input, non-finite candidates, > 50 % new abort, isolated vertex -> NaN in smooth -> dropped next tick (gskel.cpp:41,68,286,414,180)"""
+    from osep_path_planner_b200 import GSkel, GSkelConfig
+    gr, _, _ = _pyref()
+    cfg = dict(gnd_th=-100.0)
+    gs = GSkel(GSkelConfig(**cfg)); ref = gr.GSkelRef(**cfg)
+    gs.set_input(np.zeros((0, 3), np.float32))
+    assert gs.gskel_run() is False and ref.run(np.zeros((0, 3), np.float32)) is False and gs.failed_stage == ref.failed_stage == 1
+    base = np.array([[0, 0, 0], [4, 0, 0], [8, 0, 0], [12, 0, 0], [np.nan, 0, 0]], np.float32)
+    far = np.array([[0, 0, 0], [4, 0, 0], [8, 0, 0], [12, 0, 0], [60, 0, 0]], np.float32)
+    saw_nan = False
+    for k, c in enumerate([base] * 4 + [far] * 7):
+        gs.set_input(c)
+        a, b = gs.gskel_run(), ref.run(c)
+        assert a == b and gs.failed_stage == ref.failed_stage, "tick %d" % k
+        _compare_gskel_with_pyref(gs, ref, "edge tick %d" % k)
+        saw_nan = saw_nan or bool(np.isnan(ref.positions()).any())
+    assert saw_nan and not np.isnan(ref.positions()).any()
+    gs.close()
