@@ -9,6 +9,10 @@ skeleton graph) over one synthetic 100k-point turbine frame (BASELINE.json confi
           -> H2D -> 7 stages -> D2H of the vertices), wall clock around the synchronous call.
 N > 1 (torchrun): one process per GPU, each rank runs its own frames (independent frames are
 the unit the path shards by; no data-path collective), value = frames of all ranks / max time.
+Extra blocks on the same JSON line: `batched` (configs[3]: 256 distinct frames from pinned host
+buffers through osep_rosa_run_batch, results gathered over NCCL inside the timed region),
+`stream` (configs[2] in miniature: frames with a different n each, p50/p99 latency) and, for
+N >= 2, `tiled` (configs[4]: one map split into spatial tiles with a halo exchange).
 --impl reference: the CPU restatement of the reference (oracle, faithful mode, the reference
 is single threaded) on the host cores, same metric.
 """
@@ -203,10 +207,11 @@ def run_ours(args, rank, world, local_rank):
             flush.zero_()                       # L2 flush, outside the per-step events
             ev[k][0].record(stream)
         step_device()
-        with torch.cuda.stream(stream):
-            ev[k][1].record(stream)
         ok = r.finish()
         assert ok
+        g = r.graph(3.0)                        # graph_adj + mst + graph_decomp of this frame's vertices (device), CSR on the host
+        with torch.cuda.stream(stream):
+            ev[k][1].record(stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = r.launches - launches0
@@ -235,11 +240,12 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.steps):
         rc = L.osep_rosa_run(r._h, C.c_void_p(host.data_ptr()), n, 4, C.byref(res))
         assert rc == 0
+        g = r.graph(3.0)
     barrier()
     e2e_s = shard.max_over_ranks(time.perf_counter() - t0)
     clk = clocks.stop()
     e2e_value = world * args.steps / e2e_s
-    d2h = 16 * 1024 + 256        # vertices staging (first 1024 float4) + frame state
+    d2h = 12 * 1024 + 256 + int(g["n_vertices"]) * 40 + int(g["n_edges"]) * 12 + 16     # vertices staging (first 768 float4) + frame state + graph lists
 
     stage_ms = dict(zip(r.STAGE_NAMES, (stage_acc / n_prof).tolist()))
     stage_ms.pop("-", None)
@@ -277,29 +283,82 @@ def run_ours(args, rank, world, local_rank):
                                       "frac": (knn_bytes / (knn_ms * 1e-3) / 1e9) / peak if knn_ms > 0 else None,
                                       "note": "issue/latency-bound selection (ncu: 71 M warp instructions, 38 % issue-active at 3 CTAs per SM), L1/L2 resident"}}
 
-    # ---- extra (not the headline): batched independent frames on this GPU (BASELINE.json configs[3] in miniature)
+    # ---- BASELINE.json configs[3]: 256 DISTINCT independent frames (seeds 0..255, random yaw / stand-off), 256 / N per rank,
+    # through the host entry point osep_rosa_run_batch from pinned host buffers (H2D inside the timed region), per-frame
+    # vertices gathered over NCCL inside the timed region.  All runs are listed; the worst one is reported next to the median.
     batched = None
     if args.batch > 0:
-        nb = args.batch
+        nb = max(1, args.batch // world)
         r.set_lanes(args.lanes)
-        devs = [torch.from_numpy(fx.to_xyz4(fx.batch_frame(rank * nb + b, n=args.points))).cuda() for b in range(min(nb, 16))]
-        ptrs = [devs[b % len(devs)].data_ptr() for b in range(nb)]
-        cnts = [devs[b % len(devs)].shape[0] for b in range(nb)]
-        wu = [k % nb for k in range(args.lanes * 3)]
-        r.run_batch([ptrs[k] for k in wu], device_ptrs=True, counts=[cnts[k] for k in wu])      # warm-up: every lane gets its CUDA graph
+        frames_h = [torch.from_numpy(fx.to_xyz4(fx.batch_frame(rank * nb + b, n=args.points))).pin_memory() for b in range(nb)]
+        ptrs = [f.data_ptr() for f in frames_h]
+        cnts = [int(f.shape[0]) for f in frames_h]
+
+        def run_batch_host():
+            B = len(ptrs)
+            pa = (C.c_void_p * B)(*ptrs); na = (C.c_int * B)(*cnts)
+            resv = (osep.RosaResult * B)()
+            rc = L.osep_rosa_run_batch(r._h, pa, na, B, 4, resv)
+            assert rc == 0 and all(x.status == 0 for x in resv), "batched run failed: %d" % rc
+            local = {}
+            for b in range(B):
+                pp = C.POINTER(C.c_float)(); nv = C.c_int()
+                L.osep_rosa_batch_vertices(r._h, b, C.byref(pp), C.byref(nv))
+                local[rank * nb + b] = np.ctypeslib.as_array(pp, shape=(3, nv.value)).T if nv.value else np.zeros((0, 3), np.float32)
+            counts, _ = shard.gather_frame_results(local, nb * world)
+            return resv, counts
+        run_batch_host()                                                         # warm-up: every lane captures its CUDA graph
         runs = []
-        for _ in range(3):                      # three timed repetitions, the median is reported (all three are listed)
+        for _ in range(args.batch_runs):
             barrier()
             t0 = time.perf_counter()
-            bres, _ = r.run_batch(ptrs, device_ptrs=True, counts=cnts)
+            bres, bcounts = run_batch_host()
             barrier()
             runs.append(shard.max_over_ranks(time.perf_counter() - t0))
-            assert all(x.status == 0 for x in bres)
-        bt = sorted(runs)[1]
-        batched = {"frames": nb * world, "lanes_per_gpu": args.lanes, "frames_per_s": nb * world / bt, "ms_per_frame_amortised": 1e3 * bt / nb,
-                   "frames_per_s_runs": [nb * world / t for t in runs],
-                   "distinct_frames": len(devs), "note": "device-resident frames, %d streams per GPU, wall clock around osep_rosa_run_batch_device, median of 3 runs" % args.lanes}
+        bt = float(np.median(runs)); total = nb * world
+        b_alg = float(np.mean([algorithmic_bytes(cnts[b], bres[b].n_filtered, bres[b].n_passes, bres[b].n_downsampled, bres[b].n_vertices) for b in range(nb)]))
+        b_gbs = b_alg * total / bt / 1e9
+        batched = {"frames": total, "distinct_frames": total, "frames_per_rank": nb, "lanes_per_gpu": args.lanes,
+                   "frames_per_s": total / bt, "frames_per_s_worst_run": total / max(runs), "frames_per_s_runs": [total / t for t in runs],
+                   "max_over_median_run_time": max(runs) / bt, "ms_per_frame_amortised": 1e3 * bt / nb,
+                   "e2e": {"value": total / bt, "unit": "frames/s", "h2d_bytes_per_frame": int(np.mean(cnts)) * 16, "d2h_bytes_per_frame": 12 * 1024 + 256,
+                           "gather": "per-frame vertices all_gathered over NCCL inside the timed region" if world > 1 else "single rank: no gather"},
+                   "roofline": {"bound": "hbm", "algorithmic_bytes_per_frame": b_alg, "achieved": b_gbs, "peak": peak * world, "unit": "GB/s", "frac": b_gbs / (peak * world),
+                                "note": "SURVEY.md 8(d) bytes per frame x frames/s over all ranks / (measured HBM peak x ranks): the configuration where the HBM fraction is meaningful"},
+                   "mean_vertices_per_frame": float(np.mean(bcounts)),
+                   "note": "pinned HOST frames through osep_rosa_run_batch, %d frames in flight per GPU, wall clock max over ranks, %d runs" % (args.lanes, args.batch_runs)}
         r.set_lanes(1)
+        del frames_h
+    # ---- BASELINE.json configs[2] in miniature: a stream of C3 frames whose point count changes every frame (a real LiDAR never
+    # repeats n), Rosa (host entry point) + TF + GSkel tick per frame; per-frame latency percentiles.  Rank 0 only.
+    stream = None
+    if args.stream > 0 and rank == 0:
+        from osep_path_planner_b200 import GSkel, GSkelConfig
+        rng = np.random.default_rng(7)
+        sf = []
+        for f in range(args.stream):
+            P, Rm, tv = fx.stream_frame(f * 5, n=50000)
+            keep_n = int(rng.integers(42000, 50001))
+            sf.append((torch.from_numpy(fx.to_xyz4(P[:keep_n])).pin_memory(), Rm, tv))
+        gsk = GSkel(GSkelConfig(gnd_th=-100.0), device=local_rank)
+        lat_r, lat_g, replays0 = [], [], int(r.tap("graph_replays")[0])
+        for wu in range(3):
+            L.osep_rosa_run(r._h, C.c_void_p(sf[wu][0].data_ptr()), int(sf[wu][0].shape[0]), 4, C.byref(res))
+        for buf, Rm, tv in sf:
+            t0 = time.perf_counter()
+            rc = L.osep_rosa_run(r._h, C.c_void_p(buf.data_ptr()), int(buf.shape[0]), 4, C.byref(res))
+            t1 = time.perf_counter()
+            if rc == 0:
+                v = np.ascontiguousarray(r.output_vertices_now())
+                gsk.set_input((v.astype(np.float64) @ Rm.T + tv).astype(np.float32)); gsk.gskel_run()
+            lat_r.append(1e3 * (t1 - t0)); lat_g.append(1e3 * (time.perf_counter() - t1))
+        stream = {"frames": len(sf), "points_per_frame": [int(min(x[0].shape[0] for x in sf)), int(max(x[0].shape[0] for x in sf))],
+                  "distinct_point_counts": len(set(int(x[0].shape[0]) for x in sf)),
+                  "rosa_ms_p50": float(np.percentile(lat_r, 50)), "rosa_ms_p99": float(np.percentile(lat_r, 99)), "rosa_ms_max": float(np.max(lat_r)),
+                  "gskel_ms_p50": float(np.percentile(lat_g, 50)), "gskel_ms_p99": float(np.percentile(lat_g, 99)),
+                  "graph_replays": int(r.tap("graph_replays")[0]) - replays0, "global_vertices": int(len(gsk.output_gskel())),
+                  "note": "host pinned frame -> osep_rosa_run (H2D + frame + D2H) wall clock per frame; every frame has a different n and replays the same CUDA graph"}
+        gsk.close()
     if world > 1:
         counts, _ = shard.gather_frame_results({rank: np.ascontiguousarray(r.output_vertices())}, world, cap=1024)
     cpu_baseline = None
@@ -317,7 +376,7 @@ def run_ours(args, rank, world, local_rank):
                            "parallelism": "1 frame per GPU per step; ranks = independent frames (no collective on the data path)"},
                 "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": 1e3 * e2e_s / args.steps, "h2d_bytes_per_step": int(n * 16), "d2h_bytes_per_step": d2h},
-                "gpu_launches": int(launches), "stage_ms": stage_ms, "clocks": clk, "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps, "batched": batched}
+                "gpu_launches": int(launches), "stage_ms": stage_ms, "clocks": clk, "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps, "batched": batched, "stream": stream}
         print(json.dumps(line), flush=True)
     r.close()
     if world > 1:
@@ -333,7 +392,9 @@ def main():
     ap.add_argument("--points", type=int, default=100000)
     ap.add_argument("--cpu-frames", type=int, default=20, help="frames of the bounded CPU-baseline sample (~0.4 s each)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--batch", type=int, default=64, help="frames of the extra batched-throughput measurement (0 = skip)")
+    ap.add_argument("--batch", type=int, default=256, help="total frames of the batched measurement, configs[3] (split over the ranks; 0 = skip)")
+    ap.add_argument("--batch-runs", type=int, default=5, help="timed repetitions of the batched measurement (all are listed)")
+    ap.add_argument("--stream", type=int, default=200, help="frames of the varying-n stream measurement, configs[2] in miniature (0 = skip)")
     ap.add_argument("--prewarm", type=float, default=0.5, help="seconds of untimed frames before the W warm-up steps")
     ap.add_argument("--lanes", type=int, default=12, help="concurrent frames (streams) per GPU in the batched measurement")
     args = ap.parse_args()

@@ -39,6 +39,7 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
     const size_t N = d.Ncap, M = d.Mcap, T = d.T;
     const size_t tmpcap = std::max<size_t>(N, d.Scap);
     CK(dalloc(&d.st, 1)); CK(cudaMemset(d.st, 0, sizeof(FrameState)));
+    CK(dalloc(&d.prm, 1)); CK(cudaMemset(d.prm, 0, sizeof(FrameParams)));
     CK(dalloc(&d.in, N * 4));
     CK(dalloc(&d.P, N)); CK(dalloc(&d.filt_idx, N)); CK(dalloc(&d.blk_cnt, N / 256 + 2));
     { unsigned* g4; CK(dalloc(&g4, 4 * T)); d.gtab = (unsigned long long*)g4; d.g_cnt = (int*)(g4 + 2 * T); d.g_fill = (int*)(g4 + 3 * T); }
@@ -65,6 +66,7 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
     CK(dalloc(&d.skel, M)); CK(dalloc(&d.skel2, M)); CK(dalloc(&d.skel_sampled, M)); CK(dalloc(&d.vtmp, M));
     CK(dalloc(&d.vs_off, M + 2)); CK(dalloc(&d.vs_idx, (size_t)d.Scap));
     CK(cudaMallocHost((void**)&h->st_host, sizeof(FrameState)));
+    CK(cudaMallocHost((void**)&h->prm_host, sizeof(FrameParams)));
     CK(cudaMallocHost((void**)&h->skel_host, sizeof(float4) * M));
     memset(h->st_host, 0, sizeof(FrameState));
     mscale_set_attributes(d.Mcap);
@@ -74,13 +76,14 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
 
 static void rosa_free(osep_rosa_impl* h) {
     RosaDev& d = h->d;
-    void* ptrs[] = {d.st, d.in, d.in_raw, d.P, d.filt_idx, d.blk_cnt, d.gtab, d.g_start, d.units, d.slow_list, d.over_list, d.p_slot, d.Pc, d.Nrm, d.knn_full, d.vtab, d.vkeys, d.vid,
+    void* ptrs[] = {d.st, d.prm, d.in, d.in_raw, d.P, d.filt_idx, d.blk_cnt, d.gtab, d.g_start, d.units, d.slow_list, d.over_list, d.p_slot, d.Pc, d.Nrm, d.knn_full, d.vtab, d.vkeys, d.vid,
                     d.vox_cnt, d.vox_fill, d.rk0, d.rk1, d.rv0, d.rv1, d.pts, d.nrms, d.pset, d.pset2, d.vset, d.vnew, d.vvar, d.surf,
                     d.simi_off, d.simi_idx, d.simi_bits, d.nraw, d.vnd, d.vset_it, d.vnew_it, d.fused_flags, d.fused_dbg, d.level, d.level_off, d.level_pts, d.good, d.centers, d.good_rank, d.poor_idx, d.active_size,
                     d.pcloud, d.adj_bits, d.seeds, d.corresp, d.skel, d.skel2, d.skel_sampled, d.vtmp, d.vs_off, d.vs_idx, d.vset_iters};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->graph) graph_destroy(h->graph);
     if (h->st_host) cudaFreeHost(h->st_host);
+    if (h->prm_host) cudaFreeHost(h->prm_host);
     if (h->skel_host) cudaFreeHost(h->skel_host);
     for (int i = 0; i < osep_rosa_impl::NSTAGE_EV; ++i) if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -94,9 +97,13 @@ static void rosa_free(osep_rosa_impl* h) {
 static int rosa_enqueue(osep_rosa_impl* h, const float* xyz_dev, int n, int stride) {
     RosaDev& d = h->d;
     h->last_n = n;
+    // the previous frame of this handle has been collected (one frame in flight per handle), so the pinned mirror is free
+    h->prm_host->in = xyz_dev; h->prm_host->n = n; h->prm_host->stride = stride; h->prm_host->pad = 0;
+    const int big = n > 400000 ? 1 : 0;              // the only host-side launch heuristics: kNN grid occupancy / CTAs per SM
     cudaEventRecord(h->ev0, h->stream);
     auto enqueue_all = [&]() {
-        launch_preprocess(h, xyz_dev, n, stride);
+        cudaMemcpyAsync(d.prm, h->prm_host, sizeof(FrameParams), cudaMemcpyHostToDevice, h->stream);    // a copy NODE in the graph: re-read at every replay
+        launch_preprocess(h, big ? 400001 : 1);
         launch_mscale(h);
         cudaMemcpyAsync(h->st_host, d.st, sizeof(FrameState), cudaMemcpyDeviceToHost, h->stream);
         cudaMemcpyAsync(h->skel_host, d.skel, sizeof(float4) * d.Mcap / 4, cudaMemcpyDeviceToHost, h->stream);   // first Mcap/4 vertices; rest on demand
@@ -104,10 +111,10 @@ static int rosa_enqueue(osep_rosa_impl* h, const float* xyz_dev, int n, int stri
     bool done = false;
     if (h->use_graphs && !h->profile && !h->debug) {
         osep_rosa_impl::FrameGraph& g = h->fg;
-        if (g.exec && g.xyz == xyz_dev && g.n == n && g.stride == stride && g.epoch == h->cfg_epoch) {
-            if (cudaGraphLaunch(g.exec, h->stream) == cudaSuccess) { h->n_launches += g.launches; done = true; }
+        if (g.exec && g.big == big && g.epoch == h->cfg_epoch) {
+            if (cudaGraphLaunch(g.exec, h->stream) == cudaSuccess) { h->n_launches += g.launches; ++h->n_graph_replays; done = true; }
             else cudaGetLastError();
-        } else if (g.seen_xyz == xyz_dev && g.seen_n == n && g.seen_stride == stride && g.seen_epoch == h->cfg_epoch) {
+        } else if (g.seen_big == big && g.seen_epoch == h->cfg_epoch) {
             if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
             const long long l0 = h->n_launches;
             if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
@@ -120,13 +127,13 @@ static int rosa_enqueue(osep_rosa_impl* h, const float* xyz_dev, int n, int stri
                 g.launches = h->n_launches - l0; h->n_launches = l0;
                 if (!g.exec) { cudaGetLastError(); h->use_graphs = false; }          // capture unsupported here: plain launches from now on
                 else {
-                    g.xyz = xyz_dev; g.n = n; g.stride = stride; g.epoch = h->cfg_epoch;
-                    if (cudaGraphLaunch(g.exec, h->stream) == cudaSuccess) { h->n_launches += g.launches; done = true; }
+                    g.big = big; g.epoch = h->cfg_epoch;
+                    if (cudaGraphLaunch(g.exec, h->stream) == cudaSuccess) { h->n_launches += g.launches; ++h->n_graph_replays; done = true; }
                     else cudaGetLastError();
                 }
             } else { cudaGetLastError(); h->use_graphs = false; }
         }
-        g.seen_xyz = xyz_dev; g.seen_n = n; g.seen_stride = stride; g.seen_epoch = h->cfg_epoch;
+        g.seen_big = big; g.seen_epoch = h->cfg_epoch;
     }
     if (!done) enqueue_all();
     cudaEventRecord(h->ev1, h->stream);
@@ -151,6 +158,12 @@ static int rosa_collect(osep_rosa_impl* h, osep_rosa_result* res) {
         res->n_downsampled = s.M; res->n_vertices = V; res->n_passes = s.n_pass; res->n_simi = s.S;
         res->leaf_size = s.leaf_size; res->leaf_used = s.leaf_used;
         float ms = 0.f; cudaEventElapsedTime(&ms, h->ev0, h->ev1); res->gpu_ms = ms;
+    }
+    if (s.status < 0) {
+        // device-side capacity limits (the reference has none): say which one instead of leaving osep_last_error() stale
+        set_err("frame failed on the device with status %d: N'=%d M=%d (arena %d) S=%d (arena %d) passes=%d flags=0x%x%s%s", s.status, s.n_filt, s.M, d.Mcap, s.S,
+                d.Scap, s.n_pass, s.flags, s.pass_overflow ? "; VoxelGrid index overflow (PCL would return the input cloud unchanged)" : "",
+                s.n_keys > d.Mcap ? "; more voxels than the downsampled-point arena holds" : "");
     }
     return s.status;
 }
@@ -249,6 +262,7 @@ int osep_rosa_run_device(osep_rosa* h, const float* xyz_dev, int n, int stride_f
     int rc = check_frame(I, n, stride_floats); if (rc) return rc;
     CK(cudaSetDevice(I.device));
     if (n == 0) {                       // rosa.cpp:63-65: empty input fails preprocess
+        CK(cudaStreamSynchronize(I.stream));   // a frame still in flight on this handle writes st_host when it completes
         memset(I.st_host, 0, sizeof(FrameState)); I.st_host->status = OSEP_STAGE_1; I.last_n = 0;
         cudaEventRecord(I.ev0, I.stream); cudaEventRecord(I.ev1, I.stream);
         return OSEP_OK;
@@ -389,6 +403,7 @@ long osep_rosa_get(osep_rosa* h, const char* name, void* dst, long cap) {
     if (nm == "fused_dbg") return tap_copy(dst, cap, d.fused_dbg, 64, 8) * 2;     // 64 int64 = 128 int32 words
     if (nm == "knn_stats") { if (dst && cap >= 12) { ((int*)dst)[0] = s.n_units; ((int*)dst)[1] = s.n_slow; ((int*)dst)[2] = s.n_over; } return 3; }
     if (nm == "launches") { if (dst && cap >= 4) *(int*)dst = (int)I.n_launches; return 1; }
+    if (nm == "graph_replays") { if (dst && cap >= 4) *(int*)dst = (int)I.n_graph_replays; return 1; }
     return -1;
 }
 
@@ -434,38 +449,39 @@ static int run_batch(osep_rosa* h, const float* const* xyz, const int* n, int B,
     I.batch_vertices.assign(B, {});
     int worst = OSEP_OK;
     std::vector<int> inflight(nl, -1);
+    std::vector<int> fifo;                        // lanes in enqueue order: the oldest frame in flight is the next one collected
     auto collect = [&](int lane) {
         const int b = inflight[lane];
         if (b < 0) return;
         osep_rosa_result r; memset(&r, 0, sizeof(r));
-        rosa_collect(L[lane], &r);
+        const int rc = rosa_collect(L[lane], &r);
+        if (rc == OSEP_ERR_CUDA) r.status = OSEP_ERR_CUDA;          // stream error: rosa_collect could not read the frame state
         if (results) results[b] = r;
         I.batch_vertices[b] = L[lane]->vertices_colmajor;
         if (r.status < 0) worst = r.status;
         inflight[lane] = -1;
     };
+    auto drain = [&]() { for (int lane : fifo) collect(lane); fifo.clear(); };
     for (int b = 0; b < B; ++b) {
-        // next lane: a free one, else the first whose frame has finished (frames take different times: M, leaf passes)
+        // next lane: a free one, else BLOCK on the oldest frame in flight (no host polling: a sticky device error surfaces in
+        // rosa_collect's cudaStreamSynchronize instead of spinning forever; frames of one batch take similar times)
         int lane = -1;
         for (int k = 0; k < nl && lane < 0; ++k) if (inflight[k] < 0) lane = k;
-        while (lane < 0) {
-            for (int k = 0; k < nl && lane < 0; ++k) if (cudaStreamQuery(L[k]->stream) == cudaSuccess) lane = k;
-        }
-        collect(lane);
+        if (lane < 0) { lane = fifo.front(); fifo.erase(fifo.begin()); collect(lane); }
+        if (worst == OSEP_ERR_CUDA) { drain(); return worst; }
         osep_rosa_impl* l = L[lane];
         int rc = check_frame(*l, n[b], stride);
         if (rc == OSEP_OK && n[b] == 0) rc = OSEP_STAGE_1;
         if (rc != OSEP_OK) { if (results) { memset(&results[b], 0, sizeof(osep_rosa_result)); results[b].status = rc; } if (rc < 0) worst = rc; continue; }
         const float* src = xyz[b];
-        // frames are staged in the lane's own input buffer (H2D, or D2D for device-resident frames: 1.6 MB, ~2 us), so the
-        // lane sees one (buffer, n, stride) shape and replays its CUDA graph instead of issuing ~40 launches per frame
+        // host frames are staged in the lane's own input buffer (H2D on the lane's stream); device-resident frames are read
+        // in place -- the lane's CUDA graph takes buffer, n and stride from FrameParams
         if (host) { cudaMemcpyAsync(l->d.in, xyz[b], sizeof(float) * (size_t)n[b] * stride, cudaMemcpyHostToDevice, l->stream); src = l->d.in; }
-        else if (stride <= 4) { cudaMemcpyAsync(l->d.in, xyz[b], sizeof(float) * (size_t)n[b] * stride, cudaMemcpyDeviceToDevice, l->stream); src = l->d.in; }
         rc = rosa_enqueue(l, src, n[b], stride);
-        if (rc) return rc;
-        inflight[lane] = b;
+        if (rc) { drain(); return rc; }           // frames already in flight are collected (their results[] are valid) before the error is reported
+        inflight[lane] = b; fifo.push_back(lane);
     }
-    for (int lane = 0; lane < nl; ++lane) collect(lane);
+    drain();
     return worst;
 }
 

@@ -79,7 +79,8 @@ __device__ __forceinline__ bool keep_point(float x, float y, float z, float r2) 
     return fin(x) && fin(y) && fin(z) && d2 <= r2;
 }
 
-__global__ void k_filter_count(const float* __restrict__ in, int n, int stride, float r2, int* __restrict__ blk_cnt) {
+__global__ void k_filter_count(const FrameParams* __restrict__ prm, float r2, int* __restrict__ blk_cnt) {
+    const float* __restrict__ in = prm->in; const int n = prm->n, stride = prm->stride;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool keep = false;
     if (i < n) {
@@ -91,8 +92,8 @@ __global__ void k_filter_count(const float* __restrict__ in, int n, int stride, 
 }
 
 // single block: scan the per-block counts; R4 gate (rosa.cpp:91-95)
-__global__ void k_filter_scan(int* blk_cnt, int nblk, FrameState* st, int min_points, int n_in) {
-    if (threadIdx.x == 0) frame_init(st, n_in);          // first writer of the frame state (k_filter_count does not touch it)
+__global__ void k_filter_scan(int* blk_cnt, int nblk, FrameState* st, int min_points, const FrameParams* __restrict__ prm) {
+    if (threadIdx.x == 0) frame_init(st, prm->n);          // first writer of the frame state (k_filter_count does not touch it)
     const int total = block_excl_scan(blk_cnt, nblk);
     if (threadIdx.x == 0) {
         st->n_filt = total;
@@ -101,8 +102,9 @@ __global__ void k_filter_scan(int* blk_cnt, int nblk, FrameState* st, int min_po
 }
 
 __device__ void leaf_step(FrameState* st, int p, int max_points);
-__global__ void k_filter_scatter(const float* __restrict__ in, int n, int stride, float r2, const int* __restrict__ blk_off,
+__global__ void k_filter_scatter(const FrameParams* __restrict__ prm, float r2, const int* __restrict__ blk_off,
                                  float4* __restrict__ P, int* __restrict__ filt_idx, FrameState* st, int max_points) {
+    const float* __restrict__ in = prm->in; const int n = prm->n, stride = prm->stride;
     __shared__ int warp_cnt[NT / 32];
     __shared__ int s_last;
     __shared__ int s_lo[3], s_hi[3];
@@ -1103,14 +1105,16 @@ static void launch_knn(osep_rosa_impl* h, int n, int k_req, cudaStream_t s) {
                                                               d.knn_full, k_req, d.slow_list, d.over_list);
     k_knn_big<K><<<h->sms * 4, BIG_WARPS * 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units, d.knn_full, k_req, d.slow_list, d.over_list);
     k_knn_exact<K><<<64, 128, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.knn_full, k_req, d.slow_list);
-    k_normals<<<div_up(n, 128), 128, 0, s>>>(d.P, d.st, d.knn_full, k_req, d.Nrm);
+    k_normals<<<div_up(d.Ncap, 128), 128, 0, s>>>(d.P, d.st, d.knn_full, k_req, d.Nrm);
 }
 
-void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int stride) {
+void launch_preprocess(osep_rosa_impl* h, int n) {
     RosaDev& d = h->d;
     cudaStream_t s = h->stream;
     const osep_rosa_config& c = h->cfg;
-    const int nb = div_up(n, NT);
+    // capacity-sized grids: every kernel reads the frame's sizes from FrameParams / FrameState and surplus blocks exit at
+    // once, so the launch sequence (and its CUDA graph) is the same for every frame this handle can take
+    const int nb = div_up(d.Ncap, NT);
     const float r2 = c.pts_dist_lim * c.pts_dist_lim;
     // target points per kNN grid cell: large (dense, heavy-tailed) maps overflow the 512-point stage too often at 9
     const int ppc = h->knn_ppc > 0 ? h->knn_ppc : (n > 400000 ? 6 : 9);
@@ -1121,9 +1125,9 @@ void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int strid
         cudaMemsetAsync(d.gtab, 0, sizeof(unsigned) * 4 * (size_t)d.T, sk);   // gtab (8 B) | g_cnt | g_fill are contiguous
     }
     // R3/R4
-    k_filter_count<<<nb, NT, 0, s>>>(xyz_dev, n, stride, r2, d.blk_cnt);
-    k_filter_scan<<<1, 1024, 0, s>>>(d.blk_cnt, nb, d.st, c.min_points, n);
-    k_filter_scatter<<<nb, NT, 0, s>>>(xyz_dev, n, stride, r2, d.blk_cnt, d.P, d.filt_idx, d.st, c.max_points);
+    k_filter_count<<<nb, NT, 0, s>>>(d.prm, r2, d.blk_cnt);
+    k_filter_scan<<<1, 1024, 0, s>>>(d.blk_cnt, nb, d.st, c.min_points, d.prm);
+    k_filter_scatter<<<nb, NT, 0, s>>>(d.prm, r2, d.blk_cnt, d.P, d.filt_idx, d.st, c.max_points);
     stage_mark(h, SM_FILTER);
     // R7/R8: device-resident leaf loop (count-only passes).  The kNN grid is sized from the density seen by
     // pass 0, so the whole normals branch (grid build + kNN + covariance/eigen) only depends on pass 0 and runs

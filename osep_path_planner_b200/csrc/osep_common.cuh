@@ -62,6 +62,16 @@ struct FrameState {
     int ticket_grid;       // last-block detection (kNN grid build; runs concurrently with the voxel passes)
 };
 
+// Per-frame launch parameters.  They live in device memory (refreshed by one H2D copy node from a pinned host mirror at the
+// head of every frame) instead of being kernel arguments, so the captured CUDA graph of a frame does not depend on the
+// frame's point count, stride or buffer address: a LiDAR stream whose n changes every frame replays ONE graph.
+struct FrameParams {
+    const float* in;       // input points on the device (x, y, z at [i*stride .. i*stride+2])
+    int n;                 // points in this frame
+    int stride;            // floats per input point
+    int pad;
+};
+
 // ordered-int encoding of a float: monotone map so atomicMin/atomicMax(int) order floats
 __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }

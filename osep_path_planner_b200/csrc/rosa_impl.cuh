@@ -16,6 +16,7 @@ struct RosaDev {
     int knn = 0, nbk = 0;  // ne_knn, nb_knn
 
     FrameState* st = nullptr;
+    FrameParams* prm = nullptr;        // device copy of the per-frame launch parameters (osep_common.cuh)
     // N-scale
     float* in = nullptr;               // staged input (host-buffer path), Ncap * 4 floats
     unsigned char* in_raw = nullptr; size_t in_raw_bytes = 0;   // staged raw PointCloud2 records (osep_rosa_run_pointcloud2), grown on demand
@@ -75,18 +76,20 @@ struct osep_rosa_impl {
     static constexpr int NSTAGE_EV = 16;
     cudaEvent_t stage_ev[NSTAGE_EV] = {};
     long long n_launches = 0;          // kernels launched by this handle since create
+    long long n_graph_replays = 0;     // frames that ran as one cudaGraphLaunch
     // CUDA graph of one frame: a frame has no host decisions (osep_common.cuh), so the whole launch sequence of a
-    // repeated (buffer, n, stride) shape is captured on its second occurrence and replayed afterwards
+    // frame is captured on the second frame and replayed afterwards; n / stride / buffer travel through FrameParams
     struct FrameGraph {
         cudaGraphExec_t exec = nullptr;
-        const float* xyz = nullptr; int n = -1, stride = 0, epoch = -1;
-        const float* seen_xyz = nullptr; int seen_n = -1, seen_stride = 0, seen_epoch = -1;
+        int big = -1, epoch = -1;          // key: size class (launch heuristics) and configuration epoch -- NOT n, stride or the buffer
+        int seen_big = -1, seen_epoch = -1;
         long long launches = 0;
     } fg;
     bool use_graphs = true;            // OSEP_NO_GRAPH=1 disables; also cleared when capture is not supported
     int cfg_epoch = 0;                 // bumped by every setter that changes what a frame launches
     // host mirrors
     FrameState* st_host = nullptr;     // pinned
+    FrameParams* prm_host = nullptr;   // pinned; source of the copy node at the head of a frame
     float4* skel_host = nullptr;       // pinned, Mcap
     std::vector<float> vertices_colmajor;
     int last_n = 0;
@@ -105,7 +108,7 @@ inline void stage_mark(osep_rosa_impl* h, int which) {
 }
 
 // stage launchers (all asynchronous on h->stream, no host sync)
-void launch_preprocess(osep_rosa_impl* h, const float* xyz_dev, int n, int stride);   // R3-R11
+void launch_preprocess(osep_rosa_impl* h, int n_class);                               // R3-R11 (n_class: point count the launch heuristics are tuned for)
 void launch_mscale(osep_rosa_impl* h);                                                // R12-R22
 
 }  // namespace osep

@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import RosaConfig, RosaResult, GraphView, OsepError, ROSA_STAGES
 
 _INT_TAPS = {"filt_idx", "knn_full", "nvox_hist", "vox_count", "surf_off", "surf_idx", "simi_off", "simi_idx",
-             "poor_idx", "active_size", "corresp", "seeds", "levels", "launches", "knn_stats"}
+             "poor_idx", "active_size", "corresp", "seeds", "levels", "launches", "knn_stats", "graph_replays"}
 _U32_TAPS = {"vox_keys"}
 _V3_TAPS = {"filtered", "normals_full", "pts", "nrms", "vset", "vset_iters", "pset", "pset_drosa", "skelver_sampled", "skelver"}
 
@@ -106,6 +106,11 @@ class Rosa:
         return self.running
 
     def output_vertices(self):
+        return self._vertices
+
+    def output_vertices_now(self):
+        """vertices of the last frame when the C entry points were called directly (bench): re-reads the library's buffer"""
+        self._collect_vertices()
         return self._vertices
 
     # --- device-resident entry points (bench / pipelines) -----------------------------------

@@ -423,21 +423,27 @@ def test_degenerate_geometries(mods, name):
 
 
 def test_frame_graph_replay_equals_plain_launches(mods):
-    """A repeated (buffer, n, stride) shape is captured into a CUDA graph on its second occurrence and replayed
-    afterwards (api.cu rosa_enqueue): replays, plain launches (debug mode disables the graph) and the oracle agree,
-    also when the content of the buffer or the number of points changes between replays."""
+    """One frame = one CUDA graph whose shape does not depend on the frame: n, stride and the buffer address travel through a
+    device-side FrameParams block refreshed by a copy node (api.cu rosa_enqueue).  20 frames with 20 different point counts
+    (a LiDAR stream never repeats n), different buffers and strides: all but the first two are pure graph replays, and every
+    one matches the oracle bit-for-bit."""
     osep, po, fx = mods
-    A, B, Cc = fx.turbine(30000, seed=11), fx.turbine(30000, seed=12), fx.cylinder(18000, seed=13)
-    ref = {}
-    for name, P in (("A", A), ("B", B), ("C", Cc)):
-        o = po.RosaOracle(); assert o.run(P); ref[name] = o.tap("skelver")
-    r = osep.Rosa(capacity_points=30000)
-    seq = ["A", "A", "A", "B", "B", "C", "C", "C", "A", "A"]          # 3rd+ A and 2nd+ B / C are replays; C re-captures (n differs)
-    clouds = {"A": A, "B": B, "C": Cc}
-    for k, name in enumerate(seq):
-        r.set_input(clouds[name])
+    r = osep.Rosa(capacity_points=32000)
+    rng = np.random.default_rng(5)
+    sizes = [int(x) for x in rng.integers(9000, 32000, 20)]
+    assert len(set(sizes)) == 20
+    for k, n in enumerate(sizes):
+        P = fx.turbine(n, seed=100 + k) if k % 3 else fx.cylinder(n, seed=100 + k)
+        o = po.RosaOracle(); assert o.run(P)
+        r.set_input(P if k % 2 else fx.to_xyz4(P))                 # stride 3 and stride 4 alternate
         assert r.rosa_run()
-        assert_bit_equal(np.ascontiguousarray(r.output_vertices()), ref[name], "frame %d (%s)" % (k, name))
+        assert_bit_equal(np.ascontiguousarray(r.output_vertices()), o.tap("skelver"), "frame %d (n=%d)" % (k, n))
+    assert int(r.tap("graph_replays")[0]) >= 18, "frames with different n must replay the same graph"
+    r.set_debug(True)                                              # debug mode = plain launches: same results
+    P = fx.turbine(sizes[3], seed=103)
+    o = po.RosaOracle(); assert o.run(P)
+    r.set_input(P); assert r.rosa_run()
+    assert_bit_equal(np.ascontiguousarray(r.output_vertices()), o.tap("skelver"), "plain launches")
     r.close()
 
 
