@@ -177,6 +177,7 @@ def run_ours(args, rank, world, local_rank):
     host = torch.from_numpy(P4).pin_memory()
     dev = host.cuda(non_blocking=False)
     r = osep.Rosa(device=local_rank, capacity_points=n)
+    r.set_graph(True, 3.0)             # frame -> skeleton graph in one launch sequence: graph_adj + mst run inside the frame
     stream = torch.cuda.ExternalStream(r.stream, device=local_rank)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")      # > 126 MB L2
 
@@ -206,12 +207,12 @@ def run_ours(args, rank, world, local_rank):
         with torch.cuda.stream(stream):
             flush.zero_()                       # L2 flush, outside the per-step events
             ev[k][0].record(stream)
-        step_device()
-        ok = r.finish()
-        assert ok
-        g = r.graph(3.0)                        # graph_adj + mst + graph_decomp of this frame's vertices (device), CSR on the host
+        step_device()                           # 7 Rosa stages + graph_adj + mst + result copies: one launch sequence (CUDA graph)
         with torch.cuda.stream(stream):
             ev[k][1].record(stream)
+        ok = r.finish()
+        assert ok
+        g = r.graph(3.0)                        # host views (CSR, joints, leafs) of the graph the frame built on the device
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = r.launches - launches0

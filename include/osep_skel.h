@@ -181,6 +181,10 @@ typedef struct osep_graph_view {
     const int32_t* rng_idx;
 } osep_graph_view;
 int osep_rosa_graph(osep_rosa* h, float fuse_dist_th, osep_graph_view* out);  /* graph of the last frame's vertices */
+/* enable != 0: graph_adj + mst (gskel.cpp:201-281) run INSIDE every frame, behind vertex_smooth on the frame's stream (one
+ * launch sequence / CUDA graph from point cloud to skeleton graph); osep_rosa_graph(h, same fuse_dist_th, ...) then only
+ * assembles the host views.  Off by default: the reference's Rosa class stops at the vertices (rosa.hpp:53). */
+int osep_rosa_set_graph(osep_rosa* h, int enable, float fuse_dist_th);
 
 /* ---- GSkel --------------------------------------------------------------------------- */
 int osep_gskel_create(const osep_gskel_config* cfg, int device, int capacity_vertices, osep_gskel** out);

@@ -60,7 +60,7 @@ SYMBOLS = [
     "osep_last_error", "osep_abi_version", "osep_device_count", "osep_rosa_default_config", "osep_gskel_default_config",
     "osep_rosa_create", "osep_rosa_destroy", "osep_rosa_run", "osep_rosa_run_pointcloud2", "osep_rosa_run_device", "osep_rosa_finish", "osep_rosa_stream",
     "osep_rosa_vertices", "osep_rosa_get", "osep_rosa_set_debug", "osep_rosa_set_profile", "osep_rosa_run_batch", "osep_rosa_run_batch_device",
-    "osep_rosa_batch_vertices", "osep_rosa_set_lanes", "osep_rosa_graph",
+    "osep_rosa_batch_vertices", "osep_rosa_set_lanes", "osep_rosa_graph", "osep_rosa_set_graph",
     "osep_gskel_create", "osep_gskel_destroy", "osep_gskel_run", "osep_gskel_run_tf", "osep_gskel_vertices", "osep_gskel_graph", "osep_gskel_get",
     "osep_graph_build",
 ]
@@ -103,6 +103,7 @@ def load():
     L.osep_rosa_batch_vertices.argtypes = [vp, ip, C.POINTER(C.POINTER(C.c_float)), C.POINTER(ip)]
     L.osep_rosa_set_lanes.argtypes = [vp, ip]
     L.osep_rosa_graph.argtypes = [vp, fp, C.POINTER(GraphView)]
+    L.osep_rosa_set_graph.argtypes = [vp, ip, fp]
     L.osep_gskel_create.argtypes = [C.POINTER(GSkelConfig), ip, ip, C.POINTER(vp)]
     L.osep_gskel_destroy.argtypes = [vp]
     L.osep_gskel_run.argtypes = [vp, vp, ip, ip]

@@ -16,6 +16,11 @@ struct GraphHost;
 GraphHost* graph_create(int cap, int device, cudaStream_t stream);
 void graph_destroy(GraphHost* g);
 int graph_run_device(GraphHost* g, const float4* pos_dev, int G, float fuse_dist_th, osep_graph_view* out);
+int graph_enqueue_in_frame(GraphHost* g, const float4* pos_dev, const FrameState* st, float fuse_dist_th, cudaStream_t s);
+int graph_collect_in_frame(GraphHost* g, osep_graph_view* out);
+size_t frame_export_enqueue(GraphHost* g, const FrameState* st, const float4* skel, int Mq, unsigned char* exp_dev, cudaStream_t s);
+size_t frame_export_bytes(int Mq);
+void graph_set_mirrors(GraphHost* g, unsigned char* exp_host, int Mq);
 
 
 static thread_local std::string g_err;
@@ -65,9 +70,13 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
     CK(dalloc(&d.seeds, M)); CK(dalloc(&d.corresp, M));
     CK(dalloc(&d.skel, M)); CK(dalloc(&d.skel2, M)); CK(dalloc(&d.skel_sampled, M)); CK(dalloc(&d.vtmp, M));
     CK(dalloc(&d.vs_off, M + 2)); CK(dalloc(&d.vs_idx, (size_t)d.Scap));
-    CK(cudaMallocHost((void**)&h->st_host, sizeof(FrameState)));
+    // one pinned result block per frame: frame state | first Mcap/4 vertices | in-frame graph lists (graph.cu k_export)
+    CK(cudaMalloc((void**)&d.exp, frame_export_bytes(d.Mcap / 4)));
+    CK(cudaMallocHost((void**)&h->exp_host, frame_export_bytes(d.Mcap / 4)));
+    memset(h->exp_host, 0, frame_export_bytes(d.Mcap / 4));
+    h->st_host = reinterpret_cast<FrameState*>(h->exp_host);
+    h->skel_host = reinterpret_cast<float4*>(h->exp_host + 512);
     CK(cudaMallocHost((void**)&h->prm_host, sizeof(FrameParams)));
-    CK(cudaMallocHost((void**)&h->skel_host, sizeof(float4) * M));
     memset(h->st_host, 0, sizeof(FrameState));
     mscale_set_attributes(d.Mcap);
     if (h->fused && !drosa_fused_supported(h->sms)) h->fused = false;     // falls back to the per-iteration kernels (same results)
@@ -82,9 +91,9 @@ static void rosa_free(osep_rosa_impl* h) {
                     d.pcloud, d.adj_bits, d.seeds, d.corresp, d.skel, d.skel2, d.skel_sampled, d.vtmp, d.vs_off, d.vs_idx, d.vset_iters};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->graph) graph_destroy(h->graph);
-    if (h->st_host) cudaFreeHost(h->st_host);
+    if (h->exp_host) cudaFreeHost(h->exp_host);
+    if (d.exp) cudaFree(d.exp);
     if (h->prm_host) cudaFreeHost(h->prm_host);
-    if (h->skel_host) cudaFreeHost(h->skel_host);
     for (int i = 0; i < osep_rosa_impl::NSTAGE_EV; ++i) if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -97,6 +106,7 @@ static void rosa_free(osep_rosa_impl* h) {
 static int rosa_enqueue(osep_rosa_impl* h, const float* xyz_dev, int n, int stride) {
     RosaDev& d = h->d;
     h->last_n = n;
+    h->graph_in_frame = h->auto_graph && h->graph != nullptr;
     // the previous frame of this handle has been collected (one frame in flight per handle), so the pinned mirror is free
     h->prm_host->in = xyz_dev; h->prm_host->n = n; h->prm_host->stride = stride; h->prm_host->pad = 0;
     const int big = n > 400000 ? 1 : 0;              // the only host-side launch heuristics: kNN grid occupancy / CTAs per SM
@@ -105,8 +115,10 @@ static int rosa_enqueue(osep_rosa_impl* h, const float* xyz_dev, int n, int stri
         cudaMemcpyAsync(d.prm, h->prm_host, sizeof(FrameParams), cudaMemcpyHostToDevice, h->stream);    // a copy NODE in the graph: re-read at every replay
         launch_preprocess(h, big ? 400001 : 1);
         launch_mscale(h);
-        cudaMemcpyAsync(h->st_host, d.st, sizeof(FrameState), cudaMemcpyDeviceToHost, h->stream);
-        cudaMemcpyAsync(h->skel_host, d.skel, sizeof(float4) * d.Mcap / 4, cudaMemcpyDeviceToHost, h->stream);   // first Mcap/4 vertices; rest on demand
+        const bool wg = h->auto_graph && h->graph;
+        if (wg) { graph_enqueue_in_frame(h->graph, d.skel, d.st, h->graph_fuse, h->stream); h->n_launches += 2; }   // frame -> skeleton graph in the same launch sequence
+        const size_t nbytes = frame_export_enqueue(wg ? h->graph : nullptr, d.st, d.skel, d.Mcap / 4, d.exp, h->stream); h->n_launches += 1;
+        cudaMemcpyAsync(h->exp_host, d.exp, nbytes, cudaMemcpyDeviceToHost, h->stream);       // the frame's only device-to-host copy (larger results on demand)
     };
     bool done = false;
     if (h->use_graphs && !h->profile && !h->debug) {
@@ -146,12 +158,17 @@ static int rosa_collect(osep_rosa_impl* h, osep_rosa_result* res) {
     const FrameState& s = *h->st_host;
     RosaDev& d = h->d;
     int V = (s.status == 0) ? s.V : 0;
-    if (V > d.Mcap / 4) CK(cudaMemcpy(h->skel_host, d.skel, sizeof(float4) * V, cudaMemcpyDeviceToHost));
+    const float4* sk = h->skel_host;
+    if (V > d.Mcap / 4) {                         // more vertices than the export block carries: fetch them all
+        h->skel_big.resize(V);
+        CK(cudaMemcpy(h->skel_big.data(), d.skel, sizeof(float4) * V, cudaMemcpyDeviceToHost));
+        sk = h->skel_big.data();
+    }
     h->vertices_colmajor.resize((size_t)3 * V);
     for (int i = 0; i < V; ++i) {
-        h->vertices_colmajor[i] = h->skel_host[i].x;
-        h->vertices_colmajor[(size_t)V + i] = h->skel_host[i].y;
-        h->vertices_colmajor[(size_t)2 * V + i] = h->skel_host[i].z;
+        h->vertices_colmajor[i] = sk[i].x;
+        h->vertices_colmajor[(size_t)V + i] = sk[i].y;
+        h->vertices_colmajor[(size_t)2 * V + i] = sk[i].z;
     }
     if (res) {
         res->status = s.status; res->flags = s.flags; res->n_input = h->last_n; res->n_filtered = s.n_filt;
@@ -414,9 +431,22 @@ int osep_rosa_graph(osep_rosa* h, float fuse_dist_th, osep_graph_view* out) {
     osep_rosa_impl& I = h->impl;
     CK(cudaSetDevice(I.device));
     CK(cudaStreamSynchronize(I.stream));
-    if (!I.graph) { I.graph = graph_create(I.d.Mcap, I.device, I.stream); if (!I.graph) { set_err("graph arena allocation failed"); return OSEP_ERR_CUDA; } }
+    if (!I.graph) { I.graph = graph_create(I.d.Mcap, I.device, I.stream); if (!I.graph) { set_err("graph arena allocation failed"); return OSEP_ERR_CUDA; } graph_set_mirrors(I.graph, I.exp_host, I.d.Mcap / 4); }
+    if (I.graph_in_frame && fuse_dist_th == I.graph_fuse) return graph_collect_in_frame(I.graph, out);    // built inside the frame (osep_rosa_set_graph): host assembly only
     const int V = (I.st_host->status == 0) ? I.st_host->V : 0;
     return graph_run_device(I.graph, I.d.skel, V, fuse_dist_th, out);
+}
+
+// Build the skeleton graph (graph_adj + mst, gskel.cpp:201-281) INSIDE every frame: the two kernels and the result copies join the
+// frame's launch sequence / CUDA graph, osep_rosa_graph() then only assembles the host views.  enable = 0 restores the default.
+int osep_rosa_set_graph(osep_rosa* h, int enable, float fuse_dist_th) {
+    if (!h) return OSEP_ERR_ARG;
+    osep_rosa_impl& I = h->impl;
+    CK(cudaSetDevice(I.device));
+    CK(cudaStreamSynchronize(I.stream));
+    if (enable && !I.graph) { I.graph = graph_create(I.d.Mcap, I.device, I.stream); if (!I.graph) { set_err("graph arena allocation failed"); return OSEP_ERR_CUDA; } graph_set_mirrors(I.graph, I.exp_host, I.d.Mcap / 4); }
+    I.auto_graph = enable != 0; I.graph_fuse = fuse_dist_th; I.graph_in_frame = false; ++I.cfg_epoch;
+    return OSEP_OK;
 }
 
 // ---- batched independent frames: `lanes` sub-handles, each with its own stream and arena

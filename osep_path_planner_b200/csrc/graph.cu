@@ -24,66 +24,95 @@ constexpr int GACC = GK - 1;           // accepted neighbours per vertex (rank 0
 struct GraphDevState { int n_edges; int n_mst; int overflow; int pad; };
 
 // brute-force kNN(10) by (d2, index) + RNG test restricted to the kNN list.  One thread per vertex.
-__global__ void k_graph_adj(const float4* __restrict__ pos, int G, float max_dist_th, int* __restrict__ acc, int* __restrict__ acc_cnt) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= G) return;
-    const float4 pi4 = pos[i];
-    const f3 pi{pi4.x, pi4.y, pi4.z};
-    float d[GK]; int id[GK];
+// G: vertex count known on the host, or (st != nullptr) read from the frame state of the Rosa frame that is still running on the
+// same stream: the graph of a frame is then built inside the frame's launch sequence / CUDA graph, without a host round trip
+__device__ __forceinline__ int graph_count(const FrameState* st, int G) { return st ? (st->status == 0 ? st->V : 0) : G; }
+
+// One WARP per vertex: distances to all vertices by the lanes (strided), kNN(10) by ten rounds of warp arg-min over the
+// (d2, index) order, then the relative-neighbourhood test of gskel.cpp:221-235 with one lane per candidate.
+constexpr int GADJ_WARPS = 4;
+constexpr int GADJ_ROW = 3072;          // vertices whose distance row fits the per-warp shared stage; more fall back to global scratch-free recompute
+__global__ void __launch_bounds__(GADJ_WARPS * 32)
+k_graph_adj(const float4* __restrict__ pos, int G_arg, const FrameState* __restrict__ st, float max_dist_th, int* __restrict__ acc, int* __restrict__ acc_cnt) {
+    __shared__ float s_d[GADJ_WARPS][GADJ_ROW - 32];
+    __shared__ int s_id[GADJ_WARPS][32];
+    const int G = graph_count(st, G_arg);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned FULLW = 0xffffffffu;
+    for (int i = blockIdx.x * GADJ_WARPS + wib; i < G; i += gridDim.x * GADJ_WARPS) {
+        const float4 pi4 = pos[i];
+        const f3 pi{pi4.x, pi4.y, pi4.z};
+        const bool staged = G <= GADJ_ROW - 32;
+        if (staged) for (int j = lane; j < G; j += 32) { const float4 q = pos[j]; s_d[wib][j] = dist2(pi.x, pi.y, pi.z, q.x, q.y, q.z); }
+        __syncwarp();
+        const int n_nbs = min(GK, G);
+        int my_id = -1;                              // lane r (< n_nbs) ends up holding the r-th nearest vertex
+        float last_d = -1.0f; int last_i = -1;
+        for (int r = 0; r < n_nbs; ++r) {
+            float bd = __int_as_float(0x7f800000); int bi = 0x7fffffff;
+            for (int j = lane; j < G; j += 32) {
+                float dd;
+                if (staged) dd = s_d[wib][j]; else { const float4 q = pos[j]; dd = dist2(pi.x, pi.y, pi.z, q.x, q.y, q.z); }
+                const bool after = (dd > last_d) || (dd == last_d && j > last_i);          // strictly after the previous pick in (d2, index) order
+                if (after && nb_less(dd, j, bd, bi)) { bd = dd; bi = j; }
+            }
 #pragma unroll
-    for (int t = 0; t < GK; ++t) { d[t] = __int_as_float(0x7f800000); id[t] = 0x7fffffff; }
-    for (int j = 0; j < G; ++j) {
-        const float4 q = pos[j];
-        const float dd = dist2(pi.x, pi.y, pi.z, q.x, q.y, q.z);
-        if (!nb_less(dd, j, d[GK - 1], id[GK - 1])) continue;
-#pragma unroll
-        for (int t = GK - 1; t > 0; --t) {
-            const bool lp = nb_less(dd, j, d[t - 1], id[t - 1]);
-            const bool lc = nb_less(dd, j, d[t], id[t]);
-            d[t] = lp ? d[t - 1] : (lc ? dd : d[t]);
-            id[t] = lp ? id[t - 1] : (lc ? j : id[t]);
+            for (int off = 16; off >= 1; off >>= 1) {
+                const float od = __shfl_xor_sync(FULLW, bd, off); const int oi = __shfl_xor_sync(FULLW, bi, off);
+                if (nb_less(od, oi, bd, bi)) { bd = od; bi = oi; }
+            }
+            if (lane == r) my_id = bi;
+            last_d = bd; last_i = bi;
         }
-        if (nb_less(dd, j, d[0], id[0])) { d[0] = dd; id[0] = j; }
-    }
-    const int n_nbs = min(GK, G);
-    int cnt = 0;
-#pragma unroll
-    for (int j = 1; j < GK; ++j) {
-        if (j < n_nbs) {
-            const float4 q4 = pos[id[j]];
+        // lane j in [1, n_nbs) tests candidate id_j against every other kNN member (rank 0 is skipped like gskel.cpp:217)
+        s_id[wib][lane] = my_id;
+        __syncwarp();
+        bool good = false;
+        if (lane >= 1 && lane < n_nbs && my_id >= 0 && my_id < G) {         // (non-finite positions never enter a kNN list)
+            const float4 q4 = pos[my_id];
             const f3 pn{q4.x, q4.y, q4.z};
             const float dist_to_nb = norm3(sub3(pi, pn));
-            bool good = !(dist_to_nb > max_dist_th);
-            if (good) {
-#pragma unroll
-                for (int k = 1; k < GK; ++k) {
-                    if (k < n_nbs && k != j && good) {
-                        const float4 o4 = pos[id[k]];
-                        const f3 po{o4.x, o4.y, o4.z};
-                        const float d_nb_o = norm3(sub3(pn, po));
-                        const float d_i_o = norm3(sub3(pi, po));
-                        if (d_nb_o < dist_to_nb && d_i_o < dist_to_nb) good = false;
-                    }
-                }
+            good = !(dist_to_nb > max_dist_th);
+            for (int k = 1; k < n_nbs && good; ++k) {
+                const int ok_id = s_id[wib][k];
+                if (k == lane || ok_id < 0 || ok_id >= G) continue;
+                const float4 o4 = pos[ok_id];
+                const f3 po{o4.x, o4.y, o4.z};
+                const float d_nb_o = norm3(sub3(pn, po));
+                const float d_i_o = norm3(sub3(pi, po));
+                if (d_nb_o < dist_to_nb && d_i_o < dist_to_nb) good = false;
             }
-            if (good) { acc[i * GACC + cnt] = id[j]; ++cnt; }
         }
+        const unsigned gm = __ballot_sync(FULLW, good);
+        if (good) acc[i * GACC + __popc(gm & ((1u << lane) - 1u))] = my_id;      // ascending rank = the reference's push order
+        if (lane == 0) acc_cnt[i] = __popc(gm);
+        __syncwarp();
     }
-    acc_cnt[i] = cnt;
 }
 
 // Single block.  Edge keys = (weight bits << 32 | u << 16 | v) for every accepted pair, u < v
 // (the reference's "nb <= i" skip, gskel.cpp:254); bitonic sort = the canonical (w,u,v) order
 // (C6); duplicates (i accepts nb and nb accepts i) sit next to each other and Kruskal ignores
 // the second exactly as the reference's loop does.  Kruskal: thread 0, UnionFind of gskel.hpp:43-68.
-__global__ void k_graph_mst(const float4* __restrict__ pos, int G, const int* __restrict__ acc, const int* __restrict__ acc_cnt,
-                            unsigned long long* keys, int keycap, int* parent, int* __restrict__ mst_uv, float* __restrict__ mst_w, GraphDevState* gs) {
-    __shared__ int s_n;
-    if (threadIdx.x == 0) s_n = 0;
+// Keys and the parent array live in shared memory when they fit (every single-frame skeleton does).
+constexpr int GMST_SKEYS = 4096;
+constexpr int GMST_SPARENT = 3072;
+__global__ void __launch_bounds__(1024)
+k_graph_mst(const float4* __restrict__ pos, int G_arg, const FrameState* __restrict__ st, const int* __restrict__ acc, const int* __restrict__ acc_cnt,
+            unsigned long long* gkeys, int keycap, int* gparent, int* __restrict__ mst_uv, float* __restrict__ mst_w, GraphDevState* gs) {
+    __shared__ unsigned long long skeys[GMST_SKEYS];
+    __shared__ int sparent[GMST_SPARENT];
+    __shared__ int s_n, s_tot;
+    const int G = graph_count(st, G_arg);
+    if (threadIdx.x == 0) { s_n = 0; s_tot = 0; }
     __syncthreads();
+    for (int i = threadIdx.x; i < G; i += blockDim.x) atomicAdd(&s_tot, acc_cnt[i]);
+    __syncthreads();
+    int P2t = 1; while (P2t < s_tot) P2t <<= 1;
+    unsigned long long* keys = (P2t <= GMST_SKEYS) ? skeys : gkeys;
+    int* parent = (G <= GMST_SPARENT) ? sparent : gparent;
     for (int i = threadIdx.x; i < G; i += blockDim.x) {
         const int c = acc_cnt[i];
-        const float4 a = pos[i];
         for (int t = 0; t < c; ++t) {
             const int nb = acc[i * GACC + t];
             const int u = min(i, nb), v = max(i, nb);
@@ -93,12 +122,11 @@ __global__ void k_graph_mst(const float4* __restrict__ pos, int G, const int* __
             const float w = norm3(sub3(f3{pu.x, pu.y, pu.z}, f3{pv.x, pv.y, pv.z}));
             const int slot = atomicAdd(&s_n, 1);
             if (slot < keycap) keys[slot] = ((unsigned long long)__float_as_uint(w) << 32) | ((unsigned long long)u << 16) | (unsigned long long)v;
-            (void)a;
         }
     }
     __syncthreads();
     int n = s_n;
-    if (n > keycap) { if (threadIdx.x == 0) { gs->overflow = 1; gs->n_edges = 0; gs->n_mst = 0; } return; }
+    if (n > keycap) { if (threadIdx.x == 0) { gs->overflow = 1; gs->n_edges = 0; gs->n_mst = 0; gs->pad = G; } return; }
     int P2 = 1; while (P2 < n) P2 <<= 1;
     for (int i = n + threadIdx.x; i < P2; i += blockDim.x) keys[i] = ~0ull;
     __syncthreads();
@@ -119,8 +147,11 @@ __global__ void k_graph_mst(const float4* __restrict__ pos, int G, const int* __
     __syncthreads();
     if (threadIdx.x == 0) {
         int m = 0;
+        unsigned long long prev = ~0ull;
         for (int e = 0; e < n; ++e) {
             const unsigned long long key = keys[e];
+            if (key == prev) continue;            // the same pair accepted from both ends: the reference's second unite() returns false
+            prev = key;
             const int u = (int)((key >> 16) & 0xffffu), v = (int)(key & 0xffffu);
             int rx = u; while (parent[rx] != rx) rx = parent[rx];
             { int x = u; while (parent[x] != rx) { const int nx = parent[x]; parent[x] = rx; x = nx; } }
@@ -131,8 +162,33 @@ __global__ void k_graph_mst(const float4* __restrict__ pos, int G, const int* __
             mst_uv[2 * m] = u; mst_uv[2 * m + 1] = v; mst_w[m] = __uint_as_float((unsigned)(key >> 32));
             ++m;
         }
-        gs->n_edges = n; gs->n_mst = m; gs->overflow = 0;
+        gs->n_edges = n; gs->n_mst = m; gs->overflow = 0; gs->pad = G;
     }
+}
+
+// One result block per frame: [FrameState | first Mq vertices | GraphDevState | acc_cnt[Mq] | acc[Mq*9] | mst_uv[2 Mq] | mst_w[Mq]].
+// A single block gathers it at the end of the frame, so the frame needs ONE device-to-host copy node instead of seven.
+__host__ __device__ inline size_t exp_off_skel() { return 512; }
+__host__ __device__ inline size_t exp_off_graph(int Mq) { return exp_off_skel() + sizeof(float4) * (size_t)Mq; }
+__host__ __device__ inline size_t exp_bytes(int Mq, bool with_graph) { return exp_off_graph(Mq) + (with_graph ? 16 + (size_t)Mq * (4 + 4 * GACC + 8 + 4) : 0); }
+__global__ void __launch_bounds__(1024) k_export(const FrameState* __restrict__ st, const float4* __restrict__ skel, int Mq, const GraphDevState* __restrict__ gs,
+                                                 const int* __restrict__ acc_cnt, const int* __restrict__ acc, const int* __restrict__ mst_uv, const float* __restrict__ mst_w,
+                                                 unsigned char* __restrict__ out) {
+    static_assert(sizeof(FrameState) <= 512, "FrameState outgrew its slot of the export block");
+    const int* s32 = reinterpret_cast<const int*>(st); int* o32 = reinterpret_cast<int*>(out);
+    for (int i = threadIdx.x; i < (int)(sizeof(FrameState) / 4); i += blockDim.x) o32[i] = s32[i];
+    const int V = (st->status == 0 || st->status == OSEP_STAGE_7) ? min(st->V, Mq) : 0;
+    float4* os = reinterpret_cast<float4*>(out + exp_off_skel());
+    for (int i = threadIdx.x; i < V; i += blockDim.x) os[i] = skel[i];
+    if (!gs) return;
+    int* og = reinterpret_cast<int*>(out + exp_off_graph(Mq));
+    if (threadIdx.x < 4) og[threadIdx.x] = reinterpret_cast<const int*>(gs)[threadIdx.x];
+    const int G = min(gs->pad, Mq), nm = min(gs->n_mst, Mq);
+    int* o_cnt = og + 4; int* o_acc = o_cnt + Mq; int* o_uv = o_acc + (size_t)Mq * GACC; float* o_w = reinterpret_cast<float*>(o_uv + 2 * (size_t)Mq);
+    for (int i = threadIdx.x; i < G; i += blockDim.x) o_cnt[i] = acc_cnt[i];
+    for (int i = threadIdx.x; i < G * GACC; i += blockDim.x) o_acc[i] = acc[i];
+    for (int i = threadIdx.x; i < 2 * nm; i += blockDim.x) o_uv[i] = mst_uv[i];
+    for (int i = threadIdx.x; i < nm; i += blockDim.x) o_w[i] = mst_w[i];
 }
 
 struct GraphHost {
@@ -148,6 +204,9 @@ struct GraphHost {
     std::vector<std::vector<int>> adj;      // MST adjacency in push order
     std::vector<std::vector<int>> rng;      // graph_adj adjacency in push order (duplicates kept)
     int G = 0;
+    // pinned mirrors of the in-frame graph (graph_enqueue_frame): the first `mcap` vertices' lists travel with the frame
+    // (they point into the owning Rosa handle's pinned export block)
+    int mcap = 0; GraphDevState* m_gs = nullptr; int* m_acc = nullptr; int* m_acc_cnt = nullptr; int* m_uv = nullptr; float* m_w = nullptr;
 };
 
 static void graph_free(GraphHost* g) {
@@ -186,15 +245,24 @@ static void to_csr(const std::vector<std::vector<int>>& a, std::vector<int>& off
     for (size_t i = 0; i < a.size(); ++i) { off[i + 1] = off[i] + (int)a[i].size(); idx.insert(idx.end(), a[i].begin(), a[i].end()); }
 }
 
+// host half: adjacency lists in the reference's push order, graph_decomp, CSR views
+static void graph_assemble(GraphHost* g, int G, int n_mst, const int* acc, const int* acc_cnt, const int* uv, const float* w) {
+    g->G = G;
+    g->adj.assign(G, {}); g->rng.assign(G, {});
+    g->edges.assign(uv, uv + (size_t)2 * n_mst); g->edge_w.assign(w, w + n_mst);
+    for (int i = 0; i < G; ++i) for (int t = 0; t < acc_cnt[i]; ++t) { const int nb = acc[(size_t)i * GACC + t]; g->rng[i].push_back(nb); g->rng[nb].push_back(i); }
+    for (int e = 0; e < n_mst; ++e) { const int u = uv[2 * e], v = uv[2 * e + 1]; g->adj[u].push_back(v); g->adj[v].push_back(u); }
+    decomp_host(g->adj, g->joints, g->leafs, g->type);
+    to_csr(g->adj, g->adj_off, g->adj_idx); to_csr(g->rng, g->rng_off, g->rng_idx);
+}
+
 // pos_dev: G float4 on the device (already resident).  Runs G3+G4 on the device, G5 on the host.
 static int graph_run(GraphHost* g, const float4* pos_dev, int G, float fuse_dist_th) {
-    g->G = G;
-    g->adj.assign(G, {}); g->rng.assign(G, {}); g->edges.clear(); g->edge_w.clear();
-    if (G == 0) { decomp_host(g->adj, g->joints, g->leafs, g->type); to_csr(g->adj, g->adj_off, g->adj_idx); to_csr(g->rng, g->rng_off, g->rng_idx); return OSEP_OK; }
+    if (G == 0) { graph_assemble(g, 0, 0, nullptr, nullptr, nullptr, nullptr); return OSEP_OK; }
     if (G > g->cap || G > 65535) return OSEP_ERR_CAPACITY;
     const float max_dist_th = 2.5f * fuse_dist_th;
-    k_graph_adj<<<div_up(G, 128), 128, 0, g->stream>>>(pos_dev, G, max_dist_th, g->acc, g->acc_cnt);
-    k_graph_mst<<<1, 1024, 0, g->stream>>>(pos_dev, G, g->acc, g->acc_cnt, g->keys, g->keycap, g->parent, g->mst_uv, g->mst_w, g->gs);
+    k_graph_adj<<<div_up(G, GADJ_WARPS), GADJ_WARPS * 32, 0, g->stream>>>(pos_dev, G, nullptr, max_dist_th, g->acc, g->acc_cnt);
+    k_graph_mst<<<1, 1024, 0, g->stream>>>(pos_dev, G, nullptr, g->acc, g->acc_cnt, g->keys, g->keycap, g->parent, g->mst_uv, g->mst_w, g->gs);
     GraphDevState gs;
     if (cudaMemcpyAsync(&gs, g->gs, sizeof(gs), cudaMemcpyDeviceToHost, g->stream) != cudaSuccess) return OSEP_ERR_CUDA;
     g->h_acc.resize((size_t)G * GACC); g->h_acc_cnt.resize(G);
@@ -202,16 +270,35 @@ static int graph_run(GraphHost* g, const float4* pos_dev, int G, float fuse_dist
     cudaMemcpyAsync(g->h_acc_cnt.data(), g->acc_cnt, sizeof(int) * G, cudaMemcpyDeviceToHost, g->stream);
     if (cudaStreamSynchronize(g->stream) != cudaSuccess) return OSEP_ERR_CUDA;
     if (gs.overflow) return OSEP_ERR_CAPACITY;
-    g->edges.resize((size_t)2 * gs.n_mst); g->edge_w.resize(gs.n_mst);
+    std::vector<int> uv((size_t)2 * gs.n_mst); std::vector<float> w(gs.n_mst);
     if (gs.n_mst) {
-        cudaMemcpy(g->edges.data(), g->mst_uv, sizeof(int) * 2 * gs.n_mst, cudaMemcpyDeviceToHost);
-        cudaMemcpy(g->edge_w.data(), g->mst_w, sizeof(float) * gs.n_mst, cudaMemcpyDeviceToHost);
+        cudaMemcpy(uv.data(), g->mst_uv, sizeof(int) * 2 * gs.n_mst, cudaMemcpyDeviceToHost);
+        cudaMemcpy(w.data(), g->mst_w, sizeof(float) * gs.n_mst, cudaMemcpyDeviceToHost);
     }
-    // adjacency lists in the reference's push order
-    for (int i = 0; i < G; ++i) for (int t = 0; t < g->h_acc_cnt[i]; ++t) { const int nb = g->h_acc[(size_t)i * GACC + t]; g->rng[i].push_back(nb); g->rng[nb].push_back(i); }
-    for (int e = 0; e < gs.n_mst; ++e) { const int u = g->edges[2 * e], v = g->edges[2 * e + 1]; g->adj[u].push_back(v); g->adj[v].push_back(u); }
-    decomp_host(g->adj, g->joints, g->leafs, g->type);
-    to_csr(g->adj, g->adj_off, g->adj_idx); to_csr(g->rng, g->rng_off, g->rng_idx);
+    graph_assemble(g, G, gs.n_mst, g->h_acc.data(), g->h_acc_cnt.data(), uv.data(), w.data());
+    return OSEP_OK;
+}
+
+// In-frame variant: enqueue G3 + G4 behind the Rosa stages of the frame running on `s` (vertex count read from the frame
+// state on the device) and copy the first `mcap` vertices' lists to pinned mirrors -- all capturable, no host round trip.
+static int graph_enqueue_frame(GraphHost* g, const float4* pos_dev, const FrameState* st, float fuse_dist_th, cudaStream_t s) {
+    const float max_dist_th = 2.5f * fuse_dist_th;
+    k_graph_adj<<<148 * 2, GADJ_WARPS * 32, 0, s>>>(pos_dev, 0, st, max_dist_th, g->acc, g->acc_cnt);
+    k_graph_mst<<<1, 512, 0, s>>>(pos_dev, 0, st, g->acc, g->acc_cnt, g->keys, g->keycap, g->parent, g->mst_uv, g->mst_w, g->gs);
+    return OSEP_OK;
+}
+// after the frame's stream has been synchronised: host half from the mirrors (graphs larger than the mirrors are fetched on demand)
+static int graph_collect_frame(GraphHost* g) {
+    const GraphDevState gs = *g->m_gs;
+    if (gs.overflow) return OSEP_ERR_CAPACITY;
+    const int G = gs.pad;
+    if (G <= g->mcap) { graph_assemble(g, G, gs.n_mst, g->m_acc, g->m_acc_cnt, g->m_uv, g->m_w); return OSEP_OK; }
+    g->h_acc.resize((size_t)G * GACC); g->h_acc_cnt.resize(G);
+    std::vector<int> uv((size_t)2 * gs.n_mst); std::vector<float> w(gs.n_mst);
+    if (cudaMemcpy(g->h_acc.data(), g->acc, sizeof(int) * G * GACC, cudaMemcpyDeviceToHost) != cudaSuccess) return OSEP_ERR_CUDA;
+    cudaMemcpy(g->h_acc_cnt.data(), g->acc_cnt, sizeof(int) * G, cudaMemcpyDeviceToHost);
+    if (gs.n_mst) { cudaMemcpy(uv.data(), g->mst_uv, sizeof(int) * 2 * gs.n_mst, cudaMemcpyDeviceToHost); cudaMemcpy(w.data(), g->mst_w, sizeof(float) * gs.n_mst, cudaMemcpyDeviceToHost); }
+    graph_assemble(g, G, gs.n_mst, g->h_acc.data(), g->h_acc_cnt.data(), uv.data(), w.data());
     return OSEP_OK;
 }
 
@@ -512,6 +599,24 @@ GraphHost* graph_create(int cap, int device, cudaStream_t stream) { return graph
 void graph_destroy(GraphHost* g) { graph_free(g); }
 int graph_run_device(GraphHost* g, const float4* pos_dev, int G, float fuse_dist_th, osep_graph_view* out) {
     const int rc = graph_run(g, pos_dev, G, fuse_dist_th);
+    if (rc == OSEP_OK && out) graph_view(g, out);
+    return rc;
+}
+int graph_enqueue_in_frame(GraphHost* g, const float4* pos_dev, const FrameState* st, float fuse_dist_th, cudaStream_t s) { return graph_enqueue_frame(g, pos_dev, st, fuse_dist_th, s); }
+// gather the frame's results into the export block (g == nullptr: no graph part); returns the bytes the host copy must move
+size_t frame_export_enqueue(GraphHost* g, const FrameState* st, const float4* skel, int Mq, unsigned char* exp_dev, cudaStream_t s) {
+    if (g) k_export<<<1, 1024, 0, s>>>(st, skel, Mq, g->gs, g->acc_cnt, g->acc, g->mst_uv, g->mst_w, exp_dev);
+    else k_export<<<1, 1024, 0, s>>>(st, skel, Mq, nullptr, nullptr, nullptr, nullptr, nullptr, exp_dev);
+    return exp_bytes(Mq, g != nullptr);
+}
+size_t frame_export_bytes(int Mq) { return exp_bytes(Mq, true); }
+void graph_set_mirrors(GraphHost* g, unsigned char* exp_host, int Mq) {
+    int* og = reinterpret_cast<int*>(exp_host + exp_off_graph(Mq));
+    g->mcap = Mq; g->m_gs = reinterpret_cast<GraphDevState*>(og); g->m_acc_cnt = og + 4; g->m_acc = g->m_acc_cnt + Mq;
+    g->m_uv = g->m_acc + (size_t)Mq * GACC; g->m_w = reinterpret_cast<float*>(g->m_uv + 2 * (size_t)Mq);
+}
+int graph_collect_in_frame(GraphHost* g, osep_graph_view* out) {
+    const int rc = graph_collect_frame(g);
     if (rc == OSEP_OK && out) graph_view(g, out);
     return rc;
 }

@@ -16,6 +16,7 @@ struct RosaDev {
     int knn = 0, nbk = 0;  // ne_knn, nb_knn
 
     FrameState* st = nullptr;
+    unsigned char* exp = nullptr;      // per-frame result block gathered by k_export (graph.cu)
     FrameParams* prm = nullptr;        // device copy of the per-frame launch parameters (osep_common.cuh)
     // N-scale
     float* in = nullptr;               // staged input (host-buffer path), Ncap * 4 floats
@@ -88,13 +89,17 @@ struct osep_rosa_impl {
     bool use_graphs = true;            // OSEP_NO_GRAPH=1 disables; also cleared when capture is not supported
     int cfg_epoch = 0;                 // bumped by every setter that changes what a frame launches
     // host mirrors
-    FrameState* st_host = nullptr;     // pinned
+    unsigned char* exp_host = nullptr; // pinned result block: st_host and skel_host point into it
+    FrameState* st_host = nullptr;
     FrameParams* prm_host = nullptr;   // pinned; source of the copy node at the head of a frame
-    float4* skel_host = nullptr;       // pinned, Mcap
+    float4* skel_host = nullptr;       // first Mcap/4 vertices
+    std::vector<float4> skel_big;      // frames with more vertices than the export block carries
     std::vector<float> vertices_colmajor;
     int last_n = 0;
     // graph outputs (osep_rosa_graph)
     struct GraphHost* graph = nullptr;
+    bool auto_graph = false; float graph_fuse = 3.0f;   // osep_rosa_set_graph: graph_adj + mst run inside every frame
+    bool graph_in_frame = false;                       // the last enqueued frame carried its graph
     // batch
     std::vector<osep_rosa_impl*> lanes;
     std::vector<std::vector<float>> batch_vertices;

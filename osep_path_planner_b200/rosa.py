@@ -186,6 +186,12 @@ class Rosa:
             out.append(v)
         return list(res), out
 
+    def set_graph(self, enable=True, fuse_dist_th=3.0):
+        """build the skeleton graph inside every frame (osep_rosa_set_graph); graph(fuse_dist_th) then costs no device work"""
+        rc = self._L.osep_rosa_set_graph(self._h, 1 if enable else 0, fuse_dist_th)
+        if rc != 0:
+            raise OsepError("osep_rosa_set_graph failed (%d): %s" % (rc, _lib.last_error()))
+
     def graph(self, fuse_dist_th=3.0):
         """graph_adj + mst + graph_decomp (gskel.cpp:201-281,539-567) of the last frame's vertices."""
         v = GraphView()

@@ -218,6 +218,26 @@ def test_frame_to_graph(mods):
     r.close()
 
 
+def test_in_frame_graph_equals_separate_graph_call(mods):
+    """osep_rosa_set_graph: graph_adj + mst inside the frame's launch sequence (vertex count read on the device) give the same
+    views as the separate osep_rosa_graph call and as the oracle, across frames with different vertex counts, graph replays
+    included; a different fuse_dist_th falls back to the separate call."""
+    osep, po, fx = mods
+    r = osep.Rosa(capacity_points=40000)
+    r.set_graph(True, 3.0)
+    for k, P in enumerate([fx.cylinder(12000, seed=2), fx.turbine(40000, seed=3), fx.turbine(25000, seed=4), fx.cylinder(9000, seed=5), fx.turbine(33000, seed=6)]):
+        o = po.RosaOracle(); assert o.run(P)
+        r.set_input(P); assert r.rosa_run()
+        g = r.graph(3.0)
+        go = po.GraphOracle(o.tap("skelver"), 3.0)
+        assert g["n_vertices"] == len(o.tap("skelver"))
+        for key, tap in [("edges", "mst_edges"), ("adj_idx", "adj_idx"), ("rng_idx", "rng_idx"), ("type", "type"), ("joints", "joints"), ("leafs", "leafs")]:
+            assert_bit_equal(np.asarray(g[key]).reshape(-1), go.tap(tap), "%s frame %d" % (key, k))
+        g2 = r.graph(2.0); go2 = po.GraphOracle(o.tap("skelver"), 2.0)
+        assert_bit_equal(np.asarray(g2["edges"]).reshape(-1), go2.tap("mst_edges"), "fuse 2.0 frame %d" % k)
+    r.close()
+
+
 def test_gskel_stateful_replay(mods):
     """Stream of frames (BASELINE configs[2] in miniature): Rosa vertices -> analytic sensor->odom
     transform -> GSkel::gskel_run, oracle and CUDA library side by side, compared every tick."""
