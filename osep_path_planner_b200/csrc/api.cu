@@ -59,7 +59,10 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
     { const char* e = getenv("OSEP_KNN_CTAS"); if (e && atoi(e) > 0) h->knn_ctas_per_sm = atoi(e); }
     { const char* e = getenv("OSEP_DROSA_UNFUSED"); if (e && e[0] == '1') h->fused = false;
       const char* e3 = getenv("OSEP_NO_GRAPH"); if (e3 && e3[0] == '1') h->use_graphs = false;
-      const char* e4 = getenv("OSEP_FUSED_DETAIL"); if (e4 && e4[0] == '1') h->fused_detail = true;
+      const char* e4 = getenv("OSEP_FUSED_DETAIL"); if (e4 && e4[0] == '1') { h->fused_detail = true; CK(dalloc(&d.fused_tl, M * 9 * 16)); CK(cudaMemset(d.fused_tl, 0, M * 9 * 16 * 8)); }
+      const char* e6 = getenv("OSEP_FUSED_GRID"); if (e6 && atoi(e6) > 0) h->fused_grid = atoi(e6);
+      const char* e7 = getenv("OSEP_HOT_CTAS"); if (e7 && atoi(e7) > 0) h->hot_ctas = atoi(e7);
+      const char* e5 = getenv("OSEP_SPIN_NS"); if (e5 && atoi(e5) >= 0) h->spin_ns = atoi(e5);
       const char* e2 = getenv("OSEP_DROSA_LAG"); if (e2 && atoi(e2) >= 0) h->sched_lag = atoi(e2);
       int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device); if (!coop) h->fused = false; }
     { int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device)); h->sms = sms > 0 ? sms : 148; } CK(dalloc(&d.surf, M * (size_t)std::max(d.nbk, 1)));
@@ -87,7 +90,7 @@ static void rosa_free(osep_rosa_impl* h) {
     RosaDev& d = h->d;
     void* ptrs[] = {d.st, d.prm, d.in, d.in_raw, d.P, d.filt_idx, d.blk_cnt, d.gtab, d.g_start, d.units, d.slow_list, d.over_list, d.p_slot, d.Pc, d.Nrm, d.knn_full, d.vtab, d.vkeys, d.vid,
                     d.vox_cnt, d.vox_fill, d.rk0, d.rk1, d.rv0, d.rv1, d.pts, d.nrms, d.pset, d.pset2, d.vset, d.vnew, d.vvar, d.surf,
-                    d.simi_off, d.simi_idx, d.simi_bits, d.nraw, d.vnd, d.vset_it, d.vnew_it, d.fused_flags, d.fused_dbg, d.level, d.level_off, d.level_pts, d.good, d.centers, d.good_rank, d.poor_idx, d.active_size,
+                    d.simi_off, d.simi_idx, d.simi_bits, d.nraw, d.vnd, d.vset_it, d.vnew_it, d.fused_flags, d.fused_dbg, d.fused_tl, d.level, d.level_off, d.level_pts, d.good, d.centers, d.good_rank, d.poor_idx, d.active_size,
                     d.pcloud, d.adj_bits, d.seeds, d.corresp, d.skel, d.skel2, d.skel_sampled, d.vtmp, d.vs_off, d.vs_idx, d.vset_iters};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->graph) graph_destroy(h->graph);
@@ -417,6 +420,7 @@ long osep_rosa_get(osep_rosa* h, const char* name, void* dst, long cap) {
         }
         return SM_COUNT;
     }
+    if (nm == "fused_tl") { if (!d.fused_tl) return 0; return tap_copy(dst, cap, d.fused_tl, (size_t)d.Mcap * 9 * 16, 8) * 2; }
     if (nm == "fused_dbg") return tap_copy(dst, cap, d.fused_dbg, 64, 8) * 2;     // 64 int64 = 128 int32 words
     if (nm == "knn_stats") { if (dst && cap >= 12) { ((int*)dst)[0] = s.n_units; ((int*)dst)[1] = s.n_slow; ((int*)dst)[2] = s.n_over; } return 3; }
     if (nm == "launches") { if (dst && cap >= 4) *(int*)dst = (int)I.n_launches; return 1; }

@@ -19,8 +19,11 @@
 namespace osep {
 
 constexpr unsigned FULLM = 0xffffffffu;
-constexpr int SEED_WARPS = 8;
-constexpr int SEED_SMEM_BUDGET = 200 * 1024;
+#ifndef OSEP_SEED_WARPS
+#define OSEP_SEED_WARPS 8
+#endif
+constexpr int SEED_WARPS = OSEP_SEED_WARPS;
+constexpr int SEED_SMEM_BUDGET = 226 * 1024;
 constexpr int GS_THREADS = 256;
 constexpr int GS_SMEM_BUDGET = 200 * 1024;
 constexpr int MAX_FUSED_ITERS = 8;
@@ -54,15 +57,55 @@ __global__ void k_normal_prep(const FrameState* __restrict__ st, const float4* _
     vnd[i] = make_float4(u.x, u.y, u.z, il_f);
 }
 
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+
+// shared-memory access by 32-bit shared-window address: LDS/STS instead of generic loads, 32-bit address arithmetic
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds_f4(unsigned a) { float4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 lds_u4(unsigned a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+__device__ __forceinline__ unsigned lds_u16v(unsigned a) { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_u16v(unsigned a, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "h"((unsigned short)v) : "memory"); }
+
+// What a seed warp reads.  Points, raw normals and hoisted unit normals are always staged (48 bytes per point: 147 KB at the
+// arena's 3072 points); the bit matrix is staged when it fits, with its rows padded to a multiple of 4 words so that a
+// row is read with 16-byte loads, plus one member list per warp for the breadth-first search.
 struct SeedCtx {
-    const float4* pts; const float4* nraw; const float4* vnd;
-    const unsigned* bits; int bstride;
+    unsigned pts_s, nraw_s, vnd_s;      // shared-window byte addresses of float4[M]
+    unsigned bits_s; int Wp;            // staged bit matrix (0 = not staged), row stride in words
+    unsigned list_s;                    // this warp's member list, ushort[M]
+    const unsigned* bits; int bstride;  // the matrix in global memory (dense rows), used when it is not staged
     int M, Wn; float leaf;
 };
+__device__ __forceinline__ float4 seed_pt(const SeedCtx& c, int i) { return lds_f4(c.pts_s + 16u * (unsigned)i); }
+__device__ __forceinline__ float4 seed_nraw(const SeedCtx& c, int i) { return lds_f4(c.nraw_s + 16u * (unsigned)i); }
+__device__ __forceinline__ float4 seed_vnd(const SeedCtx& c, int i) { return lds_f4(c.vnd_s + 16u * (unsigned)i); }
+
+__host__ __device__ __forceinline__ size_t seed_small_bytes(int M) { return (size_t)3 * 16 * M; }
+__host__ __device__ __forceinline__ size_t seed_mat_bytes(int M) { const int Wp = (((M + 31) >> 5) + 3) & ~3; return (size_t)4 * M * Wp + (size_t)SEED_WARPS * (((size_t)2 * M + 15) & ~(size_t)15); }
+
+// stage the per-frame read-only data of the seed warps; every thread of the CTA calls it (ends with __syncthreads)
+__device__ __forceinline__ SeedCtx seed_stage(uint4* smem, const float4* __restrict__ pts, const float4* __restrict__ nraw, const float4* __restrict__ vnd,
+                                              const unsigned* __restrict__ bits, int M, float leaf) {
+    const int Wn = (M + 31) >> 5, Wp = (Wn + 3) & ~3;
+    float4* s_pts = reinterpret_cast<float4*>(smem);
+    float4* s_nraw = s_pts + M; float4* s_vnd = s_nraw + M;
+    unsigned* s_bits = reinterpret_cast<unsigned*>(s_vnd + M);
+    const bool mat_in = seed_small_bytes(M) + seed_mat_bytes(M) <= (size_t)SEED_SMEM_BUDGET;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) { s_pts[i] = pts[i]; s_nraw[i] = nraw[i]; s_vnd[i] = vnd[i]; }
+    if (mat_in) stage_bit_rows(s_bits, bits, M, Wp);          // rows are padded to Wp words in global memory too (k_simi)
+    __syncthreads();
+    SeedCtx c;
+    c.pts_s = smem_addr(s_pts); c.nraw_s = smem_addr(s_nraw); c.vnd_s = smem_addr(s_vnd);
+    c.bits_s = mat_in ? smem_addr(s_bits) : 0u; c.Wp = Wp;
+    c.list_s = smem_addr(s_bits + (size_t)M * Wp) + (unsigned)(threadIdx.x >> 5) * (unsigned)((2 * M + 15) & ~15);
+    c.bits = bits; c.bstride = Wp;
+    c.M = M; c.Wn = Wn; c.leaf = leaf;
+    return c;
+}
 
 // R14 compute_active_samples: returns |active|; vis[k] = this lane's word (lane + 32 k) of the member set
 template <int WPL>
-__device__ __forceinline__ int active_set(const SeedCtx& c, int seed, const f3& p, const f3& n, unsigned (&vis)[WPL]) {
+__device__ __forceinline__ int active_set(const SeedCtx& c, int seed, const f3& p, const f3& n, unsigned (&vis)[WPL], long long* tl = nullptr) {
     const int lane = threadIdx.x & 31;
     unsigned slab[WPL], front[WPL];
 #pragma unroll
@@ -71,7 +114,7 @@ __device__ __forceinline__ int active_set(const SeedCtx& c, int seed, const f3& 
         const int i = t * 32 + lane;
         bool in = false;
         if (i < c.M) {
-            const float4 q = c.pts[i];
+            const float4 q = seed_pt(c, i);
             const float d = n.x * (p.x - q.x) + n.y * (p.y - q.y) + n.z * (p.z - q.z);      // rosa.cpp:660
             in = fabsf(d) < c.leaf;
         }
@@ -79,6 +122,7 @@ __device__ __forceinline__ int active_set(const SeedCtx& c, int seed, const f3& 
 #pragma unroll
         for (int k = 0; k < WPL; ++k) if (t == lane + 32 * k) slab[k] = word;
     }
+    if (tl && lane == 0) tl[7] = gtime();
     const int sw = seed >> 5; const unsigned sbit = 1u << (seed & 31);
     bool seed_in = false;
 #pragma unroll
@@ -88,29 +132,83 @@ __device__ __forceinline__ int active_set(const SeedCtx& c, int seed, const f3& 
         seed_in |= (vis[k] != 0u);
     }
     if (!__any_sync(FULLM, seed_in)) return 0;                                              // rosa.cpp:664
-    while (true) {
-        unsigned acc[WPL];
-#pragma unroll
-        for (int k = 0; k < WPL; ++k) acc[k] = 0u;
-#pragma unroll
-        for (int k = 0; k < WPL; ++k) {
-            unsigned nz = __ballot_sync(FULLM, front[k] != 0u);
-            while (nz) {
-                const int sl = __ffs(nz) - 1; nz &= nz - 1;
-                unsigned fw = __shfl_sync(FULLM, front[k], sl);
-                const int nbase = (sl + 32 * k) * 32;
-                while (fw) {
-                    const int b = __ffs(fw) - 1; fw &= fw - 1;
-                    const unsigned* row = c.bits + (size_t)(nbase + b) * c.bstride;
-#pragma unroll
-                    for (int kk = 0; kk < WPL; ++kk) { const int w = lane + 32 * kk; if (w < c.Wn) acc[kk] |= row[w]; }
+    if (c.bits_s) {
+        // staged matrix: the frontier is listed in shared memory (warp scan of the per-lane popcounts), then LPR lanes
+        // read one member's row with 16-byte loads -- 32 / LPR independent rows per round of loads instead of one
+        // dependent ffs -> address -> load -> or chain per member
+        constexpr int LPR = 8 * WPL;                      // lanes per row: 4 * LPR words >= 32 * WPL >= Wn
+        const int g = lane / LPR, ch = lane % LPR;
+        const bool chv = 4 * ch < c.Wp;
+        const unsigned rowb = c.bits_s + 16u * (unsigned)ch;
+        const unsigned rstride = 4u * (unsigned)c.Wp;
+        int f = 1;                                        // members in the list
+        if (seed_in) sts_u16v(c.list_s, (unsigned)seed);
+        __syncwarp();
+        while (true) {
+            uint4 a4 = make_uint4(0u, 0u, 0u, 0u);
+            if (chv) {
+#pragma unroll 4
+                for (int i = g; i < f; i += 32 / LPR) {
+                    const unsigned mb = lds_u16v(c.list_s + 2u * (unsigned)i);
+                    const uint4 r4 = lds_u4(rowb + mb * rstride);
+                    a4.x |= r4.x; a4.y |= r4.y; a4.z |= r4.z; a4.w |= r4.w;
                 }
             }
-        }
-        bool any = false;
 #pragma unroll
-        for (int k = 0; k < WPL; ++k) { const unsigned nw = acc[k] & slab[k] & ~vis[k]; vis[k] |= nw; front[k] = nw; any |= (nw != 0u); }
-        if (!__any_sync(FULLM, any)) break;
+            for (int off = LPR; off < 32; off <<= 1) {
+                a4.x |= __shfl_xor_sync(FULLM, a4.x, off); a4.y |= __shfl_xor_sync(FULLM, a4.y, off);
+                a4.z |= __shfl_xor_sync(FULLM, a4.z, off); a4.w |= __shfl_xor_sync(FULLM, a4.w, off);
+            }
+            bool any = false; int cnt = 0;
+#pragma unroll
+            for (int k = 0; k < WPL; ++k) {
+                const int src = (lane + 32 * k) >> 2;     // lane `src` of group 0 holds chunk src = words 4 src .. 4 src + 3
+                const unsigned x = __shfl_sync(FULLM, a4.x, src), y = __shfl_sync(FULLM, a4.y, src);
+                const unsigned z = __shfl_sync(FULLM, a4.z, src), w = __shfl_sync(FULLM, a4.w, src);
+                const unsigned acc = (lane & 2) ? ((lane & 1) ? w : z) : ((lane & 1) ? y : x);
+                const unsigned nw = acc & slab[k] & ~vis[k];
+                vis[k] |= nw; front[k] = nw; any |= (nw != 0u); cnt += __popc(nw);
+            }
+            if (!__any_sync(FULLM, any)) break;
+            // list the new frontier
+            int incl = cnt;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(FULLM, incl, off); if (lane >= off) incl += t; }
+            f = __shfl_sync(FULLM, incl, 31);
+            unsigned pos = c.list_s + 2u * (unsigned)(incl - cnt);
+#pragma unroll
+            for (int k = 0; k < WPL; ++k) {
+                unsigned b = front[k];
+                const unsigned base = (unsigned)(lane + 32 * k) * 32u;
+                while (b) { sts_u16v(pos, base + (unsigned)(__ffs(b) - 1)); b &= b - 1; pos += 2u; }
+            }
+            __syncwarp();
+        }
+    } else {
+        while (true) {
+            unsigned acc[WPL];
+#pragma unroll
+            for (int k = 0; k < WPL; ++k) acc[k] = 0u;
+#pragma unroll
+            for (int k = 0; k < WPL; ++k) {
+                unsigned nz = __ballot_sync(FULLM, front[k] != 0u);
+                while (nz) {
+                    const int sl = __ffs(nz) - 1; nz &= nz - 1;
+                    unsigned fw = __shfl_sync(FULLM, front[k], sl);
+                    const int nbase = (sl + 32 * k) * 32;
+                    while (fw) {
+                        const int b = __ffs(fw) - 1; fw &= fw - 1;
+                        const unsigned* row = c.bits + (size_t)(nbase + b) * c.bstride;
+#pragma unroll
+                        for (int kk = 0; kk < WPL; ++kk) { const int w = lane + 32 * kk; if (w < c.Wn) acc[kk] |= __ldg(row + w); }
+                    }
+                }
+            }
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < WPL; ++k) { const unsigned nw = acc[k] & slab[k] & ~vis[k]; vis[k] |= nw; front[k] = nw; any |= (nw != 0u); }
+            if (!__any_sync(FULLM, any)) break;
+        }
     }
     int m = 0;
 #pragma unroll
@@ -133,7 +231,7 @@ template <int WPL> __device__ __forceinline__ void normal_cov_sums(const SeedCtx
 #pragma unroll
     for (int k = 0; k < 9; ++k) s[k] = 0.0f;
     for_members<WPL>(vis, [&](int i) {
-        const float4 u = c.vnd[i];
+        const float4 u = seed_vnd(c, i);
         s[0] += u.x; s[1] += u.y; s[2] += u.z;
         s[3] += u.x * u.x; s[4] += u.y * u.x; s[5] += u.y * u.y;
         s[6] += u.z * u.x; s[7] += u.z * u.y; s[8] += u.z * u.z;
@@ -158,6 +256,7 @@ struct SeedOut {
     int pack_w;                                                   // fused path: weight travels in vnew[].w, no vvar array
     float4* pset; int* good; float4* centers; int* active_size;   // position pass
     float max_proj_range;
+    long long* tl = nullptr;                                      // detail mode: stamps of the current task (slots 5, 6)
 };
 
 // MODE 0: R15-R17 Jacobi half of one drosa iteration (rosa.cpp:275-292)
@@ -166,7 +265,8 @@ template <int MODE, int WPL>
 __device__ __forceinline__ void seed_body(const SeedCtx& c, int seed, const f3& p, const f3& n, const SeedOut& o) {
     const int lane = threadIdx.x & 31;
     unsigned vis[WPL];
-    const int m = active_set<WPL>(c, seed, p, n, vis);
+    const int m = active_set<WPL>(c, seed, p, n, vis, MODE == 0 ? o.tl : nullptr);
+    if (MODE == 0 && o.tl && lane == 0) { o.tl[5] = gtime(); o.tl[8] = clock64(); }
     if (MODE == 0) {
         if (m == 0) {                                     // vvar = 0 (rosa.cpp:285-287) -> 1/(0^4+eps); vnew row kept
             if (lane == 0) {
@@ -180,10 +280,11 @@ __device__ __forceinline__ void seed_body(const SeedCtx& c, int seed, const f3& 
         const float inv_m = 1.0f / (float)m;
         const Eig3 E = normal_cov_eig(s, inv_m);
         const f3 sym = eig_col(E, 0);                                                   // compute_symmetrynormal (rosa.cpp:685-706)
+        if (o.tl && lane == 0) { o.tl[6] = gtime() + (sym.x == 123.0f ? 1 : 0); o.tl[9] = clock64(); }
         float a2[2] = {0.0f, 0.0f};                                                     // symmnormal_variance (rosa.cpp:708-732)
         for_members<WPL>(vis, [&](int i) {
-            const float4 v = c.nraw[i];
-            const float il = c.vnd[i].w;
+            const float4 v = seed_nraw(c, i);
+            const float il = seed_vnd(c, i).w;
             const float a = dot3(f3{v.x, v.y, v.z}, sym) * il;
             a2[0] += a; a2[1] += a * a;
         });
@@ -209,7 +310,7 @@ __device__ __forceinline__ void seed_body(const SeedCtx& c, int seed, const f3& 
         if (planar_score < 0.1f) {                                                      // rosa.cpp:334-349
             float t[6] = {0, 0, 0, 0, 0, 0};
             for_members<WPL>(vis, [&](int i) {
-                const float4 q = c.pts[i]; const float4 v = c.nraw[i]; const float il = c.vnd[i].w;
+                const float4 q = seed_pt(c, i); const float4 v = seed_nraw(c, i); const float il = seed_vnd(c, i).w;
                 t[0] += q.x; t[1] += q.y; t[2] += q.z; t[3] += v.x * il; t[4] += v.y * il; t[5] += v.z * il;
             });
             bfly<6>(t);
@@ -221,7 +322,7 @@ __device__ __forceinline__ void seed_body(const SeedCtx& c, int seed, const f3& 
 #pragma unroll
             for (int k = 0; k < 12; ++k) t[k] = 0.0f;
             for_members<WPL>(vis, [&](int i) {
-                const float4 q = c.pts[i]; const float4 v = c.nraw[i];
+                const float4 q = seed_pt(c, i); const float4 v = seed_nraw(c, i);
                 const f3 vn{v.x * v.w, v.y * v.w, v.z * v.w};
                 const float P00 = 1.0f - vn.x * vn.x, P01 = 0.0f - vn.x * vn.y, P02 = 0.0f - vn.x * vn.z;
                 const float P10 = 0.0f - vn.y * vn.x, P11 = 1.0f - vn.y * vn.y, P12 = 0.0f - vn.y * vn.z;
@@ -255,22 +356,8 @@ k_drosa_seed(FrameState* st, const float4* __restrict__ pts, const float4* __res
     const int M = st->M;
     if ((int)blockIdx.x >= M) return;
     const int Wn = (M + 31) >> 5;
-    const size_t small_bytes = (size_t)3 * 16 * M;
-    const bool small_in = small_bytes <= (size_t)SEED_SMEM_BUDGET;
-    const bool mat_in = small_in && (small_bytes + (size_t)4 * M * Wn <= (size_t)SEED_SMEM_BUDGET);
-    float4* s_pts = reinterpret_cast<float4*>(seed_smem);
-    float4* s_nraw = s_pts + M; float4* s_vnd = s_nraw + M;
-    unsigned* s_bits = reinterpret_cast<unsigned*>(s_vnd + M);
-    if (small_in) {
-        for (int i = threadIdx.x; i < M; i += blockDim.x) { s_pts[i] = pts[i]; s_nraw[i] = nraw[i]; s_vnd[i] = vnd[i]; }
-    }
-    if (mat_in) stage_bit_rows(s_bits, bits, M, Wn);
-    __syncthreads();
-    SeedCtx c;
-    c.pts = small_in ? s_pts : pts; c.nraw = small_in ? s_nraw : nraw; c.vnd = small_in ? s_vnd : vnd;
-    c.bits = mat_in ? s_bits : bits; c.bstride = Wn;          // the matrix is dense (row stride Wn) in global memory too
     (void)W;
-    c.M = M; c.Wn = Wn; c.leaf = st->leaf_size;
+    const SeedCtx c = seed_stage(seed_smem, pts, nraw, vnd, bits, M, st->leaf_size);
     const int wib = threadIdx.x >> 5;
     for (int seed = blockIdx.x + gridDim.x * wib; seed < M; seed += gridDim.x * SEED_WARPS) {
         const f3 p = ld3f(pset, seed), n = ld3f(vset, seed);
@@ -340,21 +427,32 @@ __device__ __forceinline__ void sched_sort(int M, const int* key, int* hist, int
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(1024) k_gs_schedule(FrameState* st, const int* __restrict__ surf, int nbk, int* __restrict__ level,
-                                                      int* __restrict__ level_off, int* __restrict__ level_pts) {
-    extern __shared__ int lsm[];          // ta[M] | hist[SCHED_BINS] | surf as ushort [M*nbk]
+template <int NBK>
+__device__ __forceinline__ void chain_schedule_pass(int w, int M, int nbk, int k_eff, const unsigned short* ssurf,
+                                                    unsigned short* sT, volatile int* prog, volatile int* tmax, int lag);
+
+// Dependency levels of the smoothing pass (T_0 of the fused kernel's schedule model, see chain_schedule_pass) and the points
+// sorted by level, on the side stream next to the similarity stage: one warp walks the index chunks, the block sorts.
+__global__ void __launch_bounds__(256) k_gs_schedule(FrameState* st, const int* __restrict__ surf, int nbk, int* __restrict__ level,
+                                                     int* __restrict__ level_off, int* __restrict__ level_pts) {
+    extern __shared__ int lsm[];          // lvl[M] | hist[SCHED_BINS] | surf as ushort [M*nbk] | T_0 as ushort [M]
     __shared__ int s_tot;
+    __shared__ int s_prog[2];
     if (st->status != 0) return;
     const int M = st->M;
     int* ta = lsm; int* hist = ta + M;
     unsigned short* ss = reinterpret_cast<unsigned short*>(hist + SCHED_BINS);
+    unsigned short* sT = ss + (size_t)M * nbk;
     const int k_eff = min(nbk, M);
-    const bool fast10 = (nbk == 10 && k_eff == 10);
-    for (int p = threadIdx.x; p < M; p += blockDim.x) ta[p] = 1;
-    for (int i = threadIdx.x; i < M * nbk; i += blockDim.x) { const int j = surf[i]; ss[i] = (unsigned short)(j < 0 ? 0xffff : j); }
+    for (int i = threadIdx.x; i < M * nbk; i += blockDim.x) { const int j = surf[i]; ss[i] = (unsigned short)(j < 0 ? 0 : j); }
     __syncthreads();
-    if (fast10) sched_relax<10>(M, nbk, k_eff, ss, ta, nullptr); else sched_relax<0>(M, nbk, k_eff, ss, ta, nullptr);
-    for (int p = threadIdx.x; p < M; p += blockDim.x) level[p] = ta[p];
+    if (threadIdx.x < 32) {
+        if (nbk == 10 && k_eff == 10) chain_schedule_pass<10>(0, M, nbk, k_eff, ss, sT, s_prog, nullptr, 0);
+        else chain_schedule_pass<0>(0, M, nbk, k_eff, ss, sT, s_prog, nullptr, 0);
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < M; p += blockDim.x) { ta[p] = sT[p]; level[p] = sT[p]; }
+    __syncthreads();
     sched_sort(M, ta, hist, &s_tot, level_pts, level_off, &st->n_levels);
 }
 
@@ -453,58 +551,63 @@ struct FusedArgs {
     const int* surf; int nbk; int dbg_detail; int lag;
     int* good; float4* centers; int* active_size; float max_proj_range;
     long long* dbg;        // per chain: [t_begin, t_first_step, t_end, steps, spins, points] (globaltimer ns)
+    const int* level; const int* level_pts;   // T_0 = dependency level of every point and the points sorted by it (k_gs_schedule, side stream)
+    int hot_ctas;          // worker CTAs that serve the ready queue after the iteration-0 tasks
+    unsigned spin_ns;      // idle workers sleep this long between two polls of their queue slot (0 = busy poll)
+    long long* tl;         // detail mode: per (it, p) 8 globaltimer stamps [G solved, task published, worker start, O flag, O staged] (tools/fused_dbg.py)
 };
 
-__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ int ld_vol(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 __device__ __forceinline__ void st_vol(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
 
 __device__ __forceinline__ void fused_worker(const FusedArgs& a, uint4* smem, int M) {
     const int Wn = (M + 31) >> 5;
-    const size_t small_bytes = (size_t)3 * 16 * M;
-    const bool small_in = small_bytes <= (size_t)SEED_SMEM_BUDGET;
-    const bool mat_in = small_in && (small_bytes + (size_t)4 * M * Wn <= (size_t)SEED_SMEM_BUDGET);
-    float4* s_pts = reinterpret_cast<float4*>(smem);
-    float4* s_nraw = s_pts + M; float4* s_vnd = s_nraw + M;
-    unsigned* s_bits = reinterpret_cast<unsigned*>(s_vnd + M);
-    if (small_in) for (int i = threadIdx.x; i < M; i += blockDim.x) { s_pts[i] = a.pts[i]; s_nraw[i] = a.nraw[i]; s_vnd[i] = a.vnd[i]; }
-    if (mat_in) stage_bit_rows(s_bits, a.bits, M, Wn);
-    __syncthreads();
-    SeedCtx c;
-    c.pts = small_in ? s_pts : a.pts; c.nraw = small_in ? s_nraw : a.nraw; c.vnd = small_in ? s_vnd : a.vnd;
-    c.bits = mat_in ? s_bits : a.bits; c.bstride = Wn;
-    c.M = M; c.Wn = Wn; c.leaf = a.st->leaf_size;
+    const SeedCtx c = seed_stage(smem, a.pts, a.nraw, a.vnd, a.bits, M, a.st->leaf_size);
     const int lane = threadIdx.x & 31;
     const int total = (a.nit + 1) * M;
     SeedOut o; o.vvar = nullptr; o.pack_w = 1; o.pset = a.pset; o.good = a.good; o.centers = a.centers; o.active_size = a.active_size;
     o.max_proj_range = a.max_proj_range;
+    const bool hot = ((int)blockIdx.x - a.nit) < a.hot_ctas;
+    bool phase2 = false;
     while (true) {
-        // claim the next slot of the ready queue: slots [0, M) are the iteration-0 tasks (ready at start, low
-        // levels first), later slots are filled by the chain publishers as orientations get final
-        int t = 0;
-        if (lane == 0) t = atomicAdd(a.qctr, 1);
-        t = __shfl_sync(FULLM, t, 0);
-        if (t >= total) break;
+        // phase 1: every worker CTA takes iteration-0 tasks (all ready at start; counter qctr[2]).  phase 2: only the first
+        // `hot_ctas` worker CTAs keep claiming slots of the ready queue, which the chain publishers fill as orientations
+        // get final (counter qctr[0]).  A lone task warp on an otherwise idle SM runs ~3x slower than the same warp on an
+        // SM where several warps execute the same code (instruction supply: measured, tools/fused_timeline.py), and the
+        // chains only release ~6 tasks per microsecond, so the tasks are concentrated on few SMs.
         int it = 0, p = 0;
-        if (t < M) p = t;
-        else {
+        if (!phase2) {
+            int t = 0;
+            if (lane == 0) t = atomicAdd(a.qctr + 2, 1);
+            t = __shfl_sync(FULLM, t, 0);
+            if (t >= M) { if (!hot) break; phase2 = true; continue; }
+            p = t;
+        } else {
+            int t = 0;
+            if (lane == 0) t = atomicAdd(a.qctr, 1);
+            t = __shfl_sync(FULLM, t, 0);
+            if (t >= total - M) break;
             int e = 0;
-            if (lane == 0) { const int* q = a.taskq + (t - M); while ((e = ld_vol(q)) == 0) __nanosleep(20); }
-            e = __shfl_sync(FULLM, e, 0) - 1;
+            // every lane polls the slot (one broadcast transaction): a warp whose lane 0 spins while the other 31 wait at the
+            // reconvergence point takes issue slots from the task warp that shares its scheduler (measured: tasks ran 3x slower)
+            { const int* q = a.taskq + t; while ((e = ld_vol(q)) == 0) { if (a.spin_ns) __nanosleep(a.spin_ns); } }
+            e = e - 1;
             __threadfence();
             it = e / a.Mcap; p = e - it * a.Mcap;
         }
+        if (a.tl && lane == 0) a.tl[((size_t)it * a.Mcap + p) * 16 + 2] = gtime();
         const float4 n4 = __ldcg(a.vset_it + (size_t)it * a.Mcap + p);
         const float4 p4 = __ldcg(a.pset + p);
         const f3 pp{p4.x, p4.y, p4.z}, nn{n4.x, n4.y, n4.z};
         if (it < a.nit) {
             o.vnew = a.vnew_it + (size_t)it * a.Mcap;
             o.prev = it > 0 ? a.vnew_it + (size_t)(it - 1) * a.Mcap : nullptr;
+            o.tl = a.tl ? a.tl + ((size_t)it * a.Mcap + p) * 16 : nullptr;
             if (Wn <= 32) seed_body<0, 1>(c, p, pp, nn, o);
             else if (Wn <= 64) seed_body<0, 2>(c, p, pp, nn, o);
             else seed_body<0, 4>(c, p, pp, nn, o);
             __syncwarp();
-            if (lane == 0) { __threadfence(); st_vol(a.flagO + (size_t)it * a.Mcap + p, 1); }
+            if (lane == 0) { __threadfence(); st_vol(a.flagO + (size_t)it * a.Mcap + p, 1); if (a.tl) a.tl[((size_t)it * a.Mcap + p) * 16 + 3] = gtime(); }
         } else {
             if (Wn <= 32) seed_body<1, 1>(c, p, pp, nn, o);
             else if (Wn <= 64) seed_body<1, 2>(c, p, pp, nn, o);
@@ -564,14 +667,30 @@ __device__ __forceinline__ void chain_schedule_pass(int w, int M, int nbk, int k
             for (int u = 0; u < k_eff; ++u) { const int jj = ssurf[p * nbk + u]; if (jj < base) vext = max(vext, (int)Tc[jj]); }
         }
         int v = vext + 1;
+        if (NBK == 10) {
+            // in-chunk dependencies: a register fixpoint; per round 10 independent shuffles, a max TREE (not a chain) and a vote
+            int src[10]; bool in[10];
+#pragma unroll
+            for (int u = 0; u < 10; ++u) { in[u] = (j[u] >= base && j[u] < p); src[u] = j[u] & 31; }
+            bool mine = false;
+#pragma unroll
+            for (int u = 0; u < 10; ++u) mine |= in[u];
+            if (__any_sync(FULLM, mine)) {
+                while (true) {
+                    int tv[10];
+#pragma unroll
+                    for (int u = 0; u < 10; ++u) { const int t = __shfl_sync(FULLM, v, src[u]); tv[u] = in[u] ? t : 0; }
+                    const int m01 = max(tv[0], tv[1]), m23 = max(tv[2], tv[3]), m45 = max(tv[4], tv[5]), m67 = max(tv[6], tv[7]), m89 = max(tv[8], tv[9]);
+                    const int nv = max(max(max(m01, m23), max(m45, m67)), max(m89, vext)) + 1;
+                    const bool changed = nv != v;
+                    v = nv;
+                    if (!__any_sync(FULLM, changed)) break;
+                }
+            }
+        } else
         while (true) {
             int nv = vext;
-            if (NBK > 0) {
-#pragma unroll
-                for (int u = 0; u < NBK; ++u) { const int tv = __shfl_sync(FULLM, v, j[u] & 31); if (j[u] >= base && j[u] < p) nv = max(nv, tv); }
-            } else {
-                for (int u = 0; u < k_eff; ++u) { const int jj = ssurf[p * nbk + u]; const int tv = __shfl_sync(FULLM, v, jj & 31); if (jj >= base && jj < p) nv = max(nv, tv); }
-            }
+            for (int u = 0; u < k_eff; ++u) { const int jj = ssurf[p * nbk + u]; const int tv = __shfl_sync(FULLM, v, jj & 31); if (jj >= base && jj < p) nv = max(nv, tv); }
             nv += 1;
             const bool changed = nv != v;
             v = nv;
@@ -619,7 +738,11 @@ __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const int k_eff = min(nbk, M);
     const bool fast10 = (nbk == 10 && k_eff == 10);
-    if (warp <= it) {
+    // pass 0 (the dependency levels) was computed by k_gs_schedule on the side stream while the similarity stage ran
+    for (int i = threadIdx.x; i < M; i += blockDim.x) sT[i] = (unsigned short)min(a.level[i], 65535);
+    if (threadIdx.x == 0) s_ctl[4] = M;
+    __syncthreads();
+    if (warp >= 1 && warp <= it) {
         int* tmax = (warp == it) ? s_ctl + 2 : nullptr;      // only the last pass reports its maximum (the sort's bin count)
         if (fast10) chain_schedule_pass<10>(warp, M, nbk, k_eff, ssurf, sT, s_ctl + 4, tmax, a.lag);
         else chain_schedule_pass<0>(warp, M, nbk, k_eff, ssurf, sT, s_ctl + 4, tmax, a.lag);
@@ -629,7 +752,9 @@ __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int
         // counting sort by T_it (ties in any order); a schedule deeper than the histogram falls back to the index order
         const unsigned short* T = sT + (size_t)it * M;
         const int nb = s_ctl[2];                          // written by warp `it` only
-        if (nb >= SCHED_BINS) {
+        if (it == 0) {
+            for (int i = threadIdx.x; i < M; i += blockDim.x) sorder[i] = (unsigned short)a.level_pts[i];
+        } else if (nb >= SCHED_BINS) {
             for (int i = threadIdx.x; i < M; i += blockDim.x) sorder[i] = (unsigned short)i;
         } else {
             for (int l = threadIdx.x; l <= nb; l += blockDim.x) shist[l] = 0;
@@ -723,6 +848,7 @@ __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int
                 const f3 d = normalize3_dev(eig_col(E, 2));                                         // rosa.cpp:305-307
                 snew[cand] = make_float4(d.x, d.y, d.z, wself);
                 vstate[cand] = 3;
+                if (a.tl) a.tl[((size_t)it * a.Mcap + cand) * 16 + 0] = gtime();
                 solist[ndone + r] = (unsigned short)cand;
                 cand = ncand;
 #pragma unroll
@@ -814,30 +940,46 @@ __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int
                 __threadfence();
                 const int slot = atomicAdd(a.qctr + 1, 1);
                 st_vol(a.taskq + slot, (it + 1) * a.Mcap + p + 1);
+                if (a.tl) a.tl[((size_t)(it + 1) * a.Mcap + p) * 16 + 1] = gtime();
                 idx += 32;
             }
         }
-    } else {
-        // ---- prefetchers: stage O(it,j) = (symmetry normal, weight) as soon as its flag is up (window order)
-        const int npf = nw - 2;
+    } else if ((warp & 3) != 0) {
+        // ---- prefetchers: stage O(it,j) = (symmetry normal, weight) as soon as its flag is up (window order).
+        // Warps 4, 8, ... share the walker's scheduler (warp id mod 4) and leave the kernel instead: a spinning warp -- above
+        // all a DIVERGED one, some lanes looping while the others wait at the reconvergence point -- takes issue slots from
+        // the warps of its scheduler (measured on the task warps: 3x).  The poll loop below is uniform: every lane runs the
+        // same instruction stream over its (at most 32) entries, all flag loads of a round in flight together.
+        const int npf = (nw - 2) - ((nw - 2) >> 2);
+        const int pfi = (warp - 1) - (warp >> 2);
         const int stride = npf * 32;
-        const int first = (warp - 1) * 32 + lane;
+        const int first = pfi * 32 + lane;
+        const int kmax = (M + stride - 1) / stride;
         unsigned pend = 0u;
         for (int k = 0; k < 32; ++k) if (first + k * stride < M) pend |= 1u << k;
         while (__any_sync(FULLM, pend != 0u)) {
-            unsigned scan = pend;
-            while (scan) {
-                const int k = __ffs(scan) - 1; scan &= scan - 1;
-                const int j = sorder[first + k * stride];
-                if (ld_vol(fO + j) != 0) {
-                    __threadfence();
-                    sold[j] = __ldcg(vn + j);
-                    __threadfence_block();
-                    vstate[j] = 1;
-                    pend &= ~(1u << k);
+            for (int kb = 0; kb < kmax; kb += 8) {
+                int j[8], f[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const bool want = (pend >> (kb + u)) & 1u;
+                    j[u] = want ? (int)sorder[first + (kb + u) * stride] : 0;
+                    f[u] = want ? ld_vol(fO + j[u]) : 0;
+                }
+                __threadfence();
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) if (f[u] != 0) v[u] = __ldcg(vn + j[u]);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) if (f[u] != 0) sold[j[u]] = v[u];
+                __threadfence_block();
+#pragma unroll
+                for (int u = 0; u < 8; ++u) if (f[u] != 0) {
+                    vstate[j[u]] = 1;
+                    if (a.tl) a.tl[((size_t)it * a.Mcap + j[u]) * 16 + 4] = gtime();
+                    pend &= ~(1u << (kb + u));
                 }
             }
-            if (pend) __nanosleep(20);
         }
     }
 }
@@ -888,8 +1030,8 @@ void launch_drosa_prep(osep_rosa_impl* h, cudaStream_t sk) {
         cudaMemsetAsync(d.fused_flags, 0, sizeof(int) * ((size_t)2 * MAX_FUSED_ITERS * d.Mcap + 16), sk);
         cudaMemcpyAsync(d.vset_it, d.vset, sizeof(float4) * d.Mcap, cudaMemcpyDeviceToDevice, sk);
     }
-    if (!fused) {
-        k_gs_schedule<<<1, 1024, sizeof(int) * (d.Mcap + SCHED_BINS) + sizeof(unsigned short) * d.Mcap * d.nbk, sk>>>(d.st, d.surf, d.nbk, d.level, d.level_off, d.level_pts);
+    {
+        k_gs_schedule<<<1, 256, sizeof(int) * (d.Mcap + SCHED_BINS) + sizeof(unsigned short) * d.Mcap * (d.nbk + 1), sk>>>(d.st, d.surf, d.nbk, d.level, d.level_off, d.level_pts);
         h->n_launches += 1;
     }
     h->n_launches += 1;
@@ -910,9 +1052,9 @@ void launch_drosa(osep_rosa_impl* h, int sms) {
         a.st = d.st; a.pts = d.pts; a.nraw = d.nraw; a.vnd = d.vnd; a.pset = d.pset; a.bits = d.simi_bits; a.W = d.W;
         a.vset_it = d.vset_it; a.vnew_it = d.vnew_it;
         a.flagO = d.fused_flags; a.taskq = d.fused_flags + (size_t)MAX_FUSED_ITERS * d.Mcap; a.qctr = d.fused_flags + (size_t)2 * MAX_FUSED_ITERS * d.Mcap;
-        a.Mcap = d.Mcap; a.nit = c.niter_drosa; a.surf = d.surf; a.nbk = d.nbk; a.dbg_detail = h->fused_detail ? 1 : 0; a.lag = h->sched_lag;
+        a.Mcap = d.Mcap; a.nit = c.niter_drosa; a.surf = d.surf; a.nbk = d.nbk; a.dbg_detail = h->fused_detail ? 1 : 0; a.lag = h->sched_lag; a.spin_ns = (unsigned)h->spin_ns; a.hot_ctas = h->hot_ctas; a.level = d.level; a.level_pts = d.level_pts;
         a.good = d.good; a.centers = d.centers; a.active_size = d.active_size; a.max_proj_range = c.max_proj_range;
-        a.dbg = d.fused_dbg;
+        a.dbg = d.fused_dbg; a.tl = h->fused_detail ? d.fused_tl : nullptr;
         if (h->fused_detail) { cudaMemsetAsync(d.fused_dbg + 56, 0xff, 8, s); cudaMemsetAsync(d.fused_dbg + 57, 0, 8, s); }
         int grid = h->fused_grid > 0 ? h->fused_grid : sms;
         if (grid < c.niter_drosa + 1) grid = c.niter_drosa + 1;

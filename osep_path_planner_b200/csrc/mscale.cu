@@ -137,7 +137,8 @@ __device__ __forceinline__ void simi_row(FrameState* st, const float4* __restric
         }
     }
     if (!FILL) {
-        if (!n1ok) for (int w = lane; w < ((M + 31) >> 5); w += 32) simi_bits[(size_t)i * W + w] = 0u;
+        if (!n1ok) for (int w = lane; w < W; w += 32) simi_bits[(size_t)i * W + w] = 0u;
+        else if (lane < W - ((M + 31) >> 5)) simi_bits[(size_t)i * W + ((M + 31) >> 5) + lane] = 0u;   // padding words of the row
         if (lane == 0) simi_off[i] = cnt;
         return;
     }
@@ -156,7 +157,7 @@ __global__ void k_simi(FrameState* st, const float4* __restrict__ pts, const flo
                        unsigned* __restrict__ simi_bits, int Scap) {
     if (st->status != 0) return;
     const int M = st->M;
-    const int W = (M + 31) >> 5;           // dense row stride of the bit matrix
+    const int W = (((M + 31) >> 5) + 3) & ~3;   // row stride of the bit matrix: padded to 16 bytes (drosa.cu reads rows with 16-byte loads)
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (i < M) simi_row<FILL>(st, pts, nrms, simi_off, simi_idx, tmp_j, tmp_d, simi_bits, M, W, i, lane);

@@ -42,7 +42,7 @@ struct RosaDev {
     float* vvar = nullptr;
     unsigned* simi_bits = nullptr;     // Mcap x W bit matrix of the similarity graph
     float4* nraw = nullptr; float4* vnd = nullptr;   // hoisted per-point normal quantities (drosa.cu)
-    float4* vset_it = nullptr; float4* vnew_it = nullptr; int* fused_flags = nullptr; long long* fused_dbg = nullptr;   // fused drosa (drosa.cu): per-iteration state + flags
+    float4* vset_it = nullptr; float4* vnew_it = nullptr; int* fused_flags = nullptr; long long* fused_dbg = nullptr; long long* fused_tl = nullptr;   // fused drosa (drosa.cu): per-iteration state + flags
     int* surf = nullptr;               // Mcap * nbk
     int* simi_off = nullptr; int* simi_idx = nullptr;
     int* level = nullptr; int* level_off = nullptr; int* level_pts = nullptr;
@@ -70,6 +70,8 @@ struct osep_rosa_impl {
     bool fused = true;                 // drosa as one persistent cooperative kernel (OSEP_DROSA_UNFUSED=1 disables)
     int knn_ctas_per_sm = 0;           // grid of the persistent kNN kernel in CTAs per SM; 0 = by frame size (OSEP_KNN_CTAS)
     int knn_ppc = 0;                   // target points per kNN grid cell; 0 = by frame size: 9, or 6 above 400k points (OSEP_KNN_PPC)
+    int hot_ctas = 1 << 20;                 // fused drosa: worker CTAs serving the ready queue after the iteration-0 tasks (OSEP_HOT_CTAS)
+    int spin_ns = 20;                  // fused drosa: sleep between two polls of an idle worker warp (OSEP_SPIN_NS)
     int sched_lag = 3;                 // fused drosa schedule model: walker steps from G(k-1,j) to the staged O(k,j) (OSEP_DROSA_LAG)
     bool fused_detail = false;         // per-step cycle counters in the chain walkers (OSEP_FUSED_DETAIL=1; costs ~4 % of the stage)
     int fused_grid = 0;                // CTAs of the fused kernel (0 = one per SM)
