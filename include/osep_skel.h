@@ -204,6 +204,26 @@ long osep_gskel_get(osep_gskel* h, const char* name, void* dst, long cap_bytes);
 /* graph of an arbitrary host vertex set on the device (stateless; used by tests and the tiled-map path) */
 int osep_graph_build(osep_gskel* h, const float* xyz, int n, int stride_floats, float fuse_dist_th, osep_graph_view* out);
 
+
+/* ---- spatially tiled maps (BASELINE.json configs[4]).  The reference has no tiling: these entry points are what
+ * a tiled caller (osep_path_planner_b200/tiled.py; one process per GPU) needs so that the map, the halos and the vertices
+ * never leave the device between the NCCL exchanges. */
+
+/* Stable compaction on the device: the records of pts_dev (n records of stride_floats floats) whose coordinate `axis`
+ * (0, 1, 2) lies in [lo, hi) are written in input order to out_dev as records of out_stride floats (3, or 4 with w = 1).
+ * Used for the halo selection (points within `halo` of a slab face) and the owned-vertex mask (vertices inside the tile's own
+ * interval).  Runs on `stream` (a cudaStream_t, may be NULL) of `device`; synchronises the stream and stores the number of
+ * matches in *count_host.  More than out_cap matches -> OSEP_ERR_CAPACITY (the first out_cap are written, the count is exact). */
+int osep_points_select_range(int device, const float* pts_dev, int n, int stride_floats, int axis, float lo, float hi,
+                             float* out_dev, int out_stride, int out_cap, int* count_host, void* stream);
+/* Device copy of output_vertices() (rosa.hpp:53): V records {x, y, z, 1} of the last frame, valid until the next run. */
+int osep_rosa_vertices_device(osep_rosa* h, const float** xyzw_dev, int* n_vertices);
+/* filter + leaf-size control law only (rosa.cpp:67-95, 118-148) on a DEVICE cloud: the converged leaf of a tile's own points
+ * sizes its halo (10 x leaf = the similarity radius, rosa.cpp:212) before the exchange.  Returns OSEP_OK / OSEP_STAGE_1. */
+int osep_rosa_leaf_device(osep_rosa* h, const float* xyz_dev, int n, int stride_floats, float* leaf_size, int* n_filtered);
+/* osep_graph_build over DEVICE vertices (the all-gathered vertices of the tiles: the seam graph) */
+int osep_graph_build_device(osep_gskel* h, const float* xyz_dev, int n, int stride_floats, float fuse_dist_th, osep_graph_view* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,9 @@ int graph_enqueue_in_frame(GraphHost* g, const float4* pos_dev, const FrameState
 int graph_collect_in_frame(GraphHost* g, osep_graph_view* out);
 size_t frame_export_enqueue(GraphHost* g, const FrameState* st, const float4* skel, int Mq, unsigned char* exp_dev, cudaStream_t s);
 size_t frame_export_bytes(int Mq);
+int select_range_enqueue(const float* in, int n, int stride, int axis, float lo, float hi, float* out, int out_stride, int out_cap,
+                         int* blk_cnt, int* total_dev, cudaStream_t s);
+void launch_leaf_only(osep_rosa_impl* h);
 void graph_set_mirrors(GraphHost* g, unsigned char* exp_host, int Mq);
 
 
@@ -48,7 +51,8 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
     CK(dalloc(&d.in, N * 4));
     CK(dalloc(&d.P, N)); CK(dalloc(&d.filt_idx, N)); CK(dalloc(&d.blk_cnt, N / 256 + 2));
     { unsigned* g4; CK(dalloc(&g4, 4 * T)); d.gtab = (unsigned long long*)g4; d.g_cnt = (int*)(g4 + 2 * T); d.g_fill = (int*)(g4 + 3 * T); }
-    CK(dalloc(&d.g_start, T)); CK(dalloc(&d.units, N + 8)); CK(dalloc(&d.slow_list, N)); CK(dalloc(&d.over_list, N + 8)); CK(dalloc(&d.knn_full, N * (size_t)d.knn)); CK(dalloc(&d.p_slot, N)); CK(dalloc(&d.Pc, N)); CK(dalloc(&d.Nrm, N));
+    CK(dalloc(&d.g_start, T)); CK(dalloc(&d.units, N + 8)); CK(dalloc(&d.slow_list, N)); CK(dalloc(&d.over_list, N + 8)); CK(dalloc(&d.knn_retry, N + 8)); CK(dalloc(&d.knn_grow, N + 8));
+    d.cell_cap = (int)(N / 3 + 1024); CK(dalloc(&d.g_cell, T)); CK(dalloc(&d.cell_slots, (size_t)d.cell_cap)); CK(dalloc(&d.pc_cell, N)); CK(dalloc(&d.nbr, (size_t)d.cell_cap * 27)); CK(dalloc(&d.nbr_tau, (size_t)d.cell_cap)); CK(dalloc(&d.knn_full, N * (size_t)d.knn)); CK(dalloc(&d.p_slot, N)); CK(dalloc(&d.Pc, N)); CK(dalloc(&d.Nrm, N));
     CK(dalloc(&d.vtab, T)); CK(cudaMemset(d.vtab, 0, T * sizeof(unsigned long long)));
     CK(dalloc(&d.vkeys, M)); CK(dalloc(&d.vid, N)); CK(dalloc(&d.vox_cnt, M + 2)); CK(dalloc(&d.vox_fill, M + 2));
     CK(dalloc(&d.rk0, tmpcap)); CK(dalloc(&d.rk1, tmpcap)); CK(dalloc(&d.rv0, tmpcap)); CK(dalloc(&d.rv1, tmpcap));
@@ -56,6 +60,8 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
     CK(dalloc(&d.vvar, M)); CK(dalloc(&d.simi_bits, M * (size_t)d.W)); CK(dalloc(&d.nraw, M)); CK(dalloc(&d.vnd, M));
     CK(dalloc(&d.vset_it, M * 9)); CK(dalloc(&d.vnew_it, M * 8)); CK(dalloc(&d.fused_flags, M * 16 + 16)); CK(dalloc(&d.fused_dbg, 64)); CK(cudaMemset(d.fused_dbg, 0, 64 * 8));
     { const char* e = getenv("OSEP_KNN_PPC"); if (e && atoi(e) > 0) h->knn_ppc = atoi(e); }
+    { const char* e = getenv("OSEP_KNN_TARGET"); if (e && atof(e) > 0) h->knn_target = (float)atof(e); }
+    { const char* e = getenv("OSEP_KNN_WARP"); if (e && e[0] == '1') h->knn_warp_path = true; }
     { const char* e = getenv("OSEP_KNN_CTAS"); if (e && atoi(e) > 0) h->knn_ctas_per_sm = atoi(e); }
     { const char* e = getenv("OSEP_DROSA_UNFUSED"); if (e && e[0] == '1') h->fused = false;
       const char* e3 = getenv("OSEP_NO_GRAPH"); if (e3 && e3[0] == '1') h->use_graphs = false;
@@ -88,7 +94,7 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
 
 static void rosa_free(osep_rosa_impl* h) {
     RosaDev& d = h->d;
-    void* ptrs[] = {d.st, d.prm, d.in, d.in_raw, d.P, d.filt_idx, d.blk_cnt, d.gtab, d.g_start, d.units, d.slow_list, d.over_list, d.p_slot, d.Pc, d.Nrm, d.knn_full, d.vtab, d.vkeys, d.vid,
+    void* ptrs[] = {d.st, d.prm, d.in, d.in_raw, d.P, d.filt_idx, d.blk_cnt, d.gtab, d.g_start, d.units, d.slow_list, d.over_list, d.knn_retry, d.knn_grow, d.g_cell, d.cell_slots, d.pc_cell, d.nbr, d.nbr_tau, d.p_slot, d.Pc, d.Nrm, d.knn_full, d.vtab, d.vkeys, d.vid,
                     d.vox_cnt, d.vox_fill, d.rk0, d.rk1, d.rv0, d.rv1, d.pts, d.nrms, d.pset, d.pset2, d.vset, d.vnew, d.vvar, d.surf,
                     d.simi_off, d.simi_idx, d.simi_bits, d.nraw, d.vnd, d.vset_it, d.vnew_it, d.fused_flags, d.fused_dbg, d.fused_tl, d.level, d.level_off, d.level_pts, d.good, d.centers, d.good_rank, d.poor_idx, d.active_size,
                     d.pcloud, d.adj_bits, d.seeds, d.corresp, d.skel, d.skel2, d.skel_sampled, d.vtmp, d.vs_off, d.vs_idx, d.vset_iters};
@@ -422,7 +428,7 @@ long osep_rosa_get(osep_rosa* h, const char* name, void* dst, long cap) {
     }
     if (nm == "fused_tl") { if (!d.fused_tl) return 0; return tap_copy(dst, cap, d.fused_tl, (size_t)d.Mcap * 9 * 16, 8) * 2; }
     if (nm == "fused_dbg") return tap_copy(dst, cap, d.fused_dbg, 64, 8) * 2;     // 64 int64 = 128 int32 words
-    if (nm == "knn_stats") { if (dst && cap >= 12) { ((int*)dst)[0] = s.n_units; ((int*)dst)[1] = s.n_slow; ((int*)dst)[2] = s.n_over; } return 3; }
+    if (nm == "knn_stats") { if (dst && cap >= 20) { int* o = (int*)dst; o[0] = s.n_units; o[1] = s.n_slow; o[2] = s.n_over; o[3] = s.n_retry; o[4] = s.n_grow; } return 5; }
     if (nm == "launches") { if (dst && cap >= 4) *(int*)dst = (int)I.n_launches; return 1; }
     if (nm == "graph_replays") { if (dst && cap >= 4) *(int*)dst = (int)I.n_graph_replays; return 1; }
     return -1;
@@ -451,6 +457,58 @@ int osep_rosa_set_graph(osep_rosa* h, int enable, float fuse_dist_th) {
     if (enable && !I.graph) { I.graph = graph_create(I.d.Mcap, I.device, I.stream); if (!I.graph) { set_err("graph arena allocation failed"); return OSEP_ERR_CUDA; } graph_set_mirrors(I.graph, I.exp_host, I.d.Mcap / 4); }
     I.auto_graph = enable != 0; I.graph_fuse = fuse_dist_th; I.graph_in_frame = false; ++I.cfg_epoch;
     return OSEP_OK;
+}
+
+// ---- tiled maps
+int osep_points_select_range(int device, const float* pts_dev, int n, int stride_floats, int axis, float lo, float hi,
+                             float* out_dev, int out_stride, int out_cap, int* count_host, void* stream) {
+    if (n < 0 || stride_floats < 3 || axis < 0 || axis > 2 || (out_stride != 3 && out_stride != 4) || out_cap < 0 || !count_host) { set_err("osep_points_select_range: bad argument"); return OSEP_ERR_ARG; }
+    *count_host = 0;
+    if (n == 0) return OSEP_OK;
+    if (!pts_dev || (!out_dev && out_cap > 0)) return OSEP_ERR_ARG;
+    CK(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int* scratch = nullptr;                           // per-block counts + the total (stream-ordered allocation)
+    const size_t nb = (size_t)(n + 255) / 256;
+    CK(cudaMallocAsync((void**)&scratch, sizeof(int) * (nb + 2), s));
+    int rc = select_range_enqueue(pts_dev, n, stride_floats, axis, lo, hi, out_dev, out_stride, out_cap, scratch, scratch + nb + 1, s);
+    int total = 0;
+    if (rc == OSEP_OK && cudaMemcpyAsync(&total, scratch + nb + 1, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = OSEP_ERR_CUDA;
+    cudaFreeAsync(scratch, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) rc = OSEP_ERR_CUDA;
+    if (rc != OSEP_OK) { set_err("osep_points_select_range: %s", cudaGetErrorString(cudaGetLastError())); return rc; }
+    *count_host = total;
+    if (total > out_cap) { set_err("osep_points_select_range: %d matches, room for %d", total, out_cap); return OSEP_ERR_CAPACITY; }
+    return OSEP_OK;
+}
+
+int osep_rosa_vertices_device(osep_rosa* h, const float** xyzw_dev, int* n_vertices) {
+    if (!h || !xyzw_dev || !n_vertices) return OSEP_ERR_ARG;
+    osep_rosa_impl& I = h->impl;
+    CK(cudaSetDevice(I.device));
+    CK(cudaStreamSynchronize(I.stream));
+    *xyzw_dev = reinterpret_cast<const float*>(I.d.skel);
+    *n_vertices = (I.st_host->status == 0) ? I.st_host->V : 0;
+    return OSEP_OK;
+}
+
+int osep_rosa_leaf_device(osep_rosa* h, const float* xyz_dev, int n, int stride_floats, float* leaf_size, int* n_filtered) {
+    if (!h || !leaf_size) return OSEP_ERR_ARG;
+    osep_rosa_impl& I = h->impl;
+    int rc = check_frame(I, n, stride_floats); if (rc) return rc;
+    CK(cudaSetDevice(I.device));
+    *leaf_size = 0.0f; if (n_filtered) *n_filtered = 0;
+    if (n == 0) return OSEP_STAGE_1;
+    CK(cudaStreamSynchronize(I.stream));
+    I.prm_host->in = xyz_dev; I.prm_host->n = n; I.prm_host->stride = stride_floats; I.prm_host->pad = 0;
+    CK(cudaMemcpyAsync(I.d.prm, I.prm_host, sizeof(FrameParams), cudaMemcpyHostToDevice, I.stream));
+    launch_leaf_only(&I);
+    CK(cudaMemcpyAsync(I.st_host, I.d.st, sizeof(FrameState), cudaMemcpyDeviceToHost, I.stream));
+    CK(cudaStreamSynchronize(I.stream));
+    *leaf_size = I.st_host->leaf_size; if (n_filtered) *n_filtered = I.st_host->n_filt;
+    const int status = I.st_host->status;
+    I.st_host->status = OSEP_STAGE_1; I.st_host->V = 0;      // not a frame: accessors of the last frame's results read "no vertices"
+    return status;
 }
 
 // ---- batched independent frames: `lanes` sub-handles, each with its own stream and arena

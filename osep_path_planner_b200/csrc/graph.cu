@@ -755,4 +755,20 @@ int osep_graph_build(osep_gskel* h, const float* xyz, int n, int stride_floats, 
     return rc;
 }
 
+int osep_graph_build_device(osep_gskel* h, const float* xyz_dev, int n, int stride_floats, float fuse_dist_th, osep_graph_view* out) {
+    if (!h || !out || n < 0 || (stride_floats != 3 && stride_floats != 4)) return OSEP_ERR_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return OSEP_ERR_CUDA;
+    GraphHost* g = h->impl.g;
+    if (n > g->cap) return OSEP_ERR_CAPACITY;
+    if (n) {
+        cudaError_t e;
+        if (stride_floats == 4) e = cudaMemcpyAsync(g->pos, xyz_dev, sizeof(float4) * n, cudaMemcpyDeviceToDevice, g->stream);
+        else e = cudaMemcpy2DAsync(g->pos, sizeof(float4), xyz_dev, 12, 12, n, cudaMemcpyDeviceToDevice, g->stream);   // w is not read by the graph kernels
+        if (e != cudaSuccess) return OSEP_ERR_CUDA;
+    }
+    const int rc = graph_run(g, g->pos, n, fuse_dist_th);
+    if (rc == OSEP_OK) graph_view(g, out);
+    return rc;
+}
+
 }  // extern "C"

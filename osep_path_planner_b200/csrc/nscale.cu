@@ -305,7 +305,7 @@ __device__ void grid_params(FrameState* st, int target_ppc) {
     const int nv = st->nvox_hist[0];
     float h = st->leaf_hist[0] * sqrtf((float)target_ppc * (float)(nv > 0 ? nv : 1) / (float)(n > 0 ? n : 1));
     grid_set_h(st, h);
-    st->g_cells_used = 0; st->n_units = 0; st->n_slow = 0; st->n_over = 0; st->unit_ctr = 0;
+    st->g_cells_used = 0; st->n_units = 0; st->n_slow = 0; st->n_over = 0; st->unit_ctr = 0; st->n_retry = 0; st->n_grow = 0; st->n_cells = 0;
     st->g_ncells = 0; st->g_redo = 0;
 }
 
@@ -370,29 +370,98 @@ __global__ void k_grid_insert(const float4* __restrict__ P, FrameState* st, unsi
 #define OSEP_QCH 12
 #endif
 constexpr int QCH = OSEP_QCH;            // queries per kNN work unit
-__global__ void k_grid_alloc(FrameState* st, const int* __restrict__ g_cnt, int* __restrict__ g_start, int T, int2* __restrict__ units) {
-    __shared__ int s_pts, s_units, b_pts, b_units;
+__global__ void k_grid_alloc(FrameState* st, const int* __restrict__ g_cnt, int* __restrict__ g_start, int T, int2* __restrict__ units,
+                             int* __restrict__ g_cell, int* __restrict__ cell_slots, int cell_cap) {
+    __shared__ int s_pts, s_units, s_cells, b_pts, b_units, b_cells;
     if (st->status != 0) return;
-    if (threadIdx.x == 0) { s_pts = 0; s_units = 0; }
+    if (threadIdx.x == 0) { s_pts = 0; s_units = 0; s_cells = 0; }
     __syncthreads();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const int c = s < T ? g_cnt[s] : 0;
     // dense cells have long candidate lists: fewer queries per unit there, so more warps share the work
     const int chunk = (c >= 64) ? 2 : QCH;
     const int nu = (c + chunk - 1) / chunk;
-    int op = 0, ou = 0;
-    if (c > 0) { op = atomicAdd(&s_pts, c); ou = atomicAdd(&s_units, nu); }     // block-local cursors: two global atomics per block
+    int op = 0, ou = 0, oc = 0;
+    if (c > 0) { op = atomicAdd(&s_pts, c); ou = atomicAdd(&s_units, nu); oc = atomicAdd(&s_cells, 1); }     // block-local cursors: three global atomics per block
     __syncthreads();
-    if (threadIdx.x == 0 && s_pts > 0) { b_pts = atomicAdd(&st->g_cells_used, s_pts); b_units = atomicAdd(&st->n_units, s_units); }
+    if (threadIdx.x == 0 && s_pts > 0) { b_pts = atomicAdd(&st->g_cells_used, s_pts); b_units = atomicAdd(&st->n_units, s_units); b_cells = atomicAdd(&st->n_cells, s_cells); }
     __syncthreads();
     if (c > 0) {
         g_start[s] = b_pts + op;
         const int ub = b_units + ou;
         for (int u = 0; u < nu; ++u) units[ub + u] = make_int2(s, (u * chunk) | (chunk << 24));
+        const int ci = b_cells + oc;                      // compact cell id (thread-per-query kNN: row of the neighbour table)
+        g_cell[s] = ci;
+        if (ci < cell_cap) cell_slots[ci] = s;
     }
 }
+// neighbour table: row ci = (start, count) of the occupied cells among the 27 around cell ci, one warp per cell (lanes probe
+// the hash table in parallel), so that the query threads of k_knn_scan read one packed row instead of running 27 dependent
+// probes each.  The warp also runs a PILOT query for the cell's first point: the radius^2 that holds `target` of the
+// block's points (bisection over the staged distances) -- the scan radius of every query of the cell (nbr_tau).
+constexpr int PILOT_CAP = 256;
+__global__ void __launch_bounds__(256) k_grid_nbrs(const FrameState* __restrict__ st, const float4* __restrict__ Pc, const unsigned long long* __restrict__ gtab,
+                            const int* __restrict__ g_cnt, const int* __restrict__ g_start, unsigned mask, const int* __restrict__ cell_slots, int cell_cap,
+                            int2* __restrict__ nbr, float* __restrict__ nbr_tau, float target) {
+    __shared__ float sd[8][PILOT_CAP];
+    if (st->status != 0) return;
+    const int nc = min(st->n_cells, cell_cap);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int dimx = st->g_dim[0], dimy = st->g_dim[1], dimz = st->g_dim[2];
+    for (int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ci < nc; ci += (gridDim.x * blockDim.x) >> 5) {
+        const unsigned long long key = gtab[cell_slots[ci]] - 1ull;
+        const int cx = (int)(key & 0x1fffffull), cy = (int)((key >> 21) & 0x1fffffull), cz = (int)(key >> 42);
+        int2 e = make_int2(0, 0);
+        if (lane < 27) {
+            const int x = cx + (lane % 3) - 1, y = cy + ((lane / 3) % 3) - 1, z = cz + (lane / 9) - 1;
+            if (x >= 0 && x < dimx && y >= 0 && y < dimy && z >= 0 && z < dimz) {
+                const unsigned long long key1 = cell_key1(x, y, z);
+                unsigned s = cell_slot(x, y, z, mask);
+                unsigned long long cur;
+                while ((cur = gtab[s]) != key1 && cur != 0ull) s = (s + 1) & mask;
+                if (cur != 0ull) e = make_int2(g_start[s], g_cnt[s]);
+            }
+        }
+        // occupied cells first (rows are scanned until the first empty entry)
+        const unsigned occ = __ballot_sync(0xffffffffu, e.y > 0);
+        if (e.y > 0) nbr[(size_t)ci * 27 + __popc(occ & ((1u << lane) - 1u))] = e;
+        if (lane >= __popc(occ) && lane < 27) nbr[(size_t)ci * 27 + lane] = make_int2(0, 0);
+        // pilot: distances from the cell's first point to the block's points (the first PILOT_CAP of them)
+        const int own = __shfl_sync(0xffffffffu, e.x, 13);
+        const float4 q = Pc[own];
+        int total = 0;
+        __syncwarp();
+        for (unsigned mm = occ; mm; mm &= mm - 1) {
+            const int src = __ffs(mm) - 1;
+            const int b = __shfl_sync(0xffffffffu, e.x, src), m = __shfl_sync(0xffffffffu, e.y, src);
+            for (int j = lane; j < m && total + j < PILOT_CAP; j += 32) { const float4 p = __ldg(Pc + b + j); sd[wib][total + j] = dist2(q.x, q.y, q.z, p.x, p.y, p.z); }
+            total = min(total + m, PILOT_CAP);
+        }
+        __syncwarp();
+        float v[PILOT_CAP / 32];
+        float vmax = 0.0f;
+#pragma unroll
+        for (int r = 0; r < PILOT_CAP / 32; ++r) { const int t = r * 32 + lane; v[r] = t < total ? sd[wib][t] : 3.0e38f; if (t < total) vmax = fmaxf(vmax, v[r]); }
+        vmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(vmax)));
+        float tau = 3.0e38f;                              // fewer than `target` points in the block: the scan radius is the block's bound
+        if ((float)total > target) {
+            float lo = 0.0f, hi = vmax * 1.0001f + 1e-30f;
+            for (int it = 0; it < 14; ++it) {
+                const float mid = 0.5f * (lo + hi);
+                int c = 0;
+#pragma unroll
+                for (int r = 0; r < PILOT_CAP / 32; ++r) c += (v[r] < mid) ? 1 : 0;
+                c = __reduce_add_sync(0xffffffffu, c);
+                if ((float)c >= target) hi = mid; else lo = mid;
+            }
+            tau = hi;
+        }
+        if (lane == 0) nbr_tau[ci] = tau;
+    }
+}
+
 __global__ void k_grid_scatter(const float4* __restrict__ P, const FrameState* __restrict__ st, const int* __restrict__ p_slot,
-                               const int* __restrict__ g_start, int* g_fill, float4* __restrict__ Pc) {
+                               const int* __restrict__ g_start, int* g_fill, float4* __restrict__ Pc, const int* __restrict__ g_cell, int* __restrict__ pc_cell) {
     if (st->status != 0) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= st->n_filt) return;
@@ -400,6 +469,7 @@ __global__ void k_grid_scatter(const float4* __restrict__ P, const FrameState* _
     const int pos = g_start[s] + atomicAdd(&g_fill[s], 1);
     float4 p = P[i]; p.w = __int_as_float(i);
     Pc[pos] = p;
+    pc_cell[pos] = g_cell[s];
 }
 
 // ---- register-resident top-K by (d2, index); sentinels (inf, INT_MAX) mark empty slots
@@ -768,17 +838,22 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cells(const float4* __re
 #endif
 constexpr int KNN_BIG = OSEP_KNN_BIG;        // candidates per query (one warp); more go to k_knn_exact
 constexpr int BIG_WARPS = OSEP_BIG_WARPS;    // queries (warps) per CTA
-template <int K>
-__global__ void __launch_bounds__(BIG_WARPS * 32) k_knn_big(const float4* __restrict__ Pc, FrameState* st,
+// mode 0: work items are (unit, query) codes of k_knn_cells' overflow list.  mode 1: positions in Pc (k_knn_scan's fall-back
+// chain).  mode 2: positions in Pc, and the R = 1 candidate cells come from the neighbour table row of the query's cell
+// instead of 27 hash probes; a query that needs more (5x5x5 block, or more than CAPQ candidates) goes on `next_list`.
+template <int K, int CAPQ, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_knn_big(const float4* __restrict__ Pc, FrameState* st,
                                                 const unsigned long long* __restrict__ gtab, const int* __restrict__ g_cnt,
                                                 const int* __restrict__ g_start, unsigned mask, const int2* __restrict__ units,
                                                 int* __restrict__ knn_idx, int k_req, int* __restrict__ slow_list,
-                                                const int* __restrict__ over_list) {
-    __shared__ int2 tab_[BIG_WARPS][KNN_TAB];
-    __shared__ int pre_[BIG_WARPS][KNN_TAB + 1];
-    __shared__ float sd_[BIG_WARPS][KNN_BIG];
-    __shared__ int si_[BIG_WARPS][KNN_BIG];
-    __shared__ unsigned long long keys_[BIG_WARPS][KNN_LIST];
+                                                const int* __restrict__ over_list, const int* __restrict__ n_work_ptr, int mode,
+                                                const int* __restrict__ pc_cell, const int2* __restrict__ nbr,
+                                                int* __restrict__ next_list, int* __restrict__ n_next) {
+    __shared__ int2 tab_[WARPS][KNN_TAB];
+    __shared__ int pre_[WARPS][KNN_TAB + 1];
+    __shared__ float sd_[WARPS][CAPQ];
+    __shared__ int si_[WARPS][CAPQ];
+    __shared__ unsigned long long keys_[WARPS][KNN_LIST];
     const int wib = threadIdx.x >> 5;
     int2* tab = tab_[wib]; int* pre = pre_[wib]; float* sd = sd_[wib]; int* si = si_[wib]; unsigned long long* keys = keys_[wib];
     if (st->status != 0) return;
@@ -789,17 +864,16 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) k_knn_big(const float4* __rest
     const int dimx = st->g_dim[0], dimy = st->g_dim[1], dimz = st->g_dim[2];
     const float h = st->g_h;
     const float diag2 = ((float)dimx * h) * ((float)dimx * h) + ((float)dimy * h) * ((float)dimy * h) + ((float)dimz * h) * ((float)dimz * h);
-    const int n_work = st->n_over;
+    const int n_work = *n_work_ptr;
     const unsigned long long KINF = ~0ull;
-    for (int w = blockIdx.x * BIG_WARPS + wib; w < n_work; w += gridDim.x * BIG_WARPS) {
+    for (int w = blockIdx.x * WARPS + wib; w < n_work; w += gridDim.x * WARPS) {
         const int code = over_list[w];
-        const int2 un = units[code >> 5];
-        const int cstart = g_start[un.x];
-        const int qpos = cstart + (un.y & 0xffffff) + (code & 31);
+        int qpos = code;
+        if (mode == 0) { const int2 un = units[code >> 5]; qpos = g_start[un.x] + (un.y & 0xffffff) + (code & 31); }
         const float4 q = Pc[qpos];
         int cx, cy, cz; cell_of(st, q.x, q.y, q.z, cx, cy, cz);
         bool done = false;
-        for (int R = 1; R <= 2 && !done; ++R) {
+        for (int R = 1; R <= (mode == 2 ? 1 : 2) && !done; ++R) {
             const int x0 = max(cx - R, 0), x1 = min(cx + R, dimx - 1);
             const int y0 = max(cy - R, 0), y1 = min(cy + R, dimy - 1);
             const int z0 = max(cz - R, 0), z1 = min(cz + R, dimz - 1);
@@ -811,7 +885,8 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) k_knn_big(const float4* __rest
             for (int c0 = 0; c0 < ncell; c0 += 32) {
                 const int c = c0 + lane;
                 int2 e = make_int2(0, 0);
-                if (c < ncell) {
+                if (mode == 2) { if (c < 27) e = __ldg(nbr + (size_t)pc_cell[qpos] * 27 + c); }      // packed row: occupied cells first, in any order
+                else if (c < ncell) {
                     const int x = x0 + c % nx, y = y0 + (c / nx) % ny, z = z0 + c / (nx * ny);
                     const unsigned long long key1 = cell_key1(x, y, z);
                     unsigned s = cell_slot(x, y, z, mask);
@@ -828,7 +903,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) k_knn_big(const float4* __rest
                 total += __shfl_sync(0xffffffffu, incl, 31);
             }
             __syncwarp();
-            if (total > KNN_BIG) break;                       // exact slow path
+            if (total > CAPQ) break;                          // next kernel of the chain
             // every candidate's (d2, index) once, 32 candidates per round, all rounds' loads independent
 #pragma unroll 4
             for (int t0 = 0; t0 < total; t0 += 32) {
@@ -897,8 +972,143 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) k_knn_big(const float4* __rest
             if (lane + 32 < k_eff) knn_idx[(size_t)qidx * k_eff + lane + 32] = (int)(unsigned)(k1 & 0xffffffffull);
             done = true;
         }
-        if (!done && lane == 0) slow_list[atomicAdd(&st->n_slow, 1)] = qpos;
+        if (!done && lane == 0) { if (mode == 2) next_list[atomicAdd(n_next, 1)] = qpos; else slow_list[atomicAdd(&st->n_slow, 1)] = qpos; }
         __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// R5, K <= 24: one THREAD per query.  k_knn_cells above spends most of its ~720 warp instructions per query on warp-wide
+// selection (ballot compaction, 64-bit shuffle sorts, one query at a time); here 32 queries run their selection in
+// lockstep, each in its own registers:
+//   1. the (start, count) of the (2R+1)^3 cells around the query's cell -> registers (R = 1) / local memory (R = 2);
+//   2. ONE scan of the candidates with a radius^2 `tau` chosen from the block's point density (surface model:
+//      N(r) ~ n_block * pi r^2 / (block side)^2), capped by the certification bound of the block; candidates inside tau
+//      are appended to the thread's column of a shared-memory list (SCAN_CAP entries);
+//   3. SCAN_K <= count <= SCAN_CAP (and tau <= bound^2) certifies the list: it holds the k nearest by (d2, index).  It is
+//      sorted as 32-bit keys (d2 bits with the low 6 bits replaced by the list slot: one IMNMX pair per compare-exchange,
+//      a 32-key bitonic network in registers + a bubble pass for slots 32..47); if two of the first k+1 keys agree in
+//      the 26 kept bits the thread redoes its selection exactly by (d2, index).
+// A miss (count outside the window) does not loop in place -- 31 lanes would idle: the query goes on a RETRY list with a
+// rescaled tau and a second launch of the same kernel runs all retries together (up to 3 attempts each); queries whose
+// block cannot certify k points go on the GROW list (R = 2 launch), what is left goes to k_knn_exact.
+constexpr int SCAN_THREADS = 128;
+constexpr int SCAN_CAP = 40;
+
+__device__ __forceinline__ void cex(unsigned& a, unsigned& b) { const unsigned lo = min(a, b), hi = max(a, b); a = lo; b = hi; }
+__device__ __forceinline__ void sts_u32(unsigned a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+
+template <int K>
+__global__ void __launch_bounds__(SCAN_THREADS) k_knn_scan(const float4* __restrict__ Pc, FrameState* st, const int* __restrict__ pc_cell,
+                                                           const int2* __restrict__ nbr, const float* __restrict__ nbr_tau, int cell_cap,
+                                                           int* __restrict__ knn_idx, int k_req, int* __restrict__ grow_list) {
+    constexpr int R = 1, NC = 27;
+    __shared__ unsigned lst[2 * (SCAN_CAP + 1)][SCAN_THREADS];    // rows [0, CAP]: d2 bits (row CAP = overflow sink); rows [CAP + 1, 2 CAP + 1]: point index
+    unsigned (*ld)[SCAN_THREADS] = lst;
+    unsigned (*li)[SCAN_THREADS] = lst + (SCAN_CAP + 1);
+    if (st->status != 0) return;
+    const int n = st->n_filt;
+    const int k_eff = min(k_req, n);
+    const int tid = threadIdx.x;
+    const int dimx = st->g_dim[0], dimy = st->g_dim[1], dimz = st->g_dim[2];
+    const float h = st->g_h;
+    const float diag2 = ((float)dimx * h) * ((float)dimx * h) + ((float)dimy * h) * ((float)dimy * h) + ((float)dimz * h) * ((float)dimz * h);
+    const bool table_ok = st->n_cells <= cell_cap;       // more occupied cells than the neighbour table holds: every query takes the warp-per-query path
+    const unsigned ld0 = (unsigned)__cvta_generic_to_shared(&lst[0][tid]);
+    constexpr unsigned ROW = SCAN_THREADS * 4u, LI_OFF = (SCAN_CAP + 1) * ROW;
+    const unsigned ld_end = ld0 + SCAN_CAP * ROW;
+    for (int wbase = (blockIdx.x * SCAN_THREADS + (tid & ~31)); wbase < n; wbase += gridDim.x * SCAN_THREADS) {
+        const int t = wbase + (tid & 31);
+        const bool valid = t < n;
+        if (!table_ok) { if (valid) grow_list[atomicAdd(&st->n_grow, 1)] = t; continue; }
+        const float4 q = valid ? Pc[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+        int cx, cy, cz; cell_of(st, q.x, q.y, q.z, cx, cy, cz);
+        const int x0 = max(cx - R, 0), x1 = min(cx + R, dimx - 1);
+        const int y0 = max(cy - R, 0), y1 = min(cy + R, dimy - 1);
+        const int z0 = max(cz - R, 0), z1 = min(cz + R, dimz - 1);
+        const bool whole = (x0 == 0 && y0 == 0 && z0 == 0 && x1 == dimx - 1 && y1 == dimy - 1 && z1 == dimz - 1);
+        float b2;
+        if (whole) b2 = 4.0f * diag2 + 1.0f;
+        else {
+            const float bound = block_bound(st, q.x - st->bmin[0], q.y - st->bmin[1], q.z - st->bmin[2], x0, x1, y0, y1, z0, z1);
+            b2 = bound > 0.0f ? bound * bound : 0.0f;
+        }
+        // 1. the query's row of the neighbour table and the cell's pilot radius
+        const int ci = valid ? pc_cell[t] : 0;
+        const int2* row = nbr + (size_t)ci * NC;
+        const float tau = valid ? fminf(nbr_tau[ci], b2) : 0.0f;
+        // 2. one scan: candidates inside tau go to the thread's list column
+        unsigned pl = ld0;
+        auto visit = [&](const float4& p, bool on) {
+            const float d2 = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
+            if (on && d2 < tau) { sts_u32(pl, __float_as_uint(d2)); sts_u32(pl + LI_OFF, __float_as_uint(p.w)); pl = min(pl + ROW, ld_end); }
+        };
+        int2 cur = valid ? __ldg(row) : make_int2(0, 0);
+#pragma unroll 1
+        for (int c = 0; c < NC && cur.y > 0; ++c) {
+            const float4* base = Pc + cur.x; const int m = cur.y;
+            cur = (c + 1 < NC) ? __ldg(row + c + 1) : make_int2(0, 0);      // next cell's entry is in flight during this cell's scan
+            int e = 0;
+#pragma unroll 1
+            for (; e + 4 <= m; e += 4) {                  // 4 candidates per round: their loads are in flight together
+                const float4 p0 = __ldg(base + e), p1 = __ldg(base + e + 1), p2 = __ldg(base + e + 2), p3 = __ldg(base + e + 3);
+                visit(p0, true); visit(p1, true); visit(p2, true); visit(p3, true);
+            }
+            if (e < m) {
+                const float4 p0 = __ldg(base + e), p1 = __ldg(base + min(e + 1, m - 1)), p2 = __ldg(base + min(e + 2, m - 1));
+                visit(p0, true); visit(p1, e + 1 < m); visit(p2, e + 2 < m);
+            }
+        }
+        const int cnt = (int)((pl - ld0) / ROW);          // SCAN_CAP = "SCAN_CAP or more": one slot of the window is given up for the test
+        const bool sortme = valid && cnt >= k_eff && cnt < SCAN_CAP;
+        // the count missed the window or the block cannot certify k points: warp-per-query kernel
+        if (valid && !sortme) grow_list[atomicAdd(&st->n_grow, 1)] = t;
+        // 3. sort: 32-bit keys = d2 bits (>= 0: ordered like the floats) with the low 6 bits replaced by the list slot
+        unsigned key[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) key[i] = (sortme && i < cnt) ? ((ld[i][tid] & ~63u) | (unsigned)i) : 0xffffffffu;
+#pragma unroll
+        for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int l = i ^ j;
+                    if (l > i) { if ((i & kk) == 0) cex(key[i], key[l]); else cex(key[l], key[i]); }
+                }
+            }
+        }
+        {   // slots 32.. bubble through the first K + 1 positions (all that the output and the tie test read)
+            const int extra = sortme ? cnt - 32 : 0;
+            const int wmax = __reduce_max_sync(0xffffffffu, extra);
+            for (int i = 0; i < wmax; ++i) {
+                unsigned x = (i < extra) ? ((ld[32 + i][tid] & ~63u) | (unsigned)(32 + i)) : 0xffffffffu;
+#pragma unroll
+                for (int pz = 0; pz <= K; ++pz) cex(key[pz], x);
+            }
+        }
+        bool tie = false;
+#pragma unroll
+        for (int pz = 0; pz < K; ++pz) if (pz < k_eff && key[pz + 1] != 0xffffffffu && ((key[pz] ^ key[pz + 1]) < 64u)) tie = true;
+        if (sortme) {
+            int* out = knn_idx + (size_t)__float_as_int(q.w) * k_eff;
+            if (!tie) {
+#pragma unroll
+                for (int pz = 0; pz < K; ++pz) if (pz < k_eff) out[pz] = (int)li[key[pz] & 63u][tid];
+            } else {
+                // exact selection by (d2, index) over the thread's list (rare: two of the first k+1 candidates within 2^-17 relative)
+                for (int r = 0; r < k_eff; ++r) {
+                    int bi = -1; float bd = 0.0f; int bid = 0;
+                    for (int i = 0; i < cnt; ++i) {
+                        const unsigned u = ld[i][tid];
+                        if (u == 0xffffffffu) continue;
+                        const float dd = __uint_as_float(u); const int id = (int)li[i][tid];
+                        if (bi < 0 || nb_less(dd, id, bd, bid)) { bi = i; bd = dd; bid = id; }
+                    }
+                    out[r] = bid; ld[bi][tid] = 0xffffffffu;
+                }
+            }
+        }
     }
 }
 
@@ -1097,15 +1307,86 @@ template <int K>
 static void launch_knn(osep_rosa_impl* h, int n, int k_req, cudaStream_t s) {
     RosaDev& d = h->d;
     const unsigned mask = (unsigned)(d.T - 1);
+    if constexpr (K <= 24) if (!h->knn_warp_path) {
+        // thread-per-query scan: all queries (one attempt), the retries, then the warp-per-query kernel for what the 27-cell
+        // block cannot certify, then the exact ring search
+        k_grid_nbrs<<<h->sms * 8, 256, 0, s>>>(d.st, d.Pc, d.gtab, d.g_cnt, d.g_start, mask, d.cell_slots, d.cell_cap, d.nbr, d.nbr_tau, h->knn_target);
+        k_knn_scan<K><<<div_up(d.Ncap, SCAN_THREADS), SCAN_THREADS, 0, s>>>(d.Pc, d.st, d.pc_cell, d.nbr, d.nbr_tau, d.cell_cap, d.knn_full, k_req, d.knn_grow);
+        k_knn_big<K, 384, 8><<<h->sms * 5, 256, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units, d.knn_full, k_req, d.slow_list, d.knn_grow, &d.st->n_grow, 2,
+                                                        d.pc_cell, d.nbr, d.over_list, &d.st->n_over);
+        k_knn_big<K, KNN_BIG, BIG_WARPS><<<h->sms * 4, BIG_WARPS * 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units, d.knn_full, k_req, d.slow_list, d.over_list, &d.st->n_over, 1,
+                                                                              nullptr, nullptr, nullptr, nullptr);
+        k_knn_exact<K><<<64, 128, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.knn_full, k_req, d.slow_list);
+        k_normals<<<div_up(d.Ncap, 128), 128, 0, s>>>(d.P, d.st, d.knn_full, k_req, d.Nrm);
+        return;
+    }
     // 3 CTAs per SM, not the 4 that fit: the register file would be full and the short kernels of the main stream (leaf
     // passes, voxel grouping) could not co-run; the stage alone is 13 % slower, the frame 1 % faster
     // (large maps: the stage is long, nothing competes for long, so the 4th CTA pays)
     const int ctas_per_sm = (h->knn_ctas_per_sm > 0) ? h->knn_ctas_per_sm : (n > 400000 ? 4 : 3);
     k_knn_cells<K><<<h->sms * ctas_per_sm, KNN_WARPS * 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units,
                                                               d.knn_full, k_req, d.slow_list, d.over_list);
-    k_knn_big<K><<<h->sms * 4, BIG_WARPS * 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units, d.knn_full, k_req, d.slow_list, d.over_list);
+    k_knn_big<K, KNN_BIG, BIG_WARPS><<<h->sms * 4, BIG_WARPS * 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units, d.knn_full, k_req, d.slow_list, d.over_list, &d.st->n_over, 0,
+                                                                          nullptr, nullptr, nullptr, nullptr);
     k_knn_exact<K><<<64, 128, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.knn_full, k_req, d.slow_list);
     k_normals<<<div_up(d.Ncap, 128), 128, 0, s>>>(d.P, d.st, d.knn_full, k_req, d.Nrm);
+}
+
+// ------------------------------------------------------------------------------------------
+// tiled maps: stable range compaction (osep_points_select_range) and the leaf-only pass (osep_rosa_leaf_device)
+__device__ __forceinline__ bool in_range(const float* p, int axis, float lo, float hi) { const float c = p[axis]; return c >= lo && c < hi; }
+__global__ void k_range_count(const float* __restrict__ in, int n, int stride, int axis, float lo, float hi, int* __restrict__ blk_cnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool keep = i < n && in_range(in + (size_t)i * stride, axis, lo, hi);
+    const int c = __syncthreads_count(keep);
+    if (threadIdx.x == 0) blk_cnt[blockIdx.x] = c;
+}
+__global__ void k_range_scan(int* blk_cnt, int nblk, int* total) {
+    const int t = block_excl_scan(blk_cnt, nblk);
+    if (threadIdx.x == 0) *total = t;
+}
+__global__ void k_range_scatter(const float* __restrict__ in, int n, int stride, int axis, float lo, float hi, const int* __restrict__ blk_off,
+                                float* __restrict__ out, int out_stride, int out_cap) {
+    __shared__ int warp_cnt[NT / 32];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const float* p = in + (size_t)min(i, n - 1) * stride;
+    const bool keep = i < n && in_range(p, axis, lo, hi);
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_cnt[wid] = __popc(m);
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < wid; ++w) woff += warp_cnt[w];
+    if (keep) {
+        const int pos = blk_off[blockIdx.x] + woff + __popc(m & ((1u << lane) - 1u));
+        if (pos < out_cap) {
+            float* o = out + (size_t)pos * out_stride;
+            o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+            if (out_stride > 3) o[3] = 1.0f;
+        }
+    }
+}
+int select_range_enqueue(const float* in, int n, int stride, int axis, float lo, float hi, float* out, int out_stride, int out_cap,
+                         int* blk_cnt, int* total_dev, cudaStream_t s) {
+    const int nb = div_up(n, NT);
+    k_range_count<<<nb, NT, 0, s>>>(in, n, stride, axis, lo, hi, blk_cnt);
+    k_range_scan<<<1, 1024, 0, s>>>(blk_cnt, nb, total_dev);
+    k_range_scatter<<<nb, NT, 0, s>>>(in, n, stride, axis, lo, hi, blk_cnt, out, out_stride, out_cap);
+    return cudaGetLastError() == cudaSuccess ? OSEP_OK : OSEP_ERR_CUDA;
+}
+// R3/R4 + R7/R8 only: the frame stops after the leaf-size control law
+void launch_leaf_only(osep_rosa_impl* h) {
+    RosaDev& d = h->d;
+    cudaStream_t s = h->stream;
+    const osep_rosa_config& c = h->cfg;
+    const int nb = div_up(d.Ncap, NT);
+    const float r2 = c.pts_dist_lim * c.pts_dist_lim;
+    k_filter_count<<<nb, NT, 0, s>>>(d.prm, r2, d.blk_cnt);
+    k_filter_scan<<<1, 1024, 0, s>>>(d.blk_cnt, nb, d.st, c.min_points, d.prm);
+    k_filter_scatter<<<nb, NT, 0, s>>>(d.prm, r2, d.blk_cnt, d.P, d.filt_idx, d.st, c.max_points);
+    for (int p = 0; p < LEAF_MAX_ITERS; ++p)
+        k_vox_count<<<nb, NT, 0, s>>>(d.P, d.st, d.vtab, (unsigned)(d.T - 1), p + 1, c.max_points, 9);
+    h->n_launches += 3 + LEAF_MAX_ITERS;
 }
 
 void launch_preprocess(osep_rosa_impl* h, int n) {
@@ -1142,8 +1423,8 @@ void launch_preprocess(osep_rosa_impl* h, int n) {
     k_grid_insert<<<nb, NT, 0, sk>>>(d.P, d.st, d.gtab, d.g_cnt, d.p_slot, (unsigned)(d.T - 1), 0, ppc);
     k_grid_clear_if_redo<<<div_up(d.T, NT), NT, 0, sk>>>(d.st, d.gtab, d.g_cnt, d.T);
     k_grid_insert<<<nb, NT, 0, sk>>>(d.P, d.st, d.gtab, d.g_cnt, d.p_slot, (unsigned)(d.T - 1), 1, ppc);
-    k_grid_alloc<<<div_up(d.T, NT), NT, 0, sk>>>(d.st, d.g_cnt, d.g_start, d.T, d.units);
-    k_grid_scatter<<<nb, NT, 0, sk>>>(d.P, d.st, d.p_slot, d.g_start, d.g_fill, d.Pc);
+    k_grid_alloc<<<div_up(d.T, NT), NT, 0, sk>>>(d.st, d.g_cnt, d.g_start, d.T, d.units, d.g_cell, d.cell_slots, d.cell_cap);
+    k_grid_scatter<<<nb, NT, 0, sk>>>(d.P, d.st, d.p_slot, d.g_start, d.g_fill, d.Pc, d.g_cell, d.pc_cell);
     stage_mark(h, SM_GRID);
     const int k = c.ne_knn;
     if (k == 20) launch_knn<20>(h, n, k, sk);
@@ -1165,7 +1446,7 @@ void launch_preprocess(osep_rosa_impl* h, int n) {
     if (h->overlap) cudaStreamWaitEvent(s, h->ev_join[0], 0);              // the reduce is the first consumer of the normals
     k_vox_reduce<<<1024, 256, 0, s>>>(d.st, d.rv0, d.rv1, d.vox_cnt, d.P, d.Nrm, d.pts, d.nrms, d.pset, d.vset);
     stage_mark(h, SM_VOXEL);
-    h->n_launches += 3 + LEAF_MAX_ITERS + 5 + 4 + 4 + 2;
+    h->n_launches += 3 + LEAF_MAX_ITERS + 5 + 4 + 4 + 2 + ((k <= 24 && !h->knn_warp_path) ? 2 : 0);
 }
 
 }  // namespace osep

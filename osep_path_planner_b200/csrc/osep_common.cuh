@@ -40,6 +40,8 @@ struct FrameState {
     int n_units;           // kNN work units (cell, chunk of queries)
     int n_slow;            // queries handed to the exact slow path
     int n_over;            // units whose candidate set does not fit the shared-memory stage
+    int n_cells;           // occupied grid cells with a compact id (k_grid_alloc)
+    int n_retry, n_grow;   // thread-per-query kNN: queries that repeat the scan with a rescaled radius / with the 5x5x5 block
     int unit_ctr;          // dynamic work counter of k_knn_cells
     // ---- leaf loop (rosa.cpp:118-148)
     float leaf, leaf_used, leaf_size;
@@ -61,6 +63,8 @@ struct FrameState {
     int ticket_m;          // last-block detection (similarity count pass)
     int ticket_grid;       // last-block detection (kNN grid build; runs concurrently with the voxel passes)
 };
+
+static_assert(sizeof(FrameState) <= 512, "the frame export block reserves 512 bytes for FrameState");
 
 // Per-frame launch parameters.  They live in device memory (refreshed by one H2D copy node from a pinned host mirror at the
 // head of every frame) instead of being kernel arguments, so the captured CUDA graph of a frame does not depend on the

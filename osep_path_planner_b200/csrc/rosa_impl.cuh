@@ -27,7 +27,8 @@ struct RosaDev {
     unsigned long long* gtab = nullptr;  // kNN grid: (epoch<<32 | cell key)
     int* g_cnt = nullptr; int* g_start = nullptr; int* g_fill = nullptr;
     int* p_slot = nullptr;
-    int2* units = nullptr; int* slow_list = nullptr; int* over_list = nullptr;   // kNN work units (cell, first query) and slow-path query list
+    int2* units = nullptr; int* slow_list = nullptr; int* over_list = nullptr; int2* knn_retry = nullptr; int* knn_grow = nullptr;
+    int* g_cell = nullptr; int* cell_slots = nullptr; int* pc_cell = nullptr; int2* nbr = nullptr; float* nbr_tau = nullptr; int cell_cap = 0;   // compact cell ids + 27-neighbour table (thread-per-query kNN)   // kNN work units (cell, first query) and slow-path query list
     float4* Pc = nullptr;              // points in cell order, w = filtered index (int bits)
     float4* Nrm = nullptr;             // normals of the filtered cloud
     int* knn_full = nullptr;           // kNN indices of the filtered cloud (Ncap * ne_knn), canonical order
@@ -69,6 +70,8 @@ struct osep_rosa_impl {
     bool debug = false;
     bool fused = true;                 // drosa as one persistent cooperative kernel (OSEP_DROSA_UNFUSED=1 disables)
     int knn_ctas_per_sm = 0;           // grid of the persistent kNN kernel in CTAs per SM; 0 = by frame size (OSEP_KNN_CTAS)
+    float knn_target = 29.0f;          // thread-per-query kNN: points the pilot radius of a cell holds (OSEP_KNN_TARGET); the list window is [k, 40)
+    bool knn_warp_path = false;        // OSEP_KNN_WARP=1: the warp-per-cell kernels also for K <= 24 (A/B)
     int knn_ppc = 0;                   // target points per kNN grid cell; 0 = by frame size: 9, or 6 above 400k points (OSEP_KNN_PPC)
     int hot_ctas = 1 << 20;                 // fused drosa: worker CTAs serving the ready queue after the iteration-0 tasks (OSEP_HOT_CTAS)
     int spin_ns = 20;                  // fused drosa: sleep between two polls of an idle worker warp (OSEP_SPIN_NS)

@@ -512,22 +512,29 @@ def test_gskel_run_tf_equals_transform_then_run(mods):
 
 
 def test_knn_overflow_and_exact_paths_are_bit_exact(mods, monkeypatch):
-    """The kNN stage has three paths (k_knn_cells: <= 512 staged candidates; k_knn_big: one warp per query with a
-    5120-entry list; k_knn_exact: thread-per-query ring search).  A deliberately coarse grid (OSEP_KNN_PPC) pushes
-    most queries through the overflow paths; neighbour lists and normals stay bit-identical to the oracle."""
+    """The kNN stage has a fast path and fall-backs.  Thread-per-query scan (K <= 24): one attempt over the 27-cell block with
+    the cell's pilot radius, k_knn_big (warp per query, 27 then 125 cells) for the misses, then k_knn_exact (ring search).  Warp-per-cell kernels
+    (OSEP_KNN_WARP=1, and K > 24): k_knn_cells (<= 512 staged candidates), k_knn_big, k_knn_exact.  Deliberately fine and
+    coarse grids (OSEP_KNN_PPC) push most queries through the fall-backs; neighbour lists and normals stay bit-identical
+    to the oracle."""
     osep, po, fx = mods
     P = fx.turbine(60000, seed=31)
     o = po.RosaOracle(); assert o.run(P)
-    for ppc in ("40", "400"):
-        monkeypatch.setenv("OSEP_KNN_PPC", ppc)
+    seen = np.zeros(5, np.int64)
+    for warp, ppc in (("0", "1"), ("0", "2"), ("0", "40"), ("0", "400"), ("1", "40"), ("1", "400")):
+        monkeypatch.setenv("OSEP_KNN_PPC", ppc); monkeypatch.setenv("OSEP_KNN_WARP", warp)
         r = osep.Rosa(capacity_points=60000); r.set_debug(True); r.set_input(P)
         assert r.rosa_run()
         st = r.tap("knn_stats")
-        assert st[2] > 0 or st[1] > 0, "the overflow paths were not exercised: %s" % (st,)
-        assert_bit_equal(r.tap("knn_full").reshape(-1), o.tap("knn_full").reshape(-1), "knn_full ppc=" + ppc)
+        if warp == "1":
+            assert st[2] > 0 or st[1] > 0, "the overflow paths were not exercised: %s" % (st,)
+        else:
+            seen[:len(st)] += np.asarray(st, np.int64)
+        assert_bit_equal(r.tap("knn_full").reshape(-1), o.tap("knn_full").reshape(-1), "knn_full ppc=%s warp=%s" % (ppc, warp))
         assert_bit_equal(r.tap("normals_full"), o.tap("normals_full"), "normals ppc=" + ppc)
         assert_bit_equal(np.ascontiguousarray(r.output_vertices()), o.tap("skelver"), "vertices ppc=" + ppc)
         r.close()
+    assert seen[1] > 0 and seen[4] > 0, "scan fall-backs (warp-per-query, exact) were not all exercised: %s" % (seen,)
 
 
 @pytest.mark.parametrize("cfgkw,cloud", [

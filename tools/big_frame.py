@@ -14,4 +14,4 @@ for k in range(3):
     ok = r.rosa_run()
     print(k, ok, r.result.status, "M", r.result.n_downsampled, "gpu_ms %.2f" % r.result.gpu_ms)
 print({k: round(v, 3) for k, v in r.stage_ms().items()})
-print("knn_stats [units, slow, overflow]", r.tap("knn_stats"))
+print("knn_stats [units, slow, overflow, retry, grow]", r.tap("knn_stats"))

@@ -22,5 +22,5 @@ k0, k1 = int(d[7, 0]), int(d[7, 1])
 print("kernel: entry %+.1f us, last CTA exit %+.1f us (relative to the first chain's walker start)" % ((k0 - t0) / 1e3, (k1 - t0) / 1e3))
 print(r.stage_ms())
 
-print("knn_stats [units, slow, overflow]", r.tap("knn_stats"))
+print("knn_stats [units, slow, overflow, retry, grow]", r.tap("knn_stats"))
 
