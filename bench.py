@@ -360,6 +360,14 @@ def run_ours(args, rank, world, local_rank):
                   "graph_replays": int(r.tap("graph_replays")[0]) - replays0, "global_vertices": int(len(gsk.output_gskel())),
                   "note": "host pinned frame -> osep_rosa_run (H2D + frame + D2H) wall clock per frame; every frame has a different n and replays the same CUDA graph"}
         gsk.close()
+    # ---- BASELINE.json configs[4]: one accumulated map, spatially tiled across the N GPUs, device resident (2.5 M points per GPU:
+    # 20 M at N = 8).  Halo selection kernel + NCCL send/recv + one frame per tile + NCCL all-gather of the owned vertices + seam graph.
+    tiled_blk = None
+    if world > 1 and args.tiled_points > 0:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("tiled_bench", os.path.join(ROOT, "tools", "tiled_bench.py"))
+        tb = importlib.util.module_from_spec(spec); spec.loader.exec_module(tb)
+        tiled_blk = tb.run(args.tiled_points * world, "auto", reps=3)
     if world > 1:
         counts, _ = shard.gather_frame_results({rank: np.ascontiguousarray(r.output_vertices())}, world, cap=1024)
     cpu_baseline = None
@@ -377,7 +385,7 @@ def run_ours(args, rank, world, local_rank):
                            "parallelism": "1 frame per GPU per step; ranks = independent frames (no collective on the data path)"},
                 "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": 1e3 * e2e_s / args.steps, "h2d_bytes_per_step": int(n * 16), "d2h_bytes_per_step": d2h},
-                "gpu_launches": int(launches), "stage_ms": stage_ms, "clocks": clk, "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps, "batched": batched, "stream": stream}
+                "gpu_launches": int(launches), "stage_ms": stage_ms, "clocks": clk, "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps, "batched": batched, "stream": stream, "tiled": tiled_blk}
         print(json.dumps(line), flush=True)
     r.close()
     if world > 1:
@@ -396,6 +404,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="total frames of the batched measurement, configs[3] (split over the ranks; 0 = skip)")
     ap.add_argument("--batch-runs", type=int, default=5, help="timed repetitions of the batched measurement (all are listed)")
     ap.add_argument("--stream", type=int, default=200, help="frames of the varying-n stream measurement, configs[2] in miniature (0 = skip)")
+    ap.add_argument("--tiled-points", type=int, default=2500000, help="points PER GPU of the tiled-map measurement, configs[4] (N >= 2 only; 0 = skip)")
     ap.add_argument("--prewarm", type=float, default=0.5, help="seconds of untimed frames before the W warm-up steps")
     ap.add_argument("--lanes", type=int, default=12, help="concurrent frames (streams) per GPU in the batched measurement")
     args = ap.parse_args()

@@ -62,7 +62,8 @@ SYMBOLS = [
     "osep_rosa_vertices", "osep_rosa_get", "osep_rosa_set_debug", "osep_rosa_set_profile", "osep_rosa_run_batch", "osep_rosa_run_batch_device",
     "osep_rosa_batch_vertices", "osep_rosa_set_lanes", "osep_rosa_graph", "osep_rosa_set_graph",
     "osep_gskel_create", "osep_gskel_destroy", "osep_gskel_run", "osep_gskel_run_tf", "osep_gskel_vertices", "osep_gskel_graph", "osep_gskel_get",
-    "osep_graph_build",
+    "osep_graph_build", "osep_graph_build_device",
+    "osep_points_select_range", "osep_rosa_vertices_device", "osep_rosa_leaf_device",
 ]
 
 _LIB = None
@@ -112,6 +113,10 @@ def load():
     L.osep_gskel_graph.argtypes = [vp, C.POINTER(GraphView)]
     L.osep_gskel_get.argtypes = [vp, C.c_char_p, vp, C.c_long]; L.osep_gskel_get.restype = C.c_long
     L.osep_graph_build.argtypes = [vp, vp, ip, ip, fp, C.POINTER(GraphView)]
+    L.osep_graph_build_device.argtypes = [vp, vp, ip, ip, fp, C.POINTER(GraphView)]
+    L.osep_points_select_range.argtypes = [ip, vp, ip, ip, ip, fp, fp, vp, ip, ip, C.POINTER(ip), vp]
+    L.osep_rosa_vertices_device.argtypes = [vp, C.POINTER(vp), C.POINTER(ip)]
+    L.osep_rosa_leaf_device.argtypes = [vp, vp, ip, ip, C.POINTER(fp), C.POINTER(ip)]
     _LIB = L
     return L
 

@@ -335,6 +335,41 @@ def test_tiled_map_per_tile_parity(mods):
     r.close()
 
 
+def test_device_resident_tile_primitives(mods):
+    """The C-ABI pieces of the device-resident tiled path (configs[4]): stable range compaction, the leaf-only pass, the
+    device copy of the vertices, the device graph build and TileRunner on one rank -- each against numpy / the oracle."""
+    import ctypes as C
+    import torch
+    osep, po, fx = mods
+    from osep_path_planner_b200 import tiled
+    P = fx.turbine(50000, seed=12)
+    t = torch.from_numpy(P).cuda()
+    for axis, lo, hi in ((0, -1.0, 2.5), (2, 10.0, 1e30), (1, -1e30, 0.0)):
+        sel = tiled.select_range(t, axis, lo, hi).cpu().numpy()
+        ref = P[(P[:, axis] >= lo) & (P[:, axis] < hi)]
+        assert_bit_equal(sel, ref, "select_range axis %d" % axis)            # same rows, same order
+    sel4 = tiled.select_range(t, 0, 0.0, 1.0, out_stride=4).cpu().numpy()
+    assert sel4.shape[1] == 4 and np.all(sel4[:, 3] == 1.0)
+    # leaf-only pass == the oracle's converged leaf on the same cloud
+    cfg = dict(pts_dist_lim=1.0e4)
+    o = po.RosaOracle(po.RosaConfig.default(**cfg)); assert o.run(P)
+    run = tiled.TileRunner(0, osep.RosaConfig(**cfg))
+    assert run.own_leaf(t) == np.float32(o.leaf_size)
+    # one rank: the tile is the slab, every vertex is owned; device vertices == host vertices == oracle
+    res = run.run(t, 2, -np.inf, np.inf)
+    assert res["ok"] and res["halo_points"] == 0 and res["tile_points"] == len(P)
+    v_dev = res["vertices"].cpu().numpy()
+    assert_bit_equal(v_dev[:, :3], o.tap("skelver"), "device vertices")
+    assert np.all(v_dev[:, 3] == 1.0)
+    go = po.GraphOracle(o.tap("skelver"), 3.0)
+    assert_bit_equal(res["graph"]["edges"].reshape(-1), go.tap("mst_edges"), "graph over device vertices")
+    # owned mask: a sub-interval keeps exactly the vertices inside it, in order
+    sk = o.tap("skelver"); mid = float(np.median(sk[:, 2]))
+    res2 = run.run(t, 2, -np.inf, mid, halo=1.0)
+    assert_bit_equal(res2["local"].cpu().numpy()[:, :3], sk[sk[:, 2] < mid], "owned vertices")
+    run.close()
+
+
 def test_large_voxels_global_sort_path(mods):
     """max_points small relative to N => voxels with more than 2048 points (the in-place global bitonic path)."""
     osep, po, fx = mods

@@ -1,6 +1,7 @@
-"""world_size-2 gloo test of the tiled-map path's host logic: slab partition, halo exchange (P2P send/recv),
-ownership filter and the all-gather of owned vertices.  The per-tile skeleton is a numpy stand-in here (voxel
-centroids); the real per-tile kernel parity is a GPU test."""
+"""gloo tests (world sizes 2 and 3) of the tiled-map path's exchange logic: slab partition, multi-hop halo exchange
+(P2P send/recv to every rank whose widened interval reaches into the slab), ownership filter and the all-gather of owned
+vertices.  The per-tile skeleton is a numpy stand-in here (voxel centroids); the real per-tile kernel parity and the
+device-resident pipeline are GPU tests."""
 import os
 import sys
 
@@ -69,3 +70,53 @@ def test_halo_exchange_and_vertex_gather_world2():
     assert np.array_equal(got[0][1], v0) and np.array_equal(got[1][1], v1)
     for r in range(2):
         assert np.array_equal(got[r][2][0], v0) and np.array_equal(got[r][2][1], v1)
+
+
+def _worker3(rank, world, port, q, bounds, halo):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from osep_path_planner_b200 import tiled
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    P = make_map()
+    own = tiled.slab_of(P, 0, bounds, rank)
+    res = tiled.tiled_skeleton(own, (bounds[rank], bounds[rank + 1]), 0, halo, fake_skeleton)
+    q.put((rank, res["tile"], res["local"], [np.asarray(v) for v in res["vertices"]], res["exchange"]))
+    dist.barrier(); dist.destroy_process_group()
+
+
+def test_multi_hop_halo_when_a_slab_is_thinner_than_the_halo():
+    """Three slabs, the middle one 4 m thin, halo 10 m: ranks 0 and 2 must receive each other's points THROUGH the middle
+    slab (rank +-2), not only their direct neighbour's -- a +-1-only exchange would hand them an incomplete neighbourhood."""
+    sys.path.insert(0, ROOT)
+    from osep_path_planner_b200 import tiled
+    P = make_map()
+    bounds = np.array([-np.inf, -2.0, 2.0, np.inf]); halo = 10.0
+    slabs = [tiled.slab_of(P, 0, bounds, r) for r in range(3)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29950 + (os.getpid() % 40)
+    ps = [ctx.Process(target=_worker3, args=(r, 3, port, q, bounds, halo)) for r in range(3)]
+    [p.start() for p in ps]
+    got = {}
+    for _ in range(3):
+        r, tile, local, allv, st = q.get(timeout=180)
+        got[r] = (tile, local, allv, st)
+    [p.join(60) for p in ps]
+    assert all(p.exitcode == 0 for p in ps)
+    for r in range(3):
+        lo, hi = bounds[r], bounds[r + 1]
+        parts = [slabs[r]]
+        for s in range(3):
+            if s != r:
+                c = slabs[s][:, 0]
+                parts.append(slabs[s][((c >= lo - halo) & (c < lo)) | ((c >= hi) & (c < hi + halo))])
+        exp = np.concatenate(parts)
+        assert np.array_equal(got[r][0], exp), "tile of rank %d" % r
+    assert got[0][3]["peers"] == 2 and got[2][3]["peers"] == 2       # the outer ranks serve both other ranks
+    n02 = ((slabs[2][:, 0] >= 2.0) & (slabs[2][:, 0] < 8.0)).sum()
+    assert n02 > 0 and len(got[0][0]) == len(slabs[0]) + len(slabs[1]) + n02
+    owned = [tiled.owned_filter(fake_skeleton(got[r][0]), 0, bounds[r], bounds[r + 1]) for r in range(3)]
+    for r in range(3):
+        for s in range(3):
+            assert np.array_equal(got[r][2][s], owned[s])
