@@ -224,6 +224,31 @@ int osep_rosa_leaf_device(osep_rosa* h, const float* xyz_dev, int n, int stride_
 /* osep_graph_build over DEVICE vertices (the all-gathered vertices of the tiles: the seam graph) */
 int osep_graph_build_device(osep_gskel* h, const float* xyz_dev, int n, int stride_floats, float fuse_dist_th, osep_graph_view* out);
 
+/* ---- the stages either side of the hot path, kept on the device -------------------------------- */
+
+/* tf2::doTransform(*msg, gmsg, T) (gskel_node.cpp:137-138) as a kernel: out = R(rotation_xyzw) * p + translation for n DEVICE
+ * records, in tf2_sensor_msgs' float32 arithmetic (the same sequence as osep_gskel_run_tf).  NULL translation/rotation = identity. */
+int osep_tf_points_device(int device, const float* in_dev, int n, int stride_floats, const double* translation, const double* rotation_xyzw,
+                          float* out_dev, int out_stride, void* stream);
+/* osep_gskel_run_tf with the candidates taken from the Rosa handle's DEVICE vertices (the frame that just ran): transform
+ * on the device, one small device-to-host copy of the transformed candidates for the stateful GSkel stages -- the sensor-frame
+ * vertices are never repacked or transformed on the host.  `rosa` must live on the same device as `h`. */
+int osep_gskel_run_tf_device(osep_gskel* h, osep_rosa* rosa, const double* translation, const double* rotation_xyzw);
+
+/* Accumulated map (the input of the tiled configuration, BASELINE.json configs[4]; the reference has no counterpart: its
+ * RosaNode consumes one PointCloud2 per tick, rosa_node.cpp:120-140).  A voxel hash on the device: every frame is transformed
+ * into the map frame (translation / rotation as in osep_tf_points_device) and inserted; a voxel of side voxel_size keeps the
+ * FIRST point that ever fell into it (lowest frame, then lowest index within the frame).  The kept points form an append-only
+ * dense DEVICE array in exactly that order, whatever the thread interleaving (tests/pyref/map_ref.py restates it on the CPU). */
+typedef struct osep_map osep_map;
+int osep_map_create(int device, int capacity_points, int max_frame_points, float voxel_size, osep_map** out);
+int osep_map_destroy(osep_map* m);
+int osep_map_insert_device(osep_map* m, const float* xyz_dev, int n, int stride_floats, const double* translation, const double* rotation_xyzw, int* n_new);
+int osep_map_insert(osep_map* m, const float* xyz_host, int n, int stride_floats, const double* translation, const double* rotation_xyzw, int* n_new);
+/* the dense point array: n_points records {x, y, z, 1}, DEVICE pointer, valid until the map is destroyed (it only grows) */
+int osep_map_points_device(osep_map* m, const float** xyzw_dev, int* n_points);
+int osep_map_clear(osep_map* m);
+
 #ifdef __cplusplus
 }
 #endif

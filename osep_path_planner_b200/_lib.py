@@ -64,6 +64,8 @@ SYMBOLS = [
     "osep_gskel_create", "osep_gskel_destroy", "osep_gskel_run", "osep_gskel_run_tf", "osep_gskel_vertices", "osep_gskel_graph", "osep_gskel_get",
     "osep_graph_build", "osep_graph_build_device",
     "osep_points_select_range", "osep_rosa_vertices_device", "osep_rosa_leaf_device",
+    "osep_tf_points_device", "osep_gskel_run_tf_device",
+    "osep_map_create", "osep_map_destroy", "osep_map_insert_device", "osep_map_insert", "osep_map_points_device", "osep_map_clear",
 ]
 
 _LIB = None
@@ -117,6 +119,14 @@ def load():
     L.osep_points_select_range.argtypes = [ip, vp, ip, ip, ip, fp, fp, vp, ip, ip, C.POINTER(ip), vp]
     L.osep_rosa_vertices_device.argtypes = [vp, C.POINTER(vp), C.POINTER(ip)]
     L.osep_rosa_leaf_device.argtypes = [vp, vp, ip, ip, C.POINTER(fp), C.POINTER(ip)]
+    L.osep_tf_points_device.argtypes = [ip, vp, ip, ip, vp, vp, vp, ip, vp]
+    L.osep_gskel_run_tf_device.argtypes = [vp, vp, vp, vp]
+    L.osep_map_create.argtypes = [ip, ip, ip, fp, C.POINTER(vp)]
+    L.osep_map_destroy.argtypes = [vp]
+    L.osep_map_insert_device.argtypes = [vp, vp, ip, ip, vp, vp, C.POINTER(ip)]
+    L.osep_map_insert.argtypes = [vp, vp, ip, ip, vp, vp, C.POINTER(ip)]
+    L.osep_map_points_device.argtypes = [vp, C.POINTER(vp), C.POINTER(ip)]
+    L.osep_map_clear.argtypes = [vp]
     _LIB = L
     return L
 

@@ -333,6 +333,7 @@ struct GSkelImpl {
     int failed_stage = 0;
     std::vector<float> out_xyz4;
     std::vector<float4> upload;
+    std::vector<float> tf_host;        // osep_gskel_run_tf_device: transformed candidates (device -> host, 16 bytes per vertex)
     // views
     std::vector<int> v_adj_off, v_adj_idx, v_type, v_edges; std::vector<float> v_w;
 
@@ -689,6 +690,25 @@ int osep_gskel_run_tf(osep_gskel* h, const float* cand_xyz, int n, int stride_fl
         g[3 * (size_t)i + 2] = sum3(r20 * x, r21 * y, r22 * z) + t2;
     }
     return osep_gskel_run(h, g.data(), n, 3);
+}
+
+// the Rosa -> TF -> GSkel hand-off without a host-side transform: candidates = the Rosa handle's device vertices
+int osep_gskel_run_tf_device(osep_gskel* h, osep_rosa* rosa, const double* translation, const double* rotation_xyzw) {
+    if (!h || !rosa || !translation || !rotation_xyzw) return OSEP_ERR_ARG;
+    const float* src = nullptr; int n = 0;
+    int rc = osep_rosa_vertices_device(rosa, &src, &n);          // waits for the frame
+    if (rc != OSEP_OK) return rc;
+    if (cudaSetDevice(h->device) != cudaSuccess) return OSEP_ERR_CUDA;
+    GraphHost* g = h->impl.g;
+    if (n > g->cap) return OSEP_ERR_CAPACITY;
+    std::vector<float>& host = h->impl.tf_host;
+    host.resize((size_t)n * 4);
+    if (n > 0) {
+        rc = osep_tf_points_device(h->device, src, n, 4, translation, rotation_xyzw, reinterpret_cast<float*>(g->pos), 4, (void*)g->stream);
+        if (rc != OSEP_OK) return rc;
+        if (cudaMemcpyAsync(host.data(), g->pos, sizeof(float4) * n, cudaMemcpyDeviceToHost, g->stream) != cudaSuccess || cudaStreamSynchronize(g->stream) != cudaSuccess) return OSEP_ERR_CUDA;
+    }
+    return osep_gskel_run(h, host.data(), n, 4);
 }
 
 int osep_gskel_vertices(osep_gskel* h, const float** xyz4, int* n_vertices) {

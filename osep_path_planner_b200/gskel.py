@@ -76,6 +76,17 @@ class GSkel:
         self.running = rc == 0
         return self.running
 
+    def gskel_run_tf_device(self, rosa, translation, rotation_xyzw):
+        """gskel_run_tf with the candidates taken from `rosa`'s DEVICE vertices (the frame that just ran): the transform
+        runs on the device (osep_gskel_run_tf_device)."""
+        t = np.ascontiguousarray(translation, dtype=np.float64); q = np.ascontiguousarray(rotation_xyzw, dtype=np.float64)
+        rc = self._L.osep_gskel_run_tf_device(self._h, rosa._h, t.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p))
+        if rc < 0:
+            raise OsepError("osep_gskel_run_tf_device failed (%d): %s" % (rc, _lib.last_error()))
+        self.failed_stage = rc
+        self.running = rc == 0
+        return self.running
+
     def output_gskel(self):
         p = C.POINTER(C.c_float)(); n = C.c_int()
         self._L.osep_gskel_vertices(self._h, C.byref(p), C.byref(n))

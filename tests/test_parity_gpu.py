@@ -370,6 +370,68 @@ def test_device_resident_tile_primitives(mods):
     run.close()
 
 
+def test_map_accumulation_and_device_tf(mods):
+    """the TF kernel, the device hand-off Rosa -> TF -> GSkel and the accumulated voxel map against their
+    CPU restatements (tests/pyref/map_ref.py, the oracle's orc_tf_points and the host entry point osep_gskel_run_tf)."""
+    import ctypes as C
+    import torch
+    osep, po, fx = mods
+    from osep_path_planner_b200.map import SkelMap
+    from osep_path_planner_b200 import GSkel, GSkelConfig
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "pyref"))
+    import map_ref
+    L = osep.load()
+    # (1) TF kernel == float32 restatement, bit for bit
+    P, Rm, tv = fx.stream_frame(40, n=20000)
+    q = np.array([0.1, -0.2, 0.3, 0.9]); q /= np.linalg.norm(q)
+    t = np.array([12.5, -3.25, 40.0])
+    tin = torch.from_numpy(np.ascontiguousarray(P)).cuda(); tout = torch.empty((len(P), 3), dtype=torch.float32, device="cuda")
+    rc = L.osep_tf_points_device(0, C.c_void_p(tin.data_ptr()), len(P), 3, t.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p),
+                                 C.c_void_p(tout.data_ptr()), 3, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert_bit_equal(tout.cpu().numpy(), map_ref.tf_points(P, t, q), "tf kernel")
+    # (2) accumulated map: 6 overlapping stream frames, each with its pose; same voxels, same points, same order
+    m = SkelMap(capacity_points=400000, max_frame_points=30000, voxel_size=0.25)
+    ref = map_ref.MapRef(0.25)
+    for f in range(6):
+        Pf, Rm, tv = fx.stream_frame(f * 20, n=25000)
+        qf = np.array([0.0, 0.0, np.sin(0.05 * f), np.cos(0.05 * f)]); tf_ = np.array([0.3 * f, -0.1 * f, 0.0])
+        if f == 3:
+            Pf = Pf.copy(); Pf[::997] = np.nan                                   # non-finite points are dropped
+        got = m.insert(Pf, tf_, qf) if f % 2 == 0 else m.insert_device(torch.from_numpy(np.ascontiguousarray(Pf)).cuda().data_ptr(), len(Pf), 3, tf_, qf)
+        assert got == ref.insert(Pf, tf_, qf), "new voxels of frame %d" % f
+    mp = m.points_tensor().cpu().numpy()
+    assert_bit_equal(mp[:, :3], ref.array(), "accumulated map points (order = first appearance)")
+    assert np.all(mp[:, 3] == 1.0) and len(mp) > 20000
+    # the map feeds the tiled path without leaving the device
+    from osep_path_planner_b200 import tiled
+    run = tiled.TileRunner(0, osep.RosaConfig(pts_dist_lim=1.0e4))
+    res = run.run(m.points_tensor(), 0, -np.inf, np.inf)
+    o = po.RosaOracle(po.RosaConfig.default(pts_dist_lim=1.0e4)); ok_o = o.run(ref.array())
+    assert res["ok"] == ok_o
+    if ok_o:
+        assert_bit_equal(res["vertices"].cpu().numpy()[:, :3], o.tap("skelver"), "skeleton of the accumulated map")
+    run.close(); m.close()
+    # (3) Rosa -> TF -> GSkel on the device == host TF entry point, tick by tick
+    r = osep.Rosa(capacity_points=60000)
+    ga, gb = GSkel(GSkelConfig(gnd_th=-100.0)), GSkel(GSkelConfig(gnd_th=-100.0))
+    for f in range(8):
+        Pf, Rm, tv = fx.stream_frame(f * 10, n=30000)
+        r.set_input(Pf)
+        if not r.rosa_run():
+            continue
+        qf = np.array([0.0, 0.0, np.sin(0.02 * f), np.cos(0.02 * f)]); tf_ = np.array([0.5 * f, 0.2 * f, 1.0])
+        ga.set_input(np.ascontiguousarray(r.output_vertices())); oka = ga.gskel_run_tf(tf_, qf)
+        okb = gb.gskel_run_tf_device(r, tf_, qf)
+        assert bool(okb) == bool(oka)
+        assert_bit_equal(np.ascontiguousarray(ga.output_gskel()), np.ascontiguousarray(gb.output_gskel()), "global skeleton tick %d" % f)
+        ea, eb = ga.graph(), gb.graph()
+        assert_bit_equal(ea["edges"].reshape(-1), eb["edges"].reshape(-1), "global graph tick %d" % f)
+    ga.close(); gb.close(); r.close()
+
+
 def test_large_voxels_global_sort_path(mods):
     """max_points small relative to N => voxels with more than 2048 points (the in-place global bitonic path)."""
     osep, po, fx = mods

@@ -152,3 +152,30 @@ def test_gskel_edge_cases_of_the_reference():
     # the `del > size` guard of vertex_merge (gskel.cpp:329) admits del == size; to_delete only ever holds indices < size,
     # so the erase it would permit is unreachable -- checked on the restatement's own bookkeeping
     assert all(i < len(ref.glob) for i in ref.new_idx)
+
+
+def test_map_reference_and_tf_restatements_agree():
+    """tests/pyref/map_ref.py (numpy) against the C++ oracle's orc_tf_points (both restate tf2_sensor_msgs' float32 transform,
+    gskel_node.cpp:137-138) bit for bit, and the first-point-per-voxel map law on a case small enough to check by hand."""
+    import ctypes as C
+    from pyref import map_ref
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(3)
+    P = rng.uniform(-40, 40, (5000, 3)).astype(np.float32)
+    q = np.array([0.3, -0.1, 0.2, 0.9]); q /= np.linalg.norm(q)
+    t = np.array([3.5, -7.25, 11.0])
+    out = np.empty((len(P), 3), np.float32)
+    L = po.lib()
+    L.orc_tf_points.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_tf_points(P.ctypes.data_as(C.c_void_p), len(P), 3, t.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    got = map_ref.tf_points(P, t, q)
+    assert got.tobytes() == out.tobytes()
+    # float64 rigid transform within float32 rounding
+    x, y, z, w = q
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    assert np.abs(got - (P.astype(np.float64) @ R.T + t)).max() < 2e-5
+    m = map_ref.MapRef(1.0)
+    assert m.insert(np.array([[0.2, 0.2, 0.2], [0.7, 0.1, 0.9], [1.2, 0.0, 0.0], [np.nan, 0, 0]], np.float32)) == 2
+    assert m.insert(np.array([[0.5, 0.5, 0.5], [-0.1, 0.0, 0.0], [1.9, 0.9, 0.1]], np.float32)) == 1
+    assert np.array_equal(m.array(), np.array([[0.2, 0.2, 0.2], [1.2, 0, 0], [-0.1, 0, 0]], np.float32))
