@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libosep_skel.so")
+LIB_PATH = os.environ.get("OSEP_SKEL_LIB") or os.path.join(_HERE, "libosep_skel.so")     # OSEP_SKEL_LIB: an instrumented build of the same library (make stress)
 
 OSEP_OK = 0
 ERR_CUDA, ERR_ARG, ERR_CAPACITY = -1, -2, -3

@@ -308,13 +308,16 @@ int osep_rosa_run(osep_rosa* h, const float* xyz_host, int n, int stride_floats,
     int rc = check_frame(I, n, stride_floats);
     if (rc) { if (res) { memset(res, 0, sizeof(*res)); res->status = rc; } return rc; }
     CK(cudaSetDevice(I.device));
+    int dev_stride = stride_floats;
     if (n > 0) {
-        if (stride_floats > 4) {        // pack wide points on the host side of the copy: only xyz travels
-            set_err("stride_floats > 4 not supported by the host entry point"); return OSEP_ERR_ARG;
+        if (stride_floats > 4) {        // wide records (intensity, ring, time ...): only x, y, z travel, packed into 16-byte records
+            CK(cudaMemcpy2DAsync(I.d.in, 16, xyz_host, sizeof(float) * (size_t)stride_floats, 12, (size_t)n, cudaMemcpyHostToDevice, I.stream));
+            dev_stride = 4;
+        } else {
+            CK(cudaMemcpyAsync(I.d.in, xyz_host, sizeof(float) * (size_t)n * stride_floats, cudaMemcpyHostToDevice, I.stream));
         }
-        CK(cudaMemcpyAsync(I.d.in, xyz_host, sizeof(float) * (size_t)n * stride_floats, cudaMemcpyHostToDevice, I.stream));
     }
-    rc = osep_rosa_run_device(h, I.d.in, n, stride_floats);
+    rc = osep_rosa_run_device(h, I.d.in, n, dev_stride);
     if (rc) { if (res) { memset(res, 0, sizeof(*res)); res->status = rc; } return rc; }
     return rosa_collect(&I, res);
 }

@@ -557,8 +557,20 @@ struct FusedArgs {
     long long* tl;         // detail mode: per (it, p) 8 globaltimer stamps [G solved, task published, worker start, O flag, O staged] (tools/fused_dbg.py)
 };
 
-__device__ __forceinline__ int ld_vol(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
-__device__ __forceinline__ void st_vol(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
+// -DOSEP_STRESS (make stress -> libosep_skel_stress.so): a pseudo-random delay of 0..4 us in front of every flag / queue /
+// state-byte access of the fused kernel, so that orderings a normal run never produces do occur; tools/soak.py then has
+// to reproduce every frame bit for bit (profiles/r2_stress_soak.log).  compute-sanitizer is not usable on this pool.
+#ifdef OSEP_STRESS
+__device__ __forceinline__ void stress_delay() {
+    unsigned x = (unsigned)clock64() * 2654435761u + threadIdx.x * 40503u + blockIdx.x * 9176u;
+    x ^= x >> 13; x *= 2246822519u; x ^= x >> 15;
+    if ((x & 3u) == 0u) __nanosleep((x >> 8) & 4095u);
+}
+#else
+__device__ __forceinline__ void stress_delay() {}
+#endif
+__device__ __forceinline__ int ld_vol(const int* p) { stress_delay(); return *reinterpret_cast<const volatile int*>(p); }
+__device__ __forceinline__ void st_vol(int* p, int v) { stress_delay(); *reinterpret_cast<volatile int*>(p) = v; }
 
 __device__ __forceinline__ void fused_worker(const FusedArgs& a, uint4* smem, int M) {
     const int Wn = (M + 31) >> 5;
@@ -808,6 +820,7 @@ __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int
                 int j[10]; unsigned sj[10];
 #pragma unroll
                 for (int k = 0; k < 5; ++k) { j[2 * k] = (int)(nb[k] & 0xffffu); j[2 * k + 1] = (int)(nb[k] >> 16); }
+                stress_delay();
                 const unsigned sc = vstate[cand];
 #pragma unroll
                 for (int u = 0; u < 10; ++u) sj[u] = vstate[j[u]];
@@ -847,6 +860,7 @@ __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int
                 my_it = E.iters;
                 const f3 d = normalize3_dev(eig_col(E, 2));                                         // rosa.cpp:305-307
                 snew[cand] = make_float4(d.x, d.y, d.z, wself);
+                stress_delay();
                 vstate[cand] = 3;
                 if (a.tl) a.tl[((size_t)it * a.Mcap + cand) * 16 + 0] = gtime();
                 solist[ndone + r] = (unsigned short)cand;
@@ -975,6 +989,7 @@ __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int
                 __threadfence_block();
 #pragma unroll
                 for (int u = 0; u < 8; ++u) if (f[u] != 0) {
+                    stress_delay();
                     vstate[j[u]] = 1;
                     if (a.tl) a.tl[((size_t)it * a.Mcap + j[u]) * 16 + 4] = gtime();
                     pend &= ~(1u << (kb + u));

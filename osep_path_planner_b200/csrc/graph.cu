@@ -145,24 +145,39 @@ k_graph_mst(const float4* __restrict__ pos, int G_arg, const FrameState* __restr
     }
     for (int i = threadIdx.x; i < G; i += blockDim.x) parent[i] = i;
     __syncthreads();
-    if (threadIdx.x == 0) {
+    // Kruskal over the sorted keys by ONE WARP, 32 edges per round: every lane finds the roots of its edge's end points in
+    // parallel (read-only), then the 32 edges are accepted in key order -- an accepted edge redirects the root of every later
+    // lane of the round by shuffle -- and the unions are committed.  Same accept/reject decisions as the sequential loop of
+    // gskel.cpp:258-278 (a UnionFind answers "same component?" independently of its internal shape).  The loop ends when the
+    // tree is complete (G - 1 edges): the remaining edges could only be rejected.
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
         int m = 0;
-        unsigned long long prev = ~0ull;
-        for (int e = 0; e < n; ++e) {
-            const unsigned long long key = keys[e];
-            if (key == prev) continue;            // the same pair accepted from both ends: the reference's second unite() returns false
-            prev = key;
+        for (int base = 0; base < n && m < G - 1; base += 32) {
+            const int e = base + lane;
+            const unsigned long long key = e < n ? keys[e] : ~0ull;
+            const unsigned long long prevk = e > 0 && e < n ? keys[e - 1] : ~0ull;
+            bool live = e < n && key != prevk;       // the same pair accepted from both ends: the reference's second unite() returns false
             const int u = (int)((key >> 16) & 0xffffu), v = (int)(key & 0xffffu);
-            int rx = u; while (parent[rx] != rx) rx = parent[rx];
-            { int x = u; while (parent[x] != rx) { const int nx = parent[x]; parent[x] = rx; x = nx; } }
-            int ry = v; while (parent[ry] != ry) ry = parent[ry];
-            { int x = v; while (parent[x] != ry) { const int nx = parent[x]; parent[x] = ry; x = nx; } }
-            if (rx == ry) continue;
-            parent[ry] = rx;
-            mst_uv[2 * m] = u; mst_uv[2 * m + 1] = v; mst_w[m] = __uint_as_float((unsigned)(key >> 32));
-            ++m;
+            int rx = 0, ry = 0;
+            if (live) { rx = u; while (parent[rx] != rx) rx = parent[rx]; ry = v; while (parent[ry] != ry) ry = parent[ry]; }
+            bool take = false;
+            for (int l = 0; l < 32; ++l) {
+                const bool t = __shfl_sync(0xffffffffu, (int)(live && rx != ry), l) != 0;     // lane l's decision with the roots as of now
+                const int a = __shfl_sync(0xffffffffu, rx, l), b = __shfl_sync(0xffffffffu, ry, l);
+                if (!t) continue;
+                if (lane == l) { take = true; parent[b] = a; }
+                else if (lane > l) { if (rx == b) rx = a; if (ry == b) ry = a; }
+            }
+            __syncwarp();
+            const unsigned tm = __ballot_sync(0xffffffffu, take);
+            if (take) {
+                const int pos = m + __popc(tm & ((1u << lane) - 1u));
+                mst_uv[2 * pos] = u; mst_uv[2 * pos + 1] = v; mst_w[pos] = __uint_as_float((unsigned)(key >> 32));
+            }
+            m += __popc(tm);
         }
-        gs->n_edges = n; gs->n_mst = m; gs->overflow = 0; gs->pad = G;
+        if (lane == 0) { gs->n_edges = n; gs->n_mst = m; gs->overflow = 0; gs->pad = G; }
     }
 }
 

@@ -133,6 +133,10 @@ def test_ragged_input_nonfinite_far_points_duplicates_and_stride(mods):
     P3 = np.ascontiguousarray(P)
     assert L.osep_rosa_run(r._h, P3.ctypes.data_as(C.c_void_p), P3.shape[0], 3, C.byref(res)) == 0
     assert_bit_equal(r.tap("skelver"), o.tap("skelver"), "stride 3")
+    # wide host records (x, y, z, intensity, ring, time: 6 floats): only x, y, z travel to the device
+    P6 = np.ascontiguousarray(np.concatenate([P, np.full((len(P), 3), 7.0, np.float32)], axis=1))
+    assert L.osep_rosa_run(r._h, P6.ctypes.data_as(C.c_void_p), P6.shape[0], 6, C.byref(res)) == 0
+    assert_bit_equal(r.tap("skelver"), o.tap("skelver"), "stride 6")
     r.close()
 
 
