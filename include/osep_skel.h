@@ -216,6 +216,10 @@ int osep_graph_build(osep_gskel* h, const float* xyz, int n, int stride_floats, 
  * matches in *count_host.  More than out_cap matches -> OSEP_ERR_CAPACITY (the first out_cap are written, the count is exact). */
 int osep_points_select_range(int device, const float* pts_dev, int n, int stride_floats, int axis, float lo, float hi,
                              float* out_dev, int out_stride, int out_cap, int* count_host, void* stream);
+/* The same compaction with an axis-aligned box test on all three coordinates: lo[d] <= p[d] < hi[d] (pass -/+3e38 for an open
+ * side).  Tiles of a recursive-bisection partition are boxes; their halo is the box widened by the halo width. */
+int osep_points_select_box(int device, const float* pts_dev, int n, int stride_floats, const float* lo3, const float* hi3,
+                           float* out_dev, int out_stride, int out_cap, int* count_host, void* stream);
 /* Device copy of output_vertices() (rosa.hpp:53): V records {x, y, z, 1} of the last frame, valid until the next run. */
 int osep_rosa_vertices_device(osep_rosa* h, const float** xyzw_dev, int* n_vertices);
 /* filter + leaf-size control law only (rosa.cpp:67-95, 118-148) on a DEVICE cloud: the converged leaf of a tile's own points

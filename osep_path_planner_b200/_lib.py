@@ -63,7 +63,7 @@ SYMBOLS = [
     "osep_rosa_batch_vertices", "osep_rosa_set_lanes", "osep_rosa_graph", "osep_rosa_set_graph",
     "osep_gskel_create", "osep_gskel_destroy", "osep_gskel_run", "osep_gskel_run_tf", "osep_gskel_vertices", "osep_gskel_graph", "osep_gskel_get",
     "osep_graph_build", "osep_graph_build_device",
-    "osep_points_select_range", "osep_rosa_vertices_device", "osep_rosa_leaf_device",
+    "osep_points_select_range", "osep_points_select_box", "osep_rosa_vertices_device", "osep_rosa_leaf_device",
     "osep_tf_points_device", "osep_gskel_run_tf_device",
     "osep_map_create", "osep_map_destroy", "osep_map_insert_device", "osep_map_insert", "osep_map_points_device", "osep_map_clear",
 ]
@@ -117,6 +117,7 @@ def load():
     L.osep_graph_build.argtypes = [vp, vp, ip, ip, fp, C.POINTER(GraphView)]
     L.osep_graph_build_device.argtypes = [vp, vp, ip, ip, fp, C.POINTER(GraphView)]
     L.osep_points_select_range.argtypes = [ip, vp, ip, ip, ip, fp, fp, vp, ip, ip, C.POINTER(ip), vp]
+    L.osep_points_select_box.argtypes = [ip, vp, ip, ip, vp, vp, vp, ip, ip, C.POINTER(ip), vp]
     L.osep_rosa_vertices_device.argtypes = [vp, C.POINTER(vp), C.POINTER(ip)]
     L.osep_rosa_leaf_device.argtypes = [vp, vp, ip, ip, C.POINTER(fp), C.POINTER(ip)]
     L.osep_tf_points_device.argtypes = [ip, vp, ip, ip, vp, vp, vp, ip, vp]

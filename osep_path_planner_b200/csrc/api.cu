@@ -20,8 +20,8 @@ int graph_enqueue_in_frame(GraphHost* g, const float4* pos_dev, const FrameState
 int graph_collect_in_frame(GraphHost* g, osep_graph_view* out);
 size_t frame_export_enqueue(GraphHost* g, const FrameState* st, const float4* skel, int Mq, unsigned char* exp_dev, cudaStream_t s);
 size_t frame_export_bytes(int Mq);
-int select_range_enqueue(const float* in, int n, int stride, int axis, float lo, float hi, float* out, int out_stride, int out_cap,
-                         int* blk_cnt, int* total_dev, cudaStream_t s);
+int select_box_enqueue(const float* in, int n, int stride, const float* lo3, const float* hi3, float* out, int out_stride, int out_cap,
+                       int* blk_cnt, int* total_dev, cudaStream_t s);
 void launch_leaf_only(osep_rosa_impl* h);
 void graph_set_mirrors(GraphHost* g, unsigned char* exp_host, int Mq);
 
@@ -463,9 +463,9 @@ int osep_rosa_set_graph(osep_rosa* h, int enable, float fuse_dist_th) {
 }
 
 // ---- tiled maps
-int osep_points_select_range(int device, const float* pts_dev, int n, int stride_floats, int axis, float lo, float hi,
-                             float* out_dev, int out_stride, int out_cap, int* count_host, void* stream) {
-    if (n < 0 || stride_floats < 3 || axis < 0 || axis > 2 || (out_stride != 3 && out_stride != 4) || out_cap < 0 || !count_host) { set_err("osep_points_select_range: bad argument"); return OSEP_ERR_ARG; }
+int osep_points_select_box(int device, const float* pts_dev, int n, int stride_floats, const float* lo3, const float* hi3,
+                           float* out_dev, int out_stride, int out_cap, int* count_host, void* stream) {
+    if (n < 0 || stride_floats < 3 || !lo3 || !hi3 || (out_stride != 3 && out_stride != 4) || out_cap < 0 || !count_host) { set_err("osep_points_select_box: bad argument"); return OSEP_ERR_ARG; }
     *count_host = 0;
     if (n == 0) return OSEP_OK;
     if (!pts_dev || (!out_dev && out_cap > 0)) return OSEP_ERR_ARG;
@@ -474,15 +474,23 @@ int osep_points_select_range(int device, const float* pts_dev, int n, int stride
     int* scratch = nullptr;                           // per-block counts + the total (stream-ordered allocation)
     const size_t nb = (size_t)(n + 255) / 256;
     CK(cudaMallocAsync((void**)&scratch, sizeof(int) * (nb + 2), s));
-    int rc = select_range_enqueue(pts_dev, n, stride_floats, axis, lo, hi, out_dev, out_stride, out_cap, scratch, scratch + nb + 1, s);
+    int rc = select_box_enqueue(pts_dev, n, stride_floats, lo3, hi3, out_dev, out_stride, out_cap, scratch, scratch + nb + 1, s);
     int total = 0;
     if (rc == OSEP_OK && cudaMemcpyAsync(&total, scratch + nb + 1, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = OSEP_ERR_CUDA;
     cudaFreeAsync(scratch, s);
     if (cudaStreamSynchronize(s) != cudaSuccess) rc = OSEP_ERR_CUDA;
-    if (rc != OSEP_OK) { set_err("osep_points_select_range: %s", cudaGetErrorString(cudaGetLastError())); return rc; }
+    if (rc != OSEP_OK) { set_err("osep_points_select_box: %s", cudaGetErrorString(cudaGetLastError())); return rc; }
     *count_host = total;
-    if (total > out_cap) { set_err("osep_points_select_range: %d matches, room for %d", total, out_cap); return OSEP_ERR_CAPACITY; }
+    if (total > out_cap) { set_err("osep_points_select_box: %d matches, room for %d", total, out_cap); return OSEP_ERR_CAPACITY; }
     return OSEP_OK;
+}
+
+int osep_points_select_range(int device, const float* pts_dev, int n, int stride_floats, int axis, float lo, float hi,
+                             float* out_dev, int out_stride, int out_cap, int* count_host, void* stream) {
+    if (axis < 0 || axis > 2) { set_err("osep_points_select_range: bad axis"); return OSEP_ERR_ARG; }
+    float lo3[3] = {-3.0e38f, -3.0e38f, -3.0e38f}, hi3[3] = {3.0e38f, 3.0e38f, 3.0e38f};
+    lo3[axis] = lo; hi3[axis] = hi;
+    return osep_points_select_box(device, pts_dev, n, stride_floats, lo3, hi3, out_dev, out_stride, out_cap, count_host, stream);
 }
 
 int osep_rosa_vertices_device(osep_rosa* h, const float** xyzw_dev, int* n_vertices) {

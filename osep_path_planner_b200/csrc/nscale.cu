@@ -1333,11 +1333,14 @@ static void launch_knn(osep_rosa_impl* h, int n, int k_req, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------
-// tiled maps: stable range compaction (osep_points_select_range) and the leaf-only pass (osep_rosa_leaf_device)
-__device__ __forceinline__ bool in_range(const float* p, int axis, float lo, float hi) { const float c = p[axis]; return c >= lo && c < hi; }
-__global__ void k_range_count(const float* __restrict__ in, int n, int stride, int axis, float lo, float hi, int* __restrict__ blk_cnt) {
+// tiled maps: stable box / range compaction (osep_points_select_box, osep_points_select_range) and the leaf-only pass (osep_rosa_leaf_device)
+struct Box3 { float lo[3], hi[3]; };
+__device__ __forceinline__ bool in_box(const float* p, const Box3& b) {
+    return p[0] >= b.lo[0] && p[0] < b.hi[0] && p[1] >= b.lo[1] && p[1] < b.hi[1] && p[2] >= b.lo[2] && p[2] < b.hi[2];
+}
+__global__ void k_range_count(const float* __restrict__ in, int n, int stride, Box3 box, int* __restrict__ blk_cnt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool keep = i < n && in_range(in + (size_t)i * stride, axis, lo, hi);
+    const bool keep = i < n && in_box(in + (size_t)i * stride, box);
     const int c = __syncthreads_count(keep);
     if (threadIdx.x == 0) blk_cnt[blockIdx.x] = c;
 }
@@ -1345,13 +1348,13 @@ __global__ void k_range_scan(int* blk_cnt, int nblk, int* total) {
     const int t = block_excl_scan(blk_cnt, nblk);
     if (threadIdx.x == 0) *total = t;
 }
-__global__ void k_range_scatter(const float* __restrict__ in, int n, int stride, int axis, float lo, float hi, const int* __restrict__ blk_off,
+__global__ void k_range_scatter(const float* __restrict__ in, int n, int stride, Box3 box, const int* __restrict__ blk_off,
                                 float* __restrict__ out, int out_stride, int out_cap) {
     __shared__ int warp_cnt[NT / 32];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const float* p = in + (size_t)min(i, n - 1) * stride;
-    const bool keep = i < n && in_range(p, axis, lo, hi);
+    const bool keep = i < n && in_box(p, box);
     const unsigned m = __ballot_sync(0xffffffffu, keep);
     if (lane == 0) warp_cnt[wid] = __popc(m);
     __syncthreads();
@@ -1366,12 +1369,14 @@ __global__ void k_range_scatter(const float* __restrict__ in, int n, int stride,
         }
     }
 }
-int select_range_enqueue(const float* in, int n, int stride, int axis, float lo, float hi, float* out, int out_stride, int out_cap,
-                         int* blk_cnt, int* total_dev, cudaStream_t s) {
+int select_box_enqueue(const float* in, int n, int stride, const float* lo3, const float* hi3, float* out, int out_stride, int out_cap,
+                       int* blk_cnt, int* total_dev, cudaStream_t s) {
+    Box3 box;
+    for (int d = 0; d < 3; ++d) { box.lo[d] = lo3[d]; box.hi[d] = hi3[d]; }
     const int nb = div_up(n, NT);
-    k_range_count<<<nb, NT, 0, s>>>(in, n, stride, axis, lo, hi, blk_cnt);
+    k_range_count<<<nb, NT, 0, s>>>(in, n, stride, box, blk_cnt);
     k_range_scan<<<1, 1024, 0, s>>>(blk_cnt, nb, total_dev);
-    k_range_scatter<<<nb, NT, 0, s>>>(in, n, stride, axis, lo, hi, blk_cnt, out, out_stride, out_cap);
+    k_range_scatter<<<nb, NT, 0, s>>>(in, n, stride, box, blk_cnt, out, out_stride, out_cap);
     return cudaGetLastError() == cudaSuccess ? OSEP_OK : OSEP_ERR_CUDA;
 }
 // R3/R4 + R7/R8 only: the frame stops after the leaf-size control law

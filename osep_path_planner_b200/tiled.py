@@ -1,7 +1,9 @@
 """Tiled skeleton extraction of a large accumulated map (BASELINE.json configs[4]).
 
-The map is split into P slabs of (about) equal point count along its longest axis, one slab per rank /
-GPU, and STAYS ON THE DEVICE: a rank's slab is a CUDA tensor, the halo points are selected by a kernel of the
+The map is split into P axis-aligned boxes of (about) equal point count, one per rank / GPU -- slabs along one axis
+(split_axis_and_bounds) or, for structure-like maps whose points are thin along every axis somewhere, a recursive
+coordinate bisection that cuts where the fewest points lie within a halo width of the cut (rcb_boxes) -- and STAYS ON
+THE DEVICE: a rank's slab is a CUDA tensor, the halo points are selected by a kernel of the
 library (osep_points_select_range: stable compaction by the axis test), travel rank to rank with NCCL
 send/recv straight into the tail of the tile buffer, the tile runs as one frame of the hot path
 (osep_rosa_run_device), the owned vertices are masked on the device and all-gathered with NCCL, and the seam
@@ -33,13 +35,27 @@ from . import _lib
 
 
 # ---- partition helpers (single process, host: used to build the synthetic map and by the tests) ---------------------
-def split_axis_and_bounds(points, world):
-    """Longest axis and P+1 slab boundaries with equal point counts."""
+def split_axis_and_bounds(points, world, halo=None):
+    """Split axis and P+1 slab boundaries with equal point counts.  halo=None: the longest axis (the single-rank / test
+    default).  With a halo estimate the axis is the one whose largest TILE (slab + halo on both sides) is smallest: on
+    structure-like maps the longest axis can be the one most of the points are thin along (rotor planes, facades), and
+    equal-count slabs thinner than the halo make every tile several slabs wide."""
+    def bounds_of(axis):
+        q = np.quantile(points[:, axis].astype(np.float64), np.linspace(0, 1, world + 1))
+        q[0], q[-1] = -np.inf, np.inf
+        return q
     ext = points.max(0) - points.min(0)
-    axis = int(np.argmax(ext))
-    q = np.quantile(points[:, axis].astype(np.float64), np.linspace(0, 1, world + 1))
-    q[0], q[-1] = -np.inf, np.inf
-    return axis, q
+    if halo is None or world == 1:
+        axis = int(np.argmax(ext))
+        return axis, bounds_of(axis)
+    best = None
+    for axis in range(3):
+        q = bounds_of(axis)
+        c = np.sort(points[:, axis].astype(np.float64))
+        sizes = [np.searchsorted(c, q[r + 1] + halo) - np.searchsorted(c, q[r] - halo) for r in range(world)]
+        if best is None or max(sizes) < best[0]:
+            best = (max(sizes), axis, q)
+    return best[1], best[2]
 
 
 def slab_of(points, axis, bounds, r):
@@ -58,6 +74,44 @@ def owned_filter(vertices, axis, lo, hi):
         return vertices
     c = vertices[:, axis]
     return vertices[(c >= lo) & (c < hi)]
+
+
+def rcb_boxes(points, world, halo):
+    """Recursive coordinate bisection: `world` boxes (lo[3], hi[3]) of equal point count; every cut is taken along the axis
+    with the fewest points within `halo` of the cut plane (the points both sides would have to exchange).  Returns
+    (boxes float64 (world, 2, 3), owner index per point)."""
+    n = len(points)
+    boxes = np.empty((world, 2, 3)); owner = np.zeros(n, np.int32)
+    def rec(idx, lo, hi, first, k):
+        if k == 1:
+            boxes[first, 0] = lo; boxes[first, 1] = hi; owner[idx] = first
+            return
+        k1 = k // 2
+        best = None
+        for axis in range(3):
+            c = points[idx, axis].astype(np.float64)
+            cut = float(np.quantile(c, k1 / k))
+            dup = int(((c >= cut - halo) & (c < cut + halo)).sum())
+            if best is None or dup < best[0]:
+                best = (dup, axis, cut)
+        _, axis, cut = best
+        left = points[idx, axis] < cut
+        hi1 = hi.copy(); hi1[axis] = cut; lo2 = lo.copy(); lo2[axis] = cut
+        rec(idx[left], lo, hi1, first, k1); rec(idx[~left], lo2, hi, first + k1, k - k1)
+    rec(np.arange(n), np.full(3, -np.inf), np.full(3, np.inf), 0, world)
+    return boxes, owner
+
+
+def slab_box(axis, lo, hi):
+    b = np.array([[-np.inf] * 3, [np.inf] * 3]); b[0, axis] = lo; b[1, axis] = hi
+    return b
+
+
+def owned_filter_box(vertices, box):
+    if len(vertices) == 0:
+        return vertices
+    m = np.all((vertices[:, :3] >= box[0]) & (vertices[:, :3] < box[1]), axis=1)
+    return vertices[m]
 
 
 # ---- device-side primitives -------------------------------------------------------------------------------------
@@ -91,6 +145,34 @@ def select_range(t, axis, lo, hi, out=None, out_stride=None):
     return out[:cnt.value] if alloc else cnt.value
 
 
+def select_box(t, lo3, hi3, out=None, out_stride=None):
+    """Rows of t (n, 3|4) inside the box lo3 <= p < hi3, in input order (CUDA: osep_points_select_box; CPU tensors: a torch mask)."""
+    lo = np.maximum(np.asarray(lo3, np.float64), -3.0e38).astype(np.float32); hi = np.minimum(np.asarray(hi3, np.float64), 3.0e38).astype(np.float32)
+    if not t.is_cuda:
+        m = torch.ones(t.shape[0], dtype=torch.bool)
+        for d in range(3):
+            m &= (t[:, d] >= float(lo[d])) & (t[:, d] < float(hi[d]))
+        sel = t[m]
+        if out is None:
+            return sel
+        out[:len(sel), :3] = sel[:, :3]
+        if out.shape[1] > 3:
+            out[:len(sel), 3] = 1.0
+        return len(sel)
+    L = _lib.load()
+    n = int(t.shape[0])
+    alloc = out is None
+    if alloc:
+        out = torch.empty((max(n, 1), out_stride or 3), dtype=torch.float32, device=t.device)
+    cnt = C.c_int(0)
+    s = torch.cuda.current_stream(t.device).cuda_stream
+    rc = L.osep_points_select_box(t.device.index, C.c_void_p(t.data_ptr()), n, int(t.stride(0)), lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p),
+                                  C.c_void_p(out.data_ptr()), int(out.shape[1]), int(out.shape[0]), C.byref(cnt), C.c_void_p(s))
+    if rc != 0:
+        raise _lib.OsepError("osep_points_select_box failed (%d): %s" % (rc, _lib.last_error()))
+    return out[:cnt.value] if alloc else cnt.value
+
+
 def global_axis(own):
     """Collective 1: common split axis from the global bbox."""
     mn = own[:, :3].min(0).values.float(); mx = own[:, :3].max(0).values.float()
@@ -104,47 +186,52 @@ def global_axis_and_interval(own):
     return global_axis(torch.from_numpy(np.ascontiguousarray(own, dtype=np.float32)))
 
 
-def gather_table(lo, hi, halo, device):
-    """Collective 2: (lo_r, hi_r, halo_r) of every rank, as a float64 numpy (world, 3) array (scalars only)."""
+def gather_table(box, halo, device, own=None):
+    """Collective 2: (lo[3], hi[3], halo, bbox_lo[3], bbox_hi[3]) of every rank, as a float64 numpy (world, 13) array
+    (scalars only).  bbox = the extent of the rank's own points: a peer whose widened box misses it gets nothing."""
     rank, world = _world()
-    mine = torch.tensor([lo, hi, halo], dtype=torch.float64, device=device)
+    if own is not None and own.shape[0] > 0:
+        bb = torch.cat([own[:, :3].min(0).values, own[:, :3].max(0).values]).double().cpu().numpy()
+    else:
+        bb = np.array([-np.inf] * 3 + [np.inf] * 3)
+    row = np.concatenate([np.asarray(box, np.float64).reshape(6), [float(halo)], bb])
+    row = np.clip(row, -1.0e300, 1.0e300)                              # +-inf does not survive every collective backend
+    mine = torch.tensor(row, dtype=torch.float64, device=device)
     if world == 1:
-        return mine.cpu().numpy().reshape(1, 3)
+        return mine.cpu().numpy().reshape(1, 13)
     rows = [torch.zeros_like(mine) for _ in range(world)]
     dist.all_gather(rows, mine)
     return torch.stack(rows).cpu().numpy()
 
 
 def halo_plan(table, rank):
-    """What rank `rank` sends: [(peer, lo, hi)] = the part of peer's widened interval that reaches into this rank's slab.
-    Every peer whose interval lies within its own halo width of this slab gets a segment (multi-hop)."""
-    lo_s, hi_s = table[rank, 0], table[rank, 1]
+    """What rank `rank` sends: [(peer, lo3, hi3)] = peer's box widened by peer's halo, clipped to this rank's box and to the
+    extent of its points, for every peer whose widened box reaches them (boxes are disjoint, so every own point inside is a
+    halo point of the peer; with thin tiles this is more than the direct neighbours: multi-hop)."""
+    lo_s, hi_s = np.maximum(table[rank, 0:3], table[rank, 7:10]), np.minimum(table[rank, 3:6], np.nextafter(table[rank, 10:13].astype(np.float32), np.float32(np.inf)).astype(np.float64))
     plan = []
     for r in range(len(table)):
         if r == rank:
             continue
-        lo_r, hi_r, halo_r = table[r]
-        if r > rank:                      # peer is on the right: it needs [lo_r - halo_r, lo_r)
-            a, b = max(lo_s, lo_r - halo_r), min(hi_s, lo_r)
-        else:                             # peer is on the left: it needs [hi_r, hi_r + halo_r)
-            a, b = max(lo_s, hi_r), min(hi_s, hi_r + halo_r)
-        if a < b:
+        lo_r, hi_r, h = table[r, 0:3], table[r, 3:6], table[r, 6]
+        a = np.maximum(lo_s, lo_r - h); b = np.minimum(hi_s, hi_r + h)
+        if np.all(a < b):
             plan.append((r, a, b))
     return plan
 
 
-def exchange_halo(own, axis, table, tile=None):
-    """Collective 3.  own: (n, 3|4) tensor of this rank's slab (rows ordered as stored).  Returns (tile, n_halo, stats):
+def exchange_halo(own, table, tile=None):
+    """Collective 3.  own: (n, 3|4) tensor of this rank's points (rows ordered as stored).  Returns (tile, n_halo, stats):
     tile = own rows followed by the halo rows received from the other ranks in rank order, (n + n_halo, 3)."""
     rank, world = _world()
     n = int(own.shape[0])
     dev = own.device
     plan = halo_plan(table, rank)
-    send = torch.empty((max(n * max(len(plan), 1), 1), 3), dtype=torch.float32, device=dev)      # a thin slab may go whole to several peers
+    send = torch.empty((max(n * max(len(plan), 1), 1), 3), dtype=torch.float32, device=dev)      # a thin tile may go whole to several peers
     counts = torch.zeros(world, dtype=torch.int64)
     segs, off = {}, 0
     for peer, a, b in plan:
-        c = select_range(own, axis, a, b, out=send[off:])
+        c = select_box(own, a, b, out=send[off:])
         segs[peer] = (off, c); counts[peer] = c; off += c
     if world > 1:
         allc = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(world)]
@@ -224,18 +311,22 @@ class TileRunner:
             raise _lib.OsepError("osep_rosa_leaf_device failed (%d): %s" % (rc, _lib.last_error()))
         return float(leaf.value)
 
-    def run(self, own, axis, lo, hi, halo=None):
-        """own: CUDA tensor (n, 3|4) of the slab; [lo, hi) its interval along `axis`.  Returns a dict with the owned vertices
-        (CUDA tensor), the per-rank counts, all vertices (CUDA tensor) and the seam graph."""
+    def run(self, own, axis=None, lo=None, hi=None, halo=None, box=None):
+        """own: CUDA tensor (n, 3|4) of this rank's points; the tile is either the slab [lo, hi) along `axis` or the box
+        `box` = (lo[3], hi[3]).  Returns a dict with the owned vertices (CUDA tensor), the per-rank counts, all vertices
+        (CUDA tensor) and the seam graph."""
         import time
         ev = lambda: torch.cuda.Event(enable_timing=True)
         e = [ev() for _ in range(5)]
         t0 = time.perf_counter()
+        if box is None:
+            box = slab_box(axis, lo, hi)
+        box = np.asarray(box, np.float64)
         e[0].record()
         if halo is None:
             halo = 10.0 * self.own_leaf(own)
-        table = gather_table(lo, hi, halo, own.device)
-        tile, n_halo, st = exchange_halo(own, axis, table, self.tile_buf)
+        table = gather_table(box, halo, own.device, own)
+        tile, n_halo, st = exchange_halo(own, table, self.tile_buf)
         self.tile_buf = tile if self.tile_buf is None or self.tile_buf.shape[0] < tile.shape[0] else self.tile_buf
         e[1].record()
         r = self._handle(int(tile.shape[0]))
@@ -250,8 +341,9 @@ class TileRunner:
         if V:
             out = torch.empty((V, 4), dtype=torch.float32, device=own.device)
             cnt = C.c_int(0)
-            rc = self.L.osep_points_select_range(self.device, vp, V, 4, int(axis), float(max(lo, -3.0e38)), float(min(hi, 3.0e38)),
-                                                 C.c_void_p(out.data_ptr()), 4, V, C.byref(cnt), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            blo = np.maximum(box[0], -3.0e38).astype(np.float32); bhi = np.minimum(box[1], 3.0e38).astype(np.float32)
+            rc = self.L.osep_points_select_box(self.device, vp, V, 4, blo.ctypes.data_as(C.c_void_p), bhi.ctypes.data_as(C.c_void_p),
+                                               C.c_void_p(out.data_ptr()), 4, V, C.byref(cnt), C.c_void_p(torch.cuda.current_stream().cuda_stream))
             if rc != 0:
                 raise _lib.OsepError("owned-vertex mask failed (%d): %s" % (rc, _lib.last_error()))
             mine = out[:cnt.value]
@@ -284,15 +376,17 @@ class TileRunner:
             self.gskel.close(); self.gskel = None
 
 
-def tiled_skeleton(own, bounds_lo_hi, axis, halo, skeletonize):
+def tiled_skeleton(own, bounds_lo_hi, axis, halo, skeletonize, box=None):
     """Host-logic form of TileRunner.run for CPU tensors / numpy (gloo tests): `skeletonize` is a callable
     (m, 3) float32 numpy -> (V, 3) float32 numpy.  Same exchange, ownership and gather code as the device path."""
-    lo, hi = bounds_lo_hi
+    if box is None:
+        box = slab_box(axis, bounds_lo_hi[0], bounds_lo_hi[1])
+    box = np.asarray(box, np.float64)
     t = torch.from_numpy(np.ascontiguousarray(own, dtype=np.float32))
-    table = gather_table(lo, hi, halo, t.device)
-    tile, n_halo, st = exchange_halo(t, axis, table)
+    table = gather_table(box, halo, t.device, t)
+    tile, n_halo, st = exchange_halo(t, table)
     verts = np.asarray(skeletonize(tile.numpy()), np.float32).reshape(-1, 3)
-    mine = torch.from_numpy(np.ascontiguousarray(owned_filter(verts, axis, lo, hi)))
+    mine = torch.from_numpy(np.ascontiguousarray(owned_filter_box(verts, box)))
     counts, allv = gather_vertices(mine)
     allv = allv.numpy(); offs = np.concatenate([[0], np.cumsum(counts)])
     return {"tile": tile.numpy(), "halo_points": n_halo, "local": mine.numpy(), "counts": counts,

@@ -120,3 +120,26 @@ def test_multi_hop_halo_when_a_slab_is_thinner_than_the_halo():
     for r in range(3):
         for s in range(3):
             assert np.array_equal(got[r][2][s], owned[s])
+
+
+def test_recursive_bisection_partitions_the_map():
+    """rcb_boxes: disjoint boxes that cover space, equal point counts, owner == box membership; a map whose points are thin
+    along its longest axis (two walls) is cut ACROSS the walls, where few points are within a halo of the cut."""
+    sys.path.insert(0, ROOT)
+    from osep_path_planner_b200 import tiled
+    rng = np.random.default_rng(5)
+    walls = [np.c_[rng.uniform(-20, 20, 8000), rng.normal(y, 0.05, 8000), rng.uniform(0, 30, 8000)] for y in (0.0, 60.0)]
+    P = np.concatenate(walls).astype(np.float32)
+    for world in (2, 3, 4, 8):
+        boxes, owner = tiled.rcb_boxes(P, world, 5.0)
+        inside = np.stack([np.all((P >= boxes[r, 0]) & (P < boxes[r, 1]), axis=1) for r in range(world)])
+        assert np.array_equal(inside.sum(0), np.ones(len(P)))                      # every point in exactly one box
+        assert np.array_equal(np.argmax(inside, 0), owner)
+        cnt = np.bincount(owner, minlength=world)
+        assert cnt.max() - cnt.min() <= world
+        dup = sum(int(np.all((P >= boxes[r, 0] - 5.0) & (P < boxes[r, 1] + 5.0), axis=1).sum()) for r in range(world)) - len(P)
+        if world == 2:
+            assert dup == 0                                                         # the cut separates the two walls: no halo at all
+        ax, b = tiled.split_axis_and_bounds(P, world)
+        slab_dup = sum(int(((P[:, ax] >= b[r] - 5.0) & (P[:, ax] < b[r + 1] + 5.0)).sum()) for r in range(world)) - len(P)
+        assert dup <= slab_dup

@@ -25,8 +25,10 @@ def run(total, halo_arg, reps=3):
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     P = build_map(total)
-    axis, bounds = tiled.split_axis_and_bounds(P, world)
-    own = torch.from_numpy(np.ascontiguousarray(tiled.slab_of(P, axis, bounds, rank))).cuda()
+    # partition once, when the map is laid out: recursive coordinate bisection, every cut where the fewest points lie within a
+    # halo width of the cut plane (equal-count slabs along one axis are several slabs thinner than the halo on this map)
+    boxes, owner = tiled.rcb_boxes(P, world, 8.0)
+    own = torch.from_numpy(np.ascontiguousarray(P[owner == rank])).cuda()
     del P
     halo = None if halo_arg == "auto" else float(halo_arg)
     runner = tiled.TileRunner(local)
@@ -36,7 +38,7 @@ def run(total, halo_arg, reps=3):
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        res = runner.run(own, axis, bounds[rank], bounds[rank + 1], halo)
+        res = runner.run(own, halo=halo, box=boxes[rank])
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -53,7 +55,7 @@ def run(total, halo_arg, reps=3):
     if rank == 0:
         ex_ms = max(i["ms"]["leaf_select_exchange"] for i in infos)
         hb = sum(i["halo_bytes"] for i in infos)
-        out = {"config": "tiled map, %d points, %d GPU(s), halo %s along axis %d, device resident" % (total // 4 * 4, world, halo_arg, axis),
+        out = {"config": "tiled map, %d points, %d GPU(s), halo %s, recursive-bisection boxes, device resident" % (total // 4 * 4, world, halo_arg),
                "seconds_per_map": walls[-1], "seconds_per_map_runs": walls, "points_per_s": (total // 4 * 4) / walls[-1],
                "tile_points": [i["tile"] for i in infos], "own_points": [i["own"] for i in infos], "halo_m": [i["halo_m"] for i in infos],
                "halo_bytes_total": hb, "exchange_ms_max": ex_ms,
