@@ -46,14 +46,18 @@ public:
     // addition: tf2::doTransform + fromROSMsg + gskel_run (gskel_node.cpp:137-142) in one call; the
     // candidates in input_vertices() are in the sensor frame, translation / rotation_xyzw come from lookupTransform.
     bool gskel_run_tf(const double translation[3], const double rotation_xyzw[4]) { return run_impl(translation, rotation_xyzw); }
+    // same, with the candidates taken from a Rosa handle's DEVICE vertices (the frame that just ran): the transform runs on
+    // the device and the sensor-frame vertices never cross to the host (osep_gskel_run_tf_device)
+    bool gskel_run_tf_device(osep_rosa* rosa, const double translation[3], const double rotation_xyzw[4]) { return run_impl(translation, rotation_xyzw, rosa); }
 
 private:
-    bool run_impl(const double* translation, const double* rotation_xyzw) {
+    bool run_impl(const double* translation, const double* rotation_xyzw, osep_rosa* rosa = nullptr) {
         static const char* names[7] = {"increment_skeleton", "graph_adj", "mst", "vertex_merge", "prune", "smooth_vertex_positions", "extract_branches"};
         auto ts = std::chrono::high_resolution_clock::now();
         const int n = (int)new_cands_->points.size();
         const float* cands = n ? reinterpret_cast<const float*>(new_cands_->points.data()) : nullptr;
-        const int rc = translation ? osep_gskel_run_tf(h_, cands, n, 4, translation, rotation_xyzw) : osep_gskel_run(h_, cands, n, 4);
+        const int rc = rosa ? osep_gskel_run_tf_device(h_, rosa, translation, rotation_xyzw)
+                            : (translation ? osep_gskel_run_tf(h_, cands, n, 4, translation, rotation_xyzw) : osep_gskel_run(h_, cands, n, 4));
         if (rc < 0) { std::cerr << "[GSKEL] device error: " << osep_last_error() << std::endl; running = false; return false; }
         // the reference mutates the output cloud in place stage by stage; mirror the final state of this tick
         const float* xyz4 = nullptr; int G = 0;
