@@ -274,15 +274,15 @@ def run_ours(args, rank, world, local_rank):
     knn_bytes = 28 * res0.n_filtered                       # SURVEY 8(d) phase (3): read 16 N', write 12 N'
     roofline = {"bound": "hbm", "kernel": "k_drosa_fused (persistent cooperative kernel: 6 orientation iterations + position step, %.0f %% of the frame)" % (100 * drosa_ms / ms_per_step),
                 "achieved": drosa_gbs, "peak": peak, "unit": "GB/s", "frac": drosa_gbs / peak,
-                "traffic": 530432, "traffic_source": "profiles/r1_v17_ncu_full_top_kernels.txt (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture)",
+                "traffic": 790528, "traffic_source": "profiles/r2_v36_ncu_full_top_kernels.md (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture, cold cache)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": drosa_bytes, "ms_per_launch": drosa_ms,
-                "note": "latency-bound by construction: ~235 dependent 3x3 eigen solves per Gauss-Seidel chain (rosa.cpp:295-308), six chains as overlapping wavefronts, "
-                        "one warp per chain at ~4 cycles per dependent instruction; the HBM fraction is reported for the record, the signal is ms_per_launch",
+                "note": "latency-bound by construction: ~236 dependent 3x3 eigen solves per Gauss-Seidel chain (rosa.cpp:295-308), six chains as overlapping wavefronts, "
+                        "one warp per chain at ~4 cycles per dependent instruction (ncu: 7.8 % issue-active, 90 % L2 hit); the HBM fraction is reported for the record, the signal is ms_per_launch",
                 "frame": {"algorithmic_bytes": alg, "achieved": frame_gbs, "frac": frame_gbs / peak,
                           "note": "SURVEY.md 8(d) formula; 26 MB of compulsory traffic = 4 us at peak, a single frame is latency-bound (SURVEY.md H3)"},
                 "knn_normals_stage": {"ms": knn_ms, "algorithmic_bytes": knn_bytes, "achieved": knn_bytes / (knn_ms * 1e-3) / 1e9 if knn_ms > 0 else None,
                                       "frac": (knn_bytes / (knn_ms * 1e-3) / 1e9) / peak if knn_ms > 0 else None,
-                                      "note": "issue/latency-bound selection (ncu: 71 M warp instructions, 38 % issue-active at 3 CTAs per SM), L1/L2 resident"}}
+                                      "note": "thread-per-query scan + fall-backs (ncu: 16.6 M warp instructions = 168 per query in the scan, 43 % issue-active at 20 warps per SM), L1/L2 resident"}}
 
     # ---- BASELINE.json configs[3]: 256 DISTINCT independent frames (seeds 0..255, random yaw / stand-off), 256 / N per rank,
     # through the host entry point osep_rosa_run_batch from pinned host buffers (H2D inside the timed region), per-frame

@@ -108,6 +108,9 @@ static void rosa_free(osep_rosa_impl* h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (int i = 0; i < 2; ++i) { if (h->ev_fork[i]) cudaEventDestroy(h->ev_fork[i]); if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]); }
     if (h->fg.exec) cudaGraphExecDestroy(h->fg.exec);
+    if (h->ev_pts) cudaEventDestroy(h->ev_pts);
+    if (h->ev_join3) cudaEventDestroy(h->ev_join3);
+    if (h->stream3) cudaStreamDestroy(h->stream3);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
 }
@@ -237,6 +240,8 @@ int osep_rosa_create(const osep_rosa_config* cfg, int device, int capacity_point
         cudaEventCreate(&h->impl.ev0); cudaEventCreate(&h->impl.ev1);
         if (cudaStreamCreateWithFlags(&h->impl.stream2, cudaStreamNonBlocking) != cudaSuccess) { set_err("cudaStreamCreate failed"); rc = OSEP_ERR_CUDA; break; }
         for (int i = 0; i < 2; ++i) { cudaEventCreateWithFlags(&h->impl.ev_fork[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&h->impl.ev_join[i], cudaEventDisableTiming); }
+        if (cudaStreamCreateWithFlags(&h->impl.stream3, cudaStreamNonBlocking) != cudaSuccess) { set_err("cudaStreamCreate failed"); rc = OSEP_ERR_CUDA; break; }
+        cudaEventCreateWithFlags(&h->impl.ev_pts, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->impl.ev_join3, cudaEventDisableTiming);
         rc = rosa_alloc(&h->impl, capacity_points);
     } while (0);
     if (rc != OSEP_OK) { rosa_free(&h->impl); delete h; return rc; }

@@ -46,15 +46,9 @@ __global__ void k_normal_prep(const FrameState* __restrict__ st, const float4* _
     if (st->status != 0) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= st->M) return;
-    const f3 v = ld3f(nrms, i);
-    const float s2 = sqn3(v);
-    const float rt = sqrtf(s2);
-    const float il_dd = (s2 > 1e-20f) ? (float)(1.0 / (double)rt) : 0.0f;
-    const float il_d = ((double)s2 > 1e-20) ? 1.0f / rt : 0.0f;
-    const float il_f = (s2 > 1e-20f) ? 1.0f / rt : 0.0f;
-    nraw[i] = make_float4(v.x, v.y, v.z, il_dd);
-    const f3 u = mul3(v, il_d);
-    vnd[i] = make_float4(u.x, u.y, u.z, il_f);
+    float4 a, b2;
+    normal_prep_vals(ld3f(nrms, i), a, b2);
+    nraw[i] = a; vnd[i] = b2;
 }
 
 __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
@@ -1040,15 +1034,9 @@ void launch_drosa_prep(osep_rosa_impl* h, cudaStream_t sk) {
     RosaDev& d = h->d;
     const osep_rosa_config& c = h->cfg;
     const bool fused = h->fused && c.niter_drosa <= MAX_FUSED_ITERS;
-    k_normal_prep<<<div_up(d.Mcap, 128), 128, 0, sk>>>(d.st, d.nrms, d.nraw, d.vnd);
-    if (fused) {                                           // flags + the rosa_init orientation as iteration-0 input: off the critical path
-        cudaMemsetAsync(d.fused_flags, 0, sizeof(int) * ((size_t)2 * MAX_FUSED_ITERS * d.Mcap + 16), sk);
-        cudaMemcpyAsync(d.vset_it, d.vset, sizeof(float4) * d.Mcap, cudaMemcpyDeviceToDevice, sk);
-    }
-    {
-        k_gs_schedule<<<1, 256, sizeof(int) * (d.Mcap + SCHED_BINS) + sizeof(unsigned short) * d.Mcap * (d.nbk + 1), sk>>>(d.st, d.surf, d.nbk, d.level, d.level_off, d.level_pts);
-        h->n_launches += 1;
-    }
+    // (the hoisted normals nraw / vnd and the iteration-0 orientations vset_it[0] are written by the voxel reduce, nscale.cu)
+    if (fused) cudaMemsetAsync(d.fused_flags, 0, sizeof(int) * ((size_t)2 * MAX_FUSED_ITERS * d.Mcap + 16), sk);     // off the critical path
+    k_gs_schedule<<<1, 256, sizeof(int) * (d.Mcap + SCHED_BINS) + sizeof(unsigned short) * d.Mcap * (d.nbk + 1), sk>>>(d.st, d.surf, d.nbk, d.level, d.level_off, d.level_pts);
     h->n_launches += 1;
 }
 

@@ -674,19 +674,20 @@ void launch_mscale(osep_rosa_impl* h) {
     const int warp_blocks = div_up(d.Mcap, WARPS_PER_BLOCK);
     const int tb = WARPS_PER_BLOCK * 32;
     const int tblocks = div_up(d.Mcap, 128);
-    // two independent branches on the downsampled cloud: similarity lists (main stream) || surf kNN (side stream)
+    // surf kNN + smoothing schedule need only the downsampled POSITIONS (phase 0 of the voxel reduce, ev_pts): they run on a
+    // third stream while the kNN / normals branch is still busy, and have long finished when the similarity lists are done
     if (h->overlap) {
-        cudaStream_t sk = h->stream2;
-        cudaEventRecord(h->ev_fork[1], s); cudaStreamWaitEvent(sk, h->ev_fork[1], 0);
+        cudaStream_t sk = h->stream3;
+        cudaStreamWaitEvent(sk, h->ev_pts, 0);
         k_surf_knn<<<warp_blocks, tb, 0, sk>>>(d.st, d.pts, d.surf, d.nbk);   // R13
         launch_drosa_prep(h, sk);
-        cudaEventRecord(h->ev_join[1], sk);
+        cudaEventRecord(h->ev_join3, sk);
     }
     // R12
     k_simi<false><<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.nrms, d.simi_off, d.simi_idx, nullptr, nullptr, d.simi_bits, d.Scap);   // count + bit rows; its last block scans
     k_simi<true><<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.nrms, d.simi_off, d.simi_idx, d.rv1, (float*)d.rk1, d.simi_bits, d.Scap);
     stage_mark(h, SM_SIMI);
-    if (h->overlap) cudaStreamWaitEvent(s, h->ev_join[1], 0);
+    if (h->overlap) cudaStreamWaitEvent(s, h->ev_join3, 0);
     else {                                                                     // profiling: sequential, attributable
         k_surf_knn<<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.surf, d.nbk);
         launch_drosa_prep(h, s);

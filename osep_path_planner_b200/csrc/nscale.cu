@@ -1207,76 +1207,86 @@ __global__ void k_vox_scatter(const FrameState* __restrict__ st, const unsigned*
 // in flight); (3) ONE thread adds them, so the float sums stay strictly sequential in ascending point index.
 constexpr int VOX_SORT = 2048;
 constexpr int VOX_CHUNK = 256;
+// PHASE 0 (needs only the filtered cloud: runs while the kNN / normals branch is still busy): sort the voxel's point indices
+// (left in `grouped` for phase 1), sum the POSITIONS -> pts, pset.  PHASE 1 (after the normals): sum the NORMALS in the stored
+// order -> nrms, vset (R10 + R11), plus what drosa hoists per point (nraw, vnd) and its iteration-0 orientations (vset_it).
+template <int PHASE>
 __global__ void __launch_bounds__(256)
 k_vox_reduce(FrameState* st, int* grouped, int* __restrict__ scratch, const int* __restrict__ vox_off,
              const float4* __restrict__ P, const float4* __restrict__ Nrm,
-             float4* __restrict__ pts, float4* __restrict__ nrms, float4* __restrict__ pset, float4* __restrict__ vset) {
+             float4* __restrict__ pts, float4* __restrict__ nrms, float4* __restrict__ pset, float4* __restrict__ vset,
+             float4* __restrict__ nraw, float4* __restrict__ vnd, float4* __restrict__ vset_it) {
     __shared__ int sidx[VOX_SORT];
     __shared__ float4 sp[VOX_CHUNK];
-    __shared__ float4 sn[VOX_CHUNK];
     if (st->status != 0) return;
     const int M = st->M;
     for (int v = blockIdx.x; v < M; v += gridDim.x) {
         const int b = vox_off[v], e = vox_off[v + 1];
         const int cnt = e - b;
-        const int* order;
+        const int* order = grouped + b;
         __syncthreads();
-        if (cnt <= VOX_SORT) {
-            int P2 = 1; while (P2 < cnt) P2 <<= 1;
-            for (int t = threadIdx.x; t < P2; t += blockDim.x) sidx[t] = (t < cnt) ? grouped[b + t] : 0x7fffffff;
-            __syncthreads();
-            for (int k = 2; k <= P2; k <<= 1) {
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    for (int i = threadIdx.x; i < P2; i += blockDim.x) {
-                        const int ixj = i ^ j;
-                        if (ixj > i) {
-                            const int x = sidx[i], y = sidx[ixj];
-                            const bool up = ((i & k) == 0);
-                            if ((x > y) == up) { sidx[i] = y; sidx[ixj] = x; }
-                        }
-                    }
-                    __syncthreads();
-                }
-            }
-            order = sidx;
-        } else {
-            // voxels with more than VOX_SORT points (large maps): bitonic network with all comparators ascending
-            // ("flip" first stage), which needs no power-of-two padding -- missing partners act as +inf -- in place
-            // in global memory (the segment is private to this CTA)
-            int* seg = grouped + b;
-            for (int k = 2; (k >> 1) < cnt; k <<= 1) {
-                for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-                    const int ixj = i ^ (k - 1);
-                    if (ixj > i && ixj < cnt) { const int x = seg[i], y = seg[ixj]; if (x > y) { seg[i] = y; seg[ixj] = x; } }
-                }
+        if (PHASE == 0) {
+            if (cnt <= VOX_SORT) {
+                int P2 = 1; while (P2 < cnt) P2 <<= 1;
+                for (int t = threadIdx.x; t < P2; t += blockDim.x) sidx[t] = (t < cnt) ? grouped[b + t] : 0x7fffffff;
                 __syncthreads();
-                for (int j = k >> 2; j > 0; j >>= 1) {
+                for (int k = 2; k <= P2; k <<= 1) {
+                    for (int j = k >> 1; j > 0; j >>= 1) {
+                        for (int i = threadIdx.x; i < P2; i += blockDim.x) {
+                            const int ixj = i ^ j;
+                            if (ixj > i) {
+                                const int x = sidx[i], y = sidx[ixj];
+                                const bool up = ((i & k) == 0);
+                                if ((x > y) == up) { sidx[i] = y; sidx[ixj] = x; }
+                            }
+                        }
+                        __syncthreads();
+                    }
+                }
+                for (int t = threadIdx.x; t < cnt; t += blockDim.x) grouped[b + t] = sidx[t];      // phase 1 reads the order from here
+                order = sidx;
+            } else {
+                // voxels with more than VOX_SORT points (large maps): bitonic network with all comparators ascending
+                // ("flip" first stage), which needs no power-of-two padding -- missing partners act as +inf -- in place
+                // in global memory (the segment is private to this CTA)
+                int* seg = grouped + b;
+                for (int k = 2; (k >> 1) < cnt; k <<= 1) {
                     for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-                        const int ixj = i ^ j;
+                        const int ixj = i ^ (k - 1);
                         if (ixj > i && ixj < cnt) { const int x = seg[i], y = seg[ixj]; if (x > y) { seg[i] = y; seg[ixj] = x; } }
                     }
                     __syncthreads();
+                    for (int j = k >> 2; j > 0; j >>= 1) {
+                        for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+                            const int ixj = i ^ j;
+                            if (ixj > i && ixj < cnt) { const int x = seg[i], y = seg[ixj]; if (x > y) { seg[i] = y; seg[ixj] = x; } }
+                        }
+                        __syncthreads();
+                    }
                 }
+                order = seg;
             }
-            order = seg;
         }
-        float sx = 0, sy = 0, sz = 0, n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+        const float4* __restrict__ src = PHASE == 0 ? P : Nrm;
+        float s0 = 0, s1 = 0, s2 = 0, s3 = 0;
         for (int c0 = 0; c0 < cnt; c0 += VOX_CHUNK) {
             const int cn = min(VOX_CHUNK, cnt - c0);
             __syncthreads();
-            for (int t = threadIdx.x; t < cn; t += blockDim.x) { const int i = order[c0 + t]; sp[t] = P[i]; sn[t] = Nrm[i]; }
+            for (int t = threadIdx.x; t < cn; t += blockDim.x) sp[t] = src[order[c0 + t]];
             __syncthreads();
             if (threadIdx.x == 0) {
-                for (int t = 0; t < cn; ++t) {
-                    const float4 p = sp[t]; const float4 nn = sn[t];
-                    sx += p.x; sy += p.y; sz += p.z;
-                    n0 += nn.x; n1 += nn.y; n2 += nn.z; n3 += 0.0f;
-                }
+                for (int t = 0; t < cn; ++t) { const float4 q = sp[t]; s0 += q.x; s1 += q.y; s2 += q.z; s3 += 0.0f; }
             }
         }
         if (threadIdx.x != 0) continue;
-        const float cntf = (float)cnt;
-        const float px = sx / cntf, py = sy / cntf, pz = sz / cntf;
+        if (PHASE == 0) {
+            const float cntf = (float)cnt;
+            const float px = s0 / cntf, py = s1 / cntf, pz = s2 / cntf;
+            pts[v] = make_float4(px, py, pz, 1.0f);
+            pset[v] = make_float4(px, py, pz, 1.0f);         // R11: pset = pts (rosa.cpp:183-199)
+            continue;
+        }
+        const float n0 = s0, n1 = s1, n2 = s2, n3 = s3;
         // AccumulatorNormal::get: Vector4f::normalized(); squaredNorm is packet-reduced (a0+a2)+(a1+a3)
         const float zz = (n0 * n0 + n2 * n2) + (n1 * n1 + n3 * n3);
         f3 nv{n0, n1, n2};
@@ -1284,10 +1294,9 @@ k_vox_reduce(FrameState* st, int* grouped, int* __restrict__ scratch, const int*
         // R10 (rosa.cpp:156-165)
         const float L = norm3(nv);
         if (L > 1e-6f) nv = div3(nv, L); else nv = {0.0f, 0.0f, 0.0f};
-        pts[v] = make_float4(px, py, pz, 1.0f);
         nrms[v] = make_float4(nv.x, nv.y, nv.z, 0.0f);
-        // R11 (rosa.cpp:183-199, rosa.hpp:112-128): pset = pts, vset = column 0 of the orthonormal frame
-        pset[v] = make_float4(px, py, pz, 1.0f);
+        { float4 a4, b4; normal_prep_vals(nv, a4, b4); nraw[v] = a4; vnd[v] = b4; }
+        // R11 (rosa.cpp:183-199, rosa.hpp:112-128): vset = column 0 of the orthonormal frame
         f3 vs;
         const float nn_ = norm3(nv);
         if (nn_ == 0.0f) vs = {1.0f, 0.0f, 0.0f};
@@ -1299,6 +1308,7 @@ k_vox_reduce(FrameState* st, int* grouped, int* __restrict__ scratch, const int*
             vs = normalize3(sub3(a, mul3(z, az)));
         }
         vset[v] = make_float4(vs.x, vs.y, vs.z, 0.0f);
+        vset_it[v] = make_float4(vs.x, vs.y, vs.z, 0.0f);   // iteration-0 input of the fused drosa kernel
     }
 }
 
@@ -1448,10 +1458,12 @@ void launch_preprocess(osep_rosa_impl* h, int n) {
     // group by voxel with atomics, then fix the order inside every voxel in the reduce kernel (no global sort)
     cudaMemsetAsync(d.vox_fill, 0, sizeof(int) * (d.Mcap + 2), s);
     k_vox_scatter<<<nb, NT, 0, s>>>(d.st, d.rk0, d.vox_cnt, d.vox_fill, d.rv0);
-    if (h->overlap) cudaStreamWaitEvent(s, h->ev_join[0], 0);              // the reduce is the first consumer of the normals
-    k_vox_reduce<<<1024, 256, 0, s>>>(d.st, d.rv0, d.rv1, d.vox_cnt, d.P, d.Nrm, d.pts, d.nrms, d.pset, d.vset);
+    k_vox_reduce<0><<<1024, 256, 0, s>>>(d.st, d.rv0, d.rv1, d.vox_cnt, d.P, d.Nrm, d.pts, d.nrms, d.pset, d.vset, d.nraw, d.vnd, d.vset_it);
+    if (h->overlap) cudaEventRecord(h->ev_pts, s);                         // the downsampled positions exist: surf kNN + schedule may start (stream3, launch_mscale)
+    if (h->overlap) cudaStreamWaitEvent(s, h->ev_join[0], 0);              // phase 1 of the reduce is the first consumer of the normals
+    k_vox_reduce<1><<<1024, 256, 0, s>>>(d.st, d.rv0, d.rv1, d.vox_cnt, d.P, d.Nrm, d.pts, d.nrms, d.pset, d.vset, d.nraw, d.vnd, d.vset_it);
     stage_mark(h, SM_VOXEL);
-    h->n_launches += 3 + LEAF_MAX_ITERS + 5 + 4 + 4 + 2 + ((k <= 24 && !h->knn_warp_path) ? 2 : 0);
+    h->n_launches += 3 + LEAF_MAX_ITERS + 5 + 4 + 4 + 2 + ((k <= 24 && !h->knn_warp_path) ? 2 : 0) + 1;
 }
 
 }  // namespace osep

@@ -76,6 +76,21 @@ struct FrameParams {
     int pad;
 };
 
+// per-point normal quantities used inside the active-set sums of drosa, computed once per frame (by the voxel reduce):
+//   nraw = (n, il_dd)  il_dd = (s2 > 1e-20f) ? (float)(1.0 / (double)sqrtf(s2)) : 0      rosa.cpp:764-766
+//   vnd  = (n * ((double)s2 > 1e-20 ? 1/sqrtf(s2) : 0), il_f)                             rosa.cpp:694-696, 740-742
+//          il_f = (s2 > 1e-20f) ? 1.0f / sqrtf(s2) : 0                                    rosa.cpp:340-341, 717-718
+__device__ __forceinline__ void normal_prep_vals(const f3& v, float4& nraw, float4& vnd) {
+    const float s2 = sqn3(v);
+    const float rt = sqrtf(s2);
+    const float il_dd = (s2 > 1e-20f) ? (float)(1.0 / (double)rt) : 0.0f;
+    const float il_d = ((double)s2 > 1e-20) ? 1.0f / rt : 0.0f;
+    const float il_f = (s2 > 1e-20f) ? 1.0f / rt : 0.0f;
+    nraw = make_float4(v.x, v.y, v.z, il_dd);
+    const f3 u = mul3(v, il_d);
+    vnd = make_float4(u.x, u.y, u.z, il_f);
+}
+
 // ordered-int encoding of a float: monotone map so atomicMin/atomicMax(int) order floats
 __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }

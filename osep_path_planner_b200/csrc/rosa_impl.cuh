@@ -64,6 +64,8 @@ struct osep_rosa_impl {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;     // side stream: independent branches of one frame overlap (kNN normals || leaf passes; surf kNN || similarity)
     cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
+    cudaStream_t stream3 = nullptr;     // third branch: surf kNN + smoothing schedule need only the downsampled POSITIONS, so they run while the kNN normals branch is still busy
+    cudaEvent_t ev_pts = nullptr, ev_join3 = nullptr;
     bool overlap = true;                // disabled while per-stage profiling is on (stage times stay sequential and attributable)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     RosaDev d;
