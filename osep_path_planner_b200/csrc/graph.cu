@@ -446,7 +446,14 @@ static int gs_graph(GSkelImpl& S, bool& adj_ok, bool& mst_ok) {
     const int G = (int)S.gskel_size;
     S.upload.resize(G);
     for (int i = 0; i < G; ++i) S.upload[i] = make_float4(S.global_cloud[i].x, S.global_cloud[i].y, S.global_cloud[i].z, 1.0f);
-    if (G > S.g->cap) return OSEP_ERR_CAPACITY;
+    if (G > S.g->cap) {
+        // the global skeleton outgrew the device arena: grow it (the state machine above has already accepted the tick, so
+        // failing here would leave prelim / global state ahead of the graph for good).  u, v travel in 16 bits: 65535 is final.
+        if (G > 65535) return OSEP_ERR_CAPACITY;
+        GraphHost* bigger = graph_alloc(std::min(65535, std::max(2 * S.g->cap, G + 1024)), S.g->device, nullptr);
+        if (!bigger) return OSEP_ERR_CUDA;
+        graph_free(S.g); S.g = bigger;
+    }
     if (cudaMemcpyAsync(S.g->pos, S.upload.data(), sizeof(float4) * G, cudaMemcpyHostToDevice, S.g->stream) != cudaSuccess) return OSEP_ERR_CUDA;
     const int rc = graph_run(S.g, S.g->pos, G, S.cfg.fuse_dist_th);
     if (rc) return rc;

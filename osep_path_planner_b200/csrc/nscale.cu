@@ -848,7 +848,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_knn_big(const float4* __restrict
                                                 int* __restrict__ knn_idx, int k_req, int* __restrict__ slow_list,
                                                 const int* __restrict__ over_list, const int* __restrict__ n_work_ptr, int mode,
                                                 const int* __restrict__ pc_cell, const int2* __restrict__ nbr,
-                                                int* __restrict__ next_list, int* __restrict__ n_next) {
+                                                int* __restrict__ next_list, int* __restrict__ n_next, int r_first) {
     __shared__ int2 tab_[WARPS][KNN_TAB];
     __shared__ int pre_[WARPS][KNN_TAB + 1];
     __shared__ float sd_[WARPS][CAPQ];
@@ -868,12 +868,14 @@ __global__ void __launch_bounds__(WARPS * 32) k_knn_big(const float4* __restrict
     const unsigned long long KINF = ~0ull;
     for (int w = blockIdx.x * WARPS + wib; w < n_work; w += gridDim.x * WARPS) {
         const int code = over_list[w];
-        int qpos = code;
+        int qpos = code & 0x7fffffff;            // bit 31 (modes 1, 2): the 27-cell block overflowed the previous kernel's stage -- it has not been shown insufficient
         if (mode == 0) { const int2 un = units[code >> 5]; qpos = g_start[un.x] + (un.y & 0xffffff) + (code & 31); }
+        const int r0 = (mode != 0 && r_first == 2 && code >= 0) ? 2 : 1;
+        bool stage_overflow = false;
         const float4 q = Pc[qpos];
         int cx, cy, cz; cell_of(st, q.x, q.y, q.z, cx, cy, cz);
         bool done = false;
-        for (int R = 1; R <= (mode == 2 ? 1 : 2) && !done; ++R) {
+        for (int R = r0; R <= (mode == 2 ? 1 : 2) && !done; ++R) {      // r0 = 2: the 27-cell block is already known not to certify the query
             const int x0 = max(cx - R, 0), x1 = min(cx + R, dimx - 1);
             const int y0 = max(cy - R, 0), y1 = min(cy + R, dimy - 1);
             const int z0 = max(cz - R, 0), z1 = min(cz + R, dimz - 1);
@@ -903,7 +905,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_knn_big(const float4* __restrict
                 total += __shfl_sync(0xffffffffu, incl, 31);
             }
             __syncwarp();
-            if (total > CAPQ) break;                          // next kernel of the chain
+            if (total > CAPQ) { stage_overflow = true; break; }      // next kernel of the chain
             // every candidate's (d2, index) once, 32 candidates per round, all rounds' loads independent
 #pragma unroll 4
             for (int t0 = 0; t0 < total; t0 += 32) {
@@ -972,7 +974,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_knn_big(const float4* __restrict
             if (lane + 32 < k_eff) knn_idx[(size_t)qidx * k_eff + lane + 32] = (int)(unsigned)(k1 & 0xffffffffull);
             done = true;
         }
-        if (!done && lane == 0) { if (mode == 2) next_list[atomicAdd(n_next, 1)] = qpos; else slow_list[atomicAdd(&st->n_slow, 1)] = qpos; }
+        if (!done && lane == 0) { if (mode == 2) next_list[atomicAdd(n_next, 1)] = qpos | (stage_overflow ? (int)0x80000000 : 0); else slow_list[atomicAdd(&st->n_slow, 1)] = qpos; }
         __syncwarp();
     }
 }
@@ -1323,9 +1325,9 @@ static void launch_knn(osep_rosa_impl* h, int n, int k_req, cudaStream_t s) {
         k_grid_nbrs<<<h->sms * 8, 256, 0, s>>>(d.st, d.Pc, d.gtab, d.g_cnt, d.g_start, mask, d.cell_slots, d.cell_cap, d.nbr, d.nbr_tau, h->knn_target);
         k_knn_scan<K><<<div_up(d.Ncap, SCAN_THREADS), SCAN_THREADS, 0, s>>>(d.Pc, d.st, d.pc_cell, d.nbr, d.nbr_tau, d.cell_cap, d.knn_full, k_req, d.knn_grow);
         k_knn_big<K, 384, 8><<<h->sms * 5, 256, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units, d.knn_full, k_req, d.slow_list, d.knn_grow, &d.st->n_grow, 2,
-                                                        d.pc_cell, d.nbr, d.over_list, &d.st->n_over);
+                                                        d.pc_cell, d.nbr, d.over_list, &d.st->n_over, 1);
         k_knn_big<K, KNN_BIG, BIG_WARPS><<<h->sms * 4, BIG_WARPS * 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units, d.knn_full, k_req, d.slow_list, d.over_list, &d.st->n_over, 1,
-                                                                              nullptr, nullptr, nullptr, nullptr);
+                                                                              nullptr, nullptr, nullptr, nullptr, 2);
         k_knn_exact<K><<<64, 128, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.knn_full, k_req, d.slow_list);
         k_normals<<<div_up(d.Ncap, 128), 128, 0, s>>>(d.P, d.st, d.knn_full, k_req, d.Nrm);
         return;
@@ -1337,7 +1339,7 @@ static void launch_knn(osep_rosa_impl* h, int n, int k_req, cudaStream_t s) {
     k_knn_cells<K><<<h->sms * ctas_per_sm, KNN_WARPS * 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units,
                                                               d.knn_full, k_req, d.slow_list, d.over_list);
     k_knn_big<K, KNN_BIG, BIG_WARPS><<<h->sms * 4, BIG_WARPS * 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units, d.knn_full, k_req, d.slow_list, d.over_list, &d.st->n_over, 0,
-                                                                          nullptr, nullptr, nullptr, nullptr);
+                                                                          nullptr, nullptr, nullptr, nullptr, 1);
     k_knn_exact<K><<<64, 128, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.knn_full, k_req, d.slow_list);
     k_normals<<<div_up(d.Ncap, 128), 128, 0, s>>>(d.P, d.st, d.knn_full, k_req, d.Nrm);
 }
