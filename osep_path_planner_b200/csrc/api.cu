@@ -396,8 +396,9 @@ long osep_rosa_get(osep_rosa* h, const char* name, void* dst, long cap) {
     if (nm == "knn_full") { if (!d.knn_full) return 0; return tap_copy(dst, cap, d.knn_full, N * (size_t)std::min<int>(d.knn, (int)N), 4); }
     if (nm == "leaf_hist") { if (dst && cap >= (long)(4 * s.n_pass)) memcpy(dst, s.leaf_hist, 4 * s.n_pass); return s.n_pass; }
     if (nm == "nvox_hist") { if (dst && cap >= (long)(4 * s.n_pass)) memcpy(dst, s.nvox_hist, 4 * s.n_pass); return s.n_pass; }
-    if (nm == "vox_keys") return tap_copy(dst, cap, d.vkeys, M, 4);
+    if (nm == "vox_keys") return tap_copy(dst, cap, d.vkeys, s.vox_identity ? 0 : M, 4);
     if (nm == "vox_count") {
+        if (s.vox_identity) return 0;          // output = input: no voxels were formed (PCL returns before its sort)
         std::vector<int> off(M + 1);
         if (M && cudaMemcpy(off.data(), d.vox_cnt, (M + 1) * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
         if (dst && cap >= (long)(M * 4)) for (size_t i = 0; i < M; ++i) ((int*)dst)[i] = off[i + 1] - off[i];

@@ -1147,7 +1147,13 @@ __global__ void k_vox_sortkeys(FrameState* st, unsigned* vkeys, int Mcap, int* v
     __shared__ int sM;
     if (threadIdx.x == 0) {
         int M = st->n_keys;
-        if (st->pass_overflow) { st->status = OSEP_ERR_CAPACITY; M = 0; }     // VoxelGrid output = input: not supported on device
+        if (st->pass_overflow) {
+            // PCL's guard ("Leaf size is too small for the input dataset. Integer indices would overflow."): VoxelGrid returns the
+            // input cloud unchanged.  Every filtered point becomes its own voxel as long as the downsampled arena holds them
+            // (small clouds whose leaf the control law shrank; a 100k-point frame would make the reference run ROSA on 100k points).
+            if (st->n_filt <= Mcap) { M = st->n_filt; st->vox_identity = 1; }
+            else { st->status = OSEP_ERR_CAPACITY; M = 0; }
+        }
         else if (M > Mcap) { st->status = OSEP_ERR_CAPACITY; M = 0; }
         st->M = M;
         if (M == 0 && st->status == 0) st->status = OSEP_STAGE_3;   // stage gate: rosa_init always succeeds, similarity_neighbor_extraction fails on an empty cloud (rosa.cpp:205)
@@ -1180,6 +1186,7 @@ __global__ void k_vox_assign(const float4* __restrict__ P, const FrameState* __r
     if (st->status != 0) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= st->n_filt) return;
+    if (st->vox_identity) { rk[i] = (unsigned)i; rv[i] = i; atomicAdd(&vox_cnt[i], 1); return; }      // output = input
     const unsigned key = voxel_key(P[i], st->inv_leaf, st->minb[0], st->minb[1], st->minb[2], st->divb[0], st->divb[1]);
     int lo = 0, hi = st->M - 1;
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (vkeys[mid] < key) lo = mid + 1; else hi = mid; }
@@ -1292,7 +1299,7 @@ k_vox_reduce(FrameState* st, int* grouped, int* __restrict__ scratch, const int*
         // AccumulatorNormal::get: Vector4f::normalized(); squaredNorm is packet-reduced (a0+a2)+(a1+a3)
         const float zz = (n0 * n0 + n2 * n2) + (n1 * n1 + n3 * n3);
         f3 nv{n0, n1, n2};
-        if (zz > 0.0f) { const float r = sqrtf(zz); nv = {n0 / r, n1 / r, n2 / r}; }
+        if (zz > 0.0f && !st->vox_identity) { const float r = sqrtf(zz); nv = {n0 / r, n1 / r, n2 / r}; }      // output = input keeps the normal as estimated
         // R10 (rosa.cpp:156-165)
         const float L = norm3(nv);
         if (L > 1e-6f) nv = div3(nv, L); else nv = {0.0f, 0.0f, 0.0f};

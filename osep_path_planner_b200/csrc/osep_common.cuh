@@ -47,6 +47,7 @@ struct FrameState {
     float leaf, leaf_used, leaf_size;
     int leaf_done, n_pass, nvox;
     int pass_overflow;
+    int vox_identity;      // final VoxelGrid pass hit PCL's int32 index guard: output = input (every filtered point is its own voxel)
     unsigned epoch;
     float leaf_hist[LEAF_MAX_ITERS];
     int nvox_hist[LEAF_MAX_ITERS];

@@ -746,3 +746,23 @@ def test_gskel_graph_arena_grows_instead_of_failing(mods):
         assert_bit_equal(np.ascontiguousarray(gsk_small.output_gskel()), np.ascontiguousarray(gsk_big.output_gskel()), "global skeleton tick %d" % k)
     assert len(gsk_big.output_gskel()) > 16
     gsk_small.close(); gsk_big.close()
+
+
+def test_voxelgrid_index_overflow_returns_the_input_cloud(mods):
+    """PCL's int32 guard: when the leaf the control law asks for makes dx*dy*dz overflow, VoxelGrid
+    returns its input unchanged.  A small, widely spread cloud with a large max_points drives the leaf down until that happens;
+    the library must follow the oracle through it (every filtered point its own "voxel", normals not re-normalised by the
+    accumulator) to whatever stage the reference then fails or succeeds at."""
+    osep, po, fx = mods
+    rng = np.random.default_rng(11)
+    P = rng.uniform(-28, 28, (160, 3)).astype(np.float32)
+    cfg = dict(max_points=1536, min_points=50)
+    o, ok_o, r, ok_g = run_both(mods, P, cfg)
+    assert o.flags & 4, "the oracle did not reach the overflow guard: flags %d, leaves %s" % (o.flags, o.tap("leaf_hist"))
+    assert ok_g == ok_o and r.result.status == o.failed_stage, "gpu status %d vs oracle stage %d" % (r.result.status, o.failed_stage)
+    assert r.result.flags & 4 and r.result.n_downsampled == len(o.tap("pts")) == len(P)
+    for tap in ["filt_idx", "leaf_hist", "nvox_hist", "normals_full", "vox_keys", "vox_count", "pts", "nrms"]:
+        assert_bit_equal(r.tap(tap), o.tap(tap), tap)
+    if ok_o:
+        assert_bit_equal(np.ascontiguousarray(r.output_vertices()), o.tap("skelver"), "vertices")
+    r.close()
