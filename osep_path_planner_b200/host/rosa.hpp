@@ -96,6 +96,13 @@ private:
         const int rc = raw ? osep_rosa_run_pointcloud2(h_, raw, raw_n, point_step, off_x, off_x + 4, off_x + 8, &res)
                            : osep_rosa_run(h_, n ? reinterpret_cast<const float*>(orig_.points.data()) : nullptr, n, 4, &res);
         last_ = res;
+        if (mirror_filter_ && !raw && rc >= 0 && res.n_filtered >= 0 && res.n_filtered != n) {
+            std::vector<float> f((size_t)3 * res.n_filtered);
+            if (osep_rosa_get(h_, "filtered", f.data(), (long)(f.size() * sizeof(float))) == (long)f.size()) {
+                orig_.points.resize((size_t)res.n_filtered);
+                for (int i = 0; i < res.n_filtered; ++i) { auto& p = orig_.points[(size_t)i]; p.x = f[3 * (size_t)i]; p.y = f[3 * (size_t)i + 1]; p.z = f[3 * (size_t)i + 2]; }
+            }
+        }
         if (rc < 0) { std::cerr << "[ROSA] device error: " << osep_last_error() << std::endl; running = false; skelver_.resize(0, 3); return false; }
         for (int s = 1; s <= 7; ++s) {
             const bool ok = (rc == 0 || s < rc);
@@ -115,6 +122,10 @@ private:
     }
 public:
     osep::PointCloudXYZ& input_cloud() { return orig_; }
+    // The reference filters input_cloud() IN PLACE (rosa.cpp:84: orig_pcd_.swap(filtered)): after rosa_run() the caller's cloud
+    // holds only the finite points within pts_dist_lim.  Off by default (one extra device-to-host copy of N' points per frame);
+    // enable it when a caller reads input_cloud() after the run.
+    void set_filter_input_in_place(bool on) { mirror_filter_ = on; }
     osep::MatrixXf& output_vertices() { return skelver_; }
 
     // additions (not in the reference): summary of the last frame and the device handle
@@ -128,4 +139,5 @@ private:
     osep::PointCloudXYZ orig_;
     osep::MatrixXf skelver_;
     osep_rosa_result last_{};
+    bool mirror_filter_ = false;
 };
