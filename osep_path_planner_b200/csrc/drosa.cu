@@ -23,7 +23,7 @@ constexpr unsigned FULLM = 0xffffffffu;
 #define OSEP_SEED_WARPS 8
 #endif
 constexpr int SEED_WARPS = OSEP_SEED_WARPS;
-constexpr int SEED_SMEM_BUDGET = 226 * 1024;
+constexpr int SEED_SMEM_BUDGET = 208 * 1024;       // leaves ~19 KB of the SM for the small kernels that run next to the persistent one (similarity list fill)
 constexpr int GS_THREADS = 256;
 constexpr int GS_SMEM_BUDGET = 200 * 1024;
 constexpr int MAX_FUSED_ITERS = 8;
