@@ -23,7 +23,8 @@ constexpr unsigned FULLM = 0xffffffffu;
 #define OSEP_SEED_WARPS 8
 #endif
 constexpr int SEED_WARPS = OSEP_SEED_WARPS;
-constexpr int SEED_SMEM_BUDGET = 208 * 1024;       // leaves ~19 KB of the SM for the small kernels that run next to the persistent one (similarity list fill)
+constexpr int SEED_SMEM_BUDGET = 226 * 1024;       // unfused seed kernels and the upper bound of the fused kernel's request
+constexpr int FUSED_SMEM_SINGLE = 208 * 1024;      // fused kernel, one frame at a time: leaves ~19 KB of every SM for the small kernels that run next to the persistent one (similarity list fill)
 constexpr int GS_THREADS = 256;
 constexpr int GS_SMEM_BUDGET = 200 * 1024;
 constexpr int MAX_FUSED_ITERS = 8;
@@ -79,12 +80,12 @@ __host__ __device__ __forceinline__ size_t seed_mat_bytes(int M) { const int Wp 
 
 // stage the per-frame read-only data of the seed warps; every thread of the CTA calls it (ends with __syncthreads)
 __device__ __forceinline__ SeedCtx seed_stage(uint4* smem, const float4* __restrict__ pts, const float4* __restrict__ nraw, const float4* __restrict__ vnd,
-                                              const unsigned* __restrict__ bits, int M, float leaf) {
+                                              const unsigned* __restrict__ bits, int M, float leaf, int budget = SEED_SMEM_BUDGET) {
     const int Wn = (M + 31) >> 5, Wp = (Wn + 3) & ~3;
     float4* s_pts = reinterpret_cast<float4*>(smem);
     float4* s_nraw = s_pts + M; float4* s_vnd = s_nraw + M;
     unsigned* s_bits = reinterpret_cast<unsigned*>(s_vnd + M);
-    const bool mat_in = seed_small_bytes(M) + seed_mat_bytes(M) <= (size_t)SEED_SMEM_BUDGET;
+    const bool mat_in = seed_small_bytes(M) + seed_mat_bytes(M) <= (size_t)budget;
     for (int i = threadIdx.x; i < M; i += blockDim.x) { s_pts[i] = pts[i]; s_nraw[i] = nraw[i]; s_vnd[i] = vnd[i]; }
     if (mat_in) stage_bit_rows(s_bits, bits, M, Wp);          // rows are padded to Wp words in global memory too (k_simi)
     __syncthreads();
@@ -548,6 +549,7 @@ struct FusedArgs {
     const int* level; const int* level_pts;   // T_0 = dependency level of every point and the points sorted by it (k_gs_schedule, side stream)
     int hot_ctas;          // worker CTAs that serve the ready queue after the iteration-0 tasks
     unsigned spin_ns;      // idle workers sleep this long between two polls of their queue slot (0 = busy poll)
+    int smem_budget;       // dynamic shared memory of this launch (bytes)
     long long* tl;         // detail mode: per (it, p) 8 globaltimer stamps [G solved, task published, worker start, O flag, O staged] (tools/fused_dbg.py)
 };
 
@@ -568,7 +570,7 @@ __device__ __forceinline__ void st_vol(int* p, int v) { stress_delay(); *reinter
 
 __device__ __forceinline__ void fused_worker(const FusedArgs& a, uint4* smem, int M) {
     const int Wn = (M + 31) >> 5;
-    const SeedCtx c = seed_stage(smem, a.pts, a.nraw, a.vnd, a.bits, M, a.st->leaf_size);
+    const SeedCtx c = seed_stage(smem, a.pts, a.nraw, a.vnd, a.bits, M, a.st->leaf_size, a.smem_budget);
     const int lane = threadIdx.x & 31;
     const int total = (a.nit + 1) * M;
     SeedOut o; o.vvar = nullptr; o.pack_w = 1; o.pset = a.pset; o.good = a.good; o.centers = a.centers; o.active_size = a.active_size;
@@ -999,7 +1001,7 @@ __global__ void __launch_bounds__(SEED_WARPS * 32) k_drosa_fused(const __grid_co
     const int M = a.st->M;
     // shared-memory footprint of a chain CTA (see fused_chain); evaluated identically by every CTA
     const size_t chain_bytes = fused_chain_bytes(M, a.nbk, a.nit);
-    if (chain_bytes > (size_t)SEED_SMEM_BUDGET) {
+    if (chain_bytes > (size_t)a.smem_budget) {
         if (blockIdx.x == 0 && threadIdx.x == 0) a.st->status = OSEP_ERR_CAPACITY;
         return;
     }
@@ -1063,7 +1065,8 @@ void launch_drosa(osep_rosa_impl* h, int sms) {
         if (grid < c.niter_drosa + 1) grid = c.niter_drosa + 1;
         void* args[] = {(void*)&a};
         if (grid > sms) grid = sms;
-        cudaLaunchCooperativeKernel((const void*)k_drosa_fused, dim3(grid), dim3(SEED_WARPS * 32), args, (size_t)SEED_SMEM_BUDGET, s);
+        a.smem_budget = h->fused_smem > 0 ? std::min(h->fused_smem, SEED_SMEM_BUDGET) : (h->fused_grid > 0 ? SEED_SMEM_BUDGET : FUSED_SMEM_SINGLE);
+        cudaLaunchCooperativeKernel((const void*)k_drosa_fused, dim3(grid), dim3(SEED_WARPS * 32), args, (size_t)a.smem_budget, s);
         if (h->debug) cudaMemcpyAsync(d.vset, d.vset_it + (size_t)c.niter_drosa * d.Mcap, sizeof(float4) * d.Mcap, cudaMemcpyDeviceToDevice, s);   // tap "vset"
         if (h->debug && d.vset_iters)
             for (int it = 0; it < c.niter_drosa; ++it)

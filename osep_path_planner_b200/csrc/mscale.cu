@@ -687,7 +687,8 @@ void launch_mscale(osep_rosa_impl* h) {
     k_simi<false><<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.nrms, d.simi_off, d.simi_idx, nullptr, nullptr, d.simi_bits, d.Scap);   // count + bit rows; its last block scans
     // the similarity LISTS (CSR, in (d2, index) order) are only read by dcrosa: the fill pass runs on the side stream next to
     // the fused drosa kernel (which needs the bit rows of the count pass only) and is joined before dcrosa
-    if (h->overlap) {
+    const bool simi_side = h->overlap && (h->simi_side >= 0 ? h->simi_side == 1 : h->fused_grid == 0);
+    if (simi_side) {
         cudaEventRecord(h->ev_fork[1], s); cudaStreamWaitEvent(h->stream2, h->ev_fork[1], 0);
         k_simi<true><<<warp_blocks, tb, 0, h->stream2>>>(d.st, d.pts, d.nrms, d.simi_off, d.simi_idx, d.rv1, (float*)d.rk1, d.simi_bits, d.Scap);
         cudaEventRecord(h->ev_join[1], h->stream2);
@@ -702,7 +703,7 @@ void launch_mscale(osep_rosa_impl* h) {
     k_poor_fixup<<<1, 1024, 0, s>>>(d.st, d.good, d.good_rank, d.centers, d.pset2, d.poor_idx, d.pts, d.pset);
     if (h->debug) cudaMemcpyAsync(d.centers, d.pset, sizeof(float4) * d.Mcap, cudaMemcpyDeviceToDevice, s);   // tap: pset after drosa
     stage_mark(h, SM_POSITION);
-    if (h->overlap) cudaStreamWaitEvent(s, h->ev_join[1], 0);                  // similarity lists
+    if (simi_side) cudaStreamWaitEvent(s, h->ev_join[1], 0);                   // similarity lists
     // R20
     if ((size_t)32 * d.Mcap <= (size_t)DC_SMEM_BUDGET) {
         k_dcrosa_cluster<<<DC_CLUSTER, DC_THREADS, DC_SMEM_BUDGET, s>>>(d.st, d.pset, d.simi_off, d.simi_idx, c.niter_dcrosa, (unsigned)DC_SMEM_BUDGET);
