@@ -16,9 +16,8 @@ struct GraphHost;
 GraphHost* graph_create(int cap, int device, cudaStream_t stream);
 void graph_destroy(GraphHost* g);
 int graph_run_device(GraphHost* g, const float4* pos_dev, int G, float fuse_dist_th, osep_graph_view* out);
-int graph_enqueue_in_frame(GraphHost* g, const float4* pos_dev, const FrameState* st, float fuse_dist_th, cudaStream_t s);
 int graph_collect_in_frame(GraphHost* g, osep_graph_view* out);
-size_t frame_export_enqueue(GraphHost* g, const FrameState* st, const float4* skel, int Mq, unsigned char* exp_dev, cudaStream_t s);
+size_t frame_tail_enqueue(osep_rosa_impl* h, GraphHost* g, float fuse_dist_th, cudaStream_t s);
 size_t frame_export_bytes(int Mq);
 int select_box_enqueue(const float* in, int n, int stride, const float* lo3, const float* hi3, float* out, int out_stride, int out_cap,
                        int* blk_cnt, int* total_dev, cudaStream_t s);
@@ -130,8 +129,9 @@ static int rosa_enqueue(osep_rosa_impl* h, const float* xyz_dev, int n, int stri
         launch_preprocess(h, big ? 400001 : 1);
         launch_mscale(h);
         const bool wg = h->auto_graph && h->graph;
-        if (wg) { graph_enqueue_in_frame(h->graph, d.skel, d.st, h->graph_fuse, h->stream); h->n_launches += 2; }   // frame -> skeleton graph in the same launch sequence
-        const size_t nbytes = frame_export_enqueue(wg ? h->graph : nullptr, d.st, d.skel, d.Mcap / 4, d.exp, h->stream); h->n_launches += 1;
+        // R22 vertex_smooth, the skeleton graph (graph_adj + mst) when it is on, and the result block: one single-CTA launch
+        const size_t nbytes = frame_tail_enqueue(h, wg ? h->graph : nullptr, h->graph_fuse, h->stream); h->n_launches += 1;
+        stage_mark(h, SM_VSMOOTH);
         cudaMemcpyAsync(h->exp_host, d.exp, nbytes, cudaMemcpyDeviceToHost, h->stream);       // the frame's only device-to-host copy (larger results on demand)
     };
     bool done = false;

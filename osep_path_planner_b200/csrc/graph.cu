@@ -9,7 +9,8 @@
 //   G7 prune, G8 smooth_vertex_positions, G9 extract_branches, G10 size_assert.
 // The host side keeps the exact push orders of the reference's std::vector adjacency lists,
 // because vertex_merge / extract_branches iterate them in order.
-#include "osep_common.cuh"
+#include "tail.cuh"
+#include "rosa_impl.cuh"
 #include <vector>
 #include <set>
 #include <string>
@@ -18,192 +19,85 @@
 
 namespace osep {
 
-constexpr int GK = 10;                 // kNN size of graph_adj (gskel.cpp:206)
-constexpr int GACC = GK - 1;           // accepted neighbours per vertex (rank 0 = self is skipped)
-
-struct GraphDevState { int n_edges; int n_mst; int overflow; int pad; };
-
-// brute-force kNN(10) by (d2, index) + RNG test restricted to the kNN list.  One thread per vertex.
+// brute-force kNN(10) by (d2, index) + RNG test restricted to the kNN list (tail.cuh: graph_adj_warp).
 // G: vertex count known on the host, or (st != nullptr) read from the frame state of the Rosa frame that is still running on the
 // same stream: the graph of a frame is then built inside the frame's launch sequence / CUDA graph, without a host round trip
 __device__ __forceinline__ int graph_count(const FrameState* st, int G) { return st ? (st->status == 0 ? st->V : 0) : G; }
 
-// One WARP per vertex: distances to all vertices by the lanes (strided), kNN(10) by ten rounds of warp arg-min over the
-// (d2, index) order, then the relative-neighbourhood test of gskel.cpp:221-235 with one lane per candidate.
-constexpr int GADJ_WARPS = 4;
-constexpr int GADJ_ROW = 3072;          // vertices whose distance row fits the per-warp shared stage; more fall back to global scratch-free recompute
-__global__ void __launch_bounds__(GADJ_WARPS * 32)
+constexpr int GADJ_THREADS = 32;
+__global__ void __launch_bounds__(GADJ_THREADS)
 k_graph_adj(const float4* __restrict__ pos, int G_arg, const FrameState* __restrict__ st, float max_dist_th, int* __restrict__ acc, int* __restrict__ acc_cnt) {
-    __shared__ float s_d[GADJ_WARPS][GADJ_ROW - 32];
-    __shared__ int s_id[GADJ_WARPS][32];
-    const int G = graph_count(st, G_arg);
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const unsigned FULLW = 0xffffffffu;
-    for (int i = blockIdx.x * GADJ_WARPS + wib; i < G; i += gridDim.x * GADJ_WARPS) {
-        const float4 pi4 = pos[i];
-        const f3 pi{pi4.x, pi4.y, pi4.z};
-        const bool staged = G <= GADJ_ROW - 32;
-        if (staged) for (int j = lane; j < G; j += 32) { const float4 q = pos[j]; s_d[wib][j] = dist2(pi.x, pi.y, pi.z, q.x, q.y, q.z); }
-        __syncwarp();
-        const int n_nbs = min(GK, G);
-        int my_id = -1;                              // lane r (< n_nbs) ends up holding the r-th nearest vertex
-        float last_d = -1.0f; int last_i = -1;
-        for (int r = 0; r < n_nbs; ++r) {
-            float bd = __int_as_float(0x7f800000); int bi = 0x7fffffff;
-            for (int j = lane; j < G; j += 32) {
-                float dd;
-                if (staged) dd = s_d[wib][j]; else { const float4 q = pos[j]; dd = dist2(pi.x, pi.y, pi.z, q.x, q.y, q.z); }
-                const bool after = (dd > last_d) || (dd == last_d && j > last_i);          // strictly after the previous pick in (d2, index) order
-                if (after && nb_less(dd, j, bd, bi)) { bd = dd; bi = j; }
-            }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-                const float od = __shfl_xor_sync(FULLW, bd, off); const int oi = __shfl_xor_sync(FULLW, bi, off);
-                if (nb_less(od, oi, bd, bi)) { bd = od; bi = oi; }
-            }
-            if (lane == r) my_id = bi;
-            last_d = bd; last_i = bi;
-        }
-        // lane j in [1, n_nbs) tests candidate id_j against every other kNN member (rank 0 is skipped like gskel.cpp:217)
-        s_id[wib][lane] = my_id;
-        __syncwarp();
-        bool good = false;
-        if (lane >= 1 && lane < n_nbs && my_id >= 0 && my_id < G) {         // (non-finite positions never enter a kNN list)
-            const float4 q4 = pos[my_id];
-            const f3 pn{q4.x, q4.y, q4.z};
-            const float dist_to_nb = norm3(sub3(pi, pn));
-            good = !(dist_to_nb > max_dist_th);
-            for (int k = 1; k < n_nbs && good; ++k) {
-                const int ok_id = s_id[wib][k];
-                if (k == lane || ok_id < 0 || ok_id >= G) continue;
-                const float4 o4 = pos[ok_id];
-                const f3 po{o4.x, o4.y, o4.z};
-                const float d_nb_o = norm3(sub3(pn, po));
-                const float d_i_o = norm3(sub3(pi, po));
-                if (d_nb_o < dist_to_nb && d_i_o < dist_to_nb) good = false;
-            }
-        }
-        const unsigned gm = __ballot_sync(FULLW, good);
-        if (good) acc[i * GACC + __popc(gm & ((1u << lane) - 1u))] = my_id;      // ascending rank = the reference's push order
-        if (lane == 0) acc_cnt[i] = __popc(gm);
-        __syncwarp();
-    }
+    graph_adj_thread(pos, graph_count(st, G_arg), blockIdx.x * GADJ_THREADS + threadIdx.x, gridDim.x * GADJ_THREADS, max_dist_th, acc, acc_cnt);
 }
 
-// Single block.  Edge keys = (weight bits << 32 | u << 16 | v) for every accepted pair, u < v
-// (the reference's "nb <= i" skip, gskel.cpp:254); bitonic sort = the canonical (w,u,v) order
-// (C6); duplicates (i accepts nb and nb accepts i) sit next to each other and Kruskal ignores
-// the second exactly as the reference's loop does.  Kruskal: thread 0, UnionFind of gskel.hpp:43-68.
-// Keys and the parent array live in shared memory when they fit (every single-frame skeleton does).
+// Single block (tail.cuh: graph_mst_block).  Keys and the component arrays live in shared memory when they fit.
 constexpr int GMST_SKEYS = 4096;
-constexpr int GMST_SPARENT = 3072;
+constexpr int GMST_SWORK = 3072;
 __global__ void __launch_bounds__(1024)
 k_graph_mst(const float4* __restrict__ pos, int G_arg, const FrameState* __restrict__ st, const int* __restrict__ acc, const int* __restrict__ acc_cnt,
-            unsigned long long* gkeys, int keycap, int* gparent, int* __restrict__ mst_uv, float* __restrict__ mst_w, GraphDevState* gs) {
+            unsigned long long* gkeys, int keycap, int* gwork, int* __restrict__ mst_uv, float* __restrict__ mst_w, GraphDevState* gs) {
     __shared__ unsigned long long skeys[GMST_SKEYS];
-    __shared__ int sparent[GMST_SPARENT];
-    __shared__ int s_n, s_tot;
-    const int G = graph_count(st, G_arg);
-    if (threadIdx.x == 0) { s_n = 0; s_tot = 0; }
-    __syncthreads();
-    for (int i = threadIdx.x; i < G; i += blockDim.x) atomicAdd(&s_tot, acc_cnt[i]);
-    __syncthreads();
-    int P2t = 1; while (P2t < s_tot) P2t <<= 1;
-    unsigned long long* keys = (P2t <= GMST_SKEYS) ? skeys : gkeys;
-    int* parent = (G <= GMST_SPARENT) ? sparent : gparent;
-    for (int i = threadIdx.x; i < G; i += blockDim.x) {
-        const int c = acc_cnt[i];
-        for (int t = 0; t < c; ++t) {
-            const int nb = acc[i * GACC + t];
-            const int u = min(i, nb), v = max(i, nb);
-            if (u == v) continue;
-            const float4 pu = pos[u], pv = pos[v];
-            // weight = (ver_i - ver_nb).norm() with i = u (the smaller index owns the edge in gskel.cpp:252-263)
-            const float w = norm3(sub3(f3{pu.x, pu.y, pu.z}, f3{pv.x, pv.y, pv.z}));
-            const int slot = atomicAdd(&s_n, 1);
-            if (slot < keycap) keys[slot] = ((unsigned long long)__float_as_uint(w) << 32) | ((unsigned long long)u << 16) | (unsigned long long)v;
-        }
-    }
-    __syncthreads();
-    int n = s_n;
-    if (n > keycap) { if (threadIdx.x == 0) { gs->overflow = 1; gs->n_edges = 0; gs->n_mst = 0; gs->pad = G; } return; }
-    int P2 = 1; while (P2 < n) P2 <<= 1;
-    for (int i = n + threadIdx.x; i < P2; i += blockDim.x) keys[i] = ~0ull;
-    __syncthreads();
-    for (int k = 2; k <= P2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < P2; i += blockDim.x) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned long long a = keys[i], b = keys[ixj];
-                    const bool up = ((i & k) == 0);
-                    if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
-                }
-            }
-            __syncthreads();
-        }
-    }
-    for (int i = threadIdx.x; i < G; i += blockDim.x) parent[i] = i;
-    __syncthreads();
-    // Kruskal over the sorted keys by ONE WARP, 32 edges per round: every lane finds the roots of its edge's end points in
-    // parallel (read-only), then the 32 edges are accepted in key order -- an accepted edge redirects the root of every later
-    // lane of the round by shuffle -- and the unions are committed.  Same accept/reject decisions as the sequential loop of
-    // gskel.cpp:258-278 (a UnionFind answers "same component?" independently of its internal shape).  The loop ends when the
-    // tree is complete (G - 1 edges): the remaining edges could only be rejected.
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        int m = 0;
-        for (int base = 0; base < n && m < G - 1; base += 32) {
-            const int e = base + lane;
-            const unsigned long long key = e < n ? keys[e] : ~0ull;
-            const unsigned long long prevk = e > 0 && e < n ? keys[e - 1] : ~0ull;
-            bool live = e < n && key != prevk;       // the same pair accepted from both ends: the reference's second unite() returns false
-            const int u = (int)((key >> 16) & 0xffffu), v = (int)(key & 0xffffu);
-            int rx = 0, ry = 0;
-            if (live) { rx = u; while (parent[rx] != rx) rx = parent[rx]; ry = v; while (parent[ry] != ry) ry = parent[ry]; }
-            bool take = false;
-            for (int l = 0; l < 32; ++l) {
-                const bool t = __shfl_sync(0xffffffffu, (int)(live && rx != ry), l) != 0;     // lane l's decision with the roots as of now
-                const int a = __shfl_sync(0xffffffffu, rx, l), b = __shfl_sync(0xffffffffu, ry, l);
-                if (!t) continue;
-                if (lane == l) { take = true; parent[b] = a; }
-                else if (lane > l) { if (rx == b) rx = a; if (ry == b) ry = a; }
-            }
-            __syncwarp();
-            const unsigned tm = __ballot_sync(0xffffffffu, take);
-            if (take) {
-                const int pos = m + __popc(tm & ((1u << lane) - 1u));
-                mst_uv[2 * pos] = u; mst_uv[2 * pos + 1] = v; mst_w[pos] = __uint_as_float((unsigned)(key >> 32));
-            }
-            m += __popc(tm);
-        }
-        if (lane == 0) { gs->n_edges = n; gs->n_mst = m; gs->overflow = 0; gs->pad = G; }
-    }
+    __shared__ int swork[GMST_SWORK];
+    graph_mst_block(pos, graph_count(st, G_arg), acc, acc_cnt, skeys, GMST_SKEYS, gkeys, keycap, swork, GMST_SWORK, gwork, mst_uv, mst_w, gs, nullptr);
 }
 
-// One result block per frame: [FrameState | first Mq vertices | GraphDevState | acc_cnt[Mq] | acc[Mq*9] | mst_uv[2 Mq] | mst_w[Mq]].
-// A single block gathers it at the end of the frame, so the frame needs ONE device-to-host copy node instead of seven.
-__host__ __device__ inline size_t exp_off_skel() { return 512; }
-__host__ __device__ inline size_t exp_off_graph(int Mq) { return exp_off_skel() + sizeof(float4) * (size_t)Mq; }
-__host__ __device__ inline size_t exp_bytes(int Mq, bool with_graph) { return exp_off_graph(Mq) + (with_graph ? 16 + (size_t)Mq * (4 + 4 * GACC + 8 + 4) : 0); }
 __global__ void __launch_bounds__(1024) k_export(const FrameState* __restrict__ st, const float4* __restrict__ skel, int Mq, const GraphDevState* __restrict__ gs,
                                                  const int* __restrict__ acc_cnt, const int* __restrict__ acc, const int* __restrict__ mst_uv, const float* __restrict__ mst_w,
                                                  unsigned char* __restrict__ out) {
-    static_assert(sizeof(FrameState) <= 512, "FrameState outgrew its slot of the export block");
-    const int* s32 = reinterpret_cast<const int*>(st); int* o32 = reinterpret_cast<int*>(out);
-    for (int i = threadIdx.x; i < (int)(sizeof(FrameState) / 4); i += blockDim.x) o32[i] = s32[i];
-    const int V = (st->status == 0 || st->status == OSEP_STAGE_7) ? min(st->V, Mq) : 0;
-    float4* os = reinterpret_cast<float4*>(out + exp_off_skel());
-    for (int i = threadIdx.x; i < V; i += blockDim.x) os[i] = skel[i];
-    if (!gs) return;
-    int* og = reinterpret_cast<int*>(out + exp_off_graph(Mq));
-    if (threadIdx.x < 4) og[threadIdx.x] = reinterpret_cast<const int*>(gs)[threadIdx.x];
-    const int G = min(gs->pad, Mq), nm = min(gs->n_mst, Mq);
-    int* o_cnt = og + 4; int* o_acc = o_cnt + Mq; int* o_uv = o_acc + (size_t)Mq * GACC; float* o_w = reinterpret_cast<float*>(o_uv + 2 * (size_t)Mq);
-    for (int i = threadIdx.x; i < G; i += blockDim.x) o_cnt[i] = acc_cnt[i];
-    for (int i = threadIdx.x; i < G * GACC; i += blockDim.x) o_acc[i] = acc[i];
-    for (int i = threadIdx.x; i < 2 * nm; i += blockDim.x) o_uv[i] = mst_uv[i];
-    for (int i = threadIdx.x; i < nm; i += blockDim.x) o_w[i] = mst_w[i];
+    export_block(st, skel, Mq, gs, acc_cnt, acc, mst_uv, mst_w, out);
+}
+
+// The tail of a frame in ONE single-CTA launch: R22 vertex_smooth -> G3 graph_adj -> G4 mst -> export (tail.cuh), with the vertex
+// positions, neighbour lists, distance rows, edge keys and union-find in the shared-memory arena whenever they fit (a frame has
+// V ~ 10^2 vertices; larger ones fall back to the global scratch arrays piece by piece -- same results).
+struct TailArgs {
+    FrameState* st;
+    float4* skel; float4* skel2; float4* vtmp; int* vs_off; int* vs_idx; int* tmp_j; float* tmp_d; int cap;
+    float radius, alpha; int niter;
+    int with_graph; float max_dist_th;
+    int* acc; int* acc_cnt; unsigned long long* gkeys; int keycap; int* gwork; int* mst_uv; float* mst_w; GraphDevState* gs;
+    int Mq; unsigned char* out; unsigned arena_bytes;
+    long long* dbg;        // OSEP_FUSED_DETAIL=1: globaltimer stamps at the phase borders (tools/tail_dbg.py)
+};
+constexpr int TAIL_THREADS = 512;
+constexpr unsigned TAIL_ARENA = 96 * 1024;
+__global__ void __launch_bounds__(TAIL_THREADS) k_frame_tail(const __grid_constant__ TailArgs a) {
+    extern __shared__ uint4 tail_smem[];
+    unsigned char* arena = reinterpret_cast<unsigned char*>(tail_smem);
+    auto stamp = [&](int k) { if (a.dbg && threadIdx.x == 0) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.dbg[k] = t; } };
+    stamp(0);
+    const int status0 = a.st->status, V0 = a.st->V;
+    __syncthreads();
+    const float4* pos = a.skel;
+    if (status0 == 0) {
+        if (V0 == 0) { if (threadIdx.x == 0) a.st->status = OSEP_STAGE_7; }
+        else {
+            const float4* p = vertex_smooth_block(a.st, a.skel, a.skel2, a.vtmp, a.vs_off, a.vs_idx, a.tmp_j, a.tmp_d, a.cap, a.radius, a.alpha, a.niter, arena, a.arena_bytes);
+            if (p) pos = p;
+        }
+    }
+    __syncthreads();
+    stamp(1);
+    if (a.with_graph) {
+        const int G = a.st->status == 0 ? a.st->V : 0;
+        size_t used = (pos != a.skel) ? smooth_pos_bytes(G) : 0;                 // the smoothed positions stay where they are
+        graph_adj_thread(pos, G, threadIdx.x, TAIL_THREADS, a.max_dist_th, a.acc, a.acc_cnt);
+        __syncthreads();
+        stamp(2);
+        // component arrays first (3 G ints), the rest of the arena holds the edge keys
+        int* swork = reinterpret_cast<int*>(arena + used);
+        const size_t wbytes = tail_align16((size_t)3 * G * 4);
+        const bool w_in = used + wbytes <= a.arena_bytes;
+        const size_t kbase = used + (w_in ? wbytes : 0);
+        unsigned long long* skeys = reinterpret_cast<unsigned long long*>(arena + kbase);
+        const int skeys_cap = kbase < a.arena_bytes ? (int)((a.arena_bytes - kbase) / 8) : 0;
+        graph_mst_block(pos, G, a.acc, a.acc_cnt, skeys, skeys_cap, a.gkeys, a.keycap, swork, w_in ? 3 * G : 0, a.gwork, a.mst_uv, a.mst_w, a.gs, a.dbg ? a.dbg + 4 : nullptr);
+        __syncthreads();
+    }
+    stamp(3);
+    export_block(a.st, a.skel, a.Mq, a.with_graph ? a.gs : nullptr, a.acc_cnt, a.acc, a.mst_uv, a.mst_w, a.out);
+    __syncthreads();
+    stamp(7);
 }
 
 struct GraphHost {
@@ -212,14 +106,14 @@ struct GraphHost {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     float4* pos = nullptr; int* acc = nullptr; int* acc_cnt = nullptr; unsigned long long* keys = nullptr; int keycap = 0;
-    int* parent = nullptr; int* mst_uv = nullptr; float* mst_w = nullptr; GraphDevState* gs = nullptr;
+    int* parent = nullptr /* 3 cap ints: component label, parent, best edge */; int* mst_uv = nullptr; float* mst_w = nullptr; GraphDevState* gs = nullptr;
     // host results
     std::vector<int> h_acc, h_acc_cnt, edges, adj_off, adj_idx, type, joints, leafs, rng_off, rng_idx;
     std::vector<float> edge_w;
     std::vector<std::vector<int>> adj;      // MST adjacency in push order
     std::vector<std::vector<int>> rng;      // graph_adj adjacency in push order (duplicates kept)
     int G = 0;
-    // pinned mirrors of the in-frame graph (graph_enqueue_frame): the first `mcap` vertices' lists travel with the frame
+    // pinned mirrors of the in-frame graph (k_frame_tail): the first `mcap` vertices' lists travel with the frame
     // (they point into the owning Rosa handle's pinned export block)
     int mcap = 0; GraphDevState* m_gs = nullptr; int* m_acc = nullptr; int* m_acc_cnt = nullptr; int* m_uv = nullptr; float* m_w = nullptr;
 };
@@ -239,7 +133,7 @@ static GraphHost* graph_alloc(int cap, int device, cudaStream_t stream) {
     bool ok = cudaMalloc(&g->pos, sizeof(float4) * cap) == cudaSuccess && cudaMalloc(&g->acc, sizeof(int) * cap * GACC) == cudaSuccess &&
               cudaMalloc(&g->acc_cnt, sizeof(int) * cap) == cudaSuccess;
     int P2 = 1; while (P2 < g->keycap) P2 <<= 1;
-    ok = ok && cudaMalloc(&g->keys, sizeof(unsigned long long) * P2) == cudaSuccess && cudaMalloc(&g->parent, sizeof(int) * cap) == cudaSuccess &&
+    ok = ok && cudaMalloc(&g->keys, sizeof(unsigned long long) * P2) == cudaSuccess && cudaMalloc(&g->parent, sizeof(int) * 3 * cap) == cudaSuccess &&
          cudaMalloc(&g->mst_uv, sizeof(int) * 2 * cap) == cudaSuccess && cudaMalloc(&g->mst_w, sizeof(float) * cap) == cudaSuccess &&
          cudaMalloc(&g->gs, sizeof(GraphDevState)) == cudaSuccess;
     if (!ok) { graph_free(g); return nullptr; }
@@ -276,7 +170,7 @@ static int graph_run(GraphHost* g, const float4* pos_dev, int G, float fuse_dist
     if (G == 0) { graph_assemble(g, 0, 0, nullptr, nullptr, nullptr, nullptr); return OSEP_OK; }
     if (G > g->cap || G > 65535) return OSEP_ERR_CAPACITY;
     const float max_dist_th = 2.5f * fuse_dist_th;
-    k_graph_adj<<<div_up(G, GADJ_WARPS), GADJ_WARPS * 32, 0, g->stream>>>(pos_dev, G, nullptr, max_dist_th, g->acc, g->acc_cnt);
+    k_graph_adj<<<div_up(G, GADJ_THREADS), GADJ_THREADS, 0, g->stream>>>(pos_dev, G, nullptr, max_dist_th, g->acc, g->acc_cnt);
     k_graph_mst<<<1, 1024, 0, g->stream>>>(pos_dev, G, nullptr, g->acc, g->acc_cnt, g->keys, g->keycap, g->parent, g->mst_uv, g->mst_w, g->gs);
     GraphDevState gs;
     if (cudaMemcpyAsync(&gs, g->gs, sizeof(gs), cudaMemcpyDeviceToHost, g->stream) != cudaSuccess) return OSEP_ERR_CUDA;
@@ -294,14 +188,6 @@ static int graph_run(GraphHost* g, const float4* pos_dev, int G, float fuse_dist
     return OSEP_OK;
 }
 
-// In-frame variant: enqueue G3 + G4 behind the Rosa stages of the frame running on `s` (vertex count read from the frame
-// state on the device) and copy the first `mcap` vertices' lists to pinned mirrors -- all capturable, no host round trip.
-static int graph_enqueue_frame(GraphHost* g, const float4* pos_dev, const FrameState* st, float fuse_dist_th, cudaStream_t s) {
-    const float max_dist_th = 2.5f * fuse_dist_th;
-    k_graph_adj<<<148 * 2, GADJ_WARPS * 32, 0, s>>>(pos_dev, 0, st, max_dist_th, g->acc, g->acc_cnt);
-    k_graph_mst<<<1, 512, 0, s>>>(pos_dev, 0, st, g->acc, g->acc_cnt, g->keys, g->keycap, g->parent, g->mst_uv, g->mst_w, g->gs);
-    return OSEP_OK;
-}
 // after the frame's stream has been synchronised: host half from the mirrors (graphs larger than the mirrors are fetched on demand)
 static int graph_collect_frame(GraphHost* g) {
     const GraphDevState gs = *g->m_gs;
@@ -625,12 +511,22 @@ int graph_run_device(GraphHost* g, const float4* pos_dev, int G, float fuse_dist
     if (rc == OSEP_OK && out) graph_view(g, out);
     return rc;
 }
-int graph_enqueue_in_frame(GraphHost* g, const float4* pos_dev, const FrameState* st, float fuse_dist_th, cudaStream_t s) { return graph_enqueue_frame(g, pos_dev, st, fuse_dist_th, s); }
-// gather the frame's results into the export block (g == nullptr: no graph part); returns the bytes the host copy must move
-size_t frame_export_enqueue(GraphHost* g, const FrameState* st, const float4* skel, int Mq, unsigned char* exp_dev, cudaStream_t s) {
-    if (g) k_export<<<1, 1024, 0, s>>>(st, skel, Mq, g->gs, g->acc_cnt, g->acc, g->mst_uv, g->mst_w, exp_dev);
-    else k_export<<<1, 1024, 0, s>>>(st, skel, Mq, nullptr, nullptr, nullptr, nullptr, nullptr, exp_dev);
-    return exp_bytes(Mq, g != nullptr);
+// the tail of a frame (vertex_smooth, then -- with g -- graph_adj + mst, then the export block) as one launch; returns the
+// bytes the host copy must move
+size_t frame_tail_enqueue(osep_rosa_impl* h, GraphHost* g, float fuse_dist_th, cudaStream_t s) {
+    RosaDev& d = h->d;
+    const osep_rosa_config& c = h->cfg;
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_frame_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_ARENA); attr_set = true; }
+    TailArgs a;
+    a.st = d.st; a.skel = d.skel; a.skel2 = d.skel2; a.vtmp = d.vtmp; a.vs_off = d.vs_off; a.vs_idx = d.vs_idx; a.tmp_j = d.rv1; a.tmp_d = (float*)d.rk1; a.cap = d.Scap;
+    a.radius = c.radius_smooth; a.alpha = c.alpha_recenter; a.niter = c.niter_smooth;
+    a.with_graph = g ? 1 : 0; a.max_dist_th = 2.5f * fuse_dist_th;
+    a.acc = g ? g->acc : nullptr; a.acc_cnt = g ? g->acc_cnt : nullptr; a.gkeys = g ? g->keys : nullptr; a.keycap = g ? g->keycap : 0; a.gwork = g ? g->parent : nullptr;
+    a.mst_uv = g ? g->mst_uv : nullptr; a.mst_w = g ? g->mst_w : nullptr; a.gs = g ? g->gs : nullptr;
+    a.Mq = d.Mcap / 4; a.out = d.exp; a.arena_bytes = TAIL_ARENA; a.dbg = h->fused_detail ? d.fused_dbg + 48 : nullptr;
+    k_frame_tail<<<1, TAIL_THREADS, TAIL_ARENA, s>>>(a);
+    return exp_bytes(d.Mcap / 4, g != nullptr);
 }
 size_t frame_export_bytes(int Mq) { return exp_bytes(Mq, true); }
 void graph_set_mirrors(GraphHost* g, unsigned char* exp_host, int Mq) {

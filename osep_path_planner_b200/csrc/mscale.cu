@@ -18,14 +18,12 @@
 //   * the greedy radius cover keeps the sequential semantics on one warp over precomputed
 //     adjacency bit rows.
 #include "rosa_impl.cuh"
+#include "tail.cuh"
 #include <cooperative_groups.h>
 
 namespace osep {
 
 constexpr unsigned FULL = 0xffffffffu;
-
-__device__ __forceinline__ f3 ld3(const float4* a, int i) { const float4 v = a[i]; return {v.x, v.y, v.z}; }
-__device__ __forceinline__ void st3(float4* a, int i, const f3& v, float w = 0.0f) { a[i] = make_float4(v.x, v.y, v.z, w); }
 
 template <int K> __device__ __forceinline__ void butterfly(float (&v)[K]) {
 #pragma unroll
@@ -34,39 +32,6 @@ template <int K> __device__ __forceinline__ void butterfly(float (&v)[K]) {
         for (int k = 0; k < K; ++k) v[k] = v[k] + __shfl_xor_sync(FULL, v[k], off);
     }
 }
-
-// block-wide exclusive scan of one int per thread-strided element (single block helper, in place)
-__device__ int block_scan_inplace(int* data, int n) {
-    __shared__ int wsum[32];
-    __shared__ int s_carry, s_tile;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-    if (tid == 0) s_carry = 0;
-    __syncthreads();
-    for (int base = 0; base < n; base += blockDim.x) {
-        const int i = base + tid;
-        const int v = (i < n) ? data[i] : 0;
-        int incl = v;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += t; }
-        if (lane == 31) wsum[wid] = incl;
-        __syncthreads();
-        if (wid == 0) {
-            const int ws = (lane < nw) ? wsum[lane] : 0;
-            int wi = ws;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(FULL, wi, off); if (lane >= off) wi += t; }
-            wsum[lane] = wi - ws;
-            if (lane == 31) s_tile = wi;
-        }
-        __syncthreads();
-        if (i < n) data[i] = s_carry + wsum[wid] + incl - v;
-        __syncthreads();
-        if (tid == 0) s_carry += s_tile;
-        __syncthreads();
-    }
-    return s_carry;
-}
-
 
 // ------------------------------------------------------------------------------------------
 // R12.  similarity_metric (rosa.cpp:625-651)
@@ -552,109 +517,7 @@ k_vs_recenter(FrameState* st, const float4* __restrict__ pts, const float4* __re
     st3(skel, v, cur, 1.0f); st3(skel_sampled, v, cur, 1.0f);
 }
 
-// ------------------------------------------------------------------------------------------
-// R22 vertex_smooth (rosa.cpp:534-620), single block: finite compaction, radius neighbours
-// (sorted (d2, index), self forced first), niter Jacobi PCA-line projections.
-__global__ void k_vertex_smooth(FrameState* st, float4* skel, float4* skel2, float4* __restrict__ vtmp, int* vs_off, int* __restrict__ vs_idx,
-                                int* __restrict__ tmp_j, float* __restrict__ tmp_d, int cap, float radius, float alpha, int niter) {
-    if (st->status != 0) return;
-    const int V = st->V;
-    if (V == 0) { if (threadIdx.x == 0) st->status = OSEP_STAGE_7; return; }
-    // finite compaction (rosa.cpp:543-552)
-    for (int i = threadIdx.x; i < V; i += blockDim.x) { const float4 v = skel[i]; vs_off[i] = (fin(v.x) && fin(v.y) && fin(v.z)) ? 1 : 0; skel2[i] = v; }
-    if (threadIdx.x == 0) vs_off[V] = 0;
-    __syncthreads();
-    const int Vf = block_scan_inplace(vs_off, V + 1);
-    __syncthreads();
-    for (int i = threadIdx.x; i < V; i += blockDim.x) { const float4 v = skel[i]; if (fin(v.x) && fin(v.y) && fin(v.z)) vtmp[vs_off[i]] = v; }
-    __syncthreads();
-    const float r2 = radius * radius;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    // neighbour counts: one warp per vertex, ballots over 32 candidates at a time; `first` = smallest (d2, index)
-    for (int i = warp; i < Vf; i += nwarps) {
-        const f3 q = ld3(vtmp, i);
-        int c = 0; float bd = __int_as_float(0x7f800000); int bi = 0x7fffffff;
-        for (int j0 = 0; j0 < Vf; j0 += 32) {
-            const int j = j0 + lane;
-            float d = 0.0f; bool in = false;
-            if (j < Vf) { d = dist2(q, ld3(vtmp, j)); in = d < r2; }
-            c += __popc(__ballot_sync(FULL, in));
-            if (in && nb_less(d, j, bd, bi)) { bd = d; bi = j; }
-        }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            const float od = __shfl_xor_sync(FULL, bd, off); const int oi = __shfl_xor_sync(FULL, bi, off);
-            if (nb_less(od, oi, bd, bi)) { bd = od; bi = oi; }
-        }
-        if (c == 0) c = 1; else if (bi != i) c += 1;      // self forced first (rosa.cpp:567-573)
-        if (lane == 0) vs_off[i] = c;
-    }
-    if (threadIdx.x == 0) vs_off[Vf] = 0;
-    __syncthreads();
-    const int total = block_scan_inplace(vs_off, Vf + 1);
-    __syncthreads();
-    if (total > cap) { if (threadIdx.x == 0) st->status = OSEP_ERR_CAPACITY; return; }
-    for (int i = warp; i < Vf; i += nwarps) {
-        const f3 q = ld3(vtmp, i);
-        const int b = vs_off[i];
-        int c = 0;
-        for (int j0 = 0; j0 < Vf; j0 += 32) {
-            const int j = j0 + lane;
-            float d = 0.0f; bool in = false;
-            if (j < Vf) { d = dist2(q, ld3(vtmp, j)); in = d < r2; }
-            const unsigned m = __ballot_sync(FULL, in);
-            if (in) { const int pos = b + c + __popc(m & ((1u << lane) - 1u)); tmp_j[pos] = j; tmp_d[pos] = d; }
-            c += __popc(m);
-        }
-        __syncwarp();
-        if (c == 0) { if (lane == 0) vs_idx[b] = i; continue; }
-        // rank sort by (d2, index); if the first sorted entry is not i, i is inserted in front (rosa.cpp:567-569)
-        int myfirst = 0x7fffffff;
-        for (int e = lane; e < c; e += 32) {
-            int rank = 0;
-            for (int f = 0; f < c; ++f) rank += nb_less(tmp_d[b + f], tmp_j[b + f], tmp_d[b + e], tmp_j[b + e]) ? 1 : 0;
-            if (rank == 0) myfirst = tmp_j[b + e];
-        }
-        const int first = __reduce_min_sync(FULL, myfirst);
-        const int shift = (first != i) ? 1 : 0;
-        if (shift && lane == 0) vs_idx[b] = i;
-        for (int e = lane; e < c; e += 32) {
-            int rank = 0;
-            for (int f = 0; f < c; ++f) rank += nb_less(tmp_d[b + f], tmp_j[b + f], tmp_d[b + e], tmp_j[b + e]) ? 1 : 0;
-            vs_idx[b + shift + rank] = tmp_j[b + e];
-        }
-    }
-    __syncthreads();
-    float4* cur = skel; float4* nxt = skel2;
-    for (int it = 0; it < niter; ++it) {
-        for (int i = threadIdx.x; i < Vf; i += blockDim.x) {
-            const int b = vs_off[i], e = vs_off[i + 1];
-            const int n = e - b;
-            if (n <= 1) { nxt[i] = cur[i]; continue; }
-            f3 mean{0.0f, 0.0f, 0.0f};
-            for (int t = b; t < e; ++t) mean = add3(mean, ld3(cur, vs_idx[t]));
-            mean = div3(mean, (float)n);
-            float c00 = 0, c10 = 0, c11 = 0, c20 = 0, c21 = 0, c22 = 0;
-            for (int t = b; t < e; ++t) {
-                const f3 d = sub3(ld3(cur, vs_idx[t]), mean);
-                c00 += d.x * d.x; c10 += d.y * d.x; c11 += d.y * d.y; c20 += d.z * d.x; c21 += d.z * d.y; c22 += d.z * d.z;
-            }
-            const float fn = (float)n;
-            c00 /= fn; c10 /= fn; c11 /= fn; c20 /= fn; c21 /= fn; c22 /= fn;
-            const Eig3 E = eig3_sym_dev(c00, c10, c11, c20, c21, c22);
-            const f3 dir = eig_col(E, 2);
-            const f3 p = ld3(cur, i);
-            const f3 delta = sub3(p, mean);
-            const f3 proj = add3(mean, mul3(dir, dot3(dir, delta)));
-            st3(nxt, i, add3(mul3(p, alpha), mul3(proj, 1.0f - alpha)), 1.0f);
-        }
-        __syncthreads();
-        float4* t = cur; cur = nxt; nxt = t;
-    }
-    // RD.skelver = cur
-    if (cur != skel) { for (int i = threadIdx.x; i < V; i += blockDim.x) skel[i] = cur[i]; }
-    if (threadIdx.x == 0) st->Vf = Vf;
-}
+// R22 vertex_smooth (rosa.cpp:534-620): tail.cuh vertex_smooth_block, launched as part of k_frame_tail (graph.cu)
 
 // ------------------------------------------------------------------------------------------
 void drosa_set_attributes();
@@ -721,11 +584,8 @@ void launch_mscale(osep_rosa_impl* h) {
     k_vs_corresp<<<tblocks, 128, 0, s>>>(d.st, d.pcloud, d.seeds, d.corresp);
     k_vs_recenter<<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.pset, d.seeds, d.corresp, c.alpha_recenter, d.skel, d.skel_sampled);
     stage_mark(h, SM_VSAMPLE);
-    // R22
-    k_vertex_smooth<<<1, 1024, 0, s>>>(d.st, d.skel, d.skel2, d.vtmp, d.vs_off, d.vs_idx, d.rv1, (float*)d.rk1, d.Scap,
-                                       c.radius_smooth, c.alpha_recenter, c.niter_smooth);
-    stage_mark(h, SM_VSMOOTH);
-    h->n_launches += 2 + 1 + 1 + 1 + 5 + 1;   // + launch_drosa (dcrosa = one cluster kernel in the common case)
+    // R22 vertex_smooth runs in the frame's tail kernel (graph.cu frame_tail_enqueue)
+    h->n_launches += 2 + 1 + 1 + 1 + 5;   // + launch_drosa (dcrosa = one cluster kernel in the common case)
 }
 
 }  // namespace osep

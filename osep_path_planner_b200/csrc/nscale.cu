@@ -994,7 +994,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_knn_big(const float4* __restrict
 // A miss (count outside the window) does not loop in place -- 31 lanes would idle: the query goes on a RETRY list with a
 // rescaled tau and a second launch of the same kernel runs all retries together (up to 3 attempts each); queries whose
 // block cannot certify k points go on the GROW list (R = 2 launch), what is left goes to k_knn_exact.
-constexpr int SCAN_THREADS = 128;
+#ifndef OSEP_SCAN_THREADS
+#define OSEP_SCAN_THREADS 128
+#endif
+constexpr int SCAN_THREADS = OSEP_SCAN_THREADS;
 constexpr int SCAN_CAP = 40;
 
 __device__ __forceinline__ void cex(unsigned& a, unsigned& b) { const unsigned lo = min(a, b), hi = max(a, b); a = lo; b = hi; }

@@ -10,6 +10,7 @@ K = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 P = fx.turbine() if name == "turbine100k" else fx.cylinder()
 r = osep.Rosa(capacity_points=P.shape[0])
 r.set_input(P)
+r.set_graph(True, 3.0)          # frame -> skeleton graph inside the frame, as bench.py runs it
 for k in range(K):
     ok = r.rosa_run()
     print(k, ok, r.result.n_vertices, "gpu_ms %.3f" % r.result.gpu_ms)
