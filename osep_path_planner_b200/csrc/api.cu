@@ -11,6 +11,7 @@
 namespace osep {
 
 void mscale_set_attributes(int Mcap);
+bool dcrosa_cluster16_ok();
 bool drosa_fused_supported(int sms);
 struct GraphHost;
 GraphHost* graph_create(int cap, int device, cudaStream_t stream);
@@ -57,7 +58,7 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
     CK(dalloc(&d.rk0, tmpcap)); CK(dalloc(&d.rk1, tmpcap)); CK(dalloc(&d.rv0, tmpcap)); CK(dalloc(&d.rv1, tmpcap));
     CK(dalloc(&d.pts, M)); CK(dalloc(&d.nrms, M)); CK(dalloc(&d.pset, M)); CK(dalloc(&d.pset2, M)); CK(dalloc(&d.vset, M)); CK(dalloc(&d.vnew, M));
     CK(dalloc(&d.vvar, M)); CK(dalloc(&d.simi_bits, M * (size_t)d.W)); CK(dalloc(&d.nraw, M)); CK(dalloc(&d.vnd, M));
-    CK(dalloc(&d.vset_it, M * 9)); CK(dalloc(&d.vnew_it, M * 8)); CK(dalloc(&d.fused_flags, M * 16 + 16)); CK(dalloc(&d.fused_dbg, 64)); CK(cudaMemset(d.fused_dbg, 0, 64 * 8));
+    CK(dalloc(&d.vset_it, M * 9)); CK(dalloc(&d.vnew_it, M * 8)); CK(dalloc(&d.fused_flags, M * 16 + 16)); CK(dalloc(&d.fused_dbg, 128)); CK(cudaMemset(d.fused_dbg, 0, 128 * 8));
     { const char* e = getenv("OSEP_KNN_PPC"); if (e && atoi(e) > 0) h->knn_ppc = atoi(e); }
     { const char* e = getenv("OSEP_KNN_TARGET"); if (e && atof(e) > 0) h->knn_target = (float)atof(e); }
     { const char* e = getenv("OSEP_KNN_WARP"); if (e && e[0] == '1') h->knn_warp_path = true; }
@@ -67,6 +68,7 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
       const char* e4 = getenv("OSEP_FUSED_DETAIL"); if (e4 && e4[0] == '1') { h->fused_detail = true; CK(dalloc(&d.fused_tl, M * 9 * 16)); CK(cudaMemset(d.fused_tl, 0, M * 9 * 16 * 8)); }
       const char* e6 = getenv("OSEP_FUSED_GRID"); if (e6 && atoi(e6) > 0) h->fused_grid = atoi(e6);
       const char* e8 = getenv("OSEP_FUSED_SMEM_KB"); if (e8 && atoi(e8) > 0) h->fused_smem = atoi(e8) * 1024;
+      const char* e10 = getenv("OSEP_DC_CLUSTER"); if (e10 && (atoi(e10) == 8 || atoi(e10) == 16)) h->dc_cluster = atoi(e10);
       const char* e9 = getenv("OSEP_SIMI_SIDE"); if (e9 && (e9[0] == '0' || e9[0] == '1')) h->simi_side = e9[0] - '0';
       const char* e7 = getenv("OSEP_HOT_CTAS"); if (e7 && atoi(e7) > 0) h->hot_ctas = atoi(e7);
       const char* e5 = getenv("OSEP_SPIN_NS"); if (e5 && atoi(e5) >= 0) h->spin_ns = atoi(e5);
@@ -89,6 +91,7 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
     CK(cudaMallocHost((void**)&h->prm_host, sizeof(FrameParams)));
     memset(h->st_host, 0, sizeof(FrameState));
     mscale_set_attributes(d.Mcap);
+    h->dc16_ok = dcrosa_cluster16_ok();
     if (h->fused && !drosa_fused_supported(h->sms)) h->fused = false;     // falls back to the per-iteration kernels (same results)
     return OSEP_OK;
 }
@@ -438,7 +441,7 @@ long osep_rosa_get(osep_rosa* h, const char* name, void* dst, long cap) {
         return SM_COUNT;
     }
     if (nm == "fused_tl") { if (!d.fused_tl) return 0; return tap_copy(dst, cap, d.fused_tl, (size_t)d.Mcap * 9 * 16, 8) * 2; }
-    if (nm == "fused_dbg") return tap_copy(dst, cap, d.fused_dbg, 64, 8) * 2;     // 64 int64 = 128 int32 words
+    if (nm == "fused_dbg") return tap_copy(dst, cap, d.fused_dbg, 128, 8) * 2;     // 128 int64 = 256 int32 words
     if (nm == "knn_stats") { if (dst && cap >= 20) { int* o = (int*)dst; o[0] = s.n_units; o[1] = s.n_slow; o[2] = s.n_over; o[3] = s.n_retry; o[4] = s.n_grow; } return 5; }
     if (nm == "launches") { if (dst && cap >= 4) *(int*)dst = (int)I.n_launches; return 1; }
     if (nm == "graph_replays") { if (dst && cap >= 4) *(int*)dst = (int)I.n_graph_replays; return 1; }

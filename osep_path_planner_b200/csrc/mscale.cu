@@ -286,20 +286,35 @@ __global__ void k_dcrosa_line(const FrameState* __restrict__ st, const float4* _
 // :804-813), and broadcasts its result to the 8 copies through distributed shared memory; cluster.sync()
 // separates the Jacobi passes.  One SM alone is shared-memory-bandwidth bound on the random gathers; 8 SMs
 // with replicated operands are not, and no pass goes back to L2.
-constexpr int DC_CLUSTER = 8;
 #ifndef OSEP_DC_THREADS
 #define OSEP_DC_THREADS 256
 #endif
 #ifndef OSEP_DC_SPREAD
 #define OSEP_DC_SPREAD 2
 #endif
+#ifndef OSEP_DC_UNROLL
+#define OSEP_DC_UNROLL 8
+#endif
+#ifndef OSEP_DC_BALANCE
+#define OSEP_DC_BALANCE 48
+#endif
 constexpr int DC_THREADS = OSEP_DC_THREADS;
+constexpr int DC_UNROLL = OSEP_DC_UNROLL;
 constexpr int DC_SPREAD = OSEP_DC_SPREAD;       // every DC_SPREAD-th thread owns a point: fewer points per warp = shorter per-warp maximum of list length / eigen iterations
+constexpr int DC_BALANCE = OSEP_DC_BALANCE;     // cost of a point in list entries (eigen solve + fixed work) next to its list length, for the partition below
 constexpr int DC_SMEM_BUDGET = 200 * 1024;
 
-__global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS)
+// A CTA is bound by the number of warp instructions it issues (three list sweeps + one eigen solve per point and iteration:
+// more warps per CTA measured SLOWER, 68 -> 83 -> 124 us for 8 / 16 / 32 warps), so the lever is the number of SMs: CL = 16
+// (non-portable cluster size) when a single frame owns the GPU, the portable 8 when several frames are in flight.  Points are
+// dealt to the CTAs in contiguous ranges of equal COST (list length + DC_BALANCE per point), not equal count.
+template <int CL>
+__global__ void __launch_bounds__(DC_THREADS)
 k_dcrosa_cluster(const FrameState* __restrict__ st, float4* pset, const int* __restrict__ simi_off, const int* __restrict__ simi_idx, int niter,
-                 unsigned smem_bytes) {
+                 unsigned smem_bytes, long long* dbg) {
+    int dk = 0;
+    auto stamp = [&]() { if (dbg && threadIdx.x == 0 && blockIdx.x == 0 && dk < 60) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[dk++] = t; } };
+    stamp();
     extern __shared__ float4 dcs[];
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -308,75 +323,108 @@ k_dcrosa_cluster(const FrameState* __restrict__ st, float4* pset, const int* __r
     float4* pa = dcs; float4* pb = dcs + M;
     const unsigned rank = cluster.block_rank();
     for (int i = threadIdx.x; i < M; i += blockDim.x) pa[i] = pset[i];
+    // range [lo, hi) of this CTA: first point whose cost prefix simi_off[i] + DC_BALANCE * i reaches rank / CL of the total
+    __shared__ int s_lohi[2];
+    {
+        const long long total = (long long)simi_off[M] + (long long)DC_BALANCE * M;
+        const long long want0 = total * rank / CL, want1 = total * (rank + 1) / CL;
+        for (int i = threadIdx.x; i <= M; i += blockDim.x) {      // the prefix is strictly increasing: exactly one i per boundary
+            const long long pi = (long long)simi_off[i] + (long long)DC_BALANCE * i;
+            const long long pp = i > 0 ? (long long)simi_off[i - 1] + (long long)DC_BALANCE * (i - 1) : -1;
+            if (pi >= want0 && pp < want0) s_lohi[0] = i;
+            if (pi >= want1 && pp < want1) s_lohi[1] = i;
+        }
+    }
     __syncthreads();
-    float4* pa_r[DC_CLUSTER]; float4* pb_r[DC_CLUSTER];
-#pragma unroll
-    for (int r = 0; r < DC_CLUSTER; ++r) { pa_r[r] = cluster.map_shared_rank(pa, r); pb_r[r] = cluster.map_shared_rank(pb, r); }
-    cluster.sync();
-    const int per = (M + DC_CLUSTER - 1) / DC_CLUSTER;
-    const int lo = min(M, (int)rank * per), hi = min(M, lo + per);
+    const int lo = s_lohi[0], hi = s_lohi[1];
     // this CTA's slice of the similarity CSR, staged in shared memory when it fits
     int* sidx = reinterpret_cast<int*>(dcs + 2 * (size_t)M);
     const int seg_b = simi_off[lo], seg_e = simi_off[hi];
     const bool csr_in = ((size_t)32 * M + 4 * (size_t)(seg_e - seg_b)) <= smem_bytes;
     if (csr_in) for (int t = seg_b + threadIdx.x; t < seg_e; t += blockDim.x) sidx[t - seg_b] = simi_idx[t];
-    __syncthreads();
-    const int* nbr = csr_in ? (sidx - seg_b) : simi_idx;       // nbr[t] for t in [seg_b, seg_e)
-    for (int it = 0; it < niter; ++it) {
-        for (int i = lo + (int)(threadIdx.x / DC_SPREAD); i < hi && (threadIdx.x % DC_SPREAD) == 0; i += (int)(blockDim.x / DC_SPREAD)) {          // neighbour mean (rosa.cpp:388-399)
-            const int b = simi_off[i], e = simi_off[i + 1];
-            float4 out = pa[i];
-            if (e > b) {
-                f3 acc{0.0f, 0.0f, 0.0f};
-#pragma unroll 4
-                for (int t = b; t < e; ++t) { const float4 v = pa[nbr[t]]; acc = add3(acc, f3{v.x, v.y, v.z}); }
-                const f3 mth = div3(acc, (float)(e - b));
-                out = make_float4(mth.x, mth.y, mth.z, 1.0f);
-            }
+    float4* pa_r[CL]; float4* pb_r[CL];
 #pragma unroll
-            for (int r = 0; r < DC_CLUSTER; ++r) pb_r[r][i] = out;
-        }
-        cluster.sync();
-        for (int i = lo + (int)(threadIdx.x / DC_SPREAD); i < hi && (threadIdx.x % DC_SPREAD) == 0; i += (int)(blockDim.x / DC_SPREAD)) {          // local_line_fit + projection (rosa.cpp:402-418, 793-841)
-            const int b = simi_off[i], e = simi_off[i + 1];
-            const int m = e - b;
-            const float4 self4 = pb[i];
-            float4 out = self4;
-            if (m >= 3) {
-                f3 mean{0.0f, 0.0f, 0.0f};
-#pragma unroll 4
-                for (int t = b; t < e; ++t) { const float4 v = pb[nbr[t]]; mean = add3(mean, f3{v.x, v.y, v.z}); }
-                mean = div3(mean, (float)m);
-                float c00 = 0, c10 = 0, c11 = 0, c20 = 0, c21 = 0, c22 = 0;
-#pragma unroll 4
-                for (int t = b; t < e; ++t) {
-                    const float4 v = pb[nbr[t]];
-                    const f3 q = sub3(f3{v.x, v.y, v.z}, mean);
-                    c00 += q.x * q.x; c10 += q.y * q.x; c11 += q.y * q.y; c20 += q.z * q.x; c21 += q.z * q.y; c22 += q.z * q.z;
+    for (int r = 0; r < CL; ++r) { pa_r[r] = cluster.map_shared_rank(pa, r); pb_r[r] = cluster.map_shared_rank(pb, r); }
+    // list bounds of this thread's points do not change over the iterations: the first point's are kept in registers
+    const bool owner = (threadIdx.x % DC_SPREAD) == 0;
+    const int i_first = lo + (int)(threadIdx.x / DC_SPREAD), i_step = (int)(blockDim.x / DC_SPREAD);
+    int b_first = 0, e_first = 0;
+    if (owner && i_first < hi) { b_first = simi_off[i_first]; e_first = simi_off[i_first + 1]; }
+    cluster.sync();
+    stamp();
+    auto run = [&](auto nbr) {              // nbr[t] for t in [seg_b, seg_e): a shared-memory or a global pointer (typed, so the staged lists are read with LDS)
+        for (int it = 0; it < niter; ++it) {
+            for (int i = i_first; i < hi && owner; i += i_step) {          // neighbour mean (rosa.cpp:388-399)
+                const int b = (i == i_first) ? b_first : simi_off[i], e = (i == i_first) ? e_first : simi_off[i + 1];
+                float4 out = pa[i];
+                if (e > b) {
+                    f3 acc{0.0f, 0.0f, 0.0f};
+#pragma unroll (DC_UNROLL)
+                    for (int t = b; t < e; ++t) { const float4 v = pa[nbr[t]]; acc = add3(acc, f3{v.x, v.y, v.z}); }
+                    const f3 mth = div3(acc, (float)(e - b));
+                    out = make_float4(mth.x, mth.y, mth.z, 1.0f);
                 }
-                const float fm = (float)m;
-                c00 /= fm; c10 /= fm; c11 /= fm; c20 /= fm; c21 /= fm; c22 /= fm;
-                const Eig3 E = eig3_sym_dev(c00, c10, c11, c20, c21, c22);
-                if (E.ok) {
-                    const float denom = smax(1e-6f, sum3(E.ev[0], E.ev[1], E.ev[2]));
-                    f3 dir = eig_col(E, 2);
-                    const float nrm = norm3(dir);
-                    if (nrm > 1e-6f) dir = div3(dir, nrm); else dir = {1.0f, 0.0f, 0.0f};
-                    const float conf = E.ev[2] / denom;
-                    if (conf > 0.5f) {
-                        const f3 x{self4.x, self4.y, self4.z};
-                        const float t = dot3(dir, sub3(x, mean));
-                        const f3 pr = add3(mean, mul3(dir, t));
-                        out = make_float4(pr.x, pr.y, pr.z, 1.0f);
+#pragma unroll
+                for (int r = 0; r < CL; ++r) pb_r[r][i] = out;
+            }
+            stamp();
+            cluster.sync();
+            stamp();
+            for (int i = i_first; i < hi && owner; i += i_step) {          // local_line_fit + projection (rosa.cpp:402-418, 793-841)
+                const int b = (i == i_first) ? b_first : simi_off[i], e = (i == i_first) ? e_first : simi_off[i + 1];
+                const int m = e - b;
+                const float4 self4 = pb[i];
+                float4 out = self4;
+                if (m >= 3) {
+                    f3 mean{0.0f, 0.0f, 0.0f};
+#pragma unroll (DC_UNROLL)
+                    for (int t = b; t < e; ++t) { const float4 v = pb[nbr[t]]; mean = add3(mean, f3{v.x, v.y, v.z}); }
+                    mean = div3(mean, (float)m);
+                    float c00 = 0, c10 = 0, c11 = 0, c20 = 0, c21 = 0, c22 = 0;
+#pragma unroll (DC_UNROLL)
+                    for (int t = b; t < e; ++t) {
+                        const float4 v = pb[nbr[t]];
+                        const f3 q = sub3(f3{v.x, v.y, v.z}, mean);
+                        c00 += q.x * q.x; c10 += q.y * q.x; c11 += q.y * q.y; c20 += q.z * q.x; c21 += q.z * q.y; c22 += q.z * q.z;
+                    }
+                    const float fm = (float)m;
+                    c00 /= fm; c10 /= fm; c11 /= fm; c20 /= fm; c21 /= fm; c22 /= fm;
+                    const Eig3 E = eig3_sym_dev(c00, c10, c11, c20, c21, c22);
+                    if (E.ok) {
+                        const float denom = smax(1e-6f, sum3(E.ev[0], E.ev[1], E.ev[2]));
+                        f3 dir = eig_col(E, 2);
+                        const float nrm = norm3(dir);
+                        if (nrm > 1e-6f) dir = div3(dir, nrm); else dir = {1.0f, 0.0f, 0.0f};
+                        const float conf = E.ev[2] / denom;
+                        if (conf > 0.5f) {
+                            const f3 x{self4.x, self4.y, self4.z};
+                            const float t = dot3(dir, sub3(x, mean));
+                            const f3 pr = add3(mean, mul3(dir, t));
+                            out = make_float4(pr.x, pr.y, pr.z, 1.0f);
+                        }
                     }
                 }
-            }
 #pragma unroll
-            for (int r = 0; r < DC_CLUSTER; ++r) pa_r[r][i] = out;
+                for (int r = 0; r < CL; ++r) pa_r[r][i] = out;
+            }
+            stamp();
+            cluster.sync();
+            stamp();
         }
-        cluster.sync();
-    }
+    };
+    if (csr_in) run(static_cast<const int*>(sidx - seg_b)); else run(simi_idx);
     for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) pset[i] = pa[i];
+    stamp();
+}
+
+template <int CL>
+static void launch_dcrosa_cluster(const FrameState* st, float4* pset, const int* simi_off, const int* simi_idx, int niter, long long* dbg, cudaStream_t s) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CL); cfg.blockDim = dim3(DC_THREADS); cfg.dynamicSmemBytes = DC_SMEM_BUDGET; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k_dcrosa_cluster<CL>, st, pset, simi_off, simi_idx, niter, (unsigned)DC_SMEM_BUDGET, dbg);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -523,10 +571,22 @@ k_vs_recenter(FrameState* st, const float4* __restrict__ pts, const float4* __re
 void drosa_set_attributes();
 void launch_drosa(osep_rosa_impl* h, int sms);
 void launch_drosa_prep(osep_rosa_impl* h, cudaStream_t sk);
+bool dcrosa_cluster16_ok() {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(16); cfg.blockDim = dim3(DC_THREADS); cfg.dynamicSmemBytes = DC_SMEM_BUDGET;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k_dcrosa_cluster<16>, &cfg) != cudaSuccess) { cudaGetLastError(); return false; }
+    return n >= 1;
+}
 void mscale_set_attributes(int Mcap) {
     (void)Mcap;
     drosa_set_attributes();
-    cudaFuncSetAttribute(k_dcrosa_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, DC_SMEM_BUDGET);
+    cudaFuncSetAttribute(k_dcrosa_cluster<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, DC_SMEM_BUDGET);
+    cudaFuncSetAttribute(k_dcrosa_cluster<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, DC_SMEM_BUDGET);
+    cudaFuncSetAttribute(k_dcrosa_cluster<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaFuncSetAttribute(k_vs_greedy, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM_BUDGET);
 }
 
@@ -569,7 +629,10 @@ void launch_mscale(osep_rosa_impl* h) {
     if (simi_side) cudaStreamWaitEvent(s, h->ev_join[1], 0);                   // similarity lists
     // R20
     if ((size_t)32 * d.Mcap <= (size_t)DC_SMEM_BUDGET) {
-        k_dcrosa_cluster<<<DC_CLUSTER, DC_THREADS, DC_SMEM_BUDGET, s>>>(d.st, d.pset, d.simi_off, d.simi_idx, c.niter_dcrosa, (unsigned)DC_SMEM_BUDGET);
+        long long* dc_dbg = h->fused_detail ? d.fused_dbg + 64 : nullptr;
+        const int cl = h->dc_cluster > 0 ? h->dc_cluster : ((h->fused_grid == 0 && h->dc16_ok) ? 16 : 8);
+        if (cl == 16) launch_dcrosa_cluster<16>(d.st, d.pset, d.simi_off, d.simi_idx, c.niter_dcrosa, dc_dbg, s);
+        else launch_dcrosa_cluster<8>(d.st, d.pset, d.simi_off, d.simi_idx, c.niter_dcrosa, dc_dbg, s);
     } else {
         for (int it = 0; it < c.niter_dcrosa; ++it) {
             k_dcrosa_mean<<<tblocks, 128, 0, s>>>(d.st, d.pset, d.pset2, d.simi_off, d.simi_idx);
