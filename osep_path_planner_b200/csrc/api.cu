@@ -68,6 +68,7 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
       const char* e4 = getenv("OSEP_FUSED_DETAIL"); if (e4 && e4[0] == '1') { h->fused_detail = true; CK(dalloc(&d.fused_tl, M * 9 * 16)); CK(cudaMemset(d.fused_tl, 0, M * 9 * 16 * 8)); }
       const char* e6 = getenv("OSEP_FUSED_GRID"); if (e6 && atoi(e6) > 0) h->fused_grid = atoi(e6);
       const char* e8 = getenv("OSEP_FUSED_SMEM_KB"); if (e8 && atoi(e8) > 0) h->fused_smem = atoi(e8) * 1024;
+      const char* e11 = getenv("OSEP_VS_SEPARATE"); if (e11 && e11[0] == '1') h->vs_separate = true;
       const char* e10 = getenv("OSEP_DC_CLUSTER"); if (e10 && (atoi(e10) == 8 || atoi(e10) == 16)) h->dc_cluster = atoi(e10);
       const char* e9 = getenv("OSEP_SIMI_SIDE"); if (e9 && (e9[0] == '0' || e9[0] == '1')) h->simi_side = e9[0] - '0';
       const char* e7 = getenv("OSEP_HOT_CTAS"); if (e7 && atoi(e7) > 0) h->hot_ctas = atoi(e7);

@@ -20,6 +20,7 @@
 #include "rosa_impl.cuh"
 #include "tail.cuh"
 #include <cooperative_groups.h>
+#include <type_traits>
 
 namespace osep {
 
@@ -308,10 +309,21 @@ constexpr int DC_SMEM_BUDGET = 200 * 1024;
 // more warps per CTA measured SLOWER, 68 -> 83 -> 124 us for 8 / 16 / 32 warps), so the lever is the number of SMs: CL = 16
 // (non-portable cluster size) when a single frame owns the GPU, the portable 8 when several frames are in flight.  Points are
 // dealt to the CTAs in contiguous ranges of equal COST (list length + DC_BALANCE per point), not equal count.
+// vertex_sampling (R21, rosa.cpp:424-532) runs in the same launch (vs.on): when the last dcrosa pass is done every CTA of the
+// cluster holds the final pset in shared memory, so the five stages that used to be five launches (55 us) become phases
+// separated by cluster.sync(): finite compaction (every CTA, redundantly), cover rows (a slice of rows per CTA, written
+// into CTA 0's shared memory through DSMEM), the sequential greedy cover (one warp of CTA 0; seeds pushed to every CTA),
+// correspondences (a slice of points per CTA, pushed to every CTA) and recentring (vertices dealt to the warps of the cluster).
+struct VsArgs {
+    int on;
+    const float4* pts; float alpha;
+    unsigned* adj; int* seeds; int* corresp; float4* skel; float4* skel_sampled;
+};
+
 template <int CL>
 __global__ void __launch_bounds__(DC_THREADS)
-k_dcrosa_cluster(const FrameState* __restrict__ st, float4* pset, const int* __restrict__ simi_off, const int* __restrict__ simi_idx, int niter,
-                 unsigned smem_bytes, long long* dbg) {
+k_dcrosa_cluster(FrameState* st, float4* pset, const int* __restrict__ simi_off, const int* __restrict__ simi_idx, int niter,
+                 unsigned smem_bytes, long long* dbg, const VsArgs vs) {
     int dk = 0;
     auto stamp = [&]() { if (dbg && threadIdx.x == 0 && blockIdx.x == 0 && dk < 60) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[dk++] = t; } };
     stamp();
@@ -415,16 +427,167 @@ k_dcrosa_cluster(const FrameState* __restrict__ st, float4* pset, const int* __r
     if (csr_in) run(static_cast<const int*>(sidx - seg_b)); else run(simi_idx);
     for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) pset[i] = pa[i];
     stamp();
+    if (!vs.on) return;
+    // ---- R21 vertex_sampling.  pa = final pset (complete in every CTA; the last cluster.sync() above also retired the staged lists)
+    if (M == 0) { if (rank == 0 && threadIdx.x == 0) st->status = OSEP_STAGE_6; return; }      // uniform over the cluster
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarps = DC_THREADS / 32;
+    unsigned char* R = reinterpret_cast<unsigned char*>(dcs + 2 * (size_t)M);
+    float4* pcl = reinterpret_cast<float4*>(R);                                 // finite rows of pset, compacted (rosa.cpp:441-449)
+    int* scan = reinterpret_cast<int*>(pcl + M);                                // M + 1 (16-byte padded)
+    int* seeds_s = scan + ((M + 1 + 3) & ~3);
+    int* corr_s = seeds_s + ((M + 3) & ~3);
+    unsigned* rows_s = reinterpret_cast<unsigned*>(corr_s + ((M + 3) & ~3));     // CTA 0: Mc x Wn cover bit rows
+    __shared__ int s_V;
+    const size_t fixed_bytes = (size_t)32 * M + (size_t)16 * M + 4 * (size_t)((M + 4) & ~3) + 8 * (size_t)((M + 3) & ~3);
+    const bool rows_in = fixed_bytes + (size_t)4 * M * ((M + 31) >> 5) <= smem_bytes;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) { const float4 v = pa[i]; scan[i] = (fin(v.x) && fin(v.y) && fin(v.z)) ? 1 : 0; }
+    if (threadIdx.x == 0) scan[M] = 0;
+    __syncthreads();
+    const int Mc = block_scan_inplace(scan, M + 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < M; i += blockDim.x) { const float4 v = pa[i]; if (fin(v.x) && fin(v.y) && fin(v.z)) pcl[scan[i]] = v; }
+    __syncthreads();
+    stamp();
+    const int Wn = (Mc + 31) >> 5;
+    const float Rl = st->leaf_size; const float R2 = Rl * Rl;
+    const int per = (Mc + CL - 1) / CL;
+    const int i0 = min(Mc, (int)rank * per), i1 = min(Mc, i0 + per);
+    {   // cover rows of this CTA's points: bit j of row i = (d2(i, j) < R^2) or i == j; one warp per row, lane w keeps word w
+#ifdef OSEP_EXP2
+        unsigned* rows0 = rows_s;
+#else
+        unsigned* rows0 = rows_in ? cluster.map_shared_rank(rows_s, 0) : vs.adj;
+#endif
+        for (int i = i0 + wib; i < i1; i += nwarps) {
+            const f3 q = ld3(pcl, i);
+            for (int w0 = 0; w0 < Wn; w0 += 32) {
+                unsigned mine = 0;
+                const int wn = min(32, Wn - w0);
+#pragma unroll 4
+                for (int u = 0; u < wn; ++u) {
+                    const int j = (w0 + u) * 32 + lane;
+                    const float dd = dist2(q, ld3(pcl, min(j, Mc - 1)));            // branch-free: the load is clamped, the verdict masked
+                    const bool in = (j < Mc) && ((j == i) || (dd < R2));
+                    const unsigned word = __ballot_sync(FULL, in);
+                    mine = (lane == u) ? word : mine;
+                }
+                if (lane < wn) rows0[(size_t)i * Wn + w0 + lane] = mine;
+            }
+        }
+    }
+    stamp();
+    if (!rows_in) __threadfence();
+    cluster.sync();
+    stamp();
+    if (rank == 0) {
+        // greedy cover with the reference's sequential semantics (lowest uncovered index becomes the next vertex, rosa.cpp:462-502):
+        // each lane of warp 0 keeps its words of the covered set in registers, a step = ffs + warp min + one row OR
+        if (wib == 0) {
+            auto walk = [&](auto rows, auto WPLc) {
+                constexpr int WPL = decltype(WPLc)::value;                   // words of the covered set per lane
+                unsigned cov[WPL];
+#pragma unroll
+                for (int k = 0; k < WPL; ++k) {
+                    const int w = lane + 32 * k;
+                    unsigned c = 0xffffffffu;               // words beyond Mc count as covered
+                    if (w < Wn) { const int rem = Mc - w * 32; c = (rem >= 32) ? 0u : ~((1u << rem) - 1u); }
+                    cov[k] = c;
+                }
+                int V = 0;
+                while (true) {
+                    int cand = 0x7fffffff;
+#pragma unroll
+                    for (int k = WPL - 1; k >= 0; --k) { const unsigned u = ~cov[k]; if (u) cand = (lane + 32 * k) * 32 + __ffs(u) - 1; }
+                    const int seed = __reduce_min_sync(FULL, cand);
+                    if (seed == 0x7fffffff) break;
+                    if (lane == 0) { seeds_s[V] = seed; vs.seeds[V] = seed; }
+                    ++V;
+                    auto row = rows + (size_t)seed * Wn;
+#pragma unroll
+                    for (int k = 0; k < WPL; ++k) { const int w = lane + 32 * k; if (w < Wn) cov[k] |= row[w]; }
+                }
+                if (lane == 0) { s_V = V; st->Mc = Mc; st->V = V; if (Mc != M) st->flags |= OSEP_FLAG_NONFINITE_PSET; }
+            };
+            if (rows_in) { if (Wn <= 32) walk(static_cast<const unsigned*>(rows_s), std::integral_constant<int, 1>{}); else walk(static_cast<const unsigned*>(rows_s), std::integral_constant<int, 4>{}); }
+            else walk(static_cast<const unsigned*>(vs.adj), std::integral_constant<int, 4>{});          // up to 128 words = 4096 points
+        }
+        __syncthreads();
+        const int V = s_V;
+        stamp();
+        for (int r = 1; r < CL; ++r) {                  // push the seeds and their count to the other CTAs
+            int* sr = cluster.map_shared_rank(seeds_s, r);
+            for (int t = threadIdx.x; t < V; t += blockDim.x) sr[t] = seeds_s[t];
+            if (threadIdx.x == 0) *cluster.map_shared_rank(&s_V, r) = V;
+        }
+        stamp();
+    }
+    cluster.sync();
+    stamp();
+    const int V = s_V;
+    // corresp[idx] = vertex with the smallest d2 among those covering idx, first wins ties (rosa.cpp:490-496); the seed
+    // positions are staged contiguously (pb is free now) so that the scan has no dependent index load
+    float4* seedpos = pb;
+    for (int t = threadIdx.x; t < V; t += blockDim.x) { const int sd = seeds_s[t]; const float4 c = pcl[sd]; seedpos[t] = make_float4(c.x, c.y, c.z, __int_as_float(sd)); }
+    __syncthreads();
+    for (int idx = i0 + (int)threadIdx.x; idx < i1; idx += blockDim.x) {
+        const f3 q = ld3(pcl, idx);
+        float mind2 = __int_as_float(0x7f800000); int best = -1;
+#pragma unroll 4
+        for (int t = 0; t < V; ++t) {
+            const float4 c = seedpos[t];
+            const bool self = __float_as_int(c.w) == idx;
+            const float dd = dist2(f3{c.x, c.y, c.z}, q);
+            const float d2 = self ? 0.0f : dd;
+            const bool take = (self || d2 < R2) && d2 < mind2;
+            mind2 = take ? d2 : mind2; best = take ? t : best;
+        }
+        vs.corresp[idx] = best;
+#ifdef OSEP_EXP1
+        corr_s[idx] = best;
+#else
+#pragma unroll
+        for (int r = 0; r < CL; ++r) cluster.map_shared_rank(corr_s, r)[idx] = best;
+#endif
+    }
+    stamp();
+    cluster.sync();
+    stamp();
+    // recentring (rosa.cpp:506-530): one warp per vertex; the sum over pts_ stays in ascending point index (lanes load 32
+    // consecutive candidates, the matches are added in bit order)
+    for (int v = (int)rank * nwarps + wib; v < V; v += CL * nwarps) {
+        f3 sum{0.0f, 0.0f, 0.0f}; int cnt = 0;
+        for (int j0 = 0; j0 < Mc; j0 += 32) {
+            const int j = j0 + lane;
+            bool hit = false; float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < Mc) { hit = (corr_s[j] == v); if (hit) p = vs.pts[j]; }
+            unsigned m = __ballot_sync(FULL, hit);
+            cnt += __popc(m);
+            while (m) {
+                const int b = __ffs(m) - 1; m &= m - 1;
+                sum.x += __shfl_sync(FULL, p.x, b); sum.y += __shfl_sync(FULL, p.y, b); sum.z += __shfl_sync(FULL, p.z, b);
+            }
+        }
+        if (lane == 0) {
+            f3 cur = ld3(pa, seeds_s[v]);                    // rosa.cpp:475 (uncompacted pset, compacted index)
+            if (cnt > 0) {
+                const f3 ec = div3(sum, (float)cnt);
+                const float b = (float)(1.0 - (double)vs.alpha);    // rosa.cpp:529
+                cur = add3(mul3(cur, vs.alpha), mul3(ec, b));
+            }
+            st3(vs.skel, v, cur, 1.0f); st3(vs.skel_sampled, v, cur, 1.0f);
+        }
+    }
+    stamp();
 }
 
 template <int CL>
-static void launch_dcrosa_cluster(const FrameState* st, float4* pset, const int* simi_off, const int* simi_idx, int niter, long long* dbg, cudaStream_t s) {
+static void launch_dcrosa_cluster(FrameState* st, float4* pset, const int* simi_off, const int* simi_idx, int niter, long long* dbg, const VsArgs& vs, cudaStream_t s) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CL); cfg.blockDim = dim3(DC_THREADS); cfg.dynamicSmemBytes = DC_SMEM_BUDGET; cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, k_dcrosa_cluster<CL>, st, pset, simi_off, simi_idx, niter, (unsigned)DC_SMEM_BUDGET, dbg);
+    cudaLaunchKernelEx(&cfg, k_dcrosa_cluster<CL>, st, pset, simi_off, simi_idx, niter, (unsigned)DC_SMEM_BUDGET, dbg, vs);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -627,12 +790,17 @@ void launch_mscale(osep_rosa_impl* h) {
     if (h->debug) cudaMemcpyAsync(d.centers, d.pset, sizeof(float4) * d.Mcap, cudaMemcpyDeviceToDevice, s);   // tap: pset after drosa
     stage_mark(h, SM_POSITION);
     if (simi_side) cudaStreamWaitEvent(s, h->ev_join[1], 0);                   // similarity lists
-    // R20
+    // R20 (+ R21 in the same cluster launch when its per-point arrays fit next to the pset copies)
+    bool vs_done = false;
     if ((size_t)32 * d.Mcap <= (size_t)DC_SMEM_BUDGET) {
         long long* dc_dbg = h->fused_detail ? d.fused_dbg + 64 : nullptr;
         const int cl = h->dc_cluster > 0 ? h->dc_cluster : ((h->fused_grid == 0 && h->dc16_ok) ? 16 : 8);
-        if (cl == 16) launch_dcrosa_cluster<16>(d.st, d.pset, d.simi_off, d.simi_idx, c.niter_dcrosa, dc_dbg, s);
-        else launch_dcrosa_cluster<8>(d.st, d.pset, d.simi_off, d.simi_idx, c.niter_dcrosa, dc_dbg, s);
+        VsArgs vs{};
+        vs.on = ((size_t)60 * d.Mcap + 64 <= (size_t)DC_SMEM_BUDGET && !h->vs_separate) ? 1 : 0;
+        vs.pts = d.pts; vs.alpha = c.alpha_recenter; vs.adj = d.adj_bits; vs.seeds = d.seeds; vs.corresp = d.corresp; vs.skel = d.skel; vs.skel_sampled = d.skel_sampled;
+        vs_done = vs.on != 0;
+        if (cl == 16) launch_dcrosa_cluster<16>(d.st, d.pset, d.simi_off, d.simi_idx, c.niter_dcrosa, dc_dbg, vs, s);
+        else launch_dcrosa_cluster<8>(d.st, d.pset, d.simi_off, d.simi_idx, c.niter_dcrosa, dc_dbg, vs, s);
     } else {
         for (int it = 0; it < c.niter_dcrosa; ++it) {
             k_dcrosa_mean<<<tblocks, 128, 0, s>>>(d.st, d.pset, d.pset2, d.simi_off, d.simi_idx);
@@ -640,15 +808,17 @@ void launch_mscale(osep_rosa_impl* h) {
         }
     }
     stage_mark(h, SM_DCROSA);
-    // R21
-    k_vs_compact<<<1, 1024, 0, s>>>(d.st, d.pset, d.pcloud, d.good_rank);
-    k_vs_adj<<<warp_blocks, tb, 0, s>>>(d.st, d.pcloud, d.adj_bits, d.W);
-    k_vs_greedy<<<1, 1024, VS_SMEM_BUDGET, s>>>(d.st, d.adj_bits, d.W, d.seeds);
-    k_vs_corresp<<<tblocks, 128, 0, s>>>(d.st, d.pcloud, d.seeds, d.corresp);
-    k_vs_recenter<<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.pset, d.seeds, d.corresp, c.alpha_recenter, d.skel, d.skel_sampled);
+    // R21 as its own launches (large arenas, OSEP_VS_SEPARATE=1)
+    if (!vs_done) {
+        k_vs_compact<<<1, 1024, 0, s>>>(d.st, d.pset, d.pcloud, d.good_rank);
+        k_vs_adj<<<warp_blocks, tb, 0, s>>>(d.st, d.pcloud, d.adj_bits, d.W);
+        k_vs_greedy<<<1, 1024, VS_SMEM_BUDGET, s>>>(d.st, d.adj_bits, d.W, d.seeds);
+        k_vs_corresp<<<tblocks, 128, 0, s>>>(d.st, d.pcloud, d.seeds, d.corresp);
+        k_vs_recenter<<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.pset, d.seeds, d.corresp, c.alpha_recenter, d.skel, d.skel_sampled);
+    }
     stage_mark(h, SM_VSAMPLE);
     // R22 vertex_smooth runs in the frame's tail kernel (graph.cu frame_tail_enqueue)
-    h->n_launches += 2 + 1 + 1 + 1 + 5;   // + launch_drosa (dcrosa = one cluster kernel in the common case)
+    h->n_launches += 2 + 1 + 1 + 1 + (vs_done ? 0 : 5);   // + launch_drosa (dcrosa + vertex_sampling = one cluster kernel in the common case)
 }
 
 }  // namespace osep

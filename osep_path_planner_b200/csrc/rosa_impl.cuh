@@ -81,6 +81,7 @@ struct osep_rosa_impl {
     bool fused_detail = false;         // per-step cycle counters in the chain walkers (OSEP_FUSED_DETAIL=1; costs ~4 % of the stage)
     int fused_grid = 0;                // CTAs of the fused kernel (0 = one per SM)
     int fused_smem = 0;                // dynamic shared memory of the fused kernel in bytes; 0 = by mode (OSEP_FUSED_SMEM_KB)
+    bool vs_separate = false;          // vertex_sampling as its own five launches instead of phases of the dcrosa cluster kernel (OSEP_VS_SEPARATE=1; A/B and tests)
     bool dc16_ok = false;              // the device can place a 16-CTA cluster of k_dcrosa_cluster
     int dc_cluster = 0;                // CTAs of the dcrosa cluster: 16 (non-portable size) for single frames when the device can place it, else 8 (OSEP_DC_CLUSTER)
     int simi_side = -1;                // similarity list fill on the side stream next to the fused kernel: 1/0, -1 = only when one frame runs at a time (OSEP_SIMI_SIDE)

@@ -12,5 +12,5 @@ for k in range(3):
     r.rosa_run()
     buf = np.zeros(128, np.int64)
     r._L.osep_rosa_get(r._h, b"fused_dbg", buf.ctypes.data_as(C.c_void_p), buf.nbytes)
-    t = buf[64:64 + 24]
-    print("frame %d: stage %.1f us |" % (k, (t[1] - t[0]) / 1e3), " ".join("%.1f" % ((t[i + 1] - t[i]) / 1e3) for i in range(1, 22)), "| total %.1f" % ((t[22] - t[0]) / 1e3))
+    t = buf[64:64 + 34]
+    print("frame %d: stage %.1f us |" % (k, (t[1] - t[0]) / 1e3), " ".join("%.1f" % ((t[i + 1] - t[i]) / 1e3) for i in range(1, 22)), "| dcrosa %.1f" % ((t[22] - t[0]) / 1e3), "| vs:", " ".join("%.1f" % ((t[i + 1] - t[i]) / 1e3) for i in range(22, 31)), "| total %.1f" % ((t[31] - t[0]) / 1e3))
