@@ -68,6 +68,7 @@ __device__ __forceinline__ void frame_init(FrameState* st, int n_in) {
     FrameState z;
     memset(&z, 0, sizeof(z));
     z.epoch = epoch;                 // table epochs persist across frames
+    z.g_corr = st->g_corr;           // so does the cell-size correction of the kNN grid (a warm start: never changes a result)
     z.n_in = n_in;
     for (int d = 0; d < 3; ++d) { z.bb_lo[d] = 0x7fffffff; z.bb_hi[d] = (int)0x80000000; }
     *st = z;
@@ -304,6 +305,10 @@ __device__ void grid_params(FrameState* st, int target_ppc) {
     // points; for a surface-like cloud a cell of size h holds ~ (h/leaf)^2 * n/nv points.
     const int nv = st->nvox_hist[0];
     float h = st->leaf_hist[0] * sqrtf((float)target_ppc * (float)(nv > 0 ? nv : 1) / (float)(n > 0 ? n : 1));
+    st->g_h_est = h;
+    // a stream's frames resemble each other: start from the correction the last frame measured, so the rebuild below
+    // (clear + second insertion, 14 us of the critical kNN branch) is the exception
+    if (st->g_corr > 0.25f && st->g_corr < 4.0f) h *= st->g_corr;
     grid_set_h(st, h);
     st->g_cells_used = 0; st->n_units = 0; st->n_slow = 0; st->n_over = 0; st->unit_ctr = 0; st->n_retry = 0; st->n_grow = 0; st->n_cells = 0;
     st->g_ncells = 0; st->g_redo = 0;
@@ -316,8 +321,10 @@ __device__ __forceinline__ void grid_refine(FrameState* st, int target_ppc) {
     const int n = st->n_filt, nc = *(volatile int*)&st->g_ncells;
     if (nc <= 0) return;
     const float occ = (float)n / (float)nc;
+    const float h_fit = st->g_h * sqrtf((float)target_ppc / occ);
+    if (st->g_h_est > 0.0f) st->g_corr = h_fit / st->g_h_est;
     if (occ > 1.4f * (float)target_ppc || occ < 0.6f * (float)target_ppc) {
-        grid_set_h(st, st->g_h * sqrtf((float)target_ppc / occ));
+        grid_set_h(st, h_fit);
         st->g_redo = 1; st->g_ncells = 0;
     }
 }
@@ -1442,6 +1449,9 @@ void launch_preprocess(osep_rosa_impl* h, int n) {
     // on the side stream while the remaining passes iterate the control law.
     k_vox_count<<<nb, NT, 0, s>>>(d.P, d.st, d.vtab, (unsigned)(d.T - 1), 1, c.max_points, ppc);
     if (h->overlap) { cudaEventRecord(h->ev_fork[0], s); cudaStreamWaitEvent(sk, h->ev_fork[0], 0); }
+    // (a persistent cooperative kernel for passes 1..7 -- points in registers, one 64-bit atomic per block and pass, the
+    // next pass's parameters returned by the barrier poll -- was measured: 7.1 us per pass instead of 9.3, but its spinning
+    // blocks slow the kNN branch on the other stream down by more than that; not kept)
     for (int p = 1; p < LEAF_MAX_ITERS; ++p)
         k_vox_count<<<nb, NT, 0, s>>>(d.P, d.st, d.vtab, (unsigned)(d.T - 1), p + 1, c.max_points, ppc);
     stage_mark(h, SM_LEAF);

@@ -34,6 +34,7 @@ struct FrameState {
     float bmin[3], bmax[3];
     // ---- kNN grid
     float g_inv_h, g_h;
+    float g_h_est, g_corr; // raw cell-size estimate of this frame; measured / estimated cell size of the last frame (persists: warm start, speed only)
     int g_dim[3];
     int g_cells_used;      // allocation cursor (points)
     int g_ncells, g_redo;  // occupied cells of the current build; rebuild requested
