@@ -211,6 +211,45 @@ def test_skeleton_graph_bit_exact(mods):
         assert_bit_equal(g["joints"], go.tap("joints"), "joints"); assert_bit_equal(g["leafs"], go.tap("leafs"), "leafs")
 
 
+def test_skeleton_graph_forests_ties_and_large_graphs(mods):
+    """graph_adj (thread per vertex, register top-10) and mst (Boruvka rounds over the sorted keys) against the oracle's kd-tree
+    + Kruskal on the cases a chain does not reach: a lattice (every weight tied: the (w,u,v) order decides), clusters farther
+    apart than 2.5 x fuse_dist_th (a spanning FOREST), fewer vertices than k, non-finite vertices, and graphs whose keys and
+    component arrays do not fit the shared-memory workspaces (global scratch path)."""
+    osep, po, fx = mods
+    rng = np.random.default_rng(11)
+    gx, gy, gz = np.meshgrid(np.arange(6), np.arange(6), np.arange(6), indexing="ij")
+    lattice = (np.stack([gx, gy, gz], -1).reshape(-1, 3) * 1.5).astype(np.float32)
+    clusters = np.concatenate([rng.normal(size=(40, 3)) * 2.0 + c for c in ([0, 0, 0], [100, 0, 0], [0, 100, 50], [7.4, 0, 0])]).astype(np.float32)
+    few = (rng.normal(size=(5, 3)) * 2.0).astype(np.float32)
+    walk = np.cumsum(rng.normal(size=(2500, 3)) * 0.8 + np.array([0, 0, 1.2]), axis=0).astype(np.float32)
+    blob = (rng.normal(size=(1500, 3)) * 6.0).astype(np.float32)
+    for name, V in (("lattice", lattice), ("clusters", clusters), ("few", few), ("walk2500", walk), ("blob1500", blob)):
+        g = osep.build_graph(V, 3.0)
+        go = po.GraphOracle(V, 3.0)
+        assert_bit_equal(g["rng_off"], go.tap("rng_off"), name + " rng_off"); assert_bit_equal(g["rng_idx"], go.tap("rng_idx"), name + " rng_idx")
+        assert_bit_equal(g["edges"].reshape(-1), go.tap("mst_edges"), name + " mst edges")
+        assert_bit_equal(g["edge_w"], go.tap("mst_w"), name + " mst weights")
+        assert_bit_equal(g["adj_off"], go.tap("adj_off"), name + " adj_off"); assert_bit_equal(g["adj_idx"], go.tap("adj_idx"), name + " adj_idx")
+        assert_bit_equal(g["type"], go.tap("type"), name + " type")
+    n_comp = len(clusters) - len(osep.build_graph(clusters, 3.0)["edge_w"])
+    assert n_comp >= 3, "the cluster case must be a forest (components: %d)" % n_comp
+
+
+@pytest.mark.parametrize("mode", [dict(OSEP_DC_CLUSTER="8"), dict(OSEP_DC_CLUSTER="16"), dict(OSEP_VS_SEPARATE="1")])
+def test_dcrosa_cluster_sizes_and_separate_vertex_sampling_agree(mods, monkeypatch, mode):
+    """dcrosa + vertex_sampling as one cluster kernel of 8 CTAs (lanes of a batch), of 16 CTAs (single frames) and with
+    vertex_sampling as its own five launches: every tap equals the oracle's in each mode."""
+    osep, po, fx = mods
+    for k, v in mode.items():
+        monkeypatch.setenv(k, v)
+    for P in (fx.turbine(60000, seed=9), fx.cylinder(15000, seed=3)):
+        o, ok_o, r, ok_g = run_both(mods, P, debug=True)
+        assert ok_o and ok_g
+        check_all_taps(o, r)
+        r.close()
+
+
 def test_frame_to_graph(mods):
     osep, po, fx = mods
     P = fx.turbine(40000, seed=4)

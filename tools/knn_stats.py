@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, ctypes as C
 import osep_path_planner_b200 as osep
 from osep_path_planner_b200 import fixtures as fx
-for name, P in (("turbine100k", fx.turbine()), ("cyl20k", fx.cylinder()), ("stream0", fx.stream_frame(0)), ("stream7", fx.stream_frame(7))):
+for name, P in (("turbine100k", fx.turbine()), ("cyl20k", fx.cylinder()), ("stream0", fx.stream_frame(0)[0]), ("stream7", fx.stream_frame(7)[0])):
     r = osep.Rosa(capacity_points=P.shape[0])
     r.set_input(P)
     for k in range(2):
