@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_frame_tail(const __grid_consta
     if (status0 == 0) {
         if (V0 == 0) { if (threadIdx.x == 0) a.st->status = OSEP_STAGE_7; }
         else {
-            const float4* p = vertex_smooth_block(a.st, a.skel, a.skel2, a.vtmp, a.vs_off, a.vs_idx, a.tmp_j, a.tmp_d, a.cap, a.radius, a.alpha, a.niter, arena, a.arena_bytes);
+            const float4* p = vertex_smooth_block(a.st, a.skel, a.skel2, a.vtmp, a.vs_off, a.vs_idx, a.tmp_j, a.tmp_d, a.cap, a.radius, a.alpha, a.niter, arena, a.arena_bytes, a.dbg);
             if (p) pos = p;
         }
     }

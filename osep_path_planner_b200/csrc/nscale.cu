@@ -68,7 +68,7 @@ __device__ __forceinline__ void frame_init(FrameState* st, int n_in) {
     FrameState z;
     memset(&z, 0, sizeof(z));
     z.epoch = epoch;                 // table epochs persist across frames
-    z.g_corr = st->g_corr;           // so does the cell-size correction of the kNN grid (a warm start: never changes a result)
+    z.g_h_last = st->g_h_last;       // so does the cell size of the kNN grid (a warm start: never changes a result)
     z.n_in = n_in;
     for (int d = 0; d < 3; ++d) { z.bb_lo[d] = 0x7fffffff; z.bb_hi[d] = (int)0x80000000; }
     *st = z;
@@ -103,8 +103,9 @@ __global__ void k_filter_scan(int* blk_cnt, int nblk, FrameState* st, int min_po
 }
 
 __device__ void leaf_step(FrameState* st, int p, int max_points);
+__device__ void grid_params(FrameState* st, int target_ppc);
 __global__ void k_filter_scatter(const FrameParams* __restrict__ prm, float r2, const int* __restrict__ blk_off,
-                                 float4* __restrict__ P, int* __restrict__ filt_idx, FrameState* st, int max_points) {
+                                 float4* __restrict__ P, int* __restrict__ filt_idx, FrameState* st, int max_points, int target_ppc) {
     const float* __restrict__ in = prm->in; const int n = prm->n, stride = prm->stride;
     __shared__ int warp_cnt[NT / 32];
     __shared__ int s_last;
@@ -143,7 +144,7 @@ __global__ void k_filter_scatter(const FrameParams* __restrict__ prm, float r2, 
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1) == (int)gridDim.x - 1) ? 1 : 0;
     __syncthreads();
-    if (s_last && threadIdx.x == 0) { st->ticket = 0; __threadfence(); leaf_step(st, 0, max_points); }
+    if (s_last && threadIdx.x == 0) { st->ticket = 0; __threadfence(); leaf_step(st, 0, max_points); grid_params(st, target_ppc); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -240,7 +241,6 @@ __device__ __forceinline__ bool vset_insert(unsigned long long* tab, unsigned ma
 }
 
 // count-only VoxelGrid pass: number of distinct voxel keys at the current leaf
-__device__ void grid_params(FrameState* st, int target_ppc);
 __global__ void k_vox_count(const float4* __restrict__ P, FrameState* st, unsigned long long* vtab, unsigned mask, int next_step, int max_points, int target_ppc) {
     if (st->status != 0) return;
     if (st->pass_active && !st->pass_overflow) {
@@ -262,7 +262,6 @@ __global__ void k_vox_count(const float4* __restrict__ P, FrameState* st, unsign
     __syncthreads();
     if (s_last && threadIdx.x == 0) {
         st->ticket = 0; __threadfence(); leaf_step(st, next_step, max_points);
-        if (next_step == 1) grid_params(st, target_ppc);      // pass 0 supplies the density estimate that sizes the kNN grid
     }
 }
 
@@ -298,17 +297,19 @@ __device__ __forceinline__ unsigned cell_slot(int x, int y, int z, unsigned mask
     return ((hash_u64(coarse + 0x9e3779b97f4a7c15ull) << 6) | fine) & mask;
 }
 
+// Cell size of the kNN grid, chosen by the last block of the filter (the bounding box is complete there), so that the
+// kNN / normals branch starts right after the filter instead of after VoxelGrid pass 0: a stream's frames resemble each
+// other, so the size that hit the target occupancy on the previous frame is reused; a cold handle guesses from the faces
+// of the bounding box (surface-like cloud).  grid_refine checks the real occupancy after the first insertion pass and
+// asks for one rebuild when the guess was off (cold start, scene change): 14 us, the exception.
 __device__ void grid_params(FrameState* st, int target_ppc) {
     if (st->status != 0) return;
     const int n = st->n_filt;
-    // density estimate from VoxelGrid pass 0 (leaf_hist[0], nvox_hist[0]): nv occupied voxels of that size hold n
-    // points; for a surface-like cloud a cell of size h holds ~ (h/leaf)^2 * n/nv points.
-    const int nv = st->nvox_hist[0];
-    float h = st->leaf_hist[0] * sqrtf((float)target_ppc * (float)(nv > 0 ? nv : 1) / (float)(n > 0 ? n : 1));
-    st->g_h_est = h;
-    // a stream's frames resemble each other: start from the correction the last frame measured, so the rebuild below
-    // (clear + second insertion, 14 us of the critical kNN branch) is the exception
-    if (st->g_corr > 0.25f && st->g_corr < 4.0f) h *= st->g_corr;
+    float h = st->g_h_last;
+    if (!(h > 0.0f)) {
+        const float dx = st->bmax[0] - st->bmin[0], dy = st->bmax[1] - st->bmin[1], dz = st->bmax[2] - st->bmin[2];
+        h = sqrtf((float)target_ppc * fmaxf(1e-12f, (dx * dy + dy * dz + dx * dz) * (1.0f / 3.0f)) / (float)(n > 0 ? n : 1));
+    }
     grid_set_h(st, h);
     st->g_cells_used = 0; st->n_units = 0; st->n_slow = 0; st->n_over = 0; st->unit_ctr = 0; st->n_retry = 0; st->n_grow = 0; st->n_cells = 0;
     st->g_ncells = 0; st->g_redo = 0;
@@ -322,7 +323,7 @@ __device__ __forceinline__ void grid_refine(FrameState* st, int target_ppc) {
     if (nc <= 0) return;
     const float occ = (float)n / (float)nc;
     const float h_fit = st->g_h * sqrtf((float)target_ppc / occ);
-    if (st->g_h_est > 0.0f) st->g_corr = h_fit / st->g_h_est;
+    st->g_h_last = h_fit;
     if (occ > 1.4f * (float)target_ppc || occ < 0.6f * (float)target_ppc) {
         grid_set_h(st, h_fit);
         st->g_redo = 1; st->g_ncells = 0;
@@ -1417,7 +1418,7 @@ void launch_leaf_only(osep_rosa_impl* h) {
     const float r2 = c.pts_dist_lim * c.pts_dist_lim;
     k_filter_count<<<nb, NT, 0, s>>>(d.prm, r2, d.blk_cnt);
     k_filter_scan<<<1, 1024, 0, s>>>(d.blk_cnt, nb, d.st, c.min_points, d.prm);
-    k_filter_scatter<<<nb, NT, 0, s>>>(d.prm, r2, d.blk_cnt, d.P, d.filt_idx, d.st, c.max_points);
+    k_filter_scatter<<<nb, NT, 0, s>>>(d.prm, r2, d.blk_cnt, d.P, d.filt_idx, d.st, c.max_points, 9);
     for (int p = 0; p < LEAF_MAX_ITERS; ++p)
         k_vox_count<<<nb, NT, 0, s>>>(d.P, d.st, d.vtab, (unsigned)(d.T - 1), p + 1, c.max_points, 9);
     h->n_launches += 3 + LEAF_MAX_ITERS;
@@ -1442,13 +1443,13 @@ void launch_preprocess(osep_rosa_impl* h, int n) {
     // R3/R4
     k_filter_count<<<nb, NT, 0, s>>>(d.prm, r2, d.blk_cnt);
     k_filter_scan<<<1, 1024, 0, s>>>(d.blk_cnt, nb, d.st, c.min_points, d.prm);
-    k_filter_scatter<<<nb, NT, 0, s>>>(d.prm, r2, d.blk_cnt, d.P, d.filt_idx, d.st, c.max_points);
+    k_filter_scatter<<<nb, NT, 0, s>>>(d.prm, r2, d.blk_cnt, d.P, d.filt_idx, d.st, c.max_points, ppc);
+    if (h->overlap) { cudaEventRecord(h->ev_fork[0], s); cudaStreamWaitEvent(sk, h->ev_fork[0], 0); }      // the kNN branch needs the filtered cloud and its bounding box only
     stage_mark(h, SM_FILTER);
     // R7/R8: device-resident leaf loop (count-only passes).  The kNN grid is sized from the density seen by
     // pass 0, so the whole normals branch (grid build + kNN + covariance/eigen) only depends on pass 0 and runs
     // on the side stream while the remaining passes iterate the control law.
     k_vox_count<<<nb, NT, 0, s>>>(d.P, d.st, d.vtab, (unsigned)(d.T - 1), 1, c.max_points, ppc);
-    if (h->overlap) { cudaEventRecord(h->ev_fork[0], s); cudaStreamWaitEvent(sk, h->ev_fork[0], 0); }
     // (a persistent cooperative kernel for passes 1..7 -- points in registers, one 64-bit atomic per block and pass, the
     // next pass's parameters returned by the barrier poll -- was measured: 7.1 us per pass instead of 9.3, but its spinning
     // blocks slow the kNN branch on the other stream down by more than that; not kept)

@@ -34,7 +34,7 @@ struct FrameState {
     float bmin[3], bmax[3];
     // ---- kNN grid
     float g_inv_h, g_h;
-    float g_h_est, g_corr; // raw cell-size estimate of this frame; measured / estimated cell size of the last frame (persists: warm start, speed only)
+    float g_h_last;        // cell size that hits the target occupancy on the last frame of this handle (persists across frames: a warm start -- only the speed of the search depends on it)
     int g_dim[3];
     int g_cells_used;      // allocation cursor (points)
     int g_ncells, g_redo;  // occupied cells of the current build; rebuild requested

@@ -64,7 +64,9 @@ __host__ __device__ __forceinline__ size_t smooth_pos_bytes(int V) { return tail
 // failure (status set).  skel holds the result in either case.
 static __device__ const float4* vertex_smooth_block(FrameState* st, float4* skel, float4* skel2, float4* vtmp, int* vs_off, int* vs_idx,
                                                     int* tmp_j, float* tmp_d, int cap, float radius, float alpha, int niter,
-                                                    unsigned char* arena, size_t arena_bytes) {
+                                                    unsigned char* arena, size_t arena_bytes, long long* dbg = nullptr) {
+    int dk = 8;
+    auto stamp = [&]() { if (dbg && threadIdx.x == 0 && dk < 16) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[dk++] = t; } };
     const int V = st->V;
     const size_t pos_bytes = smooth_pos_bytes(V);
     const bool small = arena != nullptr && pos_bytes + 12 * 64 <= arena_bytes;
@@ -88,6 +90,7 @@ static __device__ const float4* vertex_smooth_block(FrameState* st, float4* skel
     __syncthreads();
     for (int i = threadIdx.x; i < V; i += blockDim.x) { const float4 v = A[i]; if (fin(v.x) && fin(v.y) && fin(v.z)) C[off[i]] = v; }
     __syncthreads();
+    stamp();
     const float r2 = radius * radius;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     // neighbour counts: one warp per vertex, ballots over 32 candidates at a time; `first` = smallest (d2, index)
@@ -115,6 +118,7 @@ static __device__ const float4* vertex_smooth_block(FrameState* st, float4* skel
     __syncthreads();
     const int total = block_scan_inplace(off, Vf + 1);
     __syncthreads();
+    stamp();
     if (total > cap) { if (threadIdx.x == 0) st->status = OSEP_ERR_CAPACITY; return nullptr; }
     int* idx = vs_idx; int* tj = tmp_j; float* td = tmp_d;
     if (small && total <= ecap_s) { idx = s_lists; tj = idx + ecap_s; td = reinterpret_cast<float*>(tj + ecap_s); }
@@ -164,6 +168,7 @@ static __device__ const float4* vertex_smooth_block(FrameState* st, float4* skel
         }
     }
     __syncthreads();
+    stamp();
     float4* cur = A; float4* nxt = B;
     for (int it = 0; it < niter; ++it) {
         for (int i = threadIdx.x; i < Vf; i += blockDim.x) {
@@ -188,6 +193,7 @@ static __device__ const float4* vertex_smooth_block(FrameState* st, float4* skel
             st3(nxt, i, add3(mul3(p, alpha), mul3(proj, 1.0f - alpha)), 1.0f);
         }
         __syncthreads();
+        stamp();
         float4* t = cur; cur = nxt; nxt = t;
     }
     // RD.skelver = cur

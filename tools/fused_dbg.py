@@ -9,7 +9,7 @@ r = osep.Rosa(capacity_points=P.shape[0]); r.set_profile(True)
 r.set_input(P)
 for k in range(3):
     r.rosa_run()
-buf = np.zeros(64, np.int64)
+buf = np.zeros(128, np.int64)
 n = r._L.osep_rosa_get(r._h, b"fused_dbg", buf.ctypes.data_as(C.c_void_p), buf.nbytes)
 d = buf.reshape(8, 8)
 t0 = d[:6, 0].min()
