@@ -443,6 +443,7 @@ long osep_rosa_get(osep_rosa* h, const char* name, void* dst, long cap) {
     }
     if (nm == "fused_tl") { if (!d.fused_tl) return 0; return tap_copy(dst, cap, d.fused_tl, (size_t)d.Mcap * 9 * 16, 8) * 2; }
     if (nm == "fused_dbg") return tap_copy(dst, cap, d.fused_dbg, 128, 8) * 2;     // 128 int64 = 256 int32 words
+    if (nm == "timeline") { if (dst && cap >= sizeof(s.tstamp)) memcpy(dst, s.tstamp, sizeof(s.tstamp)); return (long long)(sizeof(s.tstamp) / 4); }   // globaltimer ns at the entry of selected kernels (FrameStamp)
     if (nm == "knn_stats") { if (dst && cap >= 20) { int* o = (int*)dst; o[0] = s.n_units; o[1] = s.n_slow; o[2] = s.n_over; o[3] = s.n_retry; o[4] = s.n_grow; } return 5; }
     if (nm == "launches") { if (dst && cap >= 4) *(int*)dst = (int)I.n_launches; return 1; }
     if (nm == "graph_replays") { if (dst && cap >= 4) *(int*)dst = (int)I.n_graph_replays; return 1; }

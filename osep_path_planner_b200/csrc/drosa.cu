@@ -433,6 +433,7 @@ __global__ void __launch_bounds__(256) k_gs_schedule(FrameState* st, const int* 
     extern __shared__ int lsm[];          // lvl[M] | hist[SCHED_BINS] | surf as ushort [M*nbk] | T_0 as ushort [M]
     __shared__ int s_tot;
     __shared__ int s_prog[2];
+    frame_stamp(st, TS_SCHED);
     if (st->status != 0) return;
     const int M = st->M;
     int* ta = lsm; int* hist = ta + M;
@@ -449,6 +450,8 @@ __global__ void __launch_bounds__(256) k_gs_schedule(FrameState* st, const int* 
     for (int p = threadIdx.x; p < M; p += blockDim.x) { ta[p] = sT[p]; level[p] = sT[p]; }
     __syncthreads();
     sched_sort(M, ta, hist, &s_tot, level_pts, level_off, &st->n_levels);
+    __syncthreads();
+    frame_stamp(st, TS_SCHED_END);
 }
 
 // R17 smoothing half, level by level.  All operands in shared memory; one warp walks the chain.
@@ -997,6 +1000,7 @@ __device__ __forceinline__ void fused_chain(const FusedArgs& a, uint4* smem, int
 
 __global__ void __launch_bounds__(SEED_WARPS * 32) k_drosa_fused(const __grid_constant__ FusedArgs a) {
     extern __shared__ uint4 fused_smem[];
+    frame_stamp(a.st, TS_DROSA);
     if (a.st->status != 0) return;
     const int M = a.st->M;
     // shared-memory footprint of a chain CTA (see fused_chain); evaluated identically by every CTA

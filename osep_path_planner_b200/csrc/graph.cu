@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_frame_tail(const __grid_consta
     unsigned char* arena = reinterpret_cast<unsigned char*>(tail_smem);
     auto stamp = [&](int k) { if (a.dbg && threadIdx.x == 0) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.dbg[k] = t; } };
     stamp(0);
+    frame_stamp(a.st, TS_TAIL);
     const int status0 = a.st->status, V0 = a.st->V;
     __syncthreads();
     const float4* pos = a.skel;
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_frame_tail(const __grid_consta
     export_block(a.st, a.skel, a.Mq, a.with_graph ? a.gs : nullptr, a.acc_cnt, a.acc, a.mst_uv, a.mst_w, a.out);
     __syncthreads();
     stamp(7);
+    if (threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); reinterpret_cast<FrameState*>(a.out)->tstamp[TS_END] = t; }   // (the state was exported above: the last stamp goes into the exported copy)
 }
 
 struct GraphHost {

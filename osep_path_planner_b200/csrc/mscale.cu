@@ -121,6 +121,7 @@ template <bool FILL>
 __global__ void k_simi(FrameState* st, const float4* __restrict__ pts, const float4* __restrict__ nrms,
                        int* simi_off, int* __restrict__ simi_idx, int* __restrict__ tmp_j, float* __restrict__ tmp_d,
                        unsigned* __restrict__ simi_bits, int Scap) {
+    if (!FILL) frame_stamp(st, TS_SIMI);
     if (st->status != 0) return;
     const int M = st->M;
     const int W = (((M + 31) >> 5) + 3) & ~3;   // row stride of the bit matrix: padded to 16 bytes (drosa.cu reads rows with 16-byte loads)
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_surf_knn(FrameState* st, const float4* __restrict__ pts, int* __restrict__ surf, int k_req) {
     __shared__ float s_d[WARPS_PER_BLOCK][SURF_LIST];
     __shared__ int s_j[WARPS_PER_BLOCK][SURF_LIST];
+    frame_stamp(st, TS_SURF);
     if (st->status != 0) return;
     const int M = st->M;
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -194,6 +196,7 @@ k_surf_knn(FrameState* st, const float4* __restrict__ pts, int* __restrict__ sur
 // R19 part 1 (single block): compact goodCenters, list poor points in ascending index.
 __global__ void k_poor_fixup(FrameState* st, const int* __restrict__ good, int* good_rank, const float4* __restrict__ centers,
                              float4* __restrict__ good_centers, int* __restrict__ poor_idx, const float4* __restrict__ pts, float4* pset) {
+    frame_stamp(st, TS_FIXUP);
     if (st->status != 0) return;
     const int M = st->M;
     for (int i = threadIdx.x; i < M; i += blockDim.x) good_rank[i] = good[i];
@@ -324,6 +327,7 @@ template <int CL>
 __global__ void __launch_bounds__(DC_THREADS)
 k_dcrosa_cluster(FrameState* st, float4* pset, const int* __restrict__ simi_off, const int* __restrict__ simi_idx, int niter,
                  unsigned smem_bytes, long long* dbg, const VsArgs vs) {
+    frame_stamp(st, TS_DCROSA);
     int dk = 0;
     auto stamp = [&]() { if (dbg && threadIdx.x == 0 && blockIdx.x == 0 && dk < 60) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[dk++] = t; } };
     stamp();

@@ -95,6 +95,7 @@ __global__ void k_filter_count(const FrameParams* __restrict__ prm, float r2, in
 // single block: scan the per-block counts; R4 gate (rosa.cpp:91-95)
 __global__ void k_filter_scan(int* blk_cnt, int nblk, FrameState* st, int min_points, const FrameParams* __restrict__ prm) {
     if (threadIdx.x == 0) frame_init(st, prm->n);          // first writer of the frame state (k_filter_count does not touch it)
+    frame_stamp(st, TS_FILTER);
     const int total = block_excl_scan(blk_cnt, nblk);
     if (threadIdx.x == 0) {
         st->n_filt = total;
@@ -242,6 +243,7 @@ __device__ __forceinline__ bool vset_insert(unsigned long long* tab, unsigned ma
 
 // count-only VoxelGrid pass: number of distinct voxel keys at the current leaf
 __global__ void k_vox_count(const float4* __restrict__ P, FrameState* st, unsigned long long* vtab, unsigned mask, int next_step, int max_points, int target_ppc) {
+    if (next_step == 1) frame_stamp(st, TS_LEAF0);
     if (st->status != 0) return;
     if (st->pass_active && !st->pass_overflow) {
         const int n = st->n_filt;
@@ -346,6 +348,7 @@ __device__ __forceinline__ void cell_of(const FrameState* st, float x, float y, 
 // pass 0 = first build; pass 1 = rebuild, runs only when k_grid_refine asked for it.
 __global__ void k_grid_insert(const float4* __restrict__ P, FrameState* st, unsigned long long* gtab, int* g_cnt,
                               int* __restrict__ p_slot, unsigned mask, int pass, int target_ppc) {
+    frame_stamp(st, pass == 0 ? TS_GRID : TS_COUNT);
     __shared__ int s_last;
     if (st->status != 0) return;
     if (pass == 1 && !st->g_redo) return;
@@ -1016,6 +1019,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_knn_scan(const float4* __restr
                                                            const int2* __restrict__ nbr, const float* __restrict__ nbr_tau, int cell_cap,
                                                            int* __restrict__ knn_idx, int k_req, int* __restrict__ grow_list) {
     constexpr int R = 1, NC = 27;
+    frame_stamp(st, TS_KNN);
     __shared__ unsigned lst[2 * (SCAN_CAP + 1)][SCAN_THREADS];    // rows [0, CAP]: d2 bits (row CAP = overflow sink); rows [CAP + 1, 2 CAP + 1]: point index
     unsigned (*ld)[SCAN_THREADS] = lst;
     unsigned (*li)[SCAN_THREADS] = lst + (SCAN_CAP + 1);
@@ -1128,6 +1132,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_knn_scan(const float4* __restr
 // normals: one thread per point, neighbours from knn_idx (k_eff per point, canonical order)
 __global__ void __launch_bounds__(128) k_normals(const float4* __restrict__ P, const FrameState* __restrict__ st,
                                                  const int* __restrict__ knn_idx, int k_req, float4* __restrict__ Nrm) {
+    frame_stamp(st, TS_NORMALS);
     if (st->status != 0) return;
     const int n = st->n_filt;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1141,6 +1146,7 @@ __global__ void __launch_bounds__(128) k_normals(const float4* __restrict__ P, c
 // R9 final pass: distinct voxel keys -> sorted -> dense voxel ids -> points grouped by voxel (atomic
 // cursors) -> per-voxel index sort + sums in ascending point index (k_vox_reduce).
 __global__ void k_vox_collect(FrameState* st, const unsigned long long* __restrict__ vtab, int T, unsigned* __restrict__ vkeys, int Mcap) {
+    frame_stamp(st, TS_VOXFINAL);
     if (st->status != 0) return;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= T) return;
@@ -1238,6 +1244,7 @@ k_vox_reduce(FrameState* st, int* grouped, int* __restrict__ scratch, const int*
              float4* __restrict__ nraw, float4* __restrict__ vnd, float4* __restrict__ vset_it) {
     __shared__ int sidx[VOX_SORT];
     __shared__ float4 sp[VOX_CHUNK];
+    frame_stamp(st, PHASE == 0 ? TS_REDUCE0 : TS_REDUCE1);
     if (st->status != 0) return;
     const int M = st->M;
     for (int v = blockIdx.x; v < M; v += gridDim.x) {

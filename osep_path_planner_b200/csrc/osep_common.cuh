@@ -64,8 +64,16 @@ struct FrameState {
     int ticket;            // last-block detection (voxel count passes)
     int ticket_m;          // last-block detection (similarity count pass)
     int ticket_grid;       // last-block detection (kNN grid build; runs concurrently with the voxel passes)
+    // ---- where the frame's time goes: globaltimer (ns) at the entry of selected kernels, written by block 0 thread 0 (tap "timeline", tools/frame_timeline.py)
+    unsigned long long tstamp[18];
 };
+enum FrameStamp { TS_FILTER = 0, TS_LEAF0, TS_GRID, TS_KNN, TS_NORMALS, TS_VOXFINAL, TS_REDUCE0, TS_SURF, TS_SCHED, TS_SCHED_END, TS_REDUCE1, TS_SIMI, TS_DROSA, TS_FIXUP, TS_DCROSA, TS_TAIL, TS_END, TS_COUNT };
 
+#ifdef __CUDACC__
+__device__ __forceinline__ void frame_stamp(const FrameState* st, int k) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); const_cast<FrameState*>(st)->tstamp[k] = t; }
+}
+#endif
 static_assert(sizeof(FrameState) <= 512, "the frame export block reserves 512 bytes for FrameState");
 
 // Per-frame launch parameters.  They live in device memory (refreshed by one H2D copy node from a pinned host mirror at the

@@ -15,6 +15,8 @@ namespace osep {
 constexpr unsigned TAIL_FULL = 0xffffffffu;
 constexpr int GK = 10;                 // kNN size of graph_adj (gskel.cpp:206)
 constexpr int GACC = GK - 1;           // accepted neighbours per vertex (rank 0 = self is skipped)
+constexpr int SMOOTH_WIN = 32;         // vertex_smooth: window of a vertex's radius list in the single-pass path
+constexpr int SMOOTH_STRIDE = 33;      // its stride in shared memory (odd: the Jacobi passes read one window per thread)
 struct GraphDevState { int n_edges; int n_mst; int overflow; int pad; };
 
 __device__ __forceinline__ f3 ld3(const float4* a, int i) { const float4 v = a[i]; return {v.x, v.y, v.z}; }
@@ -93,78 +95,120 @@ static __device__ const float4* vertex_smooth_block(FrameState* st, float4* skel
     stamp();
     const float r2 = radius * radius;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    // neighbour counts: one warp per vertex, ballots over 32 candidates at a time; `first` = smallest (d2, index)
-    for (int i = warp; i < Vf; i += nwarps) {
-        const f3 q = ld3(C, i);
-        int c = 0; float bd = __int_as_float(0x7f800000); int bi = 0x7fffffff;
-        for (int j0 = 0; j0 < Vf; j0 += 32) {
-            const int j = j0 + lane;
-            float d = 0.0f; bool in = false;
-            if (j < Vf) { d = dist2(q, ld3(C, j)); in = d < r2; }
-            c += __popc(__ballot_sync(TAIL_FULL, in));
-            if (in && nb_less(d, j, bd, bi)) { bd = d; bi = j; }
-        }
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) {
-            const float od = __shfl_xor_sync(TAIL_FULL, bd, o); const int oi = __shfl_xor_sync(TAIL_FULL, bi, o);
-            if (nb_less(od, oi, bd, bi)) { bd = od; bi = oi; }
-        }
-        if (c == 0) c = 1; else if (bi != i) c += 1;      // self forced first (rosa.cpp:567-573)
-        __syncwarp();
-        if (lane == 0) off[i] = c;
-    }
-    __syncthreads();                                       // (the offsets of the compaction are dead: off is reused for the list offsets)
-    if (threadIdx.x == 0) off[Vf] = 0;
-    __syncthreads();
-    const int total = block_scan_inplace(off, Vf + 1);
-    __syncthreads();
-    stamp();
-    if (total > cap) { if (threadIdx.x == 0) st->status = OSEP_ERR_CAPACITY; return nullptr; }
-    int* idx = vs_idx; int* tj = tmp_j; float* td = tmp_d;
-    if (small && total <= ecap_s) { idx = s_lists; tj = idx + ecap_s; td = reinterpret_cast<float*>(tj + ecap_s); }
-    for (int i = warp; i < Vf; i += nwarps) {
-        const f3 q = ld3(C, i);
-        const int b = off[i];
-        int c = 0;
-        for (int j0 = 0; j0 < Vf; j0 += 32) {
-            const int j = j0 + lane;
-            float d = 0.0f; bool in = false;
-            if (j < Vf) { d = dist2(q, ld3(C, j)); in = d < r2; }
-            const unsigned m = __ballot_sync(TAIL_FULL, in);
-            if (in) { const int pos = b + c + __popc(m & ((1u << lane) - 1u)); tj[pos] = j; td[pos] = d; }
-            c += __popc(m);
-        }
-        __syncwarp();
-        if (c == 0) { if (lane == 0) idx[b] = i; continue; }
-        // rank sort by (d2, index); if the first sorted entry is not i, i is inserted in front (rosa.cpp:567-569)
-        int myfirst = 0x7fffffff;
-        int rank_e[4];                                     // ranks of this lane's entries e = lane + 32 u, u < 4 (longer lists recompute)
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int e = lane + 32 * u;
-            rank_e[u] = 0;
-            if (e < c) {
-                const float de = td[b + e]; const int je = tj[b + e];
-                int rank = 0;
-                for (int f = 0; f < c; ++f) rank += nb_less(td[b + f], tj[b + f], de, je) ? 1 : 0;
-                rank_e[u] = rank;
-                if (rank == 0) myfirst = je;
+    // Frames (V ~ 10^2, lists of ~10): ONE pass per vertex into a fixed window of SMOOTH_WIN entries in shared memory -- no
+    // count pass, no offset scan (15 -> 7.6 us of a single-SM kernel that is bound by its instruction count).
+    // A list that does not fit its window sends the whole block to the general two-pass CSR path below.
+    bool fixed = false;
+    int* idx = vs_idx;
+    if (small && (size_t)Vf * SMOOTH_STRIDE * 12 <= arena_bytes - pos_bytes) {
+        int* fidx = s_lists; int* ftj = fidx + (size_t)Vf * SMOOTH_STRIDE; float* ftd = reinterpret_cast<float*>(ftj + (size_t)Vf * SMOOTH_STRIDE);
+        bool over = false;
+        for (int i = warp; i < Vf; i += nwarps) {
+            const f3 q = ld3(C, i);
+            const int b = i * SMOOTH_STRIDE;
+            int c = 0;
+            for (int j0 = 0; j0 < Vf; j0 += 32) {
+                const int j = j0 + lane;
+                const float d = dist2(q, ld3(C, min(j, Vf - 1)));
+                const bool in = j < Vf && d < r2;
+                const unsigned m = __ballot_sync(TAIL_FULL, in);
+                const int pos = c + __popc(m & ((1u << lane) - 1u));
+                if (in && pos < SMOOTH_WIN) { ftj[b + pos] = j; ftd[b + pos] = d; }
+                c += __popc(m);
             }
+            __syncwarp();
+            if (c >= SMOOTH_WIN) { over = true; continue; }          // (one more entry when the vertex itself has to be put in front)
+            if (c == 0) { if (lane == 0) { fidx[b] = i; off[i] = 1; } continue; }
+            // rank sort by (d2, index): lane e holds entry e; if the first sorted entry is not i, i is inserted in front (rosa.cpp:567-569)
+            int rank = 0, je = 0x7fffffff;
+            if (lane < c) {
+                const float de = ftd[b + lane]; je = ftj[b + lane];
+#pragma unroll 4
+                for (int f = 0; f < c; ++f) rank += nb_less(ftd[b + f], ftj[b + f], de, je) ? 1 : 0;
+            }
+            const int first = __reduce_min_sync(TAIL_FULL, (lane < c && rank == 0) ? je : 0x7fffffff);
+            const int shift = (first != i) ? 1 : 0;
+            if (shift && lane == 0) fidx[b] = i;
+            if (lane < c) fidx[b + shift + rank] = je;
+            if (lane == 0) off[i] = c + shift;                       // fixed windows: off holds the list LENGTH
         }
-        for (int e = lane + 128; e < c; e += 32) {
-            int rank = 0;
-            for (int f = 0; f < c; ++f) rank += nb_less(td[b + f], tj[b + f], td[b + e], tj[b + e]) ? 1 : 0;
-            if (rank == 0) myfirst = tj[b + e];
+        fixed = __syncthreads_or(over ? 1 : 0) == 0;
+        if (fixed) idx = fidx;
+    }
+    if (!fixed) {
+        // neighbour counts: one warp per vertex, ballots over 32 candidates at a time; `first` = smallest (d2, index)
+        for (int i = warp; i < Vf; i += nwarps) {
+            const f3 q = ld3(C, i);
+            int c = 0; float bd = __int_as_float(0x7f800000); int bi = 0x7fffffff;
+            for (int j0 = 0; j0 < Vf; j0 += 32) {
+                const int j = j0 + lane;
+                float d = 0.0f; bool in = false;
+                if (j < Vf) { d = dist2(q, ld3(C, j)); in = d < r2; }
+                c += __popc(__ballot_sync(TAIL_FULL, in));
+                if (in && nb_less(d, j, bd, bi)) { bd = d; bi = j; }
+            }
+    #pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+                const float od = __shfl_xor_sync(TAIL_FULL, bd, o); const int oi = __shfl_xor_sync(TAIL_FULL, bi, o);
+                if (nb_less(od, oi, bd, bi)) { bd = od; bi = oi; }
+            }
+            if (c == 0) c = 1; else if (bi != i) c += 1;      // self forced first (rosa.cpp:567-573)
+            __syncwarp();
+            if (lane == 0) off[i] = c;
         }
-        const int first = __reduce_min_sync(TAIL_FULL, myfirst);
-        const int shift = (first != i) ? 1 : 0;
-        if (shift && lane == 0) idx[b] = i;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { const int e = lane + 32 * u; if (e < c) idx[b + shift + rank_e[u]] = tj[b + e]; }
-        for (int e = lane + 128; e < c; e += 32) {
-            int rank = 0;
-            for (int f = 0; f < c; ++f) rank += nb_less(td[b + f], tj[b + f], td[b + e], tj[b + e]) ? 1 : 0;
-            idx[b + shift + rank] = tj[b + e];
+        __syncthreads();                                       // (the offsets of the compaction are dead: off is reused for the list offsets)
+        if (threadIdx.x == 0) off[Vf] = 0;
+        __syncthreads();
+        const int total = block_scan_inplace(off, Vf + 1);
+        __syncthreads();
+        stamp();
+        if (total > cap) { if (threadIdx.x == 0) st->status = OSEP_ERR_CAPACITY; return nullptr; }
+        idx = vs_idx; int* tj = tmp_j; float* td = tmp_d;
+        if (small && total <= ecap_s) { idx = s_lists; tj = idx + ecap_s; td = reinterpret_cast<float*>(tj + ecap_s); }
+        for (int i = warp; i < Vf; i += nwarps) {
+            const f3 q = ld3(C, i);
+            const int b = off[i];
+            int c = 0;
+            for (int j0 = 0; j0 < Vf; j0 += 32) {
+                const int j = j0 + lane;
+                float d = 0.0f; bool in = false;
+                if (j < Vf) { d = dist2(q, ld3(C, j)); in = d < r2; }
+                const unsigned m = __ballot_sync(TAIL_FULL, in);
+                if (in) { const int pos = b + c + __popc(m & ((1u << lane) - 1u)); tj[pos] = j; td[pos] = d; }
+                c += __popc(m);
+            }
+            __syncwarp();
+            if (c == 0) { if (lane == 0) idx[b] = i; continue; }
+            // rank sort by (d2, index); if the first sorted entry is not i, i is inserted in front (rosa.cpp:567-569)
+            int myfirst = 0x7fffffff;
+            int rank_e[4];                                     // ranks of this lane's entries e = lane + 32 u, u < 4 (longer lists recompute)
+    #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = lane + 32 * u;
+                rank_e[u] = 0;
+                if (e < c) {
+                    const float de = td[b + e]; const int je = tj[b + e];
+                    int rank = 0;
+                    for (int f = 0; f < c; ++f) rank += nb_less(td[b + f], tj[b + f], de, je) ? 1 : 0;
+                    rank_e[u] = rank;
+                    if (rank == 0) myfirst = je;
+                }
+            }
+            for (int e = lane + 128; e < c; e += 32) {
+                int rank = 0;
+                for (int f = 0; f < c; ++f) rank += nb_less(td[b + f], tj[b + f], td[b + e], tj[b + e]) ? 1 : 0;
+                if (rank == 0) myfirst = tj[b + e];
+            }
+            const int first = __reduce_min_sync(TAIL_FULL, myfirst);
+            const int shift = (first != i) ? 1 : 0;
+            if (shift && lane == 0) idx[b] = i;
+    #pragma unroll
+            for (int u = 0; u < 4; ++u) { const int e = lane + 32 * u; if (e < c) idx[b + shift + rank_e[u]] = tj[b + e]; }
+            for (int e = lane + 128; e < c; e += 32) {
+                int rank = 0;
+                for (int f = 0; f < c; ++f) rank += nb_less(td[b + f], tj[b + f], td[b + e], tj[b + e]) ? 1 : 0;
+                idx[b + shift + rank] = tj[b + e];
+            }
         }
     }
     __syncthreads();
@@ -172,8 +216,9 @@ static __device__ const float4* vertex_smooth_block(FrameState* st, float4* skel
     float4* cur = A; float4* nxt = B;
     for (int it = 0; it < niter; ++it) {
         for (int i = threadIdx.x; i < Vf; i += blockDim.x) {
-            const int b = off[i], e = off[i + 1];
-            const int n = e - b;
+            const int b = fixed ? i * SMOOTH_STRIDE : off[i];
+            const int n = fixed ? off[i] : off[i + 1] - off[i];
+            const int e = b + n;
             if (n <= 1) { nxt[i] = cur[i]; continue; }
             f3 mean{0.0f, 0.0f, 0.0f};
             for (int t = b; t < e; ++t) mean = add3(mean, ld3(cur, idx[t]));

@@ -15,4 +15,4 @@ for k in range(4):
     t = buf[48:56]
     print("frame %d V=%d: smooth %.1f us | graph_adj %.1f | mst keys %.1f sort %.1f kruskal %.1f | export %.1f | total %.1f" % (
         k, r.result.n_vertices, (t[1] - t[0]) / 1e3, (t[2] - t[1]) / 1e3, (t[4] - t[2]) / 1e3, (t[5] - t[4]) / 1e3, (t[3] - t[5]) / 1e3, (t[7] - t[3]) / 1e3, (t[7] - t[0]) / 1e3))
-    print("   smooth: compaction %.1f counts+scan %.1f fill+sort %.1f iterations %s" % ((buf[56] - t[0]) / 1e3, (buf[57] - buf[56]) / 1e3, (buf[58] - buf[57]) / 1e3, " ".join("%.1f" % ((buf[59 + i] - buf[58 + i]) / 1e3) for i in range(3))))
+    print("   smooth: compaction %.1f lists %.1f iterations %s (single-pass lists; the two-pass path has one stamp more)" % ((buf[56] - t[0]) / 1e3, (buf[57] - buf[56]) / 1e3, " ".join("%.1f" % ((buf[58 + i] - buf[57 + i]) / 1e3) for i in range(3))))
