@@ -213,6 +213,7 @@ def run_ours(args, rank, world, local_rank):
         ok = r.finish()
         assert ok
         g = r.graph(3.0)                        # host views (CSR, joints, leafs) of the graph the frame built on the device
+    timeline_us = r.timeline()                  # kernel entry times of the last timed frame (normal overlapped run, L2 cold)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = r.launches - launches0
@@ -274,7 +275,7 @@ def run_ours(args, rank, world, local_rank):
     knn_bytes = 28 * res0.n_filtered                       # SURVEY 8(d) phase (3): read 16 N', write 12 N'
     roofline = {"bound": "hbm", "kernel": "k_drosa_fused (persistent cooperative kernel: 6 orientation iterations + position step, %.0f %% of the frame)" % (100 * drosa_ms / ms_per_step),
                 "achieved": drosa_gbs, "peak": peak, "unit": "GB/s", "frac": drosa_gbs / peak,
-                "traffic": 790528, "traffic_source": "profiles/r2_v36_ncu_full_top_kernels.md (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture, cold cache)",
+                "traffic": 543190, "traffic_source": "profiles/r2_final_ncu_full_kernels.md (dram__bytes_read.sum + dram__bytes_write.sum of k_drosa_fused, one ncu --set full capture, cold cache)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": drosa_bytes, "ms_per_launch": drosa_ms,
                 "note": "latency-bound by construction: ~236 dependent 3x3 eigen solves per Gauss-Seidel chain (rosa.cpp:295-308), six chains as overlapping wavefronts, "
                         "one warp per chain at ~4 cycles per dependent instruction (ncu: 7.8 % issue-active, 90 % L2 hit); the HBM fraction is reported for the record, the signal is ms_per_launch",
@@ -385,7 +386,7 @@ def run_ours(args, rank, world, local_rank):
                            "parallelism": "1 frame per GPU per step; ranks = independent frames (no collective on the data path)"},
                 "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": 1e3 * e2e_s / args.steps, "h2d_bytes_per_step": int(n * 16), "d2h_bytes_per_step": d2h},
-                "gpu_launches": int(launches), "stage_ms": stage_ms, "clocks": clk, "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps, "batched": batched, "stream": stream, "tiled": tiled_blk}
+                "gpu_launches": int(launches), "stage_ms": stage_ms, "timeline_us": timeline_us, "clocks": clk, "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps, "batched": batched, "stream": stream, "tiled": tiled_blk}
         print(json.dumps(line), flush=True)
     r.close()
     if world > 1:

@@ -219,6 +219,17 @@ class Rosa:
     def csr(self, name):
         return self.tap(name + "_off"), self.tap(name + "_idx")
 
+    TIMELINE_NAMES = ["filter", "leaf_pass0", "knn_grid", "knn_scan", "normals", "voxel_final", "voxel_reduce_positions", "surf_knn", "schedule", "schedule_end",
+                      "voxel_reduce_normals", "similarity", "drosa", "position_fixup", "dcrosa_vertex_sampling", "tail", "end"]
+
+    def timeline(self):
+        """Kernel entry times of the last frame in microseconds after the filter's scan kernel (globaltimer stamps written by
+        block 0 of selected kernels in a normal, overlapped run; csrc/osep_common.cuh FrameStamp)."""
+        buf = np.zeros(18, dtype=np.uint64)
+        self._L.osep_rosa_get(self._h, b"timeline", buf.ctypes.data_as(C.c_void_p), buf.nbytes)
+        t = buf.astype(np.int64)
+        return {n: float(t[i] - t[0]) / 1e3 for i, n in enumerate(self.TIMELINE_NAMES) if t[i] > 0}
+
     # --- helpers ----------------------------------------------------------------------------
     def _collect_vertices(self):
         p = C.POINTER(C.c_float)(); nv = C.c_int()

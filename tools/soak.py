@@ -12,10 +12,13 @@ bad = 0
 for name, P in (("turbine100k", fx.turbine()), ("cyl20k", fx.cylinder()), ("stream50k_f300", fx.stream_frame(300, n=50000)[0]), ("turbine30k", fx.turbine(30000, seed=5))):
     r = osep.Rosa(capacity_points=len(P))
     r.set_input(P)
+    r.set_graph(True, 3.0)                 # the frame's tail builds the skeleton graph as well (graph_adj + Boruvka mst)
     ref = None; mism = 0
     for k in range(iters):
         assert r.rosa_run()
-        h = hashlib.sha1(np.ascontiguousarray(r.output_vertices()).tobytes()).hexdigest() + "|%d|%d|%d" % (r.result.n_downsampled, r.result.n_simi, r.result.flags)
+        g = r.graph(3.0)
+        h = hashlib.sha1(np.ascontiguousarray(r.output_vertices()).tobytes() + np.ascontiguousarray(g["edges"]).tobytes() + np.ascontiguousarray(g["edge_w"]).tobytes()
+                         + np.ascontiguousarray(g["rng_idx"]).tobytes()).hexdigest() + "|%d|%d|%d" % (r.result.n_downsampled, r.result.n_simi, r.result.flags)
         if ref is None: ref = h
         elif h != ref: mism += 1
     print("%-16s %d runs, %d mismatches, V=%d M=%d" % (name, iters, mism, r.result.n_vertices, r.result.n_downsampled))
