@@ -3,9 +3,8 @@
 //   R13 surf_nbs kNN(nb_knn)             (rosa.cpp:259-267)
 //   R14-R17 drosa orientation loop       (rosa.cpp:270-309, 653-732)
 //   R18 position step, R19 poor fix-up   (rosa.cpp:311-376, 734-791)
-//   R20 dcrosa                           (rosa.cpp:382-422, 793-841)
-//   R21 vertex_sampling                  (rosa.cpp:424-532)
-//   R22 vertex_smooth                    (rosa.cpp:534-620)
+//   R20 dcrosa + R21 vertex_sampling     (rosa.cpp:382-532, 793-841): ONE thread-block-cluster launch, k_dcrosa_cluster
+//   (R22 vertex_smooth, rosa.cpp:534-620, runs in the frame's tail kernel: tail.cuh / graph.cu)
 //
 // The whole M-scale state (pts, nrms, pset, vset: 4 x 16 KB; similarity CSR ~250 KB) is
 // L1/L2 resident; these stages move ~0 algorithmic HBM bytes and are bounded by dependent
