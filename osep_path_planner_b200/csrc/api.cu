@@ -55,6 +55,7 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
     d.cell_cap = (int)(N / 3 + 1024); CK(dalloc(&d.g_cell, T)); CK(dalloc(&d.cell_slots, (size_t)d.cell_cap)); CK(dalloc(&d.pc_cell, N)); CK(dalloc(&d.nbr, (size_t)d.cell_cap * 27)); CK(dalloc(&d.nbr_tau, (size_t)d.cell_cap)); CK(dalloc(&d.knn_full, N * (size_t)d.knn)); CK(dalloc(&d.p_slot, N)); CK(dalloc(&d.Pc, N)); CK(dalloc(&d.Nrm, N));
     CK(dalloc(&d.vtab, T)); CK(cudaMemset(d.vtab, 0, T * sizeof(unsigned long long)));
     CK(dalloc(&d.vkeys, M)); CK(dalloc(&d.vid, N)); CK(dalloc(&d.vox_cnt, M + 2)); CK(dalloc(&d.vox_fill, M + 2));
+    if ((size_t)(N / 256 + 2) * M * sizeof(int) <= ((size_t)32 << 20)) CK(dalloc(&d.blk_hist, (size_t)(N / 256 + 2) * M));      // frames: stable partition by voxel (nscale.cu); larger arenas keep the atomic scatter + per-voxel sort
     CK(dalloc(&d.rk0, tmpcap)); CK(dalloc(&d.rk1, tmpcap)); CK(dalloc(&d.rv0, tmpcap)); CK(dalloc(&d.rv1, tmpcap));
     CK(dalloc(&d.pts, M)); CK(dalloc(&d.nrms, M)); CK(dalloc(&d.pset, M)); CK(dalloc(&d.pset2, M)); CK(dalloc(&d.vset, M)); CK(dalloc(&d.vnew, M));
     CK(dalloc(&d.vvar, M)); CK(dalloc(&d.simi_bits, M * (size_t)d.W)); CK(dalloc(&d.nraw, M)); CK(dalloc(&d.vnd, M));
@@ -100,7 +101,7 @@ static int rosa_alloc(osep_rosa_impl* h, int capacity_points) {
 static void rosa_free(osep_rosa_impl* h) {
     RosaDev& d = h->d;
     void* ptrs[] = {d.st, d.prm, d.in, d.in_raw, d.P, d.filt_idx, d.blk_cnt, d.gtab, d.g_start, d.units, d.slow_list, d.over_list, d.knn_retry, d.knn_grow, d.g_cell, d.cell_slots, d.pc_cell, d.nbr, d.nbr_tau, d.p_slot, d.Pc, d.Nrm, d.knn_full, d.vtab, d.vkeys, d.vid,
-                    d.vox_cnt, d.vox_fill, d.rk0, d.rk1, d.rv0, d.rv1, d.pts, d.nrms, d.pset, d.pset2, d.vset, d.vnew, d.vvar, d.surf,
+                    d.vox_cnt, d.vox_fill, d.blk_hist, d.rk0, d.rk1, d.rv0, d.rv1, d.pts, d.nrms, d.pset, d.pset2, d.vset, d.vnew, d.vvar, d.surf,
                     d.simi_off, d.simi_idx, d.simi_bits, d.nraw, d.vnd, d.vset_it, d.vnew_it, d.fused_flags, d.fused_dbg, d.fused_tl, d.level, d.level_off, d.level_pts, d.good, d.centers, d.good_rank, d.poor_idx, d.active_size,
                     d.pcloud, d.adj_bits, d.seeds, d.corresp, d.skel, d.skel2, d.skel_sampled, d.vtmp, d.vs_off, d.vs_idx, d.vset_iters};
     for (void* p : ptrs) if (p) cudaFree(p);

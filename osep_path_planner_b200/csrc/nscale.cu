@@ -1226,6 +1226,94 @@ __global__ void k_vox_scatter(const FrameState* __restrict__ st, const unsigned*
     grouped[vox_off[v] + atomicAdd(&fill[v], 1)] = i;
 }
 
+// ---- stable partition of the points by voxel (frames whose block-count matrix fits: blk_hist != nullptr) -------------------------
+// The atomic cursors of k_vox_scatter leave a voxel's points in arbitrary order, so k_vox_reduce had to sort every voxel's
+// index list first (6.5 M warp instructions per 100k-point frame, a third of the final pass).  Here the order is right from
+// the start: a block of 256 consecutive points ranks each point among the block's earlier points of the same voxel (warp by
+// warp: __match_any groups + a shared count per voxel), writes its per-voxel counts as one row of a [block][voxel] matrix,
+// a thread per voxel turns the matrix's columns into exclusive prefixes over the blocks (coalesced across voxels), and the
+// scatter adds voxel offset + block prefix + rank: ascending point index inside every voxel, no atomics on global memory.
+__global__ void __launch_bounds__(NT) k_vox_assign_ranked(const float4* __restrict__ P, const FrameState* __restrict__ st, const unsigned* __restrict__ vkeys,
+                                                          unsigned* __restrict__ vid_out, int* __restrict__ rank_out, int* __restrict__ blk_hist, int Mcap) {
+    extern __shared__ int vhist[];
+    if (st->status != 0) return;
+    const int n = st->n_filt, M = st->M;
+    if ((int)(blockIdx.x * blockDim.x) >= n) return;
+    for (int v = threadIdx.x; v < M; v += blockDim.x) vhist[v] = 0;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    int vid = 0;
+    if (valid) {
+        if (st->vox_identity) vid = i;                                     // output = input: every filtered point is its own voxel
+        else {
+            const unsigned key = voxel_key(P[i], st->inv_leaf, st->minb[0], st->minb[1], st->minb[2], st->divb[0], st->divb[1]);
+            int lo = 0, hi = M - 1;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (vkeys[mid] < key) lo = mid + 1; else hi = mid; }
+            vid = lo;
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    int rank = 0;
+    for (int w = 0; w < NT / 32; ++w) {                                    // warps in index order
+        if (wib == w) {
+            const unsigned grp = __match_any_sync(0xffffffffu, valid ? vid : (M + lane));
+            const int base = valid ? vhist[vid] : 0;
+            __syncwarp();
+            if (valid && lane == __ffs(grp) - 1) vhist[vid] = base + __popc(grp);
+            rank = base + __popc(grp & ((1u << lane) - 1u));
+        }
+        __syncthreads();
+    }
+    if (valid) { vid_out[i] = (unsigned)vid; rank_out[i] = rank; }
+    int* row = blk_hist + (size_t)blockIdx.x * Mcap;
+    for (int v = threadIdx.x; v < M; v += blockDim.x) row[v] = vhist[v];
+}
+// Column-wise exclusive prefix of the [block][voxel] matrix over the blocks (in place), column totals -> vox_cnt.  A CTA takes 32
+// voxels (lane = voxel: every access is coalesced across voxels), warp c the c-th chunk of 32 blocks: its 32 loads are
+// independent (one latency), the prefix inside the chunk stays in registers, chunk totals meet in shared memory.
+// (A thread per voxel walking its column -- load, add, store, next -- took 100 us: 391 dependent L2 round trips.)
+__global__ void __launch_bounds__(1024) k_vox_blockscan(const FrameState* __restrict__ st, int* __restrict__ blk_hist, int Mcap, int* __restrict__ vox_cnt) {
+    __shared__ int tot[32][33];
+    __shared__ int carry[32];
+    if (st->status != 0) return;
+    const int M = st->M;
+    if ((int)blockIdx.x * 32 > M) return;
+    const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
+    const int v = blockIdx.x * 32 + lane;
+    const int nblk = (st->n_filt + NT - 1) / NT;
+    if (c == 0) carry[lane] = 0;
+    __syncthreads();
+    int* col = blk_hist + v;
+    for (int g0 = 0; g0 < nblk; g0 += 32 * 32) {                          // 32 chunks of 32 blocks per round
+        const int b0 = g0 + c * 32;
+        int val[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) { const int b = b0 + k; val[k] = (v < M && b < nblk) ? col[(size_t)b * Mcap] : 0; }
+        int run = 0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) { const int t = val[k]; val[k] = run; run += t; }
+        tot[c][lane] = run;
+        __syncthreads();
+        int off = carry[lane];
+        for (int cc = 0; cc < c; ++cc) off += tot[cc][lane];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) { const int b = b0 + k; if (v < M && b < nblk) col[(size_t)b * Mcap] = off + val[k]; }
+        __syncthreads();
+        if (c == 31) carry[lane] = off + run;                              // (warp 31's offset covers chunks 0..30)
+        __syncthreads();
+    }
+    if (c == 0) { if (v < M) vox_cnt[v] = carry[lane]; else if (v == M) vox_cnt[M] = 0; }
+}
+__global__ void k_vox_scatter_ranked(const FrameState* __restrict__ st, const unsigned* __restrict__ vid, const int* __restrict__ rank, const int* __restrict__ vox_off,
+                                     const int* __restrict__ blk_hist, int Mcap, int* __restrict__ grouped) {
+    if (st->status != 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st->n_filt) return;
+    const int v = (int)vid[i];
+    grouped[vox_off[v] + blk_hist[(size_t)blockIdx.x * Mcap + v] + rank[i]] = i;
+}
+
 // per-voxel centroid (pcl::CentroidPoint<PointNormal>), then R10 + R11 fused.
 // One CTA per voxel: (1) the voxel's point indices are sorted ascending in shared memory (bitonic; lists
 // longer than VOX_SORT are rank-sorted through global memory) -- this restores the canonical order C3 that a
@@ -1236,7 +1324,7 @@ constexpr int VOX_CHUNK = 256;
 // PHASE 0 (needs only the filtered cloud: runs while the kNN / normals branch is still busy): sort the voxel's point indices
 // (left in `grouped` for phase 1), sum the POSITIONS -> pts, pset.  PHASE 1 (after the normals): sum the NORMALS in the stored
 // order -> nrms, vset (R10 + R11), plus what drosa hoists per point (nraw, vnd) and its iteration-0 orientations (vset_it).
-template <int PHASE>
+template <int PHASE, bool PRESORTED = false>
 __global__ void __launch_bounds__(256)
 k_vox_reduce(FrameState* st, int* grouped, int* __restrict__ scratch, const int* __restrict__ vox_off,
              const float4* __restrict__ P, const float4* __restrict__ Nrm,
@@ -1252,7 +1340,7 @@ k_vox_reduce(FrameState* st, int* grouped, int* __restrict__ scratch, const int*
         const int cnt = e - b;
         const int* order = grouped + b;
         __syncthreads();
-        if (PHASE == 0) {
+        if (PHASE == 0 && !PRESORTED) {
             if (cnt <= VOX_SORT) {
                 int P2 = 1; while (P2 < cnt) P2 <<= 1;
                 for (int t = threadIdx.x; t < P2; t += blockDim.x) sidx[t] = (t < cnt) ? grouped[b + t] : 0x7fffffff;
@@ -1483,12 +1571,21 @@ void launch_preprocess(osep_rosa_impl* h, int n) {
     k_vox_collect<<<div_up(d.T, NT), NT, 0, s>>>(d.st, d.vtab, d.T, d.vkeys, d.Mcap);
     int P2 = 1; while (P2 < d.Mcap) P2 <<= 1;
     k_vox_sortkeys<<<1, 1024, sizeof(unsigned) * P2, s>>>(d.st, d.vkeys, d.Mcap, d.vox_cnt);
-    k_vox_assign<<<nb, NT, 0, s>>>(d.P, d.st, d.vkeys, d.rk0, d.rv0, d.vox_cnt);
-    k_scan_counts<<<1, 1024, 0, s>>>(d.st, d.vox_cnt, 0);
-    // group by voxel with atomics, then fix the order inside every voxel in the reduce kernel (no global sort)
-    cudaMemsetAsync(d.vox_fill, 0, sizeof(int) * (d.Mcap + 2), s);
-    k_vox_scatter<<<nb, NT, 0, s>>>(d.st, d.rk0, d.vox_cnt, d.vox_fill, d.rv0);
-    k_vox_reduce<0><<<1024, 256, 0, s>>>(d.st, d.rv0, d.rv1, d.vox_cnt, d.P, d.Nrm, d.pts, d.nrms, d.pset, d.vset, d.nraw, d.vnd, d.vset_it);
+    if (d.blk_hist) {
+        // stable partition by voxel: the reduce kernel finds every voxel's points in ascending index, nothing to sort
+        k_vox_assign_ranked<<<nb, NT, sizeof(int) * d.Mcap, s>>>(d.P, d.st, d.vkeys, d.rk0, (int*)d.rk1, d.blk_hist, d.Mcap);
+        k_vox_blockscan<<<div_up(d.Mcap + 1, 32), 1024, 0, s>>>(d.st, d.blk_hist, d.Mcap, d.vox_cnt);
+        k_scan_counts<<<1, 1024, 0, s>>>(d.st, d.vox_cnt, 0);
+        k_vox_scatter_ranked<<<nb, NT, 0, s>>>(d.st, d.rk0, (const int*)d.rk1, d.vox_cnt, d.blk_hist, d.Mcap, d.rv0);
+        k_vox_reduce<0, true><<<1024, 256, 0, s>>>(d.st, d.rv0, d.rv1, d.vox_cnt, d.P, d.Nrm, d.pts, d.nrms, d.pset, d.vset, d.nraw, d.vnd, d.vset_it);
+    } else {
+        k_vox_assign<<<nb, NT, 0, s>>>(d.P, d.st, d.vkeys, d.rk0, d.rv0, d.vox_cnt);
+        k_scan_counts<<<1, 1024, 0, s>>>(d.st, d.vox_cnt, 0);
+        // large arenas (maps): group by voxel with atomics, then fix the order inside every voxel in the reduce kernel (no global sort)
+        cudaMemsetAsync(d.vox_fill, 0, sizeof(int) * (d.Mcap + 2), s);
+        k_vox_scatter<<<nb, NT, 0, s>>>(d.st, d.rk0, d.vox_cnt, d.vox_fill, d.rv0);
+        k_vox_reduce<0><<<1024, 256, 0, s>>>(d.st, d.rv0, d.rv1, d.vox_cnt, d.P, d.Nrm, d.pts, d.nrms, d.pset, d.vset, d.nraw, d.vnd, d.vset_it);
+    }
     if (h->overlap) cudaEventRecord(h->ev_pts, s);                         // the downsampled positions exist: surf kNN + schedule may start (stream3, launch_mscale)
     if (h->overlap) cudaStreamWaitEvent(s, h->ev_join[0], 0);              // phase 1 of the reduce is the first consumer of the normals
     k_vox_reduce<1><<<1024, 256, 0, s>>>(d.st, d.rv0, d.rv1, d.vox_cnt, d.P, d.Nrm, d.pts, d.nrms, d.pset, d.vset, d.nraw, d.vnd, d.vset_it);

@@ -36,6 +36,7 @@ struct RosaDev {
     unsigned* vkeys = nullptr;         // distinct voxel keys, sorted
     int* vid = nullptr;                // voxel id per filtered point
     int* vox_cnt = nullptr; int* vox_off = nullptr; int* vox_fill = nullptr;
+    int* blk_hist = nullptr;          // [block of 256 points][voxel] counts / prefixes of the stable partition by voxel (nullptr: arena too large, atomic scatter + per-voxel sort)
     unsigned* rk0 = nullptr; unsigned* rk1 = nullptr; int* rv0 = nullptr; int* rv1 = nullptr;
     // M-scale
     float4* pts = nullptr; float4* nrms = nullptr;
