@@ -61,7 +61,7 @@ struct TailArgs {
 };
 constexpr int TAIL_THREADS = 512;
 constexpr unsigned TAIL_ARENA = 96 * 1024;
-__global__ void __launch_bounds__(TAIL_THREADS) k_frame_tail(const __grid_constant__ TailArgs a) {
+__global__ void __launch_bounds__(TAIL_THREADS, 1) k_frame_tail(const __grid_constant__ TailArgs a) {
     extern __shared__ uint4 tail_smem[];
     unsigned char* arena = reinterpret_cast<unsigned char*>(tail_smem);
     auto stamp = [&](int k) { if (a.dbg && threadIdx.x == 0) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.dbg[k] = t; } };

@@ -348,18 +348,25 @@ static __device__ void graph_mst_block(const float4* pos, int G, const int* acc,
     unsigned long long* keys = (P2t <= skeys_cap) ? skeys : gkeys;
     int* work = (3 * G <= swork_cap) ? swork : gwork;
     int* comp = work; int* parent = work + G; int* best = work + 2 * G;
-    // one thread per (vertex, accepted slot)
-    for (int e = threadIdx.x; e < G * GACC; e += blockDim.x) {
-        const int i = e / GACC, t = e - i * GACC;
-        if (t >= acc_cnt[i]) continue;
-        const int nb = acc[e];
-        const int u = min(i, nb), v = max(i, nb);
-        if (u == v) continue;
-        const float4 pu = pos[u], pv = pos[v];
-        // weight = (ver_i - ver_nb).norm() with i = u (the smaller index owns the edge in gskel.cpp:252-263)
-        const float w = norm3(sub3(f3{pu.x, pu.y, pu.z}, f3{pv.x, pv.y, pv.z}));
-        const int slot = atomicAdd(&s_n, 1);
-        if (slot < keycap) keys[slot] = ((unsigned long long)__float_as_uint(w) << 32) | ((unsigned long long)u << 16) | (unsigned long long)v;
+    // one thread per (vertex, accepted slot); a warp reserves its key slots with one shared-memory atomic
+    for (int e0 = 0; e0 < G * GACC; e0 += blockDim.x) {
+        const int e = e0 + threadIdx.x;
+        bool have = false; int u = 0, v = 0;
+        if (e < G * GACC) {
+            const int i = e / GACC, t = e - i * GACC;
+            if (t < acc_cnt[i]) { const int nb = acc[e]; u = min(i, nb); v = max(i, nb); have = u != v; }
+        }
+        const unsigned hm = __ballot_sync(TAIL_FULL, have);
+        int base = 0;
+        if ((threadIdx.x & 31) == 0 && hm) base = atomicAdd(&s_n, __popc(hm));
+        base = __shfl_sync(TAIL_FULL, base, 0);
+        if (have) {
+            const float4 pu = pos[u], pv = pos[v];
+            // weight = (ver_i - ver_nb).norm() with i = u (the smaller index owns the edge in gskel.cpp:252-263)
+            const float w = norm3(sub3(f3{pu.x, pu.y, pu.z}, f3{pv.x, pv.y, pv.z}));
+            const int slot = base + __popc(hm & ((1u << (threadIdx.x & 31)) - 1u));
+            if (slot < keycap) keys[slot] = ((unsigned long long)__float_as_uint(w) << 32) | ((unsigned long long)u << 16) | (unsigned long long)v;
+        }
     }
     __syncthreads();
     stamp(0);
