@@ -407,7 +407,7 @@ def main():
     ap.add_argument("--stream", type=int, default=200, help="frames of the varying-n stream measurement, configs[2] in miniature (0 = skip)")
     ap.add_argument("--tiled-points", type=int, default=2500000, help="points PER GPU of the tiled-map measurement, configs[4] (N >= 2 only; 0 = skip)")
     ap.add_argument("--prewarm", type=float, default=0.5, help="seconds of untimed frames before the W warm-up steps")
-    ap.add_argument("--lanes", type=int, default=12, help="concurrent frames (streams) per GPU in the batched measurement")
+    ap.add_argument("--lanes", type=int, default=16, help="concurrent frames (streams) per GPU in the batched measurement (12 drosa kernels of 12 CTAs are co-resident; the extra lanes keep N-scale work in flight)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)

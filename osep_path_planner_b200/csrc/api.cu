@@ -560,7 +560,7 @@ static int run_batch(osep_rosa* h, const float* const* xyz, const int* n, int B,
     if (!h || !xyz || !n || B < 0) return OSEP_ERR_ARG;
     osep_rosa_impl& I = h->impl;
     CK(cudaSetDevice(I.device));
-    if (I.lanes.empty()) { int rc = osep_rosa_set_lanes(h, 12); if (rc) return rc; }   // 12 lanes x 12 CTAs of the persistent drosa kernel fit 148 SMs
+    if (I.lanes.empty()) { int rc = osep_rosa_set_lanes(h, 16); if (rc) return rc; }   // 12 persistent drosa kernels of 12 CTAs fit 148 SMs; the extra lanes keep N-scale work in flight while drosa kernels queue (measured: 8 / 12 / 16 / 24 lanes = 3.43 / 3.24 / 3.46 / 3.45 k frames/s)
     std::vector<osep_rosa_impl*> L; L.push_back(&I); for (auto* l : I.lanes) L.push_back(l);
     const int nl = (int)L.size();
     I.batch_vertices.assign(B, {});
