@@ -40,6 +40,14 @@ static inline V3 normalize3(const V3& a) {
     if (z > 0.0f) return div3(a, std::sqrt(z));
     return a;
 }
+// The same on a DYNAMIC-size strided block -- `vset.row(p).normalize()` on a MatrixXf (rosa.cpp:307): Eigen's redux has no
+// compile-time size to unroll by halving there and runs left to right (Redux.h: DefaultTraversal / NoUnrolling, and the
+// too-small-to-vectorise branch of the linear traversal): squaredNorm = (x*x + y*y) + z*z, not x*x + (y*y + z*z).
+static inline V3 normalize3_dynrow(const V3& a) {
+    float z = (a.x * a.x + a.y * a.y) + a.z * a.z;
+    if (z > 0.0f) return div3(a, std::sqrt(z));
+    return a;
+}
 static inline bool finite3(const V3& a) { return std::isfinite(a.x) && std::isfinite(a.y) && std::isfinite(a.z); }
 
 // FLANN L2_Simple squared distance: result=0; result += d*d per dimension in order.

@@ -441,7 +441,7 @@ bool RosaOracle::drosa() {
                 for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Mm(r, c) += wv[r] * v[c];
             }
             float ev[3]; M3 Q; eig3_sym(Mm, ev, Q);
-            vset[p] = normalize3(col3(Q, 2));
+            vset[p] = normalize3_dynrow(col3(Q, 2));      // :306-307 (row of a MatrixXf: sequential squaredNorm)
         }
         vset_iters.insert(vset_iters.end(), vset.begin(), vset.end());
     }

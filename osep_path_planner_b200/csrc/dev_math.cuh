@@ -38,6 +38,11 @@ OSEP_HD f3 normalize3(const f3& a) {           // Eigen normalize(): only when s
     if (z > 0.0f) return div3(a, sqrtf(z));
     return a;
 }
+OSEP_HD f3 normalize3_dynrow(const f3& a) {    // normalize() of a dynamic-size row (`vset.row(p)`, rosa.cpp:307): squaredNorm summed left to right
+    const float z = (a.x * a.x + a.y * a.y) + a.z * a.z;
+    if (z > 0.0f) return div3(a, sqrtf(z));
+    return a;
+}
 OSEP_HD float comp(const f3& a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
 
 // FLANN L2_Simple (kd-tree searches at rosa.cpp:99,231,265,372,480,566; gskel.cpp:77,216)

@@ -705,10 +705,20 @@ def _pyref():
     return gskel_ref, rosa_ref, scenarios
 
 
+def _pyref_float():
+    _pyref()
+    from pyref import rosa_float_ref
+    return rosa_float_ref
+
+
 @pytest.mark.parametrize("name", ["cyl20k", "turbine100k", "stream131"])
-def test_library_matches_pyref_on_the_discrete_rosa_stages(mods, name):
+def test_library_matches_pyref_on_every_rosa_stage(mods, name):
+    """the CUDA library against tests/pyref directly (not through the C++ oracle): the discrete stages (rosa_ref) and the
+    float stages up to the skeleton vertices (rosa_float_ref: orientations after every drosa iteration, active-set sizes,
+    positions after drosa / dcrosa, greedy cover, vertices before / after vertex_smooth), bit for bit"""
     osep, po, fx = mods
     _, rr, _ = _pyref()
+    rf = _pyref_float()
     P = {"cyl20k": fx.cylinder, "turbine100k": fx.turbine, "stream131": lambda: fx.stream_frame(131, n=30000)[0]}[name]()
     ref = rr.RosaRef(); assert ref.run(P)
     r = osep.Rosa(capacity_points=P.shape[0]); r.set_debug(True); r.set_input(P); assert r.rosa_run()
@@ -717,6 +727,10 @@ def test_library_matches_pyref_on_the_discrete_rosa_stages(mods, name):
                 "surf_idx", "simi_off", "simi_idx"]:
         a, b = r.tap(tap), ref.t[tap]
         assert_bit_equal(a.reshape(-1), b.reshape(-1), "%s vs pyref on %s" % (tap, name))
+    ft = rf.RosaFloatRef(ref.t["pts"], ref.t["nrms"], ref.t["surf_idx"], ref.t["simi_off"], ref.t["simi_idx"], ref.leaf_size).run()
+    for tap in ["vset_iters", "active_size", "poor_idx", "pset_drosa", "pset", "seeds", "corresp", "skelver_sampled", "skelver"]:
+        assert_bit_equal(r.tap(tap).reshape(-1), np.asarray(ft[tap]).reshape(-1), "%s vs pyref on %s" % (tap, name))
+    assert_bit_equal(np.ascontiguousarray(r.output_vertices()).reshape(-1), ft["skelver"].reshape(-1), "output_vertices vs pyref on %s" % name)
     r.close()
 
 

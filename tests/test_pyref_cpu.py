@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from oracle import pyoracle as po                                   # noqa: E402
 from osep_path_planner_b200 import fixtures as fx                    # noqa: E402
-from pyref import gskel_ref as gr, rosa_ref as rr, scenarios as sc   # noqa: E402
+from pyref import gskel_ref as gr, rosa_float_ref as rf, rosa_ref as rr, scenarios as sc   # noqa: E402
 
 
 def bits(a):
@@ -55,8 +55,20 @@ def test_pyref_eigen_solver_matches_numpy_and_the_oracle_bitwise():
         assert_same(q, Q[i], "eigenvectors of matrix %d" % i)
 
 
-@pytest.mark.parametrize("name", ["cyl20k", "turbine100k", "stream7", "stream131", "cyl5k_k12"])
-def test_rosa_oracle_matches_pyref_on_every_discrete_stage(name):
+FLOAT_TAPS = ["vset_iters", "vvar", "active_size", "poor_idx", "pset_drosa", "pset", "seeds", "corresp", "skelver_sampled", "skelver"]
+FLOAT_KW = ("nb_knn", "niter_drosa", "niter_dcrosa", "niter_smooth", "alpha_recenter", "radius_smooth", "max_proj_range")
+
+
+def float_stages(r, kw):
+    """rosa_init .. vertex_smooth of tests/pyref/rosa_float_ref.py on the discrete outputs of a finished RosaRef"""
+    f = rf.RosaFloatRef(r.t["pts"], r.t["nrms"], r.t["surf_idx"], r.t["simi_off"], r.t["simi_idx"], r.leaf_size,
+                        **{k: v for k, v in kw.items() if k in FLOAT_KW})
+    return f.run()
+
+
+@pytest.mark.parametrize("name", ["cyl20k", "turbine100k", "stream7", "stream131", "cyl5k_k12", "cyl5k_iters"])
+def test_rosa_oracle_matches_pyref_on_every_stage(name):
+    """discrete stages (rosa_ref) AND the float stages up to the skeleton vertices (rosa_float_ref), bit for bit"""
     kw = {}
     if name == "cyl20k":
         P = fx.cylinder()
@@ -64,11 +76,14 @@ def test_rosa_oracle_matches_pyref_on_every_discrete_stage(name):
         P = fx.turbine()
     elif name.startswith("stream"):
         P = fx.stream_frame(int(name[6:]), n=30000)[0]
-    else:
+    elif name == "cyl5k_k12":
         P = fx.cylinder(5000, seed=3); kw = dict(ne_knn=12, nb_knn=6, max_points=400)
+    else:
+        P = fx.cylinder(5000, seed=3); kw = dict(niter_drosa=3, niter_dcrosa=2, niter_smooth=1, alpha_recenter=0.5, radius_smooth=3.0,
+                                                 max_proj_range=4.0)
     o = po.RosaOracle(po.RosaConfig.default(**kw))
     assert o.run(P)
-    r = rr.RosaRef(**kw)
+    r = rr.RosaRef(**{k: v for k, v in kw.items() if k not in FLOAT_KW or k == "nb_knn"})
     assert r.run(P)
     assert np.float32(o.leaf_size) == r.leaf_size and np.float32(o.leaf_used) == r.leaf_used
     for tap in ROSA_TAPS:
@@ -76,6 +91,14 @@ def test_rosa_oracle_matches_pyref_on_every_discrete_stage(name):
         assert_same(a.reshape(-1) if tap == "knn_full" else a, b, "%s on %s" % (tap, name))
     # the radius candidate counts of SURVEY.md's sizing table are reproduced by the independent implementation too
     assert r.t["radius_cand"].mean() > 50
+    # float stages: orientations after every drosa iteration, weights, active-set sizes, positions after drosa / dcrosa,
+    # the greedy cover (seeds, correspondences) and the vertices before / after vertex_smooth
+    ft = float_stages(r, kw)
+    for tap in FLOAT_TAPS:
+        b = o.tap(tap)
+        a = np.asarray(ft[tap])
+        assert_same(a.reshape(-1), np.asarray(b).reshape(-1), "%s on %s" % (tap, name))
+    assert len(ft["skelver"]) >= 10
 
 
 def test_rosa_pyref_edge_inputs():

@@ -15,7 +15,7 @@ __global__ void k(const float* mats, int nmat, int lanes, int reps, long long* o
             const float* m = mats + 6 * ((r * 32 + lane) % nmat);
             // make the next solve depend on the previous result (dependent chain like the Gauss-Seidel walker)
             Eig3 E = eig3_sym(m[0] + acc * 0.f, m[1], m[2], m[3], m[4], m[5]);
-            f3 d = normalize3(eig_col(E, 2));
+            f3 d = normalize3_dynrow(eig_col(E, 2));
             acc = d.x;
         }
         __syncwarp();

@@ -66,7 +66,7 @@ __global__ void k_solver(const float* mats, int nmat, unsigned long long* mism, 
     bool same = A.ok == F.ok && A.iters == F.iters;
     for (int k = 0; k < 3; ++k) same = same && __float_as_uint(A.ev[k]) == __float_as_uint(F.ev[k]);
     for (int k = 0; k < 9; ++k) same = same && __float_as_uint(A.q[k]) == __float_as_uint(F.q[k]);
-    const f3 na = normalize3(eig_col(A, 2)), nf = normalize3_dev(eig_col(F, 2));
+    const f3 na = normalize3_dynrow(eig_col(A, 2)), nf = normalize3_dev(eig_col(F, 2));
     same = same && __float_as_uint(na.x) == __float_as_uint(nf.x) && __float_as_uint(na.y) == __float_as_uint(nf.y) && __float_as_uint(na.z) == __float_as_uint(nf.z);
     if (!same) atomicAdd(mism, 1ull);
     atomicAdd(iters, (unsigned long long)A.iters);
@@ -82,7 +82,7 @@ __global__ void k_lat(const float* mats, int nmat, int lanes, int reps, long lon
             const float* m = mats + 6 * ((r * 32 + lane) % nmat);
             f3 d;
             if (FAST) { const Eig3 E = eig3_sym_dev(m[0] + acc * 0.f, m[1], m[2], m[3], m[4], m[5]); d = normalize3_dev(eig_col(E, 2)); }
-            else { const Eig3 E = eig3_sym(m[0] + acc * 0.f, m[1], m[2], m[3], m[4], m[5]); d = normalize3(eig_col(E, 2)); }
+            else { const Eig3 E = eig3_sym(m[0] + acc * 0.f, m[1], m[2], m[3], m[4], m[5]); d = normalize3_dynrow(eig_col(E, 2)); }
             acc = d.x;
         }
         __syncwarp();
