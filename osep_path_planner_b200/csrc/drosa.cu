@@ -15,6 +15,7 @@
 // walker over a modelled schedule, six chains as overlapping wavefronts; k_drosa_smooth2: the
 // level-synchronous fallback).
 #include "rosa_impl.cuh"
+#include <type_traits>
 
 namespace osep {
 
@@ -92,7 +93,11 @@ __device__ __forceinline__ SeedCtx seed_stage(uint4* smem, const float4* __restr
     SeedCtx c;
     c.pts_s = smem_addr(s_pts); c.nraw_s = smem_addr(s_nraw); c.vnd_s = smem_addr(s_vnd);
     c.bits_s = mat_in ? smem_addr(s_bits) : 0u; c.Wp = Wp;
-    c.list_s = smem_addr(s_bits + (size_t)M * Wp) + (unsigned)(threadIdx.x >> 5) * (unsigned)((2 * M + 15) & ~15);
+    // one member list per warp: behind the staged matrix, or right behind the per-point arrays when the matrix stays in
+    // global memory (0 = no room for lists either: the per-member loop over global rows)
+    const size_t list_bytes = (size_t)SEED_WARPS * (((size_t)2 * M + 15) & ~(size_t)15);
+    const bool list_in = mat_in || seed_small_bytes(M) + list_bytes <= (size_t)budget;
+    c.list_s = list_in ? smem_addr(s_bits + (mat_in ? (size_t)M * Wp : 0)) + (unsigned)(threadIdx.x >> 5) * (unsigned)((2 * M + 15) & ~15) : 0u;
     c.bits = bits; c.bstride = Wp;
     c.M = M; c.Wn = Wn; c.leaf = leaf;
     return c;
@@ -127,57 +132,69 @@ __device__ __forceinline__ int active_set(const SeedCtx& c, int seed, const f3& 
         seed_in |= (vis[k] != 0u);
     }
     if (!__any_sync(FULLM, seed_in)) return 0;                                              // rosa.cpp:664
-    if (c.bits_s) {
-        // staged matrix: the frontier is listed in shared memory (warp scan of the per-lane popcounts), then LPR lanes
-        // read one member's row with 16-byte loads -- 32 / LPR independent rows per round of loads instead of one
-        // dependent ffs -> address -> load -> or chain per member
+    if (c.list_s) {
+        // the frontier is listed in shared memory (warp scan of the per-lane popcounts), then LPR lanes read one member's
+        // row with 16-byte loads -- 32 / LPR independent rows per round of loads instead of one dependent
+        // ffs -> address -> load -> or chain per member.  Rows come from the staged matrix, or -- when it does not fit
+        // (M > ~1100: frames whose leaf loop did not converge) -- from global memory through the same loop with twice the
+        // loads in flight (an L2 round trip per row: serialised per member it made these tasks 44 us instead of 6)
         constexpr int LPR = 8 * WPL;                      // lanes per row: 4 * LPR words >= 32 * WPL >= Wn
         const int g = lane / LPR, ch = lane % LPR;
         const bool chv = 4 * ch < c.Wp;
-        const unsigned rowb = c.bits_s + 16u * (unsigned)ch;
-        const unsigned rstride = 4u * (unsigned)c.Wp;
         int f = 1;                                        // members in the list
         if (seed_in) sts_u16v(c.list_s, (unsigned)seed);
         __syncwarp();
-        while (true) {
-            uint4 a4 = make_uint4(0u, 0u, 0u, 0u);
-            if (chv) {
-#pragma unroll 4
-                for (int i = g; i < f; i += 32 / LPR) {
-                    const unsigned mb = lds_u16v(c.list_s + 2u * (unsigned)i);
-                    const uint4 r4 = lds_u4(rowb + mb * rstride);
-                    a4.x |= r4.x; a4.y |= r4.y; a4.z |= r4.z; a4.w |= r4.w;
+        auto bfs = [&](auto load_row, auto unr) {
+            constexpr int UNR = decltype(unr)::value;
+            while (true) {
+                uint4 a4 = make_uint4(0u, 0u, 0u, 0u);
+                if (chv) {
+#pragma unroll UNR
+                    for (int i = g; i < f; i += 32 / LPR) {
+                        const unsigned mb = lds_u16v(c.list_s + 2u * (unsigned)i);
+                        const uint4 r4 = load_row(mb);
+                        a4.x |= r4.x; a4.y |= r4.y; a4.z |= r4.z; a4.w |= r4.w;
+                    }
                 }
-            }
 #pragma unroll
-            for (int off = LPR; off < 32; off <<= 1) {
-                a4.x |= __shfl_xor_sync(FULLM, a4.x, off); a4.y |= __shfl_xor_sync(FULLM, a4.y, off);
-                a4.z |= __shfl_xor_sync(FULLM, a4.z, off); a4.w |= __shfl_xor_sync(FULLM, a4.w, off);
-            }
-            bool any = false; int cnt = 0;
+                for (int off = LPR; off < 32; off <<= 1) {
+                    a4.x |= __shfl_xor_sync(FULLM, a4.x, off); a4.y |= __shfl_xor_sync(FULLM, a4.y, off);
+                    a4.z |= __shfl_xor_sync(FULLM, a4.z, off); a4.w |= __shfl_xor_sync(FULLM, a4.w, off);
+                }
+                bool any = false; int cnt = 0;
 #pragma unroll
-            for (int k = 0; k < WPL; ++k) {
-                const int src = (lane + 32 * k) >> 2;     // lane `src` of group 0 holds chunk src = words 4 src .. 4 src + 3
-                const unsigned x = __shfl_sync(FULLM, a4.x, src), y = __shfl_sync(FULLM, a4.y, src);
-                const unsigned z = __shfl_sync(FULLM, a4.z, src), w = __shfl_sync(FULLM, a4.w, src);
-                const unsigned acc = (lane & 2) ? ((lane & 1) ? w : z) : ((lane & 1) ? y : x);
-                const unsigned nw = acc & slab[k] & ~vis[k];
-                vis[k] |= nw; front[k] = nw; any |= (nw != 0u); cnt += __popc(nw);
-            }
-            if (!__any_sync(FULLM, any)) break;
-            // list the new frontier
-            int incl = cnt;
+                for (int k = 0; k < WPL; ++k) {
+                    const int src = (lane + 32 * k) >> 2;     // lane `src` of group 0 holds chunk src = words 4 src .. 4 src + 3
+                    const unsigned x = __shfl_sync(FULLM, a4.x, src), y = __shfl_sync(FULLM, a4.y, src);
+                    const unsigned z = __shfl_sync(FULLM, a4.z, src), w = __shfl_sync(FULLM, a4.w, src);
+                    const unsigned acc = (lane & 2) ? ((lane & 1) ? w : z) : ((lane & 1) ? y : x);
+                    const unsigned nw = acc & slab[k] & ~vis[k];
+                    vis[k] |= nw; front[k] = nw; any |= (nw != 0u); cnt += __popc(nw);
+                }
+                if (!__any_sync(FULLM, any)) break;
+                // list the new frontier
+                int incl = cnt;
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(FULLM, incl, off); if (lane >= off) incl += t; }
-            f = __shfl_sync(FULLM, incl, 31);
-            unsigned pos = c.list_s + 2u * (unsigned)(incl - cnt);
+                for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(FULLM, incl, off); if (lane >= off) incl += t; }
+                f = __shfl_sync(FULLM, incl, 31);
+                unsigned pos = c.list_s + 2u * (unsigned)(incl - cnt);
 #pragma unroll
-            for (int k = 0; k < WPL; ++k) {
-                unsigned b = front[k];
-                const unsigned base = (unsigned)(lane + 32 * k) * 32u;
-                while (b) { sts_u16v(pos, base + (unsigned)(__ffs(b) - 1)); b &= b - 1; pos += 2u; }
+                for (int k = 0; k < WPL; ++k) {
+                    unsigned b = front[k];
+                    const unsigned base = (unsigned)(lane + 32 * k) * 32u;
+                    while (b) { sts_u16v(pos, base + (unsigned)(__ffs(b) - 1)); b &= b - 1; pos += 2u; }
+                }
+                __syncwarp();
             }
-            __syncwarp();
+        };
+        if (c.bits_s) {
+            const unsigned rowb = c.bits_s + 16u * (unsigned)ch;
+            const unsigned rstride = 4u * (unsigned)c.Wp;
+            bfs([&](unsigned mb) { return lds_u4(rowb + mb * rstride); }, std::integral_constant<int, 4>{});
+        } else {
+            const uint4* grow = reinterpret_cast<const uint4*>(c.bits) + ch;      // rows are 16-byte aligned: bstride = Wp, a multiple of 4 words
+            const unsigned gstride = (unsigned)c.bstride >> 2;
+            bfs([&](unsigned mb) { return __ldg(grow + (size_t)mb * gstride); }, std::integral_constant<int, 8>{});
         }
     } else {
         while (true) {

@@ -524,6 +524,29 @@ def test_fused_and_unfused_drosa_agree(mods):
     assert_bit_equal(outs[0][2], o.tap("skelver"), "vertices vs oracle")
 
 
+@pytest.mark.parametrize("case", ["forced_small_budget", "stream840_unconverged", "stream840_unconverged_unfused"])
+def test_bit_matrix_in_global_memory_path_is_bit_exact(mods, monkeypatch, case):
+    """Frames whose leaf loop does not converge keep M ~ 1200-1300 points: the M x M/32 similarity bit matrix then no longer
+    fits the seed warps' shared memory and the active-set search reads its rows from global memory (list-driven, 16-byte
+    row loads).  Forced on ordinary clouds by a small shared-memory budget, and reached naturally by a frame of the 50k-point
+    stream (fused kernel and per-iteration kernels); every tap equals the oracle's."""
+    osep, po, fx = mods
+    if case.startswith("forced"):
+        monkeypatch.setenv("OSEP_FUSED_SMEM_KB", "100")
+        clouds = [fx.turbine(60000, seed=9), fx.cylinder(5000, seed=3)]
+    else:
+        if case.endswith("unfused"):
+            monkeypatch.setenv("OSEP_DROSA_UNFUSED", "1")
+        clouds = [fx.stream_frame(840, n=50000, n_frames=1000)[0]]
+    for P in clouds:
+        o, ok_o, r, ok_g = run_both(mods, P, debug=True)
+        assert ok_o and ok_g
+        if not case.startswith("forced"):
+            assert r.result.n_downsampled > 1150, "this frame is here because its bit matrix does not fit (M = %d)" % r.result.n_downsampled
+        check_all_taps(o, r)
+        r.close()
+
+
 def _weird_clouds(fx):
     rng = np.random.default_rng(77)
     out = {}

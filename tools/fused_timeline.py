@@ -8,7 +8,7 @@ import numpy as np, ctypes as C
 import osep_path_planner_b200 as osep
 from osep_path_planner_b200 import fixtures as fx
 
-P = fx.turbine()
+P = fx.turbine() if len(sys.argv) < 2 else fx.stream_frame(int(sys.argv[1]), n=50000, n_frames=1000)[0]
 r = osep.Rosa(capacity_points=P.shape[0]); r.set_profile(True)
 r.set_input(P)
 for k in range(3):
