@@ -110,17 +110,25 @@ __device__ __forceinline__ int active_set(const SeedCtx& c, int seed, const f3& 
     unsigned slab[WPL], front[WPL];
 #pragma unroll
     for (int k = 0; k < WPL; ++k) slab[k] = 0u;
-    for (int t = 0; t < c.Wn; ++t) {
-        const int i = t * 32 + lane;
-        bool in = false;
-        if (i < c.M) {
-            const float4 q = seed_pt(c, i);
-            const float d = n.x * (p.x - q.x) + n.y * (p.y - q.y) + n.z * (p.z - q.z);      // rosa.cpp:660
-            in = fabsf(d) < c.leaf;
-        }
-        const unsigned word = __ballot_sync(FULLM, in);
+    // four words per round: the four loads are issued back to back, then the four slab tests, then the four votes (one
+    // word at a time the loop was a chain of load -> 8 dependent FP operations -> vote per word)
+    for (int t0 = 0; t0 < c.Wn; t0 += 4) {
+        float4 q[4];
 #pragma unroll
-        for (int k = 0; k < WPL; ++k) if (t == lane + 32 * k) slab[k] = word;
+        for (int u = 0; u < 4; ++u) { const int i = (t0 + u) * 32 + lane; q[u] = seed_pt(c, i < c.M ? i : 0); }
+        bool in[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float d = n.x * (p.x - q[u].x) + n.y * (p.y - q[u].y) + n.z * (p.z - q[u].z);      // rosa.cpp:660
+            in[u] = ((t0 + u) * 32 + lane < c.M) && (fabsf(d) < c.leaf);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned word = __ballot_sync(FULLM, in[u]);
+            const int t = t0 + u;
+#pragma unroll
+            for (int k = 0; k < WPL; ++k) if (t == lane + 32 * k) slab[k] = word;
+        }
     }
     if (tl && lane == 0) tl[7] = gtime();
     const int sw = seed >> 5; const unsigned sbit = 1u << (seed & 31);
@@ -148,12 +156,25 @@ __device__ __forceinline__ int active_set(const SeedCtx& c, int seed, const f3& 
             constexpr int UNR = decltype(unr)::value;
             while (true) {
                 uint4 a4 = make_uint4(0u, 0u, 0u, 0u);
-                if (chv) {
+                if (chv && UNR <= 4) {
+                    // staged rows: short lists are the common case, one entry -> row pair per step
 #pragma unroll UNR
                     for (int i = g; i < f; i += 32 / LPR) {
                         const unsigned mb = lds_u16v(c.list_s + 2u * (unsigned)i);
                         const uint4 r4 = load_row(mb);
                         a4.x |= r4.x; a4.y |= r4.y; a4.z |= r4.z; a4.w |= r4.w;
+                    }
+                } else if (chv) {
+                    // rows in global memory: UNR members per round, their list entries read back to back, then their rows
+                    // (the list loads are volatile asm statements and keep their order: entry -> row -> entry -> row would
+                    // expose the latency of every entry in front of an L2 round trip).  Positions past the end repeat the
+                    // last member: OR-ing a row twice changes nothing
+                    for (int i = g; i < f; i += UNR * (32 / LPR)) {
+                        unsigned mb[UNR];
+#pragma unroll
+                        for (int u = 0; u < UNR; ++u) { const int j = i + u * (32 / LPR); mb[u] = lds_u16v(c.list_s + 2u * (unsigned)(j < f ? j : f - 1)); }
+#pragma unroll
+                        for (int u = 0; u < UNR; ++u) { const uint4 r4 = load_row(mb[u]); a4.x |= r4.x; a4.y |= r4.y; a4.z |= r4.z; a4.w |= r4.w; }
                     }
                 }
 #pragma unroll
