@@ -11,7 +11,7 @@ for k in range(3):
     r.rosa_run()
 buf = np.zeros(128, np.int64)
 n = r._L.osep_rosa_get(r._h, b"fused_dbg", buf.ctypes.data_as(C.c_void_p), buf.nbytes)
-d = buf.reshape(8, 8)
+d = buf[:64].reshape(8, 8)
 t0 = d[:6, 0].min()
 for it in range(6):
     b, f, e, steps, spins, M = d[it, :6]
