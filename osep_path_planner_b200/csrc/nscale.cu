@@ -542,55 +542,125 @@ __device__ __forceinline__ float block_bound(const FrameState* st, float rx, flo
     return bound - 1e-3f * h;
 }
 
-// R5 slow path: one thread per query, exact kNN by ring expansion (R = 1, 2, 3, then everything) with a
-// register-resident sorted top-K.  Handles whatever the cell-cooperative kernel below could not certify.
+// R5 slow path: one WARP per query, exact kNN by ring expansion (R = 1, 2, 3, 4, 6, 8, 12, ...), then everything.
+// Handles whatever the cell-cooperative kernels could not certify: points whose k nearest neighbours lie many cells away
+// (the sparse far end of a LiDAR frame; beyond a block of n / 32 cells the lanes stride over the whole cloud instead).  The lanes probe the cells of the NEW SHELL of a ring in parallel (the block
+// scanned so far is not rescanned) and push the points they find into a register-resident sorted top-K of their own; the 32
+// lists are then merged into the frame's (d2, index) order by k rounds of a warp arg-min over the list heads, which gives
+// the k-th distance for the certification test and re-seeds the lists.  One thread per query (the first version) walked
+// 15 k cells with a dependent hash probe each for such a point: 1.9 ms for 323 queries of a 42 k-point frame.
 template <int K>
 __global__ void __launch_bounds__(128) k_knn_exact(const float4* __restrict__ Pc, const FrameState* __restrict__ st,
                                                    const unsigned long long* __restrict__ gtab, const int* __restrict__ g_cnt,
                                                    const int* __restrict__ g_start, unsigned mask,
                                                    int* __restrict__ knn_idx, int k_req, const int* __restrict__ slow_list) {
     if (st->status != 0) return;
+    constexpr int RS = (K + 31) / 32;                // merged entries per lane: entry r lives in lane r & 31, slot r >> 5
     const int n = st->n_filt;
     const int nwork = st->n_slow;
-    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < nwork; w += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int k_eff = min(k_req, n);
+    const float finf = __int_as_float(0x7f800000);
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nwork; w += warps) {
         const int t = slow_list[w];
         const float4 q = Pc[t];
         const int qi = __float_as_int(q.w);
-        const int k_eff = min(k_req, n);
         const int dimx = st->g_dim[0], dimy = st->g_dim[1], dimz = st->g_dim[2];
         int cx, cy, cz; cell_of(st, q.x, q.y, q.z, cx, cy, cz);
         const float rx = q.x - st->bmin[0], ry = q.y - st->bmin[1], rz = q.z - st->bmin[2];
-        TopK<K> tk;
-        // rings R = 1, 2, 3, 4, 6, 8, 12, 16, ... while scanning the (2R+1)^3 block is cheaper than scanning every point
-        // (isolated points of a large map must not cost O(N) each as long as a moderate block certifies them)
+        TopK<K> tk; tk.init();
+        float resd[RS]; int resi[RS];
+        // merge the 32 per-lane lists: the k_eff smallest (d2, index) pairs, entry r to lane r & 31; returns the k-th pair
+        auto merge = [&](float& wd, int& wi) {
+#pragma unroll
+            for (int u = 0; u < RS; ++u) { resd[u] = finf; resi[u] = 0x7fffffff; }
+            for (int r = 0; r < k_eff; ++r) {
+                float bd = tk.d[0]; int bi = tk.id[0]; int bl = lane;
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const float od = __shfl_xor_sync(0xffffffffu, bd, off); const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                    const int ol = __shfl_xor_sync(0xffffffffu, bl, off);
+                    if (nb_less(od, oi, bd, bi)) { bd = od; bi = oi; bl = ol; }
+                }
+                if (bl == lane && bi == tk.id[0]) {       // this lane's head won: pop it
+#pragma unroll
+                    for (int u = 0; u < K - 1; ++u) { tk.d[u] = tk.d[u + 1]; tk.id[u] = tk.id[u + 1]; }
+                    tk.d[K - 1] = finf; tk.id[K - 1] = 0x7fffffff;
+                }
+#pragma unroll
+                for (int u = 0; u < RS; ++u) if ((r >> 5) == u && (r & 31) == lane) { resd[u] = bd; resi[u] = bi; }
+            }
+            const int kl = (k_eff - 1) & 31, ks = (k_eff - 1) >> 5;
+            float md = finf; int mi = 0x7fffffff;
+#pragma unroll
+            for (int u = 0; u < RS; ++u) if (u == ks) { md = resd[u]; mi = resi[u]; }
+            wd = __shfl_sync(0xffffffffu, md, kl); wi = __shfl_sync(0xffffffffu, mi, kl);
+            tk.init();                                     // the merged list is the state carried into the next ring
+#pragma unroll
+            for (int u = 0; u < RS; ++u) if (resi[u] != 0x7fffffff) tk.push(resd[u], resi[u]);
+        };
+        int ox0 = 1, ox1 = 0, oy0 = 1, oy1 = 0, oz0 = 1, oz1 = 0;      // block scanned so far (empty)
+        // the k-th pair found so far bounds the answer: candidates beyond it are dropped before they reach a list (once a
+        // ring has found k points almost every later candidate is; without it every lane's list, re-seeded with <= 2
+        // entries, took every candidate through the insertion network)
+        float wd = finf; int wi = 0x7fffffff;
         for (int R = 1;; R = (R < 4) ? R + 1 : R + (R >> 1)) {
-            tk.init();
             const long long side = 2ll * R + 1;
-            if (R > 3 && side * side * side > (long long)n / 4) {
-                for (int e = 0; e < n; ++e) { const float4 c = Pc[e]; tk.push(dist2(q.x, q.y, q.z, c.x, c.y, c.z), __float_as_int(c.w)); }
+            if (R > 3 && side * side * side > (long long)n / 32) {
+                // the block would cost more than every point: lanes stride over the cloud
+                tk.init();
+                for (int e0 = lane; e0 < n; e0 += 32 * 8) {              // eight independent loads in flight per lane
+                    float4 c8[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { const int e = e0 + 32 * u; c8[u] = Pc[e < n ? e : e0]; }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float dd = dist2(q.x, q.y, q.z, c8[u].x, c8[u].y, c8[u].z); const int ii = __float_as_int(c8[u].w);
+                        if (e0 + 32 * u < n && !nb_less(wd, wi, dd, ii)) tk.push(dd, ii);
+                    }
+                }
+                merge(wd, wi);
                 break;
             }
             const int x0 = max(cx - R, 0), x1 = min(cx + R, dimx - 1);
             const int y0 = max(cy - R, 0), y1 = min(cy + R, dimy - 1);
             const int z0 = max(cz - R, 0), z1 = min(cz + R, dimz - 1);
-            for (int z = z0; z <= z1; ++z) for (int y = y0; y <= y1; ++y) for (int x = x0; x <= x1; ++x) {
-                const unsigned long long key1 = cell_key1(x, y, z);
-                unsigned s = cell_slot(x, y, z, mask);
-                unsigned long long cur;
-                while ((cur = gtab[s]) != key1 && cur != 0ull) s = (s + 1) & mask;
-                if (cur == 0ull) continue;
-                const int b = g_start[s], c = g_cnt[s];
-                for (int e = b; e < b + c; ++e) { const float4 cc = Pc[e]; tk.push(dist2(q.x, q.y, q.z, cc.x, cc.y, cc.z), __float_as_int(cc.w)); }
+            const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, nz = z1 - z0 + 1;
+            const int total = nx * ny * nz;
+            for (int c0 = lane; c0 < total; c0 += 32 * 4) {            // four cells per lane and round: their first probes are independent loads
+                unsigned s4[4]; unsigned long long key4[4], cur4[4]; bool v4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c = c0 + 32 * u;
+                    const int x = x0 + c % nx, y = y0 + (c / nx) % ny, z = z0 + c / (nx * ny);
+                    v4[u] = c < total && !(x >= ox0 && x <= ox1 && y >= oy0 && y <= oy1 && z >= oz0 && z <= oz1);      // inside: scanned by an earlier ring
+                    key4[u] = cell_key1(x, y, z); s4[u] = cell_slot(x, y, z, mask);
+                    cur4[u] = v4[u] ? gtab[s4[u]] : 0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (!v4[u]) continue;
+                    unsigned s = s4[u]; unsigned long long cur = cur4[u];
+                    while (cur != key4[u] && cur != 0ull) { s = (s + 1) & mask; cur = gtab[s]; }
+                    if (cur == 0ull) continue;
+                    const int b = g_start[s], cn = g_cnt[s];
+#pragma unroll 4
+                    for (int e = b; e < b + cn; ++e) {
+                        const float4 cc = Pc[e];
+                        const float dd = dist2(q.x, q.y, q.z, cc.x, cc.y, cc.z); const int ii = __float_as_int(cc.w);
+                        if (!nb_less(wd, wi, dd, ii)) tk.push(dd, ii);
+                    }
+                }
             }
+            merge(wd, wi);
             if (x0 == 0 && y0 == 0 && z0 == 0 && x1 == dimx - 1 && y1 == dimy - 1 && z1 == dimz - 1) break;
             const float bound = block_bound(st, rx, ry, rz, x0, x1, y0, y1, z0, z1);
-            float wd = 0.0f; int wi = 0x7fffffff;
-#pragma unroll
-            for (int u = 0; u < K; ++u) if (u == k_eff - 1) { wd = tk.d[u]; wi = tk.id[u]; }
             if (bound > 0.0f && wi != 0x7fffffff && wd < bound * bound) break;
+            ox0 = x0; ox1 = x1; oy0 = y0; oy1 = y1; oz0 = z0; oz1 = z1;
         }
 #pragma unroll
-        for (int u = 0; u < K; ++u) if (u < k_eff) knn_idx[(size_t)qi * k_eff + u] = tk.id[u];
+        for (int u = 0; u < RS; ++u) { const int r = u * 32 + lane; if (r < k_eff) knn_idx[(size_t)qi * k_eff + r] = resi[u]; }
     }
 }
 
@@ -1441,7 +1511,7 @@ static void launch_knn(osep_rosa_impl* h, int n, int k_req, cudaStream_t s) {
                                                         d.pc_cell, d.nbr, d.over_list, &d.st->n_over, 1);
         k_knn_big<K, KNN_BIG, BIG_WARPS><<<h->sms * 4, BIG_WARPS * 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units, d.knn_full, k_req, d.slow_list, d.over_list, &d.st->n_over, 1,
                                                                               nullptr, nullptr, nullptr, nullptr, 2);
-        k_knn_exact<K><<<64, 128, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.knn_full, k_req, d.slow_list);
+        k_knn_exact<K><<<h->sms * 2, 128, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.knn_full, k_req, d.slow_list);
         k_normals<<<div_up(d.Ncap, 128), 128, 0, s>>>(d.P, d.st, d.knn_full, k_req, d.Nrm);
         return;
     }
@@ -1453,7 +1523,7 @@ static void launch_knn(osep_rosa_impl* h, int n, int k_req, cudaStream_t s) {
                                                               d.knn_full, k_req, d.slow_list, d.over_list);
     k_knn_big<K, KNN_BIG, BIG_WARPS><<<h->sms * 4, BIG_WARPS * 32, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.units, d.knn_full, k_req, d.slow_list, d.over_list, &d.st->n_over, 0,
                                                                           nullptr, nullptr, nullptr, nullptr, 1);
-    k_knn_exact<K><<<64, 128, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.knn_full, k_req, d.slow_list);
+    k_knn_exact<K><<<h->sms * 2, 128, 0, s>>>(d.Pc, d.st, d.gtab, d.g_cnt, d.g_start, mask, d.knn_full, k_req, d.slow_list);
     k_normals<<<div_up(d.Ncap, 128), 128, 0, s>>>(d.P, d.st, d.knn_full, k_req, d.Nrm);
 }
 

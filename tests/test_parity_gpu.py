@@ -547,6 +547,23 @@ def test_bit_matrix_in_global_memory_path_is_bit_exact(mods, monkeypatch, case):
         r.close()
 
 
+def test_sparse_far_points_take_the_exact_knn_path_bit_exact(mods):
+    """A frame whose last part is cut short (a stream frame truncated inside its third blade: 363 points spread over 28 m)
+    has queries whose 20 nearest neighbours lie many grid cells away: they reach k_knn_exact (warp per query, ring shells,
+    brute force beyond).  Neighbour lists, normals and everything downstream equal the oracle's; the frame stays fast."""
+    osep, po, fx = mods
+    P = fx.stream_frame(375, n=50000)[0][:42029]
+    o, ok_o, r, ok_g = run_both(mods, P, debug=True)
+    assert ok_o and ok_g
+    assert int(r.tap("knn_stats")[1]) > 100, "expected the exact path to be exercised"
+    check_all_taps(o, r)
+    r.close()
+    r = osep.Rosa(capacity_points=50000); r.set_input(P)
+    for _ in range(4): r.rosa_run()
+    assert r.result.gpu_ms < 2.0, "sparse points made the frame take %.2f ms" % r.result.gpu_ms
+    r.close()
+
+
 def _weird_clouds(fx):
     rng = np.random.default_rng(77)
     out = {}
