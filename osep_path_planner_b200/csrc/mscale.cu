@@ -61,7 +61,7 @@ __device__ __forceinline__ float similarity_metric(const f3& p1, const f3& v1, c
 template <bool FILL>
 __device__ __forceinline__ void simi_row(FrameState* st, const float4* __restrict__ pts, const float4* __restrict__ nrms,
                                          int* simi_off, int* __restrict__ simi_idx, int* __restrict__ tmp_j, float* __restrict__ tmp_d,
-                                         unsigned* __restrict__ simi_bits, int M, int W, int i, int lane) {
+                                         unsigned* __restrict__ simi_bits, int M, int W, int i, int lane, const float4* pts_scan) {
     const float leaf = st->leaf_size;
     const float radius_r = 10.0f * leaf;
     const float th_sim = 0.1f * leaf;
@@ -81,29 +81,54 @@ __device__ __forceinline__ void simi_row(FrameState* st, const float4* __restric
             cnt += __popc(m);
         }
     } else if (n1ok) {
-        for (int j0 = 0; j0 < M; j0 += 32) {
-            const int j = j0 + lane;
-            bool keep = false; float d2 = 0.0f;
-            if (j < M && j != i) {
-                const f3 P2 = ld3(pts, j);
-                d2 = dist2(P1, P2);
-                if (d2 < r2) {
-                    const f3 N2 = ld3(nrms, j);
-                    if (fin3(N2)) {
-                        const f3 v2 = normalize3(N2);
-                        keep = similarity_metric(P1, v1, P2, v2, radius_r) > th_sim;
-                    }
+        // count pass.  The radius test (cheap, ~1 candidate in 8 passes) and the metric (two square roots, five divisions)
+        // are separated: candidates inside the radius are compacted into a 64-entry window and the metric runs on DENSE
+        // batches of 32 -- evaluated inside the scan loop it ran once per 32 candidates with ~4 lanes active.  The kept
+        // bits are collected in a shared-memory copy of the row (the bit row i of the similarity graph, drosa.cu).
+        __shared__ unsigned short s_buf[WARPS_PER_BLOCK][64];
+        __shared__ unsigned s_row[WARPS_PER_BLOCK][128];
+        unsigned short* buf = s_buf[threadIdx.x >> 5];
+        unsigned* row = s_row[threadIdx.x >> 5];
+        for (int w = lane; w < W; w += 32) row[w] = 0u;
+        __syncwarp();
+        const unsigned lt = (1u << lane) - 1u;
+        auto batch = [&](int nb) {
+            bool keep = false; int j = 0;
+            if (lane < nb) {
+                j = buf[lane];
+                const f3 N2 = ld3(nrms, j);
+                if (fin3(N2)) {
+                    const f3 P2 = ld3(pts_scan, j);
+                    const f3 v2 = normalize3(N2);
+                    keep = similarity_metric(P1, v1, P2, v2, radius_r) > th_sim;
                 }
             }
-            const unsigned m = __ballot_sync(FULL, keep);
-            if (!FILL && lane == 0) simi_bits[(size_t)i * W + (j0 >> 5)] = m;      // bit row i of the similarity graph (drosa.cu)
-            if (FILL && keep) { const int pos = base + cnt + __popc(m & ((1u << lane) - 1u)); tmp_j[pos] = j; tmp_d[pos] = d2; }
-            cnt += __popc(m);
+            if (keep) atomicOr(&row[j >> 5], 1u << (j & 31));
+            cnt += __popc(__ballot_sync(FULL, keep));
+        };
+        int nbuf = 0;
+        for (int j0 = 0; j0 < M; j0 += 32) {
+            const int j = j0 + lane;
+            const bool in = (j < M && j != i) && (dist2(P1, ld3(pts_scan, j < M ? j : 0)) < r2);
+            const unsigned m = __ballot_sync(FULL, in);
+            if (in) buf[nbuf + __popc(m & lt)] = (unsigned short)j;
+            nbuf += __popc(m);
+            __syncwarp();
+            if (nbuf >= 32) {
+                batch(32);
+                const unsigned short mv = buf[32 + lane];       // the window holds < 64 entries: move the rest down
+                __syncwarp();
+                buf[lane] = mv;
+                nbuf -= 32;
+                __syncwarp();
+            }
         }
+        if (nbuf > 0) batch(nbuf);
+        __syncwarp();
+        for (int w = lane; w < W; w += 32) simi_bits[(size_t)i * W + w] = row[w];      // padding words of the row stay zero
     }
     if (!FILL) {
         if (!n1ok) for (int w = lane; w < W; w += 32) simi_bits[(size_t)i * W + w] = 0u;
-        else if (lane < W - ((M + 31) >> 5)) simi_bits[(size_t)i * W + ((M + 31) >> 5) + lane] = 0u;   // padding words of the row
         if (lane == 0) simi_off[i] = cnt;
         return;
     }
@@ -126,7 +151,18 @@ __global__ void k_simi(FrameState* st, const float4* __restrict__ pts, const flo
     const int W = (((M + 31) >> 5) + 3) & ~3;   // row stride of the bit matrix: padded to 16 bytes (drosa.cu reads rows with 16-byte loads)
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (i < M) simi_row<FILL>(st, pts, nrms, simi_off, simi_idx, tmp_j, tmp_d, simi_bits, M, W, i, lane);
+    const float4* pts_scan = pts;
+    if (!FILL) {
+        // count pass: the block's 8 warps scan the same M positions -- staged once (coalesced, every load in flight at the
+        // same time) instead of 27 dependent rounds of L2 latency per warp
+        extern __shared__ float4 s_simi_pts[];
+        if ((int)(blockIdx.x * WARPS_PER_BLOCK) < M) {
+            for (int j = threadIdx.x; j < M; j += blockDim.x) s_simi_pts[j] = pts[j];
+            pts_scan = s_simi_pts;
+        }
+        __syncthreads();
+    }
+    if (i < M) simi_row<FILL>(st, pts, nrms, simi_off, simi_idx, tmp_j, tmp_d, simi_bits, M, W, i, lane, pts_scan);
     if (FILL) return;
     // the last block of the count pass turns the counts into CSR offsets (no separate scan launch)
     __shared__ int s_last;
@@ -748,12 +784,12 @@ bool dcrosa_cluster16_ok() {
     return n >= 1;
 }
 void mscale_set_attributes(int Mcap) {
-    (void)Mcap;
     drosa_set_attributes();
     cudaFuncSetAttribute(k_dcrosa_cluster<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, DC_SMEM_BUDGET);
     cudaFuncSetAttribute(k_dcrosa_cluster<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, DC_SMEM_BUDGET);
     cudaFuncSetAttribute(k_dcrosa_cluster<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaFuncSetAttribute(k_vs_greedy, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM_BUDGET);
+    cudaFuncSetAttribute(k_simi<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float4) * (size_t)Mcap));
 }
 
 void launch_mscale(osep_rosa_impl* h) {
@@ -773,7 +809,7 @@ void launch_mscale(osep_rosa_impl* h) {
         cudaEventRecord(h->ev_join3, sk);
     }
     // R12
-    k_simi<false><<<warp_blocks, tb, 0, s>>>(d.st, d.pts, d.nrms, d.simi_off, d.simi_idx, nullptr, nullptr, d.simi_bits, d.Scap);   // count + bit rows; its last block scans
+    k_simi<false><<<warp_blocks, tb, sizeof(float4) * (size_t)d.Mcap, s>>>(d.st, d.pts, d.nrms, d.simi_off, d.simi_idx, nullptr, nullptr, d.simi_bits, d.Scap);   // count + bit rows; its last block scans
     // the similarity LISTS (CSR, in (d2, index) order) are only read by dcrosa: the fill pass runs on the side stream next to
     // the fused drosa kernel (which needs the bit rows of the count pass only) and is joined before dcrosa
     const bool simi_side = h->overlap && (h->simi_side >= 0 ? h->simi_side == 1 : h->fused_grid == 0);
