@@ -275,7 +275,7 @@ def run_ours(args, rank, world, local_rank):
     knn_bytes = 28 * res0.n_filtered                       # SURVEY 8(d) phase (3): read 16 N', write 12 N'
     roofline = {"bound": "hbm", "kernel": "k_drosa_fused (persistent cooperative kernel: 6 orientation iterations + position step, %.0f %% of the frame)" % (100 * drosa_ms / ms_per_step),
                 "achieved": drosa_gbs, "peak": peak, "unit": "GB/s", "frac": drosa_gbs / peak,
-                "traffic": 543190, "traffic_source": "profiles/r2_final_ncu_full_kernels.md (dram__bytes_read.sum + dram__bytes_write.sum of k_drosa_fused, one ncu --set full capture, cold cache)",
+                "traffic": 519168, "traffic_source": "profiles/r2_s7_ncu_full_kernels.md (dram__bytes_read.sum + dram__bytes_write.sum of k_drosa_fused, one ncu --set full capture, cold cache)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": drosa_bytes, "ms_per_launch": drosa_ms,
                 "note": "latency-bound by construction: ~236 dependent 3x3 eigen solves per Gauss-Seidel chain (rosa.cpp:295-308), six chains as overlapping wavefronts, "
                         "one warp per chain at ~4 cycles per dependent instruction (ncu: 7.8 % issue-active, 90 % L2 hit); the HBM fraction is reported for the record, the signal is ms_per_launch",
