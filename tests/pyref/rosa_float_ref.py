@@ -50,6 +50,11 @@ def eig1(a00, a10, a11, a20, a21, a22):
     return ev[0], Q[0]
 
 
+def seq0(X):
+    """sequential float32 sum of the rows of X starting from +0 (`acc = Zero(); acc += x` ...): (-0) rows give +0 like the C++ loops"""
+    return np.cumsum(np.concatenate([np.zeros((1,) + X.shape[1:], F), X.astype(F)], axis=0), axis=0, dtype=F)[-1]
+
+
 def lane_sum(idx, X):
     """Canonical sum (C4) of the rows X[k] belonging to the ascending member indices idx[k]: per-lane sequential sums in
     ascending index, then the xor butterfly.  X: (m, c) float32 -> (c,) float32."""
@@ -60,8 +65,8 @@ def lane_sum(idx, X):
     cnt = np.bincount(ls, minlength=32)
     start = np.r_[0, np.cumsum(cnt)[:-1]]
     rank = np.arange(m) - start[ls]
-    Z = np.zeros((32, max(int(cnt.max()), 1), c), F)
-    Z[ls, rank] = X[order]
+    Z = np.zeros((32, int(cnt.max()) + 1, c), F)          # slot 0 stays +0: every lane's accumulator starts from zero
+    Z[ls, rank + 1] = X[order]
     with np.errstate(all="ignore"):
         acc = np.cumsum(Z, axis=1, dtype=F)[:, -1, :]       # sequential; the zero padding after a lane's last member adds nothing
         for off in (16, 8, 4, 2, 1):
@@ -71,8 +76,8 @@ def lane_sum(idx, X):
 
 def seq_sum_lists(vals, lens):
     """vals: (n, L, c) zero padded after lens[i] entries; sequential sums in list order -> (n, c)."""
-    cs = np.cumsum(vals, axis=1, dtype=F)
-    return cs[np.arange(vals.shape[0]), np.maximum(lens, 1) - 1]
+    cs = np.cumsum(np.concatenate([np.zeros_like(vals[:, :1]), vals], axis=1), axis=1, dtype=F)      # accumulators start from +0
+    return cs[np.arange(vals.shape[0]), lens]
 
 
 def orthonormal_frame_x(nv):
@@ -224,7 +229,7 @@ class RosaFloatRef:
                     wv = self.vvar[snb][:, None] * v                               # E4
                     terms = np.stack([wv[:, 0] * v[:, 0], wv[:, 1] * v[:, 0], wv[:, 1] * v[:, 1],
                                       wv[:, 2] * v[:, 0], wv[:, 2] * v[:, 1], wv[:, 2] * v[:, 2]], axis=1).astype(F)
-                    Ms = np.cumsum(terms, axis=0, dtype=F)[-1]
+                    Ms = seq0(terms)
                     _, Q = eig1(*Ms)
                     r = Q[:, 2].copy()
                     z = (r[0] * r[0] + r[1] * r[1]) + r[2] * r[2]                  # E2
@@ -373,7 +378,7 @@ class RosaFloatRef:
                 idx = np.nonzero(corresp == v)[0]
                 if idx.size == 0:
                     continue
-                s = np.cumsum(self.pts[idx], axis=0, dtype=F)[-1]     # RD.pts_ at the COMPACTED index (rosa.cpp:523)
+                s = seq0(self.pts[idx])                               # RD.pts_ at the COMPACTED index (rosa.cpp:523)
                 ec = s / F(idx.size)
                 skel[v] = self.alpha * skel[v] + c1 * ec
         self.Mc = Mc
@@ -410,11 +415,11 @@ class RosaFloatRef:
                     n = nb.size
                     if n <= 1:
                         continue
-                    mean = np.cumsum(cur[nb], axis=0, dtype=F)[-1] / F(n)
+                    mean = seq0(cur[nb]) / F(n)
                     d = cur[nb] - mean[None, :]
                     terms = np.stack([d[:, 0] * d[:, 0], d[:, 1] * d[:, 0], d[:, 1] * d[:, 1],
                                       d[:, 2] * d[:, 0], d[:, 2] * d[:, 1], d[:, 2] * d[:, 2]], axis=1).astype(F)
-                    C = np.cumsum(terms, axis=0, dtype=F)[-1] / F(n)
+                    C = seq0(terms) / F(n)
                     _, Q = eig1(*C)
                     pd = Q[:, 2]
                     p = cur[i]

@@ -312,8 +312,9 @@ class RosaRef:
         with np.errstate(all="ignore"):
             for v in range(M):
                 idx = order[starts[v]:ends[v]]
-                sp = np.cumsum(P[idx], axis=0, dtype=F)[-1]                # sequential float sums in ascending point index
-                sn = np.cumsum(N[idx], axis=0, dtype=F)[-1]
+                z3 = np.zeros((1, 3), F)                                   # the accumulators start from +0 (Vector3f / Vector4f ::Zero())
+                sp = np.cumsum(np.concatenate([z3, P[idx]]), axis=0, dtype=F)[-1]                # sequential float sums in ascending point index
+                sn = np.cumsum(np.concatenate([z3, N[idx]]), axis=0, dtype=F)[-1]
                 pts[v] = sp / F(idx.size)
                 zz = (sn[0] * sn[0] + sn[2] * sn[2]) + (sn[1] * sn[1] + F(0.0))   # Vector4f::normalized(): packet reduction (a0+a2)+(a1+a3)
                 if zz > 0:

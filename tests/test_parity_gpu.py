@@ -565,29 +565,10 @@ def test_sparse_far_points_take_the_exact_knn_path_bit_exact(mods):
 
 
 def _weird_clouds(fx):
-    rng = np.random.default_rng(77)
-    out = {}
-    base = fx.cylinder(8000, seed=12)
-    # isolated outliers far from everything (kNN slow path: ring search beyond R = 2, brute force)
-    outl = rng.uniform(-40, 40, (12, 3)).astype(np.float32)
-    out["outliers"] = np.concatenate([base, outl])
-    # planar patch (normals all parallel -> planar branch of the position step, rosa.cpp:334)
-    pl = np.stack([rng.uniform(5, 15, 6000), rng.uniform(-5, 5, 6000), 0.01 * rng.normal(size=6000)], 1).astype(np.float32)
-    out["plane"] = pl
-    # thin line: 1-D structure, the leaf loop oscillates / runs out of passes
-    t = rng.uniform(0, 30, 5000)
-    out["line"] = np.stack([10 + 0.01 * rng.normal(size=5000), 0.01 * rng.normal(size=5000), t - 15], 1).astype(np.float32)
-    # two far-apart clusters (huge bbox, tiny occupied volume)
-    a = rng.normal(size=(3000, 3)).astype(np.float32) * 0.5 + np.array([10, -30, -20], np.float32)
-    b = rng.normal(size=(3000, 3)).astype(np.float32) * 0.5 + np.array([12, 30, 25], np.float32)
-    out["two_clusters"] = np.concatenate([a, b])
-    # heavy duplication: 400 distinct points, each repeated 10 times (distance ties everywhere)
-    d = fx.cylinder(400, seed=5)
-    out["duplicates"] = np.repeat(d, 10, axis=0)
-    # coarse lattice (many exactly equal distances)
-    g = np.stack(np.meshgrid(np.arange(10, 14, 0.25), np.arange(-3, 3, 0.25), np.arange(-4, 4, 0.25), indexing="ij"), -1).reshape(-1, 3)
-    out["lattice"] = g.astype(np.float32)
-    return out
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from pyref import scenarios
+    return scenarios.weird_clouds(fx)
 
 
 @pytest.mark.parametrize("name", ["outliers", "plane", "line", "two_clusters", "duplicates", "lattice"])

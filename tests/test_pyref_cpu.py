@@ -101,6 +101,24 @@ def test_rosa_oracle_matches_pyref_on_every_stage(name):
     assert len(ft["skelver"]) >= 10
 
 
+@pytest.mark.parametrize("name", ["plane", "line", "duplicates", "lattice"])
+def test_rosa_oracle_matches_pyref_on_degenerate_clouds(name):
+    """plane: 943 of 1050 points are 'poor' (planar branch of the position step, the fix-up with the reference's index
+    mix-up); line: the leaf loop runs out of passes; duplicates / lattice: distance ties everywhere and sums of -0 components
+    (accumulators start from +0).  Every stage, bit for bit (signs of zeros included)."""
+    P = sc.weird_clouds(fx)[name]
+    o = po.RosaOracle(); r = rr.RosaRef()
+    assert o.run(P) and r.run(P)
+    for tap in ROSA_TAPS:
+        a, b = r.t[tap], o.tap(tap)
+        assert_same(a.reshape(-1) if tap == "knn_full" else a, b, "%s on %s" % (tap, name))
+    ft = float_stages(r, {})
+    for tap in FLOAT_TAPS:
+        assert_same(np.asarray(ft[tap]).reshape(-1), np.asarray(o.tap(tap)).reshape(-1), "%s on %s" % (tap, name))
+    if name == "plane":
+        assert len(ft["poor_idx"]) > 500
+
+
 def test_rosa_pyref_edge_inputs():
     """non-finite / far points, duplicates, min_points gate -- same filter decisions as the oracle"""
     P = fx.cylinder(3000, seed=5)
