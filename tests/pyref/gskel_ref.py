@@ -496,3 +496,27 @@ class GSkelRef:
             off[i + 1] = off[i] + len(l)
         idx = np.array([x for l in lists for x in l], dtype=np.int32)
         return off, idx
+
+
+def skeleton_graph(V, fuse_dist_th=3.0):
+    """graph_adj + mst + graph_decomp (gskel.cpp:201-281, 539-567) of a bare vertex set -- what the frame's tail kernel and
+    osep_rosa_graph / osep_graph_build compute.  Returns (rng lists, mst lists, mst edges in acceptance order, weights,
+    types, joints, leafs)."""
+    g = GSkelRef(fuse_dist_th=fuse_dist_th)
+    for p in np.asarray(V, dtype=np.float32):
+        v = Vertex()
+        v.position = (F(p[0]), F(p[1]), F(p[2]))
+        g.glob.append(v)
+    g.cloud = [v.position for v in g.glob]
+    g.size = len(g.glob)
+    g.adj = [[] for _ in g.glob]
+    with np.errstate(all="ignore"):
+        if not g.graph_adj():
+            return None
+        rng = [list(a) for a in g.adj]
+        if not g.mst():
+            return None
+        edges = sorted((norm(vsub(g.glob[u].position, g.glob[v].position)), u, v) for u in range(g.size) for v in g.adj[u] if v > u)
+    return dict(rng=rng, mst=[list(a) for a in g.adj], edges=np.array([[u, v] for _, u, v in edges], np.int32).reshape(-1, 2),
+                edge_w=np.array([w for w, _, _ in edges], np.float32), type=np.array([v.type for v in g.glob], np.int32),
+                joints=np.array(g.joints, np.int32), leafs=np.array(g.leafs, np.int32))

@@ -752,6 +752,13 @@ def test_library_matches_pyref_on_every_rosa_stage(mods, name):
     for tap in ["vset_iters", "active_size", "poor_idx", "pset_drosa", "pset", "seeds", "corresp", "skelver_sampled", "skelver"]:
         assert_bit_equal(r.tap(tap).reshape(-1), np.asarray(ft[tap]).reshape(-1), "%s vs pyref on %s" % (tap, name))
     assert_bit_equal(np.ascontiguousarray(r.output_vertices()).reshape(-1), ft["skelver"].reshape(-1), "output_vertices vs pyref on %s" % name)
+    # ... and on to the skeleton graph (graph_adj + mst + graph_decomp, gskel.cpp:201-281,539-567) of those vertices
+    gr_, _, _ = _pyref()
+    g, ref_g = r.graph(3.0), gr_.skeleton_graph(ft["skelver"], 3.0)
+    assert_bit_equal(g["edges"].reshape(-1), ref_g["edges"].reshape(-1), "mst edges vs pyref on %s" % name)
+    assert_bit_equal(g["edge_w"], ref_g["edge_w"], "mst weights vs pyref on %s" % name)
+    assert_bit_equal(g["type"], ref_g["type"], "vertex types vs pyref on %s" % name)
+    assert [list(g["rng_idx"][g["rng_off"][i]:g["rng_off"][i + 1]]) for i in range(len(ref_g["rng"]))] == ref_g["rng"], "rng lists vs pyref"
     r.close()
 
 

@@ -195,6 +195,33 @@ def test_gskel_edge_cases_of_the_reference():
     assert all(i < len(ref.glob) for i in ref.new_idx)
 
 
+def test_skeleton_graph_oracle_matches_pyref():
+    """graph_adj (kNN-10 + relative-neighbourhood test) + mst + graph_decomp of bare vertex sets -- the frame's in-frame graph:
+    the oracle's GraphOracle against gskel_ref.skeleton_graph, incl. duplicates (zero-length edges, ties) and forests"""
+    rng = np.random.default_rng(5)
+    sets = []
+    for G in (2, 9, 10, 11, 60, 200):
+        V = np.cumsum(rng.normal(size=(G, 3)) * 0.8 + np.array([0, 0, 1.2]), axis=0).astype(np.float32)
+        if G > 20:
+            V[7] = V[3]
+        sets.append(V)
+    sets.append(np.concatenate([sets[3], sets[3] + np.float32(100.0)]))             # two far components: a forest
+    lat = np.stack(np.meshgrid(np.arange(4.0), np.arange(3.0), np.arange(3.0), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    sets.append(lat)                                                                # every weight tied
+    for V in sets:
+        go = po.GraphOracle(V, 3.0)
+        ref = gr.skeleton_graph(V, 3.0)
+        what = "G=%d" % len(V)
+        assert_same(ref["edges"].reshape(-1), go.tap("mst_edges"), "mst edges " + what)
+        assert_same(ref["edge_w"], go.tap("mst_w"), "mst weights " + what)
+        off, idx = go.tap("rng_off"), go.tap("rng_idx")
+        assert [list(idx[off[i]:off[i + 1]]) for i in range(len(V))] == ref["rng"], "rng lists " + what
+        off, idx = go.tap("adj_off"), go.tap("adj_idx")
+        assert [list(idx[off[i]:off[i + 1]]) for i in range(len(V))] == ref["mst"], "mst lists " + what
+        assert_same(ref["type"], go.tap("type"), "type " + what)
+        assert_same(ref["joints"], go.tap("joints"), "joints " + what); assert_same(ref["leafs"], go.tap("leafs"), "leafs " + what)
+
+
 def test_map_reference_and_tf_restatements_agree():
     """tests/pyref/map_ref.py (numpy) against the C++ oracle's orc_tf_points (both restate tf2_sensor_msgs' float32 transform,
     gskel_node.cpp:137-138) bit for bit, and the first-point-per-voxel map law on a case small enough to check by hand."""
