@@ -544,7 +544,7 @@ __device__ __forceinline__ float block_bound(const FrameState* st, float rx, flo
 
 // R5 slow path: one WARP per query, exact kNN by ring expansion (R = 1, 2, 3, 4, 6, 8, 12, ...), then everything.
 // Handles whatever the cell-cooperative kernels could not certify: points whose k nearest neighbours lie many cells away
-// (the sparse far end of a LiDAR frame; beyond a block of n / 32 cells the lanes stride over the whole cloud instead).  The lanes probe the cells of the NEW SHELL of a ring in parallel (the block
+// (the sparse far end of a LiDAR frame; beyond a block of n / 8 cells the lanes stride over the whole cloud instead).  The lanes probe the cells of the NEW SHELL of a ring in parallel (the block
 // scanned so far is not rescanned) and push the points they find into a register-resident sorted top-K of their own; the 32
 // lists are then merged into the frame's (d2, index) order by k rounds of a warp arg-min over the list heads, which gives
 // the k-th distance for the certification test and re-seeds the lists.  One thread per query (the first version) walked
@@ -605,9 +605,9 @@ __global__ void __launch_bounds__(128) k_knn_exact(const float4* __restrict__ Pc
         // ring has found k points almost every later candidate is; without it every lane's list, re-seeded with <= 2
         // entries, took every candidate through the insertion network)
         float wd = finf; int wi = 0x7fffffff;
-        for (int R = 1;; R = (R < 4) ? R + 1 : R + (R >> 1)) {
+        for (int R = 1;;) {
             const long long side = 2ll * R + 1;
-            if (R > 3 && side * side * side > (long long)n / 32) {
+            if (R > 3 && side * side * side > (long long)n / 8) {
                 // the block would cost more than every point: lanes stride over the cloud
                 tk.init();
                 for (int e0 = lane; e0 < n; e0 += 32 * 8) {              // eight independent loads in flight per lane
@@ -658,6 +658,11 @@ __global__ void __launch_bounds__(128) k_knn_exact(const float4* __restrict__ Pc
             const float bound = block_bound(st, rx, ry, rz, x0, x1, y0, y1, z0, z1);
             if (bound > 0.0f && wi != 0x7fffffff && wd < bound * bound) break;
             ox0 = x0; ox1 = x1; oy0 = y0; oy1 = y1; oz0 = z0; oz1 = z1;
+            // next ring: 2, 3, 4, 6, 9, ... while fewer than k points are known; once k are, their k-th distance bounds the
+            // answer and the block that certifies it is known -- go there directly (the test above stays the only exit)
+            int Rn = (R < 4) ? R + 1 : R + (R >> 1);
+            if (wi != 0x7fffffff) { const float need = sqrtf(wd) * st->g_inv_h + 1.0f; if (need < 1.0e6f) Rn = max(R + 1, (int)need); }
+            R = Rn;
         }
 #pragma unroll
         for (int u = 0; u < RS; ++u) { const int r = u * 32 + lane; if (r < k_eff) knn_idx[(size_t)qi * k_eff + r] = resi[u]; }
