@@ -66,7 +66,7 @@ def float_stages(r, kw):
     return f.run()
 
 
-@pytest.mark.parametrize("name", ["cyl20k", "turbine100k", "stream7", "stream131", "cyl5k_k12", "cyl5k_iters", "cyl8k_mp1500", "stream375_cut"])
+@pytest.mark.parametrize("name", ["cyl20k", "turbine100k", "stream7", "stream131", "cyl5k_k12", "cyl5k_iters", "cyl8k_mp1500", "cut_stream375"])
 def test_rosa_oracle_matches_pyref_on_every_stage(name):
     """discrete stages (rosa_ref) AND the float stages up to the skeleton vertices (rosa_float_ref), bit for bit"""
     kw = {}
@@ -76,7 +76,7 @@ def test_rosa_oracle_matches_pyref_on_every_stage(name):
         P = fx.turbine()
     elif name.startswith("stream"):
         P = fx.stream_frame(int(name[6:]), n=30000)[0]
-    elif name == "stream375_cut":
+    elif name == "cut_stream375":
         P = fx.stream_frame(375, n=50000)[0][:42029]          # cut short inside the third blade: 363 sparse points, 27 poor points
     elif name == "cyl8k_mp1500":
         # M = 1465 > 1024: the lanes of the canonical active-set sums (C4) own two words each
